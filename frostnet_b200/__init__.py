@@ -1,0 +1,12 @@
+"""frostnet_b200 - B200-native (sm_100a) implementation of FrostNet's QAT forward/backward hot path
+and the StatAssist/GradBoost optimizer step, behind the reference's nn.Module / Optimizer surface.
+
+    from frostnet_b200 import frostnet_quant_large_1_0, prepare_qat, get_optimizer
+"""
+from .frostnet import *          # noqa: F401,F403  (FrostNet, blocks, 30 factories)
+from .frostnet import FrostNet, CascadePreExBottleneck, ConvBNReLU, ConvBN
+from .qat import prepare_qat, patch_torch_quantization, FrostFakeQuantize
+from .optimizer import QSGD, QRMSprop, QAdam, QAdamW, get_optimizer
+from . import parallel
+
+__version__ = "0.1.0"

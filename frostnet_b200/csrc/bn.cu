@@ -1,0 +1,256 @@
+// bn.cu - BatchNorm(+ReLU)+activation fake-quant of one fused conv, forward and backward.
+// Restates torch/ao/nn/intrinsic/qat/modules/conv_fused.py:156-167 (+ :708-710 ReLU) and the
+// activation_post_process hook (fake_quantize.py:423-438) on top of the integer accumulators I:
+//   conv_orig = conv/scale_factor = I * m_c,  m_c = s_a*s_w/scale_factor_c
+//   v = bn(conv_orig) = A_c*I + B_c          (training: batch statistics from exact integer sums)
+//   y = FQ_a(relu(v))
+#include "common.cuh"
+
+namespace frost {
+
+void dw_launch_shape(int C, int* cg_per_block, int* nchunks, int* threads);
+
+__device__ __forceinline__ float bn_affine(int I, float A, float B) { return fmaf((float)I, A, B); }
+
+// ---------------------------------------------------------------- finalize (1 CTA)
+__global__ void __launch_bounds__(256) bn_finalize_kernel(FrostBnFinalizeArgs a) {
+  __shared__ float s_mn[8], s_mx[8];
+  const double M = (double)a.count;
+  const double sa_sw = (double)(*a.x_scale) * (double)(*a.w_scale);
+  float gmn = INFINITY, gmx = -INFINITY;
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    const FrostChanStats st = a.stats[c];
+    const double sum = (double)st.sum;
+    const double sq = (double)st.sq_hi * 4294967296.0 + (double)st.sq_lo;
+    const double mean_I = sum / M;
+    double var_I = sq / M - mean_I * mean_I;
+    if (var_I < 0.0) var_I = 0.0;
+    const double m_c = sa_sw / (double)a.sf[c];
+    double mean_u, invstd;
+    if (a.training) {
+      mean_u = m_c * mean_I;
+      const double var_u = m_c * m_c * var_I;
+      invstd = 1.0 / sqrt(var_u + (double)a.eps);
+      const double unbiased = (a.count > 1) ? var_u * (M / (M - 1.0)) : var_u;
+      a.running_mean[c] = (float)((1.0 - (double)a.momentum) * (double)a.running_mean[c] + (double)a.momentum * mean_u);
+      a.running_var[c] = (float)((1.0 - (double)a.momentum) * (double)a.running_var[c] + (double)a.momentum * unbiased);
+    } else {
+      mean_u = (double)a.running_mean[c];
+      invstd = 1.0 / sqrt((double)a.running_var[c] + (double)a.eps);
+    }
+    const double g = (double)a.gamma[c];
+    const float A = (float)(m_c * invstd * g);
+    const float B = (float)((double)a.beta[c] - mean_u * invstd * g);
+    a.A[c] = A;
+    a.B[c] = B;
+    a.mean_I[c] = (float)mean_I;
+    a.kfac[c] = (float)(m_c * invstd);
+    // v is monotone in I for fixed (A,B): the channel extrema of v sit at the integer extrema.
+    float v0 = bn_affine(st.min, A, B), v1 = bn_affine(st.max, A, B);
+    if (a.relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
+    gmn = fminf(gmn, fminf(v0, v1));
+    gmx = fmaxf(gmx, fmaxf(v0, v1));
+  }
+  gmn = warp_min(gmn);
+  gmx = warp_max(gmx);
+  if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = gmn; s_mx[threadIdx.x >> 5] = gmx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { gmn = fminf(gmn, s_mn[w]); gmx = fmaxf(gmx, s_mx[w]); }
+    if (a.training && a.num_batches_tracked) *a.num_batches_tracked += 1;
+    if (a.observe) observer_update(a.afq, gmn, gmx, 0, 255, false, a.averaging_const);
+    const float s = *a.afq.scale, zp = (float)*a.afq.zero_point;
+    const float inv = __fdiv_rn(1.0f, s);
+    const float qa = fminf(fmaxf(fq_index(gmn, inv, zp), 0.0f), 255.0f);
+    const float qb = fminf(fmaxf(fq_index(gmx, inv, zp), 0.0f), 255.0f);
+    a.cur_minmax[0] = fq_dequant(qa, zp, s);
+    a.cur_minmax[1] = fq_dequant(qb, zp, s);
+  }
+}
+
+// ---------------------------------------------------------------- apply: I -> uint8 index
+// 8 consecutive elements per thread-iteration (2x 16-byte loads, one 8-byte store).
+__global__ void __launch_bounds__(256) bnq_apply_kernel(const int32_t* __restrict__ acc, int64_t n8, int C,
+                                                       const float* __restrict__ A, const float* __restrict__ B,
+                                                       int relu, const float* __restrict__ scale_p,
+                                                       const int32_t* __restrict__ zp_p, uint8_t* __restrict__ q) {
+  extern __shared__ float s_ab[];  // A[C], B[C]
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { s_ab[c] = A[c]; s_ab[C + c] = B[c]; }
+  __syncthreads();
+  const float s = *scale_p, zp = (float)*zp_p;
+  const float inv = __fdiv_rn(1.0f, s);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const int4 v0 = __ldg(reinterpret_cast<const int4*>(acc) + 2 * i);
+    const int4 v1 = __ldg(reinterpret_cast<const int4*>(acc) + 2 * i + 1);
+    const int I[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    int c = (int)((i * 8) % C);
+    unsigned out[2] = {0u, 0u};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = bn_affine(I[e], s_ab[c], s_ab[C + c]);
+      if (relu) v = fmaxf(v, 0.0f);
+      const float qc = fminf(fmaxf(fq_index(v, inv, zp), 0.0f), 255.0f);
+      out[e >> 2] |= ((unsigned)qc) << (8 * (e & 3));
+      if (++c == C) c = 0;
+    }
+    reinterpret_cast<uint2*>(q)[i] = make_uint2(out[0], out[1]);
+  }
+}
+
+// ---------------------------------------------------------------- backward
+// dv = dy * [0 <= idx <= 255] * [v > 0 if relu]
+__device__ __forceinline__ float bn_dv(float dy, int I, float A, float B, int relu, float inv, float zp) {
+  const float v = bn_affine(I, A, B);
+  const float r = relu ? fmaxf(v, 0.0f) : v;
+  const float idx = fq_index(r, inv, zp);
+  const bool pass = (idx >= 0.0f) && (idx <= 255.0f) && (!relu || v > 0.0f);
+  return pass ? dy : 0.0f;
+}
+
+// Per-channel S1 = sum dv, S2 = sum dv*I.  Thread -> fixed 4-channel group, strided rows.
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(FrostBnBackwardArgs a, int cg_per_block) {
+  extern __shared__ double s_sum[];  // [cg_per_block*4][2]
+  const int C = a.C, CG = C >> 2;
+  const int cg_local = threadIdx.x % cg_per_block;
+  const int cg = blockIdx.y * cg_per_block + cg_local;
+  const int rows_per_block = blockDim.x / cg_per_block;
+  const int row_local = threadIdx.x / cg_per_block;
+  for (int i = threadIdx.x; i < cg_per_block * 8; i += blockDim.x) s_sum[i] = 0.0;
+  __syncthreads();
+  if (cg < CG) {
+    const float inv = __fdiv_rn(1.0f, *a.out_scale), zp = (float)*a.out_zp;
+    const float4 A = __ldg(reinterpret_cast<const float4*>(a.A) + cg);
+    const float4 B = __ldg(reinterpret_cast<const float4*>(a.B) + cg);
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    for (int64_t m = (int64_t)blockIdx.x * rows_per_block + row_local; m < a.M; m += (int64_t)gridDim.x * rows_per_block) {
+      const float4 dy = __ldg(reinterpret_cast<const float4*>(a.dy + m * C) + cg);
+      const int4 I = __ldg(reinterpret_cast<const int4*>(a.acc + m * C) + cg);
+      const float d0 = bn_dv(dy.x, I.x, A.x, B.x, a.relu, inv, zp);
+      const float d1 = bn_dv(dy.y, I.y, A.y, B.y, a.relu, inv, zp);
+      const float d2 = bn_dv(dy.z, I.z, A.z, B.z, a.relu, inv, zp);
+      const float d3 = bn_dv(dy.w, I.w, A.w, B.w, a.relu, inv, zp);
+      s1[0] += d0; s2[0] += (double)d0 * (double)I.x;
+      s1[1] += d1; s2[1] += (double)d1 * (double)I.y;
+      s1[2] += d2; s2[2] += (double)d2 * (double)I.z;
+      s1[3] += d3; s2[3] += (double)d3 * (double)I.w;
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      atomicAdd(&s_sum[(cg_local * 4 + ch) * 2], s1[ch]);
+      atomicAdd(&s_sum[(cg_local * 4 + ch) * 2 + 1], s2[ch]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cg_per_block * 4; i += blockDim.x) {
+    const int c = blockIdx.y * cg_per_block * 4 + i;
+    if (c < C) {
+      atomicAdd(a.sums + 2 * c, s_sum[2 * i]);
+      atomicAdd(a.sums + 2 * c + 1, s_sum[2 * i + 1]);
+    }
+  }
+}
+
+// Per-channel coefficients of  dz = c1*(dv - a0 - a1*(I - mean_I))  plus the BN parameter grads.
+__global__ void __launch_bounds__(256) bn_bwd_coef_kernel(FrostBnBackwardArgs a) {
+  const double M = (double)a.M;
+  const double sa_sw = (double)(*a.x_scale) * (double)(*a.w_scale);
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    const double S1 = a.sums[2 * c], S2 = a.sums[2 * c + 1];
+    const double k = (double)a.kfac[c];
+    const double T = k * (S2 - (double)a.mean_I[c] * S1);  // sum dv*xhat
+    const double g = (double)a.gamma[c];
+    const double sf = (double)a.sf[c];
+    const double invstd = k * sf / sa_sw;                  // k = m_c*invstd, m_c = sa_sw/sf
+    a.coef[3 * c + 0] = (float)((double)a.A[c] / sa_sw);   // c1 = gamma*invstd/sf
+    a.coef[3 * c + 1] = (float)(S1 / M);                   // a0
+    a.coef[3 * c + 2] = (float)(k * T / M);                // a1
+    a.dgamma_bn[c] = (float)T;
+    a.dbeta[c] = (float)S1;
+    a.dsf_bn[c] = (float)(-g * T * (double)a.eps * invstd * invstd / sf);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(FrostBnBackwardArgs a, int64_t n4) {
+  extern __shared__ float s_c[];  // A,B,mean_I,c1,a0,a1 : 6*C
+  const int C = a.C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    s_c[c] = a.A[c];
+    s_c[C + c] = a.B[c];
+    s_c[2 * C + c] = a.mean_I[c];
+    s_c[3 * C + c] = a.coef[3 * c];
+    s_c[4 * C + c] = a.coef[3 * c + 1];
+    s_c[5 * C + c] = a.coef[3 * c + 2];
+  }
+  __syncthreads();
+  const float inv = __fdiv_rn(1.0f, *a.out_scale), zp = (float)*a.out_zp;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 dy = __ldg(reinterpret_cast<const float4*>(a.dy) + i);
+    const int4 I4 = __ldg(reinterpret_cast<const int4*>(a.acc) + i);
+    const float dyv[4] = {dy.x, dy.y, dy.z, dy.w};
+    const int Iv[4] = {I4.x, I4.y, I4.z, I4.w};
+    float o[4];
+    const int c0 = (int)((i * 4) % C);  // C % 4 == 0: a float4 never straddles a row
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = c0 + e;
+      const float dv = bn_dv(dyv[e], Iv[e], s_c[c], s_c[C + c], a.relu, inv, zp);
+      o[e] = s_c[3 * C + c] * (dv - s_c[4 * C + c] - s_c[5 * C + c] * ((float)Iv[e] - s_c[2 * C + c]));
+    }
+    reinterpret_cast<float4*>(a.dz)[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+}  // namespace frost
+
+using namespace frost;
+
+extern "C" int frost_bn_finalize(const FrostBnFinalizeArgs* a, void* stream) {
+  FROST_REQUIRE(a && a->stats && a->x_scale && a->w_scale && a->sf && a->gamma && a->beta && a->running_mean &&
+                    a->running_var && a->A && a->B && a->mean_I && a->kfac && a->cur_minmax && a->afq.scale &&
+                    a->afq.zero_point && a->afq.min_val && a->afq.max_val,
+                "frost_bn_finalize: null pointer");
+  FROST_REQUIRE(a->C > 0 && a->count > 0, "frost_bn_finalize: empty tensor");
+  bn_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*a);
+  FROST_LAUNCH_CHECK("bn_finalize");
+  return FROST_OK;
+}
+
+extern "C" int frost_bnq_apply(const int32_t* acc, int64_t M, int C, const float* A, const float* B, int relu,
+                               const float* out_scale, const int32_t* out_zp, uint8_t* q, void* stream) {
+  FROST_REQUIRE(acc && A && B && out_scale && out_zp && q, "frost_bnq_apply: null pointer");
+  FROST_REQUIRE(M > 0 && C > 0 && C % 8 == 0, "frost_bnq_apply: C=%d must be a positive multiple of 8", C);
+  const int64_t n8 = M * C / 8;
+  bnq_apply_kernel<<<grid_for(n8, 256 * 2), 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(acc, n8, C, A, B, relu,
+                                                                                              out_scale, out_zp, q);
+  FROST_LAUNCH_CHECK("bnq_apply");
+  return FROST_OK;
+}
+
+extern "C" int frost_bn_backward(const FrostBnBackwardArgs* a, void* stream) {
+  FROST_REQUIRE(a && a->dy && a->acc && a->A && a->B && a->mean_I && a->kfac && a->gamma && a->sf && a->x_scale &&
+                    a->w_scale && a->out_scale && a->out_zp && a->sums && a->coef && a->dz && a->dgamma_bn &&
+                    a->dbeta && a->dsf_bn,
+                "frost_bn_backward: null pointer");
+  FROST_REQUIRE(a->M > 0 && a->C > 0 && a->C % 4 == 0, "frost_bn_backward: C=%d must be a positive multiple of 4", a->C);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(a->sums, 0, sizeof(double) * 2 * a->C, st) != cudaSuccess) {
+    set_error("frost_bn_backward: memset failed");
+    return FROST_ECUDA;
+  }
+  int cgb, chunks, threads;
+  dw_launch_shape(a->C, &cgb, &chunks, &threads);
+  const int rows_per_block = threads / cgb;
+  int gx = (int)std::min<int64_t>(ceil_div(a->M, (int64_t)rows_per_block * 4), (int64_t)kNumSMs * 8);
+  bn_bwd_reduce_kernel<<<dim3(gx, chunks), threads, sizeof(double) * cgb * 8, st>>>(*a, cgb);
+  FROST_LAUNCH_CHECK("bn_bwd_reduce");
+  bn_bwd_coef_kernel<<<1, 256, 0, st>>>(*a);
+  FROST_LAUNCH_CHECK("bn_bwd_coef");
+  const int64_t n4 = a->M * a->C / 4;
+  const size_t smem = 6 * (size_t)a->C * sizeof(float);
+  FROST_REQUIRE(smem <= 48 * 1024, "frost_bn_backward: C=%d too large for the coefficient tile", a->C);
+  bn_bwd_apply_kernel<<<grid_for(n4, 256 * 4), 256, smem, st>>>(*a, n4);
+  FROST_LAUNCH_CHECK("bn_bwd_apply");
+  return FROST_OK;
+}

@@ -1,0 +1,539 @@
+// conv_bwd.cu - dgrad / wgrad of the quantised convolutions and the classifier GEMMs
+// (aten::convolution_backward / addmm in the reference's autograd graph; SURVEY.md 8a' steps 4-5).
+// Operands: dz fp32 (gradient wrt the real-valued conv output), weights as int8 indices,
+// activations as uint8 indices; the dequantisation scale is applied once in the epilogue.
+// v1: shared-memory tiled SIMT fp32 kernels.
+#include "common.cuh"
+
+namespace frost {
+
+void dw_launch_shape(int C, int* cg_per_block, int* nchunks, int* threads);
+
+constexpr int GB_T = 64;    // output tile edge
+constexpr int GB_RC = 16;   // reduction chunk
+constexpr int GB_LD = GB_T + 4;
+
+// ---------------------------------------------------------------- pointwise dgrad
+// dx[m][k] (+)= s_w * sum_co dz[m][co] * (wq[co][k] - zp_w)
+__global__ void __launch_bounds__(256) pw_dgrad_kernel(const float* __restrict__ dz, const int8_t* __restrict__ wq,
+                                                      const float* __restrict__ w_scale_p, const int32_t* __restrict__ w_zp_p,
+                                                      int64_t M, int K, int cout, float* __restrict__ dx, int accumulate) {
+  __shared__ __align__(16) float a_s[GB_RC][GB_LD];  // dz^T : [co][m]
+  __shared__ __align__(16) float b_s[GB_RC][GB_LD];  // w    : [co][k]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.x * GB_T;
+  const int k0 = blockIdx.y * GB_T;
+  const float zp_w = (float)*w_zp_p;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  for (int c0 = 0; c0 < cout; c0 += GB_RC) {
+    {  // dz tile: 64 rows x 16 co, one float4 per thread
+      const int r = tid >> 2, c4 = tid & 3;
+      const int64_t m = m0 + r;
+      const int co = c0 + c4 * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < M && co < cout) v = __ldg(reinterpret_cast<const float4*>(dz + m * cout + co));  // cout % 4 == 0
+      a_s[c4 * 4 + 0][r] = v.x;
+      a_s[c4 * 4 + 1][r] = v.y;
+      a_s[c4 * 4 + 2][r] = v.z;
+      a_s[c4 * 4 + 3][r] = v.w;
+    }
+    {  // weight tile: 16 co x 64 k int8, 4 bytes per thread
+      const int r = tid >> 4, k4 = tid & 15;
+      const int co = c0 + r, k = k0 + k4 * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (co < cout && k < K) {
+        const unsigned pk = __ldg(reinterpret_cast<const unsigned*>(wq + (int64_t)co * K + k));
+        v.x = (float)(int8_t)(pk & 0xff) - zp_w;
+        v.y = (float)(int8_t)((pk >> 8) & 0xff) - zp_w;
+        v.z = (float)(int8_t)((pk >> 16) & 0xff) - zp_w;
+        v.w = (float)(int8_t)((pk >> 24) & 0xff) - zp_w;
+      }
+      *reinterpret_cast<float4*>(&b_s[r][k4 * 4]) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GB_RC; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&a_s[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&b_s[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const float s_w = *w_scale_p;
+  const int k = k0 + tx * 4;
+  if (k < K) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t m = m0 + ty * 4 + i;
+      if (m < M) {
+        float4* p = reinterpret_cast<float4*>(dx + m * K + k);
+        float4 r = make_float4(acc[i][0] * s_w, acc[i][1] * s_w, acc[i][2] * s_w, acc[i][3] * s_w);
+        if (accumulate) {
+          const float4 o = *p;
+          r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+        }
+        *p = r;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- pointwise wgrad (split over M)
+// dwq[co][k] += s_a * sum_m dz[m][co] * (x[m][k] - zp_a);  X = uint8 indices or fp32 (classifier)
+template <typename XT>
+__global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__ dz, const XT* __restrict__ x,
+                                                      const float* __restrict__ x_scale_p, const int32_t* __restrict__ x_zp_p,
+                                                      int64_t M, int K, int cout, int64_t rows_per_split,
+                                                      float* __restrict__ dwq) {
+  __shared__ __align__(16) float a_s[GB_RC][GB_LD];  // dz : [m][co]
+  __shared__ __align__(16) float b_s[GB_RC][GB_LD];  // x  : [m][k]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int co0 = blockIdx.x * GB_T, k0 = blockIdx.y * GB_T;
+  const int64_t m_begin = (int64_t)blockIdx.z * rows_per_split;
+  const int64_t m_end = min(M, m_begin + rows_per_split);
+  const float zp_a = x_zp_p ? (float)*x_zp_p : 0.0f;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  for (int64_t mc = m_begin; mc < m_end; mc += GB_RC) {
+    const int r = tid >> 4, c4 = tid & 15;
+    const int64_t m = mc + r;
+    {
+      const int co = co0 + c4 * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < m_end && co < cout) v = __ldg(reinterpret_cast<const float4*>(dz + m * cout + co));
+      *reinterpret_cast<float4*>(&a_s[r][c4 * 4]) = v;
+    }
+    {
+      const int k = k0 + c4 * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < m_end && k < K) {
+        if constexpr (sizeof(XT) == 1) {
+          const unsigned pk = __ldg(reinterpret_cast<const unsigned*>(x + m * K + k));
+          v.x = (float)(pk & 0xff) - zp_a;
+          v.y = (float)((pk >> 8) & 0xff) - zp_a;
+          v.z = (float)((pk >> 16) & 0xff) - zp_a;
+          v.w = (float)((pk >> 24) & 0xff) - zp_a;
+        } else {
+          v = __ldg(reinterpret_cast<const float4*>(x + m * K + k));
+        }
+      }
+      *reinterpret_cast<float4*>(&b_s[r][c4 * 4]) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GB_RC; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&a_s[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&b_s[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const float s_a = x_scale_p ? *x_scale_p : 1.0f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + ty * 4 + i;
+    if (co >= cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k < K) atomicAdd(dwq + (int64_t)co * K + k, acc[i][j] * s_a);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- depthwise dgrad
+// dx[n][ih][iw][c] (+)= s_w * sum_{r,s} dz[n][oh][ow][c] * (w[r][s][c]-zp_w),  oh*S-pad+r == ih
+template <int KS, int S>
+__global__ void __launch_bounds__(256) dw_dgrad_kernel(const float* __restrict__ dz, const int8_t* __restrict__ wq,
+                                                      const float* __restrict__ w_scale_p, const int32_t* __restrict__ w_zp_p,
+                                                      int N, int H, int W, int C, int Ho, int Wo, int cg_per_block,
+                                                      float* __restrict__ dx, int accumulate) {
+  constexpr int PAD = (KS - 1) / 2;
+  const int CG = C >> 2;
+  const int cg_local = threadIdx.x % cg_per_block;
+  const int cg = blockIdx.y * cg_per_block + cg_local;
+  const int pix_per_block = blockDim.x / cg_per_block;
+  const int pix_local = threadIdx.x / cg_per_block;
+  if (cg >= CG) return;
+  const float zp_w = (float)*w_zp_p, s_w = *w_scale_p;
+  float w[KS * KS][4];
+#pragma unroll
+  for (int t = 0; t < KS * KS; ++t) {
+    const unsigned pk = __ldg(reinterpret_cast<const unsigned*>(wq + (int64_t)t * C + cg * 4));
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) w[t][ch] = ((float)(int8_t)((pk >> (8 * ch)) & 0xff) - zp_w) * s_w;
+  }
+  const int64_t total = (int64_t)N * H * W;
+  for (int64_t p = (int64_t)blockIdx.x * pix_per_block + pix_local; p < total; p += (int64_t)gridDim.x * pix_per_block) {
+    const int iw = (int)(p % W);
+    const int64_t t1 = p / W;
+    const int ih = (int)(t1 % H);
+    const int n = (int)(t1 / H);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < KS; ++r) {
+      const int th = ih + PAD - r;
+      if (th < 0 || (th % S) != 0) continue;
+      const int oh = th / S;
+      if (oh >= Ho) continue;
+#pragma unroll
+      for (int s = 0; s < KS; ++s) {
+        const int tw = iw + PAD - s;
+        if (tw < 0 || (tw % S) != 0) continue;
+        const int ow = tw / S;
+        if (ow >= Wo) continue;
+        const float4 d = __ldg(reinterpret_cast<const float4*>(dz + (((int64_t)n * Ho + oh) * Wo + ow) * C) + cg);
+        acc[0] = fmaf(d.x, w[r * KS + s][0], acc[0]);
+        acc[1] = fmaf(d.y, w[r * KS + s][1], acc[1]);
+        acc[2] = fmaf(d.z, w[r * KS + s][2], acc[2]);
+        acc[3] = fmaf(d.w, w[r * KS + s][3], acc[3]);
+      }
+    }
+    float4* o = reinterpret_cast<float4*>(dx + p * C) + cg;
+    float4 v = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    if (accumulate) {
+      const float4 old = *o;
+      v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+    }
+    *o = v;
+  }
+}
+
+// ---------------------------------------------------------------- depthwise wgrad
+// dwq[t][c] += s_a * sum_{n,oh,ow} dz[n][oh][ow][c] * (x[n][oh*S-pad+r][ow*S-pad+s][c] - zp_a)
+template <int KS, int S>
+__global__ void __launch_bounds__(256) dw_wgrad_kernel(const float* __restrict__ dz, const uint8_t* __restrict__ xq,
+                                                      const float* __restrict__ x_scale_p, const int32_t* __restrict__ x_zp_p,
+                                                      int N, int H, int W, int C, int Ho, int Wo, int cg_per_block,
+                                                      float* __restrict__ dwq) {
+  constexpr int PAD = (KS - 1) / 2;
+  const int CG = C >> 2;
+  const int cg_local = threadIdx.x % cg_per_block;
+  const int cg = blockIdx.y * cg_per_block + cg_local;
+  const int pix_per_block = blockDim.x / cg_per_block;
+  const int pix_local = threadIdx.x / cg_per_block;
+  if (cg >= CG) return;
+  const float zp_a = (float)*x_zp_p;
+  float acc[KS * KS][4];
+#pragma unroll
+  for (int t = 0; t < KS * KS; ++t)
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) acc[t][ch] = 0.0f;
+  const int64_t total = (int64_t)N * Ho * Wo;
+  for (int64_t p = (int64_t)blockIdx.x * pix_per_block + pix_local; p < total; p += (int64_t)gridDim.x * pix_per_block) {
+    const int ow = (int)(p % Wo);
+    const int64_t t1 = p / Wo;
+    const int oh = (int)(t1 % Ho);
+    const int n = (int)(t1 / Ho);
+    const float4 d = __ldg(reinterpret_cast<const float4*>(dz + p * C) + cg);
+#pragma unroll
+    for (int r = 0; r < KS; ++r) {
+      const int ih = oh * S - PAD + r;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int s = 0; s < KS; ++s) {
+        const int iw = ow * S - PAD + s;
+        if (iw < 0 || iw >= W) continue;
+        const unsigned pk = __ldg(reinterpret_cast<const unsigned*>(xq + (((int64_t)n * H + ih) * W + iw) * C + cg * 4));
+        acc[r * KS + s][0] = fmaf(d.x, (float)(pk & 0xff) - zp_a, acc[r * KS + s][0]);
+        acc[r * KS + s][1] = fmaf(d.y, (float)((pk >> 8) & 0xff) - zp_a, acc[r * KS + s][1]);
+        acc[r * KS + s][2] = fmaf(d.z, (float)((pk >> 16) & 0xff) - zp_a, acc[r * KS + s][2]);
+        acc[r * KS + s][3] = fmaf(d.w, (float)((pk >> 24) & 0xff) - zp_a, acc[r * KS + s][3]);
+      }
+    }
+  }
+  const float s_a = *x_scale_p;
+#pragma unroll
+  for (int t = 0; t < KS * KS; ++t)
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) atomicAdd(dwq + (int64_t)t * C + cg * 4 + ch, acc[t][ch] * s_a);
+}
+
+// ---------------------------------------------------------------- stem wgrad
+// dwq[co][r][s][ci] += s_a * sum_pix dz[pix][co] * (x[patch(pix)][r][s][ci] - zp_a)
+constexpr int STEMW_PIX = 32;
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ dz, const uint8_t* __restrict__ xq,
+                                                        const float* __restrict__ x_scale_p, const int32_t* __restrict__ x_zp_p,
+                                                        int N, int H, int W, int cin, int cout, int k, int stride, int pad,
+                                                        int Ho, int Wo, int64_t pix_per_block, float* __restrict__ dwq) {
+  extern __shared__ float s_buf[];
+  const int KK = k * k * cin;
+  float* s_patch = s_buf;                      // [STEMW_PIX][KK]
+  float* s_dz = s_buf + STEMW_PIX * KK;        // [STEMW_PIX][32]
+  const int co = threadIdx.x & 31, j = threadIdx.x >> 5;  // 8 tap groups
+  const float zp_a = (float)*x_zp_p;
+  const int64_t total = (int64_t)N * Ho * Wo;
+  const int64_t p_begin = (int64_t)blockIdx.x * pix_per_block;
+  const int64_t p_end = min(total, p_begin + pix_per_block);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  for (int64_t pb = p_begin; pb < p_end; pb += STEMW_PIX) {
+    const int np = (int)min((int64_t)STEMW_PIX, p_end - pb);
+    for (int i = threadIdx.x; i < STEMW_PIX * KK; i += blockDim.x) {
+      const int pl = i / KK, t = i % KK;
+      float v = 0.0f;
+      if (pl < np) {
+        const int64_t p = pb + pl;
+        const int ow = (int)(p % Wo);
+        const int64_t t1 = p / Wo;
+        const int oh = (int)(t1 % Ho);
+        const int n = (int)(t1 / Ho);
+        const int ci = t % cin, rs = t / cin, r = rs / k, s = rs % k;
+        const int ih = oh * stride - pad + r, iw = ow * stride - pad + s;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+          v = (float)__ldg(xq + (((int64_t)n * H + ih) * W + iw) * cin + ci) - zp_a;
+      }
+      s_patch[i] = v;
+    }
+    for (int i = threadIdx.x; i < STEMW_PIX * 32; i += blockDim.x) {
+      const int pl = i >> 5, c = i & 31;
+      s_dz[i] = (pl < np && c < cout) ? __ldg(dz + (pb + pl) * cout + c) : 0.0f;
+    }
+    __syncthreads();
+    for (int pl = 0; pl < np; ++pl) {
+      const float d = s_dz[pl * 32 + co];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int t = j + 8 * i;
+        if (t < KK) acc[i] = fmaf(d, s_patch[pl * KK + t], acc[i]);
+      }
+    }
+    __syncthreads();
+  }
+  if (co < cout) {
+    const float s_a = *x_scale_p;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = j + 8 * i;
+      if (t < KK) atomicAdd(dwq + (int64_t)co * KK + t, acc[i] * s_a);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- classifier forward
+// out[n][co] = sum_k x[n][k] * (wq[co][k]-zp_w)*s_w + bias[co]
+__global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict__ x, const int8_t* __restrict__ wq,
+                                                        const float* __restrict__ w_scale_p, const int32_t* __restrict__ w_zp_p,
+                                                        const float* __restrict__ bias, int N, int K, int cout,
+                                                        float* __restrict__ out) {
+  __shared__ __align__(16) float a_s[GB_RC][GB_LD];  // x^T : [k][n]
+  __shared__ __align__(16) float b_s[GB_RC][GB_LD];  // w^T : [k][co]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int n0 = blockIdx.x * GB_T, co0 = blockIdx.y * GB_T;
+  const float zp_w = (float)*w_zp_p, s_w = *w_scale_p;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  for (int k0 = 0; k0 < K; k0 += GB_RC) {
+    const int r = tid >> 2, k4 = tid & 3;
+    const int k = k0 + k4 * 4;
+    {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 + r < N && k < K) v = __ldg(reinterpret_cast<const float4*>(x + (int64_t)(n0 + r) * K + k));
+      a_s[k4 * 4 + 0][r] = v.x; a_s[k4 * 4 + 1][r] = v.y; a_s[k4 * 4 + 2][r] = v.z; a_s[k4 * 4 + 3][r] = v.w;
+    }
+    {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (co0 + r < cout && k < K) {
+        const unsigned pk = __ldg(reinterpret_cast<const unsigned*>(wq + (int64_t)(co0 + r) * K + k));
+        v.x = ((float)(int8_t)(pk & 0xff) - zp_w) * s_w;
+        v.y = ((float)(int8_t)((pk >> 8) & 0xff) - zp_w) * s_w;
+        v.z = ((float)(int8_t)((pk >> 16) & 0xff) - zp_w) * s_w;
+        v.w = ((float)(int8_t)((pk >> 24) & 0xff) - zp_w) * s_w;
+      }
+      b_s[k4 * 4 + 0][r] = v.x; b_s[k4 * 4 + 1][r] = v.y; b_s[k4 * 4 + 2][r] = v.z; b_s[k4 * 4 + 3][r] = v.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GB_RC; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&a_s[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&b_s[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty * 4 + i;
+    if (n >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + tx * 4 + j;
+      if (co < cout) out[(int64_t)n * cout + co] = acc[i][j] + (bias ? bias[co] : 0.0f);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d, int N, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.0f;
+  for (int n = 0; n < N; ++n) s += d[(int64_t)n * C + c];
+  out[c] = s;
+}
+
+static int launch_pw_wgrad_u8(const float* dz, const uint8_t* x, const float* xs, const int32_t* xzp, int64_t M, int K,
+                              int cout, float* dwq, cudaStream_t st) {
+  const int ct = (int)ceil_div(cout, GB_T), kt = (int)ceil_div(K, GB_T);
+  int64_t splits = std::max<int64_t>(1, std::min<int64_t>(ceil_div(M, GB_RC * 8), ceil_div((int64_t)kNumSMs * 4, (int64_t)ct * kt)));
+  int64_t rows = ceil_div(ceil_div(M, splits), GB_RC) * GB_RC;
+  splits = ceil_div(M, rows);
+  pw_wgrad_kernel<uint8_t><<<dim3(ct, kt, (unsigned)splits), 256, 0, st>>>(dz, x, xs, xzp, M, K, cout, rows, dwq);
+  return 0;
+}
+
+}  // namespace frost
+
+using namespace frost;
+
+extern "C" int frost_pw_dgrad(const float* dz, const int8_t* wq, const float* w_scale, const int32_t* w_zp, int64_t M,
+                              int K, int cout, float* dx, int accumulate, void* stream) {
+  FROST_REQUIRE(dz && wq && w_scale && w_zp && dx, "frost_pw_dgrad: null pointer");
+  FROST_REQUIRE(M > 0 && K > 0 && cout > 0 && K % 4 == 0 && cout % 4 == 0, "frost_pw_dgrad: K and cout must be multiples of 4");
+  pw_dgrad_kernel<<<dim3((unsigned)ceil_div(M, GB_T), (unsigned)ceil_div(K, GB_T)), 256, 0, (cudaStream_t)stream>>>(
+      dz, wq, w_scale, w_zp, M, K, cout, dx, accumulate);
+  FROST_LAUNCH_CHECK("pw_dgrad");
+  return FROST_OK;
+}
+
+extern "C" int frost_pw_wgrad(const float* dz, const uint8_t* xq, const float* x_scale, const int32_t* x_zp, int64_t M,
+                              int K, int cout, float* dwq, void* stream) {
+  FROST_REQUIRE(dz && xq && x_scale && x_zp && dwq, "frost_pw_wgrad: null pointer");
+  FROST_REQUIRE(M > 0 && K > 0 && cout > 0 && K % 4 == 0 && cout % 4 == 0, "frost_pw_wgrad: K and cout must be multiples of 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(dwq, 0, sizeof(float) * (size_t)K * cout, st) != cudaSuccess) {
+    set_error("frost_pw_wgrad: memset failed");
+    return FROST_ECUDA;
+  }
+  launch_pw_wgrad_u8(dz, xq, x_scale, x_zp, M, K, cout, dwq, st);
+  FROST_LAUNCH_CHECK("pw_wgrad");
+  return FROST_OK;
+}
+
+extern "C" int frost_dw_dgrad(const float* dz, const int8_t* wq, const float* w_scale, const int32_t* w_zp, int N, int H,
+                              int W, int C, int k, int stride, float* dx, int accumulate, void* stream) {
+  FROST_REQUIRE(dz && wq && w_scale && w_zp && dx, "frost_dw_dgrad: null pointer");
+  FROST_REQUIRE(C > 0 && C % 4 == 0 && (k == 3 || k == 5) && (stride == 1 || stride == 2), "frost_dw_dgrad: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int pad = (k - 1) / 2;
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  int cgb, chunks, threads;
+  dw_launch_shape(C, &cgb, &chunks, &threads);
+  const int ppb = threads / cgb;
+  int gx = (int)std::min<int64_t>(ceil_div((int64_t)N * H * W, ppb), (int64_t)kNumSMs * 8);
+  dim3 grid(gx, chunks);
+#define L(KS, S) dw_dgrad_kernel<KS, S><<<grid, threads, 0, st>>>(dz, wq, w_scale, w_zp, N, H, W, C, Ho, Wo, cgb, dx, accumulate)
+  if (k == 3 && stride == 1) L(3, 1);
+  else if (k == 3 && stride == 2) L(3, 2);
+  else if (k == 5 && stride == 1) L(5, 1);
+  else L(5, 2);
+#undef L
+  FROST_LAUNCH_CHECK("dw_dgrad");
+  return FROST_OK;
+}
+
+extern "C" int frost_dw_wgrad(const float* dz, const uint8_t* xq, const float* x_scale, const int32_t* x_zp, int N, int H,
+                              int W, int C, int k, int stride, float* dwq, void* stream) {
+  FROST_REQUIRE(dz && xq && x_scale && x_zp && dwq, "frost_dw_wgrad: null pointer");
+  FROST_REQUIRE(C > 0 && C % 4 == 0 && (k == 3 || k == 5) && (stride == 1 || stride == 2), "frost_dw_wgrad: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int pad = (k - 1) / 2;
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  if (cudaMemsetAsync(dwq, 0, sizeof(float) * (size_t)k * k * C, st) != cudaSuccess) {
+    set_error("frost_dw_wgrad: memset failed");
+    return FROST_ECUDA;
+  }
+  int cgb, chunks, threads;
+  dw_launch_shape(C, &cgb, &chunks, &threads);
+  const int ppb = threads / cgb;
+  int gx = (int)std::min<int64_t>(ceil_div((int64_t)N * Ho * Wo, (int64_t)ppb * 16), (int64_t)kNumSMs * 4);
+  dim3 grid(gx, chunks);
+#define L(KS, S) dw_wgrad_kernel<KS, S><<<grid, threads, 0, st>>>(dz, xq, x_scale, x_zp, N, H, W, C, Ho, Wo, cgb, dwq)
+  if (k == 3 && stride == 1) L(3, 1);
+  else if (k == 3 && stride == 2) L(3, 2);
+  else if (k == 5 && stride == 1) L(5, 1);
+  else L(5, 2);
+#undef L
+  FROST_LAUNCH_CHECK("dw_wgrad");
+  return FROST_OK;
+}
+
+extern "C" int frost_stem_wgrad(const float* dz, const uint8_t* xq, const float* x_scale, const int32_t* x_zp, int N,
+                                int H, int W, int cin, int cout, int k, int stride, int pad, float* dwq, void* stream) {
+  FROST_REQUIRE(dz && xq && x_scale && x_zp && dwq, "frost_stem_wgrad: null pointer");
+  FROST_REQUIRE(cout > 0 && cout <= 32 && cin > 0 && k > 0 && k * k * cin <= 64, "frost_stem_wgrad: cout<=32, k*k*cin<=64");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const int KK = k * k * cin;
+  if (cudaMemsetAsync(dwq, 0, sizeof(float) * (size_t)KK * cout, st) != cudaSuccess) {
+    set_error("frost_stem_wgrad: memset failed");
+    return FROST_ECUDA;
+  }
+  const int64_t total = (int64_t)N * Ho * Wo;
+  const int64_t nblk = std::min<int64_t>(ceil_div(total, STEMW_PIX), (int64_t)kNumSMs * 8);
+  const int64_t ppb = ceil_div(ceil_div(total, nblk), STEMW_PIX) * STEMW_PIX;
+  const size_t smem = sizeof(float) * (STEMW_PIX * KK + STEMW_PIX * 32);
+  stem_wgrad_kernel<<<(unsigned)ceil_div(total, ppb), 256, smem, st>>>(dz, xq, x_scale, x_zp, N, H, W, cin, cout, k, stride,
+                                                                      pad, Ho, Wo, ppb, dwq);
+  FROST_LAUNCH_CHECK("stem_wgrad");
+  return FROST_OK;
+}
+
+extern "C" int frost_linear_forward(const float* x, const int8_t* wq, const float* w_scale, const int32_t* w_zp,
+                                    const float* bias, int N, int K, int cout, float* out, void* stream) {
+  FROST_REQUIRE(x && wq && w_scale && w_zp && out, "frost_linear_forward: null pointer");
+  FROST_REQUIRE(N > 0 && K > 0 && cout > 0 && K % 4 == 0, "frost_linear_forward: K must be a multiple of 4");
+  linear_fwd_kernel<<<dim3((unsigned)ceil_div(N, GB_T), (unsigned)ceil_div(cout, GB_T)), 256, 0, (cudaStream_t)stream>>>(
+      x, wq, w_scale, w_zp, bias, N, K, cout, out);
+  FROST_LAUNCH_CHECK("linear_fwd");
+  return FROST_OK;
+}
+
+extern "C" int frost_linear_backward(const float* dout, const float* x, const int8_t* wq, const float* w_scale,
+                                     const int32_t* w_zp, int N, int K, int cout, float* dx, float* dwq, float* dbias,
+                                     void* stream) {
+  FROST_REQUIRE(dout && x && wq && w_scale && w_zp && dx && dwq, "frost_linear_backward: null pointer");
+  FROST_REQUIRE(N > 0 && K % 4 == 0 && cout % 4 == 0, "frost_linear_backward: K and cout must be multiples of 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = frost_pw_dgrad(dout, wq, w_scale, w_zp, N, K, cout, dx, 0, stream);
+  if (rc) return rc;
+  if (cudaMemsetAsync(dwq, 0, sizeof(float) * (size_t)K * cout, st) != cudaSuccess) {
+    set_error("frost_linear_backward: memset failed");
+    return FROST_ECUDA;
+  }
+  const int ct = (int)ceil_div(cout, GB_T), kt = (int)ceil_div(K, GB_T);
+  int64_t splits = std::max<int64_t>(1, std::min<int64_t>(ceil_div(N, GB_RC), ceil_div((int64_t)kNumSMs * 2, (int64_t)ct * kt)));
+  int64_t rows = ceil_div(ceil_div(N, splits), GB_RC) * GB_RC;
+  splits = ceil_div(N, rows);
+  pw_wgrad_kernel<float><<<dim3(ct, kt, (unsigned)splits), 256, 0, st>>>(dout, x, nullptr, nullptr, N, K, cout, rows, dwq);
+  FROST_LAUNCH_CHECK("linear_wgrad");
+  if (dbias) {
+    colsum_kernel<<<(unsigned)ceil_div(cout, 256), 256, 0, st>>>(dout, N, cout, dbias);
+    FROST_LAUNCH_CHECK("colsum");
+  }
+  return FROST_OK;
+}

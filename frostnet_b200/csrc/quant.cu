@@ -1,0 +1,253 @@
+// quant.cu - per-tensor fake-quant (observer + qparams + quantise), QuantStub, weight prep/backward.
+// Restates torch.fused_moving_avg_obs_fake_quant (torch/ao/quantization/fake_quantize.py:423-438)
+// and the weight side of nniqat.ConvBn2d (torch/ao/nn/intrinsic/qat/modules/conv_fused.py:131-146).
+#include "common.cuh"
+
+namespace frost {
+
+// ---------------------------------------------------------------- min/max reduction (no atomics)
+// Each block writes its partial (min,max) to partial[2*blockIdx.x ..]; a 1-block finalize reduces.
+constexpr int kMinMaxThreads = 256;
+constexpr int kMinMaxMaxBlocks = FROST_FQ_SCRATCH_FLOATS / 2;  // 1024
+
+__global__ void __launch_bounds__(kMinMaxThreads) minmax_partial_kernel(const float* __restrict__ x, int64_t n,
+                                                                        float* __restrict__ partial) {
+  float mn = INFINITY, mx = -INFINITY;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const int64_t n4 = vec_ok ? (n >> 2) : 0;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (int64_t i = tid; i < n4; i += stride) {
+    const float4 v = __ldg(x4 + i);
+    mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
+    mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+  }
+  for (int64_t i = (n4 << 2) + tid; i < n; i += stride) {
+    const float v = __ldg(x + i);
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  block_minmax(mn, mx);
+  if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = mn;
+    partial[2 * blockIdx.x + 1] = mx;
+  }
+}
+
+__global__ void __launch_bounds__(256) fq_apply_kernel(const float* __restrict__ x, int64_t n, const float* scale_p,
+                                                       const int32_t* zp_p, int qmin, int qmax, float* __restrict__ y,
+                                                       uint8_t* __restrict__ mask, int32_t* __restrict__ q) {
+  const float s = *scale_p, zp = (float)*zp_p;
+  const float inv = __fdiv_rn(1.0f, s);
+  const float lo = (float)qmin, hi = (float)qmax;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float idx = fq_index(__ldg(x + i), inv, zp);
+    const float qc = fminf(fmaxf(idx, lo), hi);
+    if (y) y[i] = fq_dequant(qc, zp, s);
+    if (mask) mask[i] = (idx >= lo && idx <= hi) ? 1 : 0;
+    if (q) q[i] = (int32_t)qc;
+  }
+}
+
+__global__ void __launch_bounds__(256) fq_backward_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ mask,
+                                                          int64_t n, float* __restrict__ dx) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dx[i] = mask[i] ? dy[i] : 0.0f;
+}
+
+// QuantStub apply: NCHW fp32 -> NHWC uint8.  One thread per (n,h,w) pixel.
+__global__ void __launch_bounds__(256) input_quant_apply_kernel(const float* __restrict__ x, int N, int C, int HW,
+                                                                const float* scale_p, const int32_t* zp_p,
+                                                                uint8_t* __restrict__ q) {
+  const float s = *scale_p, zp = (float)*zp_p;
+  const float inv = __fdiv_rn(1.0f, s);
+  const int64_t total = (int64_t)N * HW;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t n = i / HW, p = i - n * HW;
+    const float* src = x + (n * C) * HW + p;
+    uint8_t* dst = q + i * C;
+    for (int c = 0; c < C; ++c) {
+      const float idx = fq_index(__ldg(src + (int64_t)c * HW), inv, zp);
+      dst[c] = (uint8_t)fminf(fmaxf(idx, 0.0f), 255.0f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- weights
+__device__ __forceinline__ int64_t wq_index(const FrostWeightDesc& d, int c, int ci, int y, int x) {
+  switch (d.layout) {
+    case 1: return (int64_t)(y * d.kw + x) * d.cout + c;
+    case 2: return (((int64_t)c * d.kh + y) * d.kw + x) * d.cin_g + ci;
+    default: return (((int64_t)c * d.cin_g + ci) * d.kh + y) * d.kw + x;
+  }
+}
+
+constexpr int kWeightThreads = 1024;
+
+__global__ void __launch_bounds__(kWeightThreads) weight_prep_kernel(const FrostWeightDesc* __restrict__ descs) {
+  const FrostWeightDesc d = descs[blockIdx.x];
+  const int K = d.cin_g * d.kh * d.kw;
+  const int64_t total = (int64_t)d.cout * K;
+  // phase 0: scale_factor = gamma / sqrt(running_var + eps)      (conv_fused.py:138-139)
+  for (int c = threadIdx.x; c < d.cout; c += blockDim.x) {
+    float sf = 1.0f, rstd = 1.0f;
+    if (d.bn_weight) {
+      const float std_run = __fsqrt_rn(__fadd_rn(d.bn_var[c], d.bn_eps));
+      sf = __fdiv_rn(d.bn_weight[c], std_run);
+      rstd = __fdiv_rn(1.0f, std_run);
+    }
+    d.sf[c] = sf;
+    d.rstd_run[c] = rstd;
+    d.wsum[c] = 0;
+  }
+  __syncthreads();
+  // phase 1: observer over Ws = W * scale_factor
+  if (d.observe) {
+    float mn = INFINITY, mx = -INFINITY;
+    for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
+      const int c = (int)(e / K);
+      const float ws = __fmul_rn(d.weight[e], d.sf[c]);
+      mn = fminf(mn, ws);
+      mx = fmaxf(mx, ws);
+    }
+    block_minmax(mn, mx);
+    if (threadIdx.x == 0) observer_update(d.wfq, mn, mx, -128, 127, true, d.averaging_const);
+  }
+  __syncthreads();
+  __threadfence_block();
+  // phase 2: quantise
+  const float s = *d.wfq.scale, zp = (float)*d.wfq.zero_point;
+  const float inv = __fdiv_rn(1.0f, s);
+  const int khw = d.kh * d.kw;
+  for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
+    const int c = (int)(e / K);
+    const int r = (int)(e - (int64_t)c * K);
+    const int ci = r / khw, yx = r - ci * khw;
+    const int y = yx / d.kw, x = yx - y * d.kw;
+    const float ws = __fmul_rn(d.weight[e], d.sf[c]);
+    const float idx = fq_index(ws, inv, zp);
+    const float qc = fminf(fmaxf(idx, -128.0f), 127.0f);
+    d.wq[wq_index(d, c, ci, y, x)] = (int8_t)qc;
+    d.wmask[e] = (idx >= -128.0f && idx <= 127.0f) ? 1 : 0;
+    atomicAdd(d.wsum + c, (int)qc);
+  }
+}
+
+// dW = dWq*mask*sf ; dgamma = dgamma_bn + (dsf_bn + sum_k dWq*mask*W) * rstd_run   (SURVEY 8a' 5-6)
+__global__ void __launch_bounds__(kWeightThreads) weight_backward_kernel(const FrostWeightDesc* __restrict__ descs) {
+  const FrostWeightDesc d = descs[blockIdx.x];
+  const int K = d.cin_g * d.kh * d.kw;
+  const int khw = d.kh * d.kw;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int c = warp; c < d.cout; c += nwarps) {
+    const float sf = d.sf[c];
+    float acc = 0.0f;
+    for (int r = lane; r < K; r += 32) {
+      const int64_t e = (int64_t)c * K + r;
+      const int ci = r / khw, yx = r - ci * khw;
+      const int y = yx / d.kw, x = yx - y * d.kw;
+      const float dws = d.wmask[e] ? d.dwq[wq_index(d, c, ci, y, x)] : 0.0f;
+      d.dweight[e] = dws * sf;
+      acc = fmaf(dws, d.weight[e], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0 && d.dgamma) d.dgamma[c] = d.dgamma_bn[c] + (d.dsf_bn[c] + acc) * d.rstd_run[c];
+  }
+}
+
+__global__ void stats_reset_kernel(FrostChanStats* s, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    s[i].sum = 0;
+    s[i].sq_lo = 0;
+    s[i].sq_hi = 0;
+    s[i].min = INT_MAX;
+    s[i].max = INT_MIN;
+  }
+}
+
+static int run_observer(const float* x, int64_t n, FrostFQ fq, int qmin, int qmax, int symmetric, float c,
+                        float* cur_minmax, float* scratch, cudaStream_t st, bool observe) {
+  int nblk = 1;
+  if (observe || cur_minmax) {
+    nblk = grid_for(n, kMinMaxThreads * 8, kMinMaxMaxBlocks);
+    minmax_partial_kernel<<<nblk, kMinMaxThreads, 0, st>>>(x, n, scratch);
+    FROST_LAUNCH_CHECK("minmax_partial");
+  }
+  if (observe || cur_minmax) {
+    fq_finalize_kernel<<<1, 1024, 0, st>>>(scratch, nblk, fq, qmin, qmax, symmetric, c, observe ? 1 : 0, cur_minmax);
+    FROST_LAUNCH_CHECK("fq_finalize");
+  }
+  return FROST_OK;
+}
+
+}  // namespace frost
+
+using namespace frost;
+
+extern "C" int frost_stats_reset(FrostChanStats* stats, int64_t n, void* stream) {
+  FROST_REQUIRE(stats && n >= 0, "frost_stats_reset: bad args");
+  if (n == 0) return FROST_OK;
+  stats_reset_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(stats, n);
+  FROST_LAUNCH_CHECK("stats_reset");
+  return FROST_OK;
+}
+
+extern "C" int frost_fq_forward(const float* x, int64_t n, FrostFQ fq, int qmin, int qmax, int symmetric,
+                                int observe, float averaging_const, float* y, uint8_t* mask, int32_t* q,
+                                float* scratch, void* stream) {
+  FROST_REQUIRE(x && n > 0 && fq.scale && fq.zero_point && fq.min_val && fq.max_val && scratch,
+                "frost_fq_forward: null pointer or empty tensor (n=%lld)", (long long)n);
+  FROST_REQUIRE(qmin < qmax, "frost_fq_forward: qmin >= qmax");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (observe) {
+    int rc = run_observer(x, n, fq, qmin, qmax, symmetric, averaging_const, nullptr, scratch, st, true);
+    if (rc) return rc;
+  }
+  if (y || mask || q) {
+    fq_apply_kernel<<<grid_for(n, 256 * 4), 256, 0, st>>>(x, n, fq.scale, fq.zero_point, qmin, qmax, y, mask, q);
+    FROST_LAUNCH_CHECK("fq_apply");
+  }
+  return FROST_OK;
+}
+
+extern "C" int frost_fq_backward(const float* dy, const uint8_t* mask, int64_t n, float* dx, void* stream) {
+  FROST_REQUIRE(dy && mask && dx && n > 0, "frost_fq_backward: bad args");
+  fq_backward_kernel<<<grid_for(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(dy, mask, n, dx);
+  FROST_LAUNCH_CHECK("fq_backward");
+  return FROST_OK;
+}
+
+extern "C" int frost_input_quant(const float* x_nchw, int N, int C, int H, int W, FrostFQ fq, int observe,
+                                 float averaging_const, uint8_t* q_nhwc, float* cur_minmax, float* scratch,
+                                 void* stream) {
+  FROST_REQUIRE(x_nchw && q_nhwc && scratch && N > 0 && C > 0 && H > 0 && W > 0, "frost_input_quant: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = (int64_t)N * C * H * W;
+  if (observe || cur_minmax) {
+    int rc = run_observer(x_nchw, n, fq, 0, 255, 0, averaging_const, cur_minmax, scratch, st, observe != 0);
+    if (rc) return rc;
+  }
+  input_quant_apply_kernel<<<grid_for((int64_t)N * H * W, 256), 256, 0, st>>>(x_nchw, N, C, H * W, fq.scale,
+                                                                              fq.zero_point, q_nhwc);
+  FROST_LAUNCH_CHECK("input_quant_apply");
+  return FROST_OK;
+}
+
+extern "C" int frost_weight_prep_multi(const FrostWeightDesc* descs, int n, void* stream) {
+  FROST_REQUIRE(descs && n > 0, "frost_weight_prep_multi: bad args");
+  weight_prep_kernel<<<n, kWeightThreads, 0, (cudaStream_t)stream>>>(descs);
+  FROST_LAUNCH_CHECK("weight_prep");
+  return FROST_OK;
+}
+
+extern "C" int frost_weight_backward_multi(const FrostWeightDesc* descs, int n, void* stream) {
+  FROST_REQUIRE(descs && n > 0, "frost_weight_backward_multi: bad args");
+  weight_backward_kernel<<<n, kWeightThreads, 0, (cudaStream_t)stream>>>(descs);
+  FROST_LAUNCH_CHECK("weight_backward");
+  return FROST_OK;
+}

@@ -1,0 +1,484 @@
+"""Whole-network QAT executor: FrostNet.forward / backward as a plan of sm_100a kernel launches.
+
+One ``QATEngine`` per prepared model.  ``run(x)`` is what ``FrostNet.forward`` calls after
+``prepare_qat``: the whole network is ONE autograd node (``_QATFunction``) whose forward walks
+frostnet.py:318-332 / :124-145 and whose backward walks it in reverse (SURVEY.md 8a'), issuing the
+C-ABI kernels of include/frost_b200.h on the current CUDA stream.  Module parameters and buffers
+(BN running stats, observer min/max, scale, zero_point) are read and updated IN PLACE on the
+device - no host synchronisation anywhere in a step.
+
+HBM layout: activations are NHWC uint8 indices (1 B/element), raw conv outputs NHWC int32, the
+gradients NHWC fp32; weights are re-quantised to int8 once per step by one multi-tensor launch.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from . import qat as Q
+
+BN_MOMENTUM_DEFAULT = 0.1
+
+
+class _QT:
+    """A quantised activation tensor: uint8 NHWC indices + pointers to its (scale, zero_point)
+    buffers and to the dequantised [min, max] of its current contents."""
+    __slots__ = ("q", "N", "H", "W", "C", "scale", "zp", "mm")
+
+    def __init__(self, q, N, H, W, Cc, scale, zp, mm):
+        self.q, self.N, self.H, self.W, self.C, self.scale, self.zp, self.mm = q, N, H, W, Cc, scale, zp, mm
+
+    @property
+    def M(self):
+        return self.N * self.H * self.W
+
+    def c(self):
+        return L.QTensor(self.q.data_ptr(), self.scale.data_ptr(), self.zp.data_ptr(), self.mm.data_ptr(), self.C)
+
+
+def _fq_struct(f):
+    return L.FQ(f.activation_post_process.min_val.data_ptr(), f.activation_post_process.max_val.data_ptr(),
+                f.scale.data_ptr(), f.zero_point.data_ptr())
+
+
+class _Layer:
+    """One fused conv (FrostConvBn2d) or the classifier conv, with its persistent device artefacts."""
+
+    def __init__(self, name, mod, kind):
+        self.name, self.mod, self.kind = name, mod, kind       # kind: stem | pw | dw | cls
+        w = mod.weight
+        self.cout, self.cin_g, self.kh, self.kw = w.shape
+        self.has_bn = kind != "cls"
+        self.relu = bool(getattr(mod, "relu", False))
+        if kind != "cls":
+            self.stride, self.pad = mod.stride[0], mod.padding[0]
+            self.cin = mod.in_channels
+        else:
+            self.stride, self.pad, self.cin = 1, 0, mod.in_channels
+        self.layout = {"pw": 0, "cls": 0, "dw": 1, "stem": 2}[kind]
+
+    def alloc(self, dev):
+        f32 = dict(dtype=torch.float32, device=dev)
+        n = self.cout * self.cin_g * self.kh * self.kw
+        self.wq = torch.zeros(n, dtype=torch.int8, device=dev)
+        self.wmask = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.sf = torch.ones(self.cout, **f32)
+        self.rstd = torch.ones(self.cout, **f32)
+        self.wsum = torch.zeros(self.cout, dtype=torch.int32, device=dev)
+        self.dwq = torch.zeros(n, **f32)
+        self.dgamma_bn = torch.zeros(self.cout, **f32)
+        self.dsf_bn = torch.zeros(self.cout, **f32)
+        self.A = torch.zeros(self.cout, **f32)
+        self.B = torch.zeros(self.cout, **f32)
+        self.mean_I = torch.zeros(self.cout, **f32)
+        self.kfac = torch.zeros(self.cout, **f32)
+        self.coef = torch.zeros(3 * self.cout, **f32)
+        self.sums = torch.zeros(2 * self.cout, dtype=torch.float64, device=dev)
+        self.mm = torch.zeros(2, **f32)
+
+
+class QATEngine:
+    def __init__(self, model):
+        self.model = model
+        self.features = not hasattr(model, "classifier")
+        self._built = False
+        self.last_taps = None
+        self.record_taps = False
+        self.dropout_mask = None      # tests may inject a keep mask [N,1280]
+        self.grad_sync = None         # callable(flat_grad) -> None, set by frostnet_b200.parallel
+
+    def invalidate(self):
+        self._built = False
+
+    # ------------------------------------------------------------------ build
+    def _ensure_built(self):
+        if self._built:
+            return
+        m = self.model
+        L.load()
+        named = dict(m.named_modules())
+        self.layers, self.blocks = [], []
+
+        def add(name, kind):
+            mod = named[name + ".conv.0"] if kind != "cls" else named[name]
+            if kind != "cls" and not isinstance(mod, Q.FrostConvBn2d):
+                raise RuntimeError("frostnet_b200: %s is not fused; call model.fuse_model() + prepare_qat" % name)
+            ly = _Layer(name + (".conv.0" if kind != "cls" else ""), mod, kind)
+            self.layers.append(ly)
+            return ly
+
+        self.stem = add("conv1", "stem")
+        for si, stage in enumerate(m.stages()):
+            for bi, blk in enumerate(stage):
+                p = "layer%d.%d" % (si + 1, bi)
+                b = dict(name=p, mod=blk, squeeze=None, conv1=None, stage_end=(bi == len(stage) - 1), stage=si)
+                if blk.expand_ratio != 1:
+                    if blk.block_type == "CAS":
+                        b["squeeze"] = add(p + ".squeeze_conv", "pw")
+                    b["conv1"] = add(p + ".conv1", "pw")
+                b["conv2"] = add(p + ".conv2", "dw")
+                b["reduce"] = add(p + ".reduce_conv", "pw")
+                b["skip"] = not blk.reduction
+                self.blocks.append(b)
+        if not self.features:
+            self.last = add("last_layer", "pw")
+            self.cls = add("classifier.2", "cls")
+        p0 = next(m.parameters())
+        L.require_cuda(p0, "model")
+        dev = p0.device
+        self.dev = dev
+        for ly in self.layers:
+            if ly.kind == "dw" and not (ly.kh in (3, 5) and ly.stride in (1, 2) and ly.cin_g == 1):
+                raise RuntimeError("frostnet_b200: unsupported depthwise conv %s" % ly.name)
+            ly.alloc(dev)
+        # parameter order == model.named_parameters() (the optimizer / checkpoint contract)
+        self.params = [p for _, p in m.named_parameters()]
+        self.param_off, off = {}, 0
+        for p in self.params:
+            self.param_off[id(p)] = off
+            off += p.numel()
+        self.n_param_elems = off
+        self.gflat = [torch.zeros(off, dtype=torch.float32, device=dev) for _ in range(2)]
+        # channel statistics arena
+        tot_c = sum(ly.cout for ly in self.layers if ly.has_bn)
+        self.stats = torch.zeros(tot_c * C.sizeof(L.ChanStats), dtype=torch.uint8, device=dev)
+        o = 0
+        for ly in self.layers:
+            if ly.has_bn:
+                ly.stats_ptr = self.stats.data_ptr() + o * C.sizeof(L.ChanStats)
+                o += ly.cout
+        self.n_stat_chan = tot_c
+        self.scratch = torch.zeros(L.FQ_SCRATCH_FLOATS, dtype=torch.float32, device=dev)
+        self._wdesc_dev = [self._build_wdesc(i) for i in range(2)]
+        self._built = True
+
+    def _build_wdesc(self, which):
+        arr = (L.WeightDesc * len(self.layers))()
+        g = self.gflat[which]
+        for i, ly in enumerate(self.layers):
+            d, mod = arr[i], ly.mod
+            d.weight = mod.weight.data_ptr()
+            if ly.has_bn:
+                d.bn_weight = mod.bn.weight.data_ptr()
+                d.bn_var = mod.bn.running_var.data_ptr()
+                d.bn_eps = mod.bn.eps
+            else:
+                d.bn_weight, d.bn_var, d.bn_eps = None, None, 0.0
+            d.cout, d.cin_g, d.kh, d.kw, d.layout = ly.cout, ly.cin_g, ly.kh, ly.kw, ly.layout
+            d.observe = 1 if mod.weight_fake_quant._observe else 0
+            d.averaging_const = Q.AVERAGING_CONSTANT
+            d.wfq = _fq_struct(mod.weight_fake_quant)
+            d.wq, d.wmask, d.sf, d.rstd_run, d.wsum = (ly.wq.data_ptr(), ly.wmask.data_ptr(), ly.sf.data_ptr(),
+                                                       ly.rstd.data_ptr(), ly.wsum.data_ptr())
+            d.dwq = ly.dwq.data_ptr()
+            d.dweight = g.data_ptr() + 4 * self.param_off[id(mod.weight)]
+            if ly.has_bn:
+                d.dgamma_bn, d.dsf_bn = ly.dgamma_bn.data_ptr(), ly.dsf_bn.data_ptr()
+                d.dgamma = g.data_ptr() + 4 * self.param_off[id(mod.bn.weight)]
+            else:
+                d.dgamma_bn, d.dsf_bn, d.dgamma = None, None, None
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        return host.to(self.dev)
+
+    def _observer_flags_changed(self):
+        # cheap re-encode when someone toggled observers (rare): rebuild descriptor tables
+        self._wdesc_dev = [self._build_wdesc(i) for i in range(2)]
+
+    # ------------------------------------------------------------------ forward pieces
+    def _conv_bn(self, ly, xin, training, st, saved):
+        mod, dev = ly.mod, self.dev
+        N = xin.N
+        if ly.kind == "pw":
+            Ho, Wo = xin.H, xin.W
+        else:
+            Ho = (xin.H + 2 * ly.pad - ly.kh) // ly.stride + 1
+            Wo = (xin.W + 2 * ly.pad - ly.kw) // ly.stride + 1
+        M = N * Ho * Wo
+        acc = torch.empty((M, ly.cout), dtype=torch.int32, device=dev)
+        wzp = mod.weight_fake_quant.zero_point
+        if ly.kind == "pw":
+            if xin.C != ly.cin:
+                raise RuntimeError("%s: input has %d channels, expected %d" % (ly.name, xin.C, ly.cin))
+            L.call("frost_pw_conv_forward", xin.q.data_ptr(), xin.zp.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(),
+                   ly.wsum.data_ptr(), M, ly.cin, ly.cout, acc.data_ptr(), ly.stats_ptr, st)
+        elif ly.kind == "dw":
+            L.call("frost_dw_conv_forward", xin.q.data_ptr(), xin.zp.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(),
+                   N, xin.H, xin.W, xin.C, ly.kh, ly.stride, acc.data_ptr(), ly.stats_ptr, st)
+        else:
+            L.call("frost_stem_conv_forward", xin.q.data_ptr(), xin.zp.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(),
+                   N, xin.H, xin.W, xin.C, ly.cout, ly.kh, ly.stride, ly.pad, acc.data_ptr(), ly.stats_ptr, st)
+        afq = mod.activation_post_process
+        bn = mod.bn
+        a = L.BnFinalizeArgs()
+        a.stats, a.C, a.count = ly.stats_ptr, ly.cout, M
+        a.x_scale, a.w_scale, a.sf = xin.scale.data_ptr(), mod.weight_fake_quant.scale.data_ptr(), ly.sf.data_ptr()
+        a.gamma, a.beta = bn.weight.data_ptr(), bn.bias.data_ptr()
+        a.running_mean, a.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+        a.num_batches_tracked = bn.num_batches_tracked.data_ptr()
+        a.momentum = BN_MOMENTUM_DEFAULT if bn.momentum is None else bn.momentum
+        a.eps = bn.eps
+        a.training = 1 if (training and bn.training) else 0
+        a.relu = 1 if ly.relu else 0
+        a.observe = 1 if afq._observe else 0
+        a.averaging_const = Q.AVERAGING_CONSTANT
+        a.afq = _fq_struct(afq)
+        a.A, a.B, a.mean_I, a.kfac = ly.A.data_ptr(), ly.B.data_ptr(), ly.mean_I.data_ptr(), ly.kfac.data_ptr()
+        a.cur_minmax = ly.mm.data_ptr()
+        L.call("frost_bn_finalize", C.byref(a), st)
+        q = torch.empty((M, ly.cout), dtype=torch.uint8, device=dev)
+        L.call("frost_bnq_apply", acc.data_ptr(), M, ly.cout, ly.A.data_ptr(), ly.B.data_ptr(), a.relu,
+               afq.scale.data_ptr(), afq.zero_point.data_ptr(), q.data_ptr(), st)
+        out = _QT(q, N, Ho, Wo, ly.cout, afq.scale, afq.zero_point, ly.mm)
+        if saved is not None:
+            saved[ly.name] = (xin, acc, out, a.training)
+        if self.record_taps:
+            self.last_taps[ly.name + ".out_q"] = q
+            self.last_taps[ly.name + ".acc"] = acc
+        return out
+
+    def forward(self, x, save):
+        self._ensure_built()
+        m, dev, st = self.model, self.dev, L.stream()
+        training = m.training
+        if x.device != dev:
+            raise RuntimeError("frostnet_b200: input on %s, model on %s" % (x.device, dev))
+        if self.features:
+            raise NotImplementedError("frostnet_b200: the feature backbone's QAT path needs an fp32-input stem kernel")
+        x = x.detach()
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        N, Cin, H, W = x.shape
+        saved = {} if save else None
+        if self.record_taps:
+            self.last_taps = {}
+        # all weights: scale_factor, observer, int8 indices - one launch
+        L.call("frost_weight_prep_multi", self._wdesc_dev[0].data_ptr(), len(self.layers), st)
+        L.call("frost_stats_reset", self.stats.data_ptr(), self.n_stat_chan, st)
+        # QuantStub
+        qfq = m.quant.activation_post_process
+        xq = torch.empty((N, H, W, Cin), dtype=torch.uint8, device=dev)
+        mm_in = torch.empty(2, dtype=torch.float32, device=dev)
+        L.call("frost_input_quant", x.data_ptr(), N, Cin, H, W, _fq_struct(qfq), 1 if qfq._observe else 0,
+               Q.AVERAGING_CONSTANT, xq.data_ptr(), mm_in.data_ptr(), self.scratch.data_ptr(), st)
+        t = _QT(xq, N, H, W, Cin, qfq.scale, qfq.zero_point, mm_in)
+        if self.record_taps:
+            self.last_taps["quant.q"] = xq
+        t = self._conv_bn(self.stem, t, training, st, saved)
+        for b in self.blocks:
+            blk = b["mod"]
+            xin = t
+            if saved is not None:
+                saved[b["name"] + ".in"] = xin
+            if b["conv1"] is not None:
+                if b["squeeze"] is not None:
+                    sq = self._conv_bn(b["squeeze"], xin, training, st, saved)
+                    cfq = blk.quant_cat.activation_post_process
+                    qc = torch.empty((xin.M, sq.C + xin.C), dtype=torch.uint8, device=dev)
+                    mmc = torch.empty(2, dtype=torch.float32, device=dev)
+                    L.call("frost_cat_forward", sq.c(), xin.c(), xin.M, _fq_struct(cfq), 1 if cfq._observe else 0,
+                           Q.AVERAGING_CONSTANT, qc.data_ptr(), mmc.data_ptr(), st)
+                    cat = _QT(qc, xin.N, xin.H, xin.W, sq.C + xin.C, cfq.scale, cfq.zero_point, mmc)
+                    if saved is not None:
+                        saved[b["name"] + ".cat"] = (sq, xin, cat)
+                    if self.record_taps:
+                        self.last_taps[b["name"] + ".cat_q"] = qc
+                    o = cat
+                else:
+                    o = xin
+                o = self._conv_bn(b["conv1"], o, training, st, saved)
+            else:
+                o = xin
+            o = self._conv_bn(b["conv2"], o, training, st, saved)
+            o = self._conv_bn(b["reduce"], o, training, st, saved)
+            if b["skip"]:
+                afq = blk.skip_add.activation_post_process
+                qa = torch.empty((o.M, o.C), dtype=torch.uint8, device=dev)
+                mma = torch.empty(2, dtype=torch.float32, device=dev)
+                L.call("frost_add_forward", xin.c(), o.c(), o.M * o.C, _fq_struct(afq), 1 if afq._observe else 0,
+                       Q.AVERAGING_CONSTANT, qa.data_ptr(), mma.data_ptr(), self.scratch.data_ptr(), st)
+                s = _QT(qa, o.N, o.H, o.W, o.C, afq.scale, afq.zero_point, mma)
+                if saved is not None:
+                    saved[b["name"] + ".add"] = (xin, o, s)
+                if self.record_taps:
+                    self.last_taps[b["name"] + ".add_q"] = qa
+                o = s
+            t = o
+        t = self._conv_bn(self.last, t, training, st, saved)
+        # head: avg-pool -> dropout -> classifier conv (+bias) -> FQ
+        HW = t.H * t.W
+        pooled = torch.empty((N, t.C), dtype=torch.float32, device=dev)
+        keep, keep_scale = None, 1.0
+        p_drop = m.classifier[1].p
+        if training and m.classifier[1].training and p_drop > 0:
+            keep = self.dropout_mask
+            if keep is None:
+                keep = torch.empty((N, t.C), dtype=torch.float32, device=dev).bernoulli_(1.0 - p_drop)
+            keep = keep.reshape(N, t.C).float().contiguous()
+            keep_scale = 1.0 / (1.0 - p_drop)
+        L.call("frost_pool_dropout_forward", t.q.data_ptr(), t.scale.data_ptr(), t.zp.data_ptr(), N, HW, t.C,
+               L.ptr(keep), keep_scale, pooled.data_ptr(), st)
+        cls = self.cls
+        cmod = cls.mod
+        pre = torch.empty((N, cls.cout), dtype=torch.float32, device=dev)
+        L.call("frost_linear_forward", pooled.data_ptr(), cls.wq.data_ptr(), cmod.weight_fake_quant.scale.data_ptr(),
+               cmod.weight_fake_quant.zero_point.data_ptr(), L.ptr(cmod.bias), N, cls.cin, cls.cout, pre.data_ptr(), st)
+        lfq = cmod.activation_post_process
+        logits = torch.empty((N, cls.cout), dtype=torch.float32, device=dev)
+        lmask = torch.empty((N, cls.cout), dtype=torch.uint8, device=dev)
+        L.call("frost_fq_forward", pre.data_ptr(), pre.numel(), _fq_struct(lfq), Q.ACT_QMIN, Q.ACT_QMAX, 0,
+               1 if lfq._observe else 0, Q.AVERAGING_CONSTANT, logits.data_ptr(), lmask.data_ptr(), None,
+               self.scratch.data_ptr(), st)
+        if self.record_taps:
+            self.last_taps["pooled"] = pooled
+            self.last_taps["classifier.2.pre"] = pre
+        if saved is not None:
+            saved["head"] = (t, pooled, keep, keep_scale, lmask, HW)
+            saved["N"] = N
+        return logits, saved
+
+    # ------------------------------------------------------------------ backward pieces
+    def _pick_gflat(self):
+        """Use the flat gradient buffer that no live .grad aliases (so autograd can accumulate)."""
+        for which in (0, 1):
+            g = self.gflat[which]
+            lo, hi = g.data_ptr(), g.data_ptr() + 4 * g.numel()
+            if not any(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in self.params):
+                return which
+        raise RuntimeError("frostnet_b200: both flat gradient buffers are aliased by live .grad tensors")
+
+    def _conv_bn_bwd(self, ly, dy, saved, gbase, dx, accumulate, st):
+        """dy: fp32 [M, cout] grad wrt the layer's fake-quantised output.  Writes the BN/weight grads and,
+        if dx is not None, (accumulates) the grad wrt the layer input into dx [M_in, cin]."""
+        xin, acc, out, was_training = saved[ly.name]
+        if not was_training:
+            raise RuntimeError("frostnet_b200: backward through eval-mode BatchNorm is not supported")
+        mod, dev = ly.mod, self.dev
+        M = acc.shape[0]
+        dz = torch.empty((M, ly.cout), dtype=torch.float32, device=dev)
+        a = L.BnBackwardArgs()
+        a.dy, a.acc, a.M, a.C, a.relu = dy.data_ptr(), acc.data_ptr(), M, ly.cout, 1 if ly.relu else 0
+        a.A, a.B, a.mean_I, a.kfac = ly.A.data_ptr(), ly.B.data_ptr(), ly.mean_I.data_ptr(), ly.kfac.data_ptr()
+        a.gamma, a.sf = mod.bn.weight.data_ptr(), ly.sf.data_ptr()
+        a.x_scale, a.w_scale = xin.scale.data_ptr(), mod.weight_fake_quant.scale.data_ptr()
+        a.out_scale, a.out_zp = out.scale.data_ptr(), out.zp.data_ptr()
+        a.eps = mod.bn.eps
+        a.sums, a.coef, a.dz = ly.sums.data_ptr(), ly.coef.data_ptr(), dz.data_ptr()
+        a.dgamma_bn, a.dsf_bn = ly.dgamma_bn.data_ptr(), ly.dsf_bn.data_ptr()
+        a.dbeta = gbase + 4 * self.param_off[id(mod.bn.bias)]
+        L.call("frost_bn_backward", C.byref(a), st)
+        wfq = mod.weight_fake_quant
+        if ly.kind == "pw":
+            L.call("frost_pw_wgrad", dz.data_ptr(), xin.q.data_ptr(), xin.scale.data_ptr(), xin.zp.data_ptr(), M, ly.cin,
+                   ly.cout, ly.dwq.data_ptr(), st)
+            if dx is not None:
+                L.call("frost_pw_dgrad", dz.data_ptr(), ly.wq.data_ptr(), wfq.scale.data_ptr(), wfq.zero_point.data_ptr(),
+                       M, ly.cin, ly.cout, dx.data_ptr(), 1 if accumulate else 0, st)
+        elif ly.kind == "dw":
+            L.call("frost_dw_wgrad", dz.data_ptr(), xin.q.data_ptr(), xin.scale.data_ptr(), xin.zp.data_ptr(), xin.N,
+                   xin.H, xin.W, xin.C, ly.kh, ly.stride, ly.dwq.data_ptr(), st)
+            if dx is not None:
+                L.call("frost_dw_dgrad", dz.data_ptr(), ly.wq.data_ptr(), wfq.scale.data_ptr(), wfq.zero_point.data_ptr(),
+                       xin.N, xin.H, xin.W, xin.C, ly.kh, ly.stride, dx.data_ptr(), 1 if accumulate else 0, st)
+        else:
+            L.call("frost_stem_wgrad", dz.data_ptr(), xin.q.data_ptr(), xin.scale.data_ptr(), xin.zp.data_ptr(), xin.N,
+                   xin.H, xin.W, xin.C, ly.cout, ly.kh, ly.stride, ly.pad, ly.dwq.data_ptr(), st)
+
+    def backward(self, saved, dlogits):
+        dev, st = self.dev, L.stream()
+        which = self._pick_gflat()
+        gflat = self.gflat[which]
+        gbase = gflat.data_ptr()
+        f32 = dict(dtype=torch.float32, device=dev)
+        N = saved["N"]
+        t_last, pooled, keep, keep_scale, lmask, HW = saved["head"]
+        cls, cmod = self.cls, self.cls.mod
+        dlogits = dlogits.contiguous().float()
+        dpre = torch.empty_like(dlogits)
+        L.call("frost_fq_backward", dlogits.data_ptr(), lmask.data_ptr(), dlogits.numel(), dpre.data_ptr(), st)
+        dpooled = torch.empty((N, cls.cin), **f32)
+        L.call("frost_linear_backward", dpre.data_ptr(), pooled.data_ptr(), cls.wq.data_ptr(),
+               cmod.weight_fake_quant.scale.data_ptr(), cmod.weight_fake_quant.zero_point.data_ptr(), N, cls.cin, cls.cout,
+               dpooled.data_ptr(), cls.dwq.data_ptr(), gbase + 4 * self.param_off[id(cmod.bias)], st)
+        dy = torch.empty((N * HW, t_last.C), **f32)
+        L.call("frost_pool_dropout_backward", dpooled.data_ptr(), N, HW, t_last.C, L.ptr(keep), keep_scale,
+               dy.data_ptr(), st)
+        xin_last = saved[self.last.name][0]
+        g = torch.empty((xin_last.M, xin_last.C), **f32)
+        self._conv_bn_bwd(self.last, dy, saved, gbase, g, False, st)
+        del dy
+        for b in reversed(self.blocks):
+            dout = g                                   # grad wrt the block output
+            conv2, reduce = b["conv2"], b["reduce"]
+            xin = saved[b["name"] + ".in"]
+            gx = torch.empty((xin.M, xin.C), **f32)    # grad wrt the block input
+            gx_written = False
+            if b["skip"]:
+                xa, ya, sa = saved[b["name"] + ".add"]
+                dsum = torch.empty_like(dout)
+                L.call("frost_add_backward", dout.data_ptr(), xa.c(), ya.c(), dout.numel(), sa.scale.data_ptr(),
+                       sa.zp.data_ptr(), dsum.data_ptr(), gx.data_ptr(), 0, st)
+                gx_written = True
+                d_reduce = dsum
+            else:
+                d_reduce = dout
+            x_red = saved[reduce.name][0]
+            d_dw_out = torch.empty((x_red.M, x_red.C), **f32)
+            self._conv_bn_bwd(reduce, d_reduce, saved, gbase, d_dw_out, False, st)
+            del d_reduce, dout
+            x_dw = saved[conv2.name][0]
+            if b["conv1"] is not None:
+                d_c1_out = torch.empty((x_dw.M, x_dw.C), **f32)
+                self._conv_bn_bwd(conv2, d_dw_out, saved, gbase, d_c1_out, False, st)
+                del d_dw_out
+                if b["squeeze"] is not None:
+                    sq, xc, cat = saved[b["name"] + ".cat"]
+                    d_cat = torch.empty((cat.M, cat.C), **f32)
+                    self._conv_bn_bwd(b["conv1"], d_c1_out, saved, gbase, d_cat, False, st)
+                    del d_c1_out
+                    d_sq = torch.empty((sq.M, sq.C), **f32)
+                    L.call("frost_cat_backward", d_cat.data_ptr(), sq.c(), xc.c(), cat.M, cat.scale.data_ptr(),
+                           cat.zp.data_ptr(), d_sq.data_ptr(), gx.data_ptr(), 1 if gx_written else 0, st)
+                    gx_written = True
+                    del d_cat
+                    self._conv_bn_bwd(b["squeeze"], d_sq, saved, gbase, gx, True, st)
+                else:
+                    self._conv_bn_bwd(b["conv1"], d_c1_out, saved, gbase, gx, gx_written, st)
+                    gx_written = True
+            else:
+                self._conv_bn_bwd(conv2, d_dw_out, saved, gbase, gx, gx_written, st)
+                gx_written = True
+            g = gx
+        self._conv_bn_bwd(self.stem, g, saved, gbase, None, False, st)
+        L.call("frost_weight_backward_multi", self._wdesc_dev[which].data_ptr(), len(self.layers), st)
+        if self.grad_sync is not None:
+            self.grad_sync(gflat)
+        grads = []
+        for p in self.params:
+            o = self.param_off[id(p)]
+            grads.append(gflat.narrow(0, o, p.numel()).view(p.shape))
+        return grads
+
+    # ------------------------------------------------------------------ entry point
+    def run(self, x):
+        self._ensure_built()
+        if not x.is_cuda:
+            raise RuntimeError("frostnet_b200: the QAT path runs on a CUDA device (B200) only; got a CPU tensor")
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.params)
+        if need_grad:
+            return _QATFunction.apply(self, x, *self.params)
+        logits, _ = self.forward(x, save=False)
+        return logits
+
+
+class _QATFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, x, *params):
+        logits, saved = engine.forward(x, save=True)
+        ctx.engine, ctx.saved = engine, saved
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        grads = ctx.engine.backward(ctx.saved, dlogits)
+        ctx.saved = None
+        return (None, None) + tuple(grads)

@@ -1,0 +1,220 @@
+"""QAT module tree: the shapes torch's eager-mode QAT would produce for the reference, owned by us.
+
+After ``model.fuse_model()`` + ``prepare_qat(model)`` the module tree has the same names, parameters
+and buffers (hence the same ``state_dict`` keys, dtypes and shapes) as the reference after
+``fuse_model(); model.qconfig = get_default_qat_qconfig('qnnpack'); prepare_qat(model)``
+(Classification/train.py:166-173):
+
+  <p>.conv.0           FrostConvBn2d      <-> nniqat.ConvBnReLU2d / ConvBn2d (conv_fused.py:613-710)
+  <p>.conv.0.bn        nn.BatchNorm2d     (same module object as before fusion)
+  *.weight_fake_quant / *.activation_post_process
+                       FrostFakeQuantize  <-> FusedMovingAvgObsFakeQuantize (fake_quantize.py:340-438)
+  classifier.2         FrostQATConv2d     <-> nnqat.Conv2d (torch/ao/nn/qat/modules/conv.py)
+  skip_add / quant_cat FloatFunctional    <-> torch.ao.nn.quantized.FloatFunctional
+  quant / dequant      QuantStub / DeQuantStub
+
+Parameter OBJECTS are preserved across fuse+prepare (the optimizer built on the float model keeps
+its state, S1 in SURVEY.md 8a).  These modules only hold state; the arithmetic of a prepared model
+runs in frostnet_b200.engine.QATEngine.
+"""
+import torch
+import torch.nn as nn
+
+ACT_QMIN, ACT_QMAX = 0, 255
+W_QMIN, W_QMAX = -128, 127
+AVERAGING_CONSTANT = 0.01
+
+
+class FrostObserverState(nn.Module):
+    """Buffers of MovingAverageMinMaxObserver (torch/ao/quantization/observer.py:560-683)."""
+
+    def __init__(self):
+        super().__init__()
+        self.register_buffer("eps", torch.tensor([torch.finfo(torch.float32).eps]))
+        self.register_buffer("min_val", torch.tensor(float("inf")))
+        self.register_buffer("max_val", torch.tensor(float("-inf")))
+        self.averaging_constant = AVERAGING_CONSTANT
+
+
+class FrostFakeQuantize(nn.Module):
+    """State of one FusedMovingAvgObsFakeQuantize (per-tensor).  K1 in SURVEY.md 8c."""
+
+    def __init__(self, quant_min, quant_max, symmetric):
+        super().__init__()
+        self.quant_min, self.quant_max, self.is_symmetric_quant = quant_min, quant_max, symmetric
+        self.activation_post_process = FrostObserverState()
+        self.register_buffer("fake_quant_enabled", torch.tensor([1], dtype=torch.long))
+        self.register_buffer("observer_enabled", torch.tensor([1], dtype=torch.long))
+        self.register_buffer("scale", torch.tensor([1.0], dtype=torch.float))
+        self.register_buffer("zero_point", torch.tensor([0], dtype=torch.int))
+        # host mirrors of the two enable flags (the device copies are only state_dict payload)
+        self._observe = True
+        self._fake_quant = True
+
+    @staticmethod
+    def act():
+        return FrostFakeQuantize(ACT_QMIN, ACT_QMAX, False)
+
+    @staticmethod
+    def weight():
+        return FrostFakeQuantize(W_QMIN, W_QMAX, True)
+
+    # torch.ao.quantization.{enable,disable}_{observer,fake_quant} protocol
+    def enable_observer(self, enabled=True):
+        self._observe = bool(enabled)
+        self.observer_enabled[0] = 1 if enabled else 0
+
+    def disable_observer(self):
+        self.enable_observer(False)
+
+    def enable_fake_quant(self, enabled=True):
+        if not enabled:
+            raise RuntimeError("frostnet_b200: the QAT engine computes on quantize indices; "
+                               "fake_quant cannot be disabled")
+        self._fake_quant = True
+        self.fake_quant_enabled[0] = 1
+
+    def disable_fake_quant(self):
+        self.enable_fake_quant(False)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        k = prefix + "observer_enabled"
+        if k in state_dict:
+            self._observe = bool(int(state_dict[k].reshape(-1)[0]))
+
+    def forward(self, x):
+        raise RuntimeError("frostnet_b200: FrostFakeQuantize is state only; it runs inside the QAT engine")
+
+    def extra_repr(self):
+        return "quant_min=%d, quant_max=%d, symmetric=%s" % (self.quant_min, self.quant_max, self.is_symmetric_quant)
+
+
+class FloatFunctional(nn.Module):
+    """State holder for FloatFunctional.add / .cat (functional_modules.py:50-52,80-82)."""
+
+    def __init__(self):
+        super().__init__()
+        self.activation_post_process = nn.Identity()
+
+    def forward(self, x):
+        raise RuntimeError("FloatFunctional is not intended to use the 'forward'. Please use the underlying operation")
+
+    def add(self, x, y):
+        if isinstance(self.activation_post_process, FrostFakeQuantize):
+            raise RuntimeError("frostnet_b200: prepared FloatFunctional only runs inside the QAT engine")
+        return torch.add(x, y)
+
+    def cat(self, xs, dim=0):
+        if isinstance(self.activation_post_process, FrostFakeQuantize):
+            raise RuntimeError("frostnet_b200: prepared FloatFunctional only runs inside the QAT engine")
+        return torch.cat(xs, dim)
+
+
+class QuantStub(nn.Module):
+    def forward(self, x):
+        return x
+
+
+class DeQuantStub(nn.Module):
+    def forward(self, x):
+        return x
+
+
+class FrostConvBn2d(nn.Module):
+    """Fused Conv+BN(+ReLU).  Float behaviour before prepare (== nni.ConvBn(ReLU)2d in train mode);
+    after prepare it carries weight_fake_quant / activation_post_process like nniqat.ConvBn(ReLU)2d."""
+
+    def __init__(self, conv, bn, relu):
+        super().__init__()
+        self.in_channels, self.out_channels = conv.in_channels, conv.out_channels
+        self.kernel_size, self.stride, self.padding = conv.kernel_size, conv.stride, conv.padding
+        self.dilation, self.groups = conv.dilation, conv.groups
+        self.weight = conv.weight          # same Parameter object
+        self.bias = None
+        self.bn = bn                       # same module object
+        self.relu = relu
+
+    @property
+    def is_depthwise(self):
+        return self.groups == self.in_channels and self.groups > 1
+
+    def forward(self, x):
+        if isinstance(getattr(self, "weight_fake_quant", None), FrostFakeQuantize):
+            raise RuntimeError("frostnet_b200: a prepared FrostConvBn2d only runs inside the QAT engine")
+        y = nn.functional.conv2d(x, self.weight, None, self.stride, self.padding, self.dilation, self.groups)
+        y = self.bn(y)
+        return nn.functional.relu(y) if self.relu else y
+
+    def extra_repr(self):
+        return "%d, %d, kernel_size=%s, stride=%s, groups=%d, relu=%s" % (
+            self.in_channels, self.out_channels, self.kernel_size, self.stride, self.groups, self.relu)
+
+
+class FrostQATConv2d(nn.Module):
+    """classifier.2 after prepare: nnqat.Conv2d(1280, nclass, 1) with bias."""
+
+    def __init__(self, conv):
+        super().__init__()
+        self.in_channels, self.out_channels = conv.in_channels, conv.out_channels
+        self.weight, self.bias = conv.weight, conv.bias
+        self.weight_fake_quant = FrostFakeQuantize.weight()
+        self.activation_post_process = FrostFakeQuantize.act()
+
+    def forward(self, x):
+        raise RuntimeError("frostnet_b200: a prepared FrostQATConv2d only runs inside the QAT engine")
+
+
+def is_prepared(module):
+    for m in module.modules():
+        if isinstance(m, FrostFakeQuantize):
+            return True
+    return False
+
+
+def prepare_qat(model, inplace=True):
+    """Drop-in for ``torch.quantization.prepare_qat(model, inplace=True)`` with the qnnpack QAT
+    qconfig (Classification/train.py:168-173).  ``model.qconfig`` is accepted and checked if set."""
+    from . import engine as _engine
+    from . import frostnet as _fn
+    if not inplace:
+        raise ValueError("frostnet_b200.prepare_qat only supports inplace=True (Parameter identity is the contract)")
+    if not isinstance(model, _fn._FrostTrunk):
+        raise TypeError("frostnet_b200.prepare_qat expects a frostnet_b200 FrostNet")
+    if not getattr(model, "quantized", False):
+        raise ValueError("prepare_qat needs a model built with quantized=True (frostnet_quant_* factories)")
+    if is_prepared(model):
+        return model
+    model.fuse_model()      # no-op if the caller already fused (train.py:171)
+    dev = next(model.parameters()).device
+    for m in list(model.modules()):
+        if isinstance(m, FrostConvBn2d):
+            m.weight_fake_quant = FrostFakeQuantize.weight().to(dev)
+            m.activation_post_process = FrostFakeQuantize.act().to(dev)
+        elif isinstance(m, FloatFunctional):
+            m.activation_post_process = FrostFakeQuantize.act().to(dev)
+        elif isinstance(m, QuantStub):
+            m.activation_post_process = FrostFakeQuantize.act().to(dev)
+    cls = getattr(model, "classifier", None)
+    if cls is not None and isinstance(cls[2], nn.Conv2d):
+        cls[2] = FrostQATConv2d(cls[2]).to(dev)
+    model.__dict__["_frost_engine"] = _engine.QATEngine(model)
+    return model
+
+
+def patch_torch_quantization():
+    """Route torch.quantization.prepare_qat / fuse_modules to this package for frostnet_b200 models so
+    that an unmodified caller script (Classification/train.py:166-173) works unchanged."""
+    import torch.ao.quantization as taq
+    from . import frostnet as _fn
+    orig = taq.prepare_qat
+    if getattr(orig, "_frost_patched", False):
+        return
+
+    def _prepare_qat(model, mapping=None, inplace=False):
+        if isinstance(model, _fn._FrostTrunk):
+            return prepare_qat(model, inplace=True)
+        return orig(model, mapping, inplace)
+    _prepare_qat._frost_patched = True
+    taq.prepare_qat = _prepare_qat
+    torch.quantization.prepare_qat = _prepare_qat

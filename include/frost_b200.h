@@ -1,0 +1,311 @@
+/* frost_b200.h - C ABI of the B200-native FrostNet QAT hot path (libfrost_b200.so).
+ *
+ * The reference (clovaai/frostnet) has NO FFI: it is pure Python wiring of torch.ao.quantization
+ * eager-mode QAT.  The boundary this library replaces is therefore the set of ATen ops that
+ * the reference dispatches to for one QAT training step.  Every entry
+ * point cites the reference call site / torch module it stands in for.  All pointers are raw
+ * DEVICE pointers borrowed for the duration of the call (PyTorch owns every tensor); sizes are
+ * plain integers; `stream` is a cudaStream_t passed as void*.  No torch types cross the boundary.
+ * Every function returns 0 on success or a negative FROST_E* code; frost_last_error() gives text.
+ *
+ * Data layout in HBM (the B200-first part - see DESIGN.md):
+ *   - activations: NHWC uint8 quantize INDICES q (value = (q - zero_point) * scale), 1 B/element;
+ *   - raw conv accumulators: NHWC int32  I = sum (q_a - zp_a) * (q_w - zp_w)  (exact integers);
+ *   - weights: int8 indices in a kernel-friendly layout (+ STE mask in the PyTorch layout);
+ *   - gradients: NHWC fp32.
+ */
+#ifndef FROST_B200_H_
+#define FROST_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FROST_OK 0
+#define FROST_EINVAL (-1) /* bad argument (shape, alignment, null pointer) */
+#define FROST_ECUDA (-2)  /* a CUDA runtime call or launch failed           */
+#define FROST_ENOSUP (-3) /* configuration not supported by this build      */
+
+/* ABI version; bumped on any signature change. */
+int frost_abi_version(void);
+/* Text of the last error on the calling thread ("" if none). */
+const char* frost_last_error(void);
+/* Number of kernels this library has launched since load (all threads); bench.py's gpu_launches. */
+int64_t frost_launch_count(void);
+
+/* One FusedMovingAvgObsFakeQuantize instance (torch/ao/quantization/fake_quantize.py:423-438):
+ * the four state buffers of the module, on the device.  Kernels read AND update them in place
+ * (observer EMA, then qparams), exactly the side effects of torch.fused_moving_avg_obs_fake_quant. */
+typedef struct {
+  float* min_val;      /* activation_post_process.min_val  (scalar, +inf initially) */
+  float* max_val;      /* activation_post_process.max_val  (scalar, -inf initially) */
+  float* scale;        /* scale[1]       */
+  int32_t* zero_point; /* zero_point[1]  */
+} FrostFQ;
+
+/* Per-channel integer statistics of one conv output (filled by the conv kernels with integer
+ * atomics: exact and order-independent, hence deterministic).  32 bytes per channel. */
+typedef struct {
+  long long sum;            /* sum I                                  */
+  unsigned long long sq_lo; /* sum (I*I) & 0xffffffff                 */
+  unsigned long long sq_hi; /* sum (I*I) >> 32                        */
+  int32_t min;              /* min I  (INT32_MAX when empty)          */
+  int32_t max;              /* max I  (INT32_MIN when empty)          */
+} FrostChanStats;
+
+/* Reset `n` channel-stat records (sum=0, min=INT_MAX, max=INT_MIN). */
+int frost_stats_reset(FrostChanStats* stats, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Generic per-tensor fake-quant on fp32 data (logits of classifier.2, unit tests).
+ * Replaces torch.fused_moving_avg_obs_fake_quant as called from
+ * torch/ao/quantization/fake_quantize.py:423-438 (reference call sites: frostnet.py:305-306 via
+ * prepare_qat, Classification/train.py:168-173).
+ *   observe!=0 : aminmax(x) -> EMA (first call copies; else m += 0.01*(cur-m)) -> qparams
+ *   y    = (clamp(rint(x*(1/scale)) + zp, qmin, qmax) - zp) * scale
+ *   mask = 1 iff qmin <= rint(x*(1/scale)) + zp <= qmax      (STE mask; may be NULL)
+ *   q    = clamped index as int32 (may be NULL)
+ * scratch: FROST_FQ_SCRATCH_FLOATS floats of device scratch. */
+#define FROST_FQ_SCRATCH_FLOATS 2048
+int frost_fq_forward(const float* x, int64_t n, FrostFQ fq, int qmin, int qmax, int symmetric,
+                     int observe, float averaging_const, float* y, uint8_t* mask, int32_t* q,
+                     float* scratch, void* stream);
+/* dx = dy * mask   (backward of the cachemask fake-quant kernel). */
+int frost_fq_backward(const float* dy, const uint8_t* mask, int64_t n, float* dx, void* stream);
+
+/* QuantStub (frostnet.py:304,320): observe + quantise the fp32 NCHW input image to NHWC uint8.
+ * cur_minmax[2] receives the dequantised min/max of the produced tensor. */
+int frost_input_quant(const float* x_nchw, int N, int C, int H, int W, FrostFQ fq, int observe,
+                      float averaging_const, uint8_t* q_nhwc, float* cur_minmax, float* scratch,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Weight side of nniqat.ConvBn(ReLU)2d / nnqat.Conv2d
+ * (torch/ao/nn/intrinsic/qat/modules/conv_fused.py:131-146; frostnet.py:14-28,46-60 after
+ * fuse_model): scale_factor = gamma/sqrt(running_var+eps); Ws = W*scale_factor;
+ * observer+qparams (qint8, per_tensor_symmetric); q_w = clamp(rint(Ws/s_w)+zp_w).
+ * One CTA per descriptor; `descs` lives in DEVICE memory (n of them). */
+typedef struct {
+  const float* weight;      /* [cout][cin_g][kh][kw] fp32, PyTorch layout                     */
+  const float* bn_weight;   /* gamma[cout], or NULL (classifier: scale_factor = 1)            */
+  const float* bn_var;      /* running_var[cout] (read BEFORE this step's update)             */
+  float bn_eps;
+  int32_t cout, cin_g, kh, kw;
+  int32_t layout;           /* 0: wq[cout][cin_g*kh*kw] (1x1: [cout][cin]);
+                               1: depthwise  wq[kh*kw][cout];
+                               2: dense kxk  wq[cout][kh][kw][cin_g]                           */
+  int32_t observe;
+  float averaging_const;
+  FrostFQ wfq;
+  int8_t* wq;               /* out: int8 indices in `layout`                                   */
+  uint8_t* wmask;           /* out: STE mask, PyTorch layout                                   */
+  float* sf;               /* out: scale_factor[cout]                                         */
+  float* rstd_run;          /* out: 1/sqrt(running_var+eps)[cout] as seen by this forward       */
+  int32_t* wsum;            /* out: per-cout sum_k q_w (raw index sum)                          */
+  /* backward (frost_weight_backward_multi): */
+  const float* dwq;         /* in : d/d(dequantised weight) in `layout`, fp32                  */
+  const float* dgamma_bn;   /* in : [cout] sum dv*xhat   (NULL for classifier)                 */
+  const float* dsf_bn;      /* in : [cout] d/d(scale_factor) through conv/scale_factor         */
+  float* dweight;           /* out: grad of weight, PyTorch layout                             */
+  float* dgamma;            /* out: grad of bn.weight [cout] (NULL for classifier)             */
+} FrostWeightDesc;
+int frost_weight_prep_multi(const FrostWeightDesc* descs, int n, void* stream);
+int frost_weight_backward_multi(const FrostWeightDesc* descs, int n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Convolutions on quantize indices (the F.conv2d at conv_fused.py:155, restated exactly in
+ * integers: conv = s_a*s_w*I).  All write I (int32 NHWC) and accumulate FrostChanStats. */
+/* 1x1 pointwise: xq[M][K] u8, wq[cout][K] s8 -> acc[M][cout]. K%8==0, cout%4==0. */
+int frost_pw_conv_forward(const uint8_t* xq, const int32_t* x_zp, const int8_t* wq,
+                          const int32_t* w_zp, const int32_t* wsum, int64_t M, int K, int cout,
+                          int32_t* acc, FrostChanStats* stats, void* stream);
+/* depthwise kxk (k in {3,5}), stride in {1,2}, pad=(k-1)/2: xq[N][H][W][C] -> acc[N][Ho][Wo][C]. C%4==0 */
+int frost_dw_conv_forward(const uint8_t* xq, const int32_t* x_zp, const int8_t* wq,
+                          const int32_t* w_zp, int N, int H, int W, int C, int k, int stride,
+                          int32_t* acc, FrostChanStats* stats, void* stream);
+/* dense kxk stem (frostnet.py:277: 3->32, 3x3, s2, p1): xq[N][H][W][cin] u8, wq[cout][k][k][cin]. */
+int frost_stem_conv_forward(const uint8_t* xq, const int32_t* x_zp, const int8_t* wq,
+                            const int32_t* w_zp, int N, int H, int W, int cin, int cout, int k,
+                            int stride, int pad, int32_t* acc, FrostChanStats* stats, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * BN + ReLU + activation fake-quant of one fused conv (conv_fused.py:156-167, :708-710 and the
+ * activation_post_process hook).  frost_bn_finalize turns the integer statistics into the
+ * per-channel affine  v = A_c*I + B_c  (= bn(conv/scale_factor)), updates running stats
+ * (momentum 0.1, unbiased var), derives the post-ReLU global min/max from the per-channel
+ * integer extrema (v is monotone in I), runs the observer EMA + qparams, and saves what the
+ * backward needs.  frost_bnq_apply then writes q = clamp(rint(relu(v)/s)+zp). */
+typedef struct {
+  const FrostChanStats* stats;
+  int32_t C;
+  int64_t count;               /* N*Ho*Wo                                                     */
+  const float* x_scale;        /* scale of the conv input activation                          */
+  const float* w_scale;        /* scale of the weight fake-quant                              */
+  const float* sf;             /* scale_factor[C] from weight prep                            */
+  const float* gamma;          /* bn.weight                                                   */
+  const float* beta;           /* bn.bias                                                     */
+  float* running_mean;
+  float* running_var;
+  int64_t* num_batches_tracked;
+  float momentum, eps;
+  int32_t training;            /* 1: batch statistics + running-stat update; 0: running stats */
+  int32_t relu;
+  int32_t observe;
+  float averaging_const;
+  FrostFQ afq;                 /* activation_post_process of the fused conv                   */
+  float* A;                    /* out [C] */
+  float* B;                    /* out [C] */
+  float* mean_I;               /* out [C] batch mean of I (for backward)                      */
+  float* kfac;                 /* out [C] k_c = m_c*invstd: xhat = (I-mean_I)*k_c             */
+  float* cur_minmax;           /* out [2] dequantised min/max of the produced tensor          */
+} FrostBnFinalizeArgs;
+int frost_bn_finalize(const FrostBnFinalizeArgs* a, void* stream);
+int frost_bnq_apply(const int32_t* acc, int64_t M, int C, const float* A, const float* B, int relu,
+                    const float* out_scale, const int32_t* out_zp, uint8_t* q, void* stream);
+
+/* Backward of the same chain (SURVEY.md 8a'): dy = grad wrt the fake-quantised output.
+ * reduce: S1_c = sum dv, S2_c = sum dv*I  with dv = dy*[0<=idx<=255]*[v>0]   (double[2*C], zeroed by callee)
+ * apply : dz = grad wrt the real-valued conv output (what dgrad/wgrad consume), and
+ *         dgamma_bn = sum dv*xhat, dbeta = S1, dsf_bn (see FrostWeightDesc). */
+typedef struct {
+  const float* dy;             /* [M][C] fp32                                                 */
+  const int32_t* acc;          /* [M][C] int32 I saved by the forward                         */
+  int64_t M;
+  int32_t C;
+  int32_t relu;
+  const float* A;
+  const float* B;
+  const float* mean_I;
+  const float* kfac;
+  const float* gamma;
+  const float* sf;
+  const float* x_scale;        /* scale of the conv input activation                          */
+  const float* w_scale;        /* scale of the weight fake-quant                              */
+  const float* out_scale;
+  const int32_t* out_zp;
+  float eps;
+  double* sums;                /* scratch [2*C]                                               */
+  float* coef;                 /* scratch [3*C]                                               */
+  float* dz;                   /* out [M][C]                                                  */
+  float* dgamma_bn;            /* out [C]                                                     */
+  float* dbeta;                /* out [C]                                                     */
+  float* dsf_bn;               /* out [C]                                                     */
+} FrostBnBackwardArgs;
+int frost_bn_backward(const FrostBnBackwardArgs* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * FloatFunctional.cat / .add (frostnet.py:129,142;
+ * torch/ao/nn/quantized/modules/functional_modules.py:50-52,80-82): op + own observer + FQ. */
+typedef struct {
+  const uint8_t* q;
+  const float* scale;
+  const int32_t* zp;
+  const float* cur_minmax;     /* dequantised min/max of this tensor */
+  int32_t C;
+} FrostQTensor;
+/* out[M][C1+C2] = FQ(cat([a, b], channel)) */
+int frost_cat_forward(FrostQTensor a, FrostQTensor b, int64_t M, FrostFQ fq, int observe,
+                      float averaging_const, uint8_t* q_out, float* cur_minmax_out, void* stream);
+/* da[M][C1] = dcat[:, :C1]*mask ; db[M][C2] (+)= dcat[:, C1:]*mask */
+int frost_cat_backward(const float* dcat, FrostQTensor a, FrostQTensor b, int64_t M,
+                       const float* out_scale, const int32_t* out_zp, float* da, float* db,
+                       int accumulate_b, void* stream);
+/* out[n] = FQ(a + b)  (two passes: min/max, then quantise). scratch: FROST_FQ_SCRATCH_FLOATS. */
+int frost_add_forward(FrostQTensor a, FrostQTensor b, int64_t n, FrostFQ fq, int observe,
+                      float averaging_const, uint8_t* q_out, float* cur_minmax_out, float* scratch,
+                      void* stream);
+/* dsum = dout*mask ; da (+)= dsum */
+int frost_add_backward(const float* dout, FrostQTensor a, FrostQTensor b, int64_t n,
+                       const float* out_scale, const int32_t* out_zp, float* dsum, float* da,
+                       int accumulate_a, void* stream);
+/* y (+)= x, fp32 */
+int frost_axpy(const float* x, float* y, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Head: AdaptiveAvgPool2d(1) -> Dropout -> nnqat.Conv2d(1280,nclass,1)  (frostnet.py:295-299,328) */
+/* pooled[N][C] = mean_hw((q-zp)*s) * keep[N][C] * keep_scale   (keep may be NULL) */
+int frost_pool_dropout_forward(const uint8_t* q, const float* scale, const int32_t* zp, int N,
+                               int HW, int C, const float* keep, float keep_scale, float* pooled,
+                               void* stream);
+/* dy[N][HW][C] = dpooled[N][C]*keep*keep_scale/HW */
+int frost_pool_dropout_backward(const float* dpooled, int N, int HW, int C, const float* keep,
+                                float keep_scale, float* dy, void* stream);
+/* out[N][cout] = x[N][K] . ((wq - zp_w)*s_w)^T + bias   (fp32 SIMT; wq[cout][K]) */
+int frost_linear_forward(const float* x, const int8_t* wq, const float* w_scale,
+                         const int32_t* w_zp, const float* bias, int N, int K, int cout, float* out,
+                         void* stream);
+/* dx[N][K] = dout . Wq ; dwq[cout][K] = dout^T . x ; dbias[cout] = sum_n dout */
+int frost_linear_backward(const float* dout, const float* x, const int8_t* wq,
+                          const float* w_scale, const int32_t* w_zp, int N, int K, int cout,
+                          float* dx, float* dwq, float* dbias, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * dgrad / wgrad of the convolutions (aten::convolution_backward in the reference). */
+/* dx[M][K] (+)= s_w * sum_co dz[M][co]*(wq[co][K]-zp_w) */
+int frost_pw_dgrad(const float* dz, const int8_t* wq, const float* w_scale, const int32_t* w_zp,
+                   int64_t M, int K, int cout, float* dx, int accumulate, void* stream);
+/* dwq[cout][K] = s_a * sum_m dz[m][co]*(xq[m][K]-zp_a)     (dwq zeroed by callee) */
+int frost_pw_wgrad(const float* dz, const uint8_t* xq, const float* x_scale, const int32_t* x_zp,
+                   int64_t M, int K, int cout, float* dwq, void* stream);
+int frost_dw_dgrad(const float* dz, const int8_t* wq, const float* w_scale, const int32_t* w_zp,
+                   int N, int H, int W, int C, int k, int stride, float* dx, int accumulate,
+                   void* stream);
+/* dwq[k*k][C] */
+int frost_dw_wgrad(const float* dz, const uint8_t* xq, const float* x_scale, const int32_t* x_zp,
+                   int N, int H, int W, int C, int k, int stride, float* dwq, void* stream);
+/* dwq[cout][k][k][cin] (the stem has no dgrad: its input is the image) */
+int frost_stem_wgrad(const float* dz, const uint8_t* xq, const float* x_scale, const int32_t* x_zp,
+                     int N, int H, int W, int cin, int cout, int k, int stride, int pad, float* dwq,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * GradBoost optimizers (optimizer.py:121-206 QSGD, :264-359 QRMSprop, :411-512 QAdam,
+ * :564-667 QAdamW) as ONE multi-tensor kernel.  The |Laplace(0,1)| noise and the coin toss that
+ * the reference draws on the host with numpy (optimizer.py:178-185) come from a counter-based
+ * Philox4x32-10 stream keyed by (seed, tensor index, element index, step) - or from explicit
+ * arrays (noise/coin != NULL) so tests can inject the reference's own draws. */
+#define FROST_OPT_QSGD 0
+#define FROST_OPT_QRMS 1
+#define FROST_OPT_QADAM 2
+#define FROST_OPT_QADAMW 3
+typedef struct {
+  float* p;
+  float* g;            /* mutated in place like the reference (grad.add_(noise), wd)           */
+  float* exp_min;
+  float* exp_max;
+  float* coin_toss;    /* state['coin_toss'] (NULL if !toss_coin)                               */
+  float* buf0;         /* QSGD momentum_buffer | QRMS square_avg | QAdam exp_avg               */
+  float* buf1;         /* QRMS momentum_buffer | QAdam exp_avg_sq                              */
+  float* buf2;         /* QRMS grad_avg (centered) | QAdam max_exp_avg_sq (amsgrad)            */
+  const float* noise;  /* optional injected |Laplace| draws                                    */
+  const float* coin;   /* optional injected coin draws                                         */
+  int64_t n;
+  float lr, weight_decay;
+  int32_t step;        /* state['step'] AFTER increment                                        */
+  int32_t restart_step;/* state['restart_step'] AFTER increment                                */
+  int32_t first_momentum; /* QSGD: 1 if momentum_buffer is being created this step             */
+  int32_t pad_;
+} FrostOptTensor;
+typedef struct {
+  int32_t kind;
+  int32_t is_warmup;
+  int32_t toss_coin, nesterov, centered, amsgrad;
+  float momentum, dampening, beta, beta1, beta2, eps, alpha, clip_by, noise_decay;
+  float grad_scale;    /* multiplied into g first (1/world_size after an all-reduce sum)       */
+  uint64_t seed;
+} FrostOptHyper;
+/* `tensors` (n of them) and `chunks` live in DEVICE memory; `hyper` is a host struct.
+ * chunks[i] = {tensor index, chunk index within the tensor}; a chunk is FROST_OPT_CHUNK
+ * consecutive elements, one CTA each, so no CTA is launched without work. */
+#define FROST_OPT_CHUNK 2048
+typedef struct { int32_t tensor; int32_t chunk; } FrostOptChunk;
+int frost_gradboost_multi(const FrostOptTensor* tensors, int n, const FrostOptChunk* chunks,
+                          int n_chunks, const FrostOptHyper* hyper, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FROST_B200_H_ */

@@ -1,0 +1,32 @@
+"""Shared helpers for the parity tests (the oracle is imported here and ONLY in tests/bench/smoke)."""
+import os
+
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+
+
+def build_model_from_golden(g, device):
+    """frostnet_b200 model in the reference's post-prepare state of the golden fixture."""
+    import frostnet_b200 as F
+    model = F.FrostNet(nclass=g["nclass"], mode=g["mode"], width_mult=g["width_mult"], quantized=True, drop_rate=0.0)
+    model.train()
+    model.fuse_model()
+    F.prepare_qat(model)
+    missing, unexpected = model.load_state_dict(g["sd0"], strict=True)
+    assert not missing and not unexpected
+    return model.to(device)
+
+
+def nchw_idx_to_nhwc_u8(idx):
+    """oracle tap (unclamped float index, NCHW) -> clamped uint8 NHWC"""
+    return idx.clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+
+
+def rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
