@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py - images/s of one FrostNet-Large QAT training step (fwd + bwd + GradBoost QSGD step),
+bs=256 per GPU, 224x224x3 synthetic fp32 batches (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Prints ONE JSON line (rank 0).  `value` = whole-job images/s with the batch resident in HBM;
+`e2e` = the same step through the public nn.Module/Optimizer API with the fp32 batch copied from
+pinned host memory and the loss read back every step.  `roofline` describes the dominant C-ABI
+entry point (per-call CUDA-event timing in a second pass over the same steps); `cpu_baseline` is the
+CPU oracle (a port of the reference path: oracle/frost_oracle.py) on a bounded sample.
+`--impl reference` times that CPU path alone (the reference itself is Python/torch wiring that
+cannot travel to the GPU box; the oracle is bit-identical to it - tests/golden/make_golden.py).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec FrostNet-L QAT fwd+bwd+GradBoost step, bs=256/GPU, 224x224"
+UNIT = "images/s"
+FLOP_PER_IMG = 2.563e9           # fwd+bwd conv FLOPs per image (FrostNet-L 1.0 @224)
+
+
+class Args:                       # Classification/setting/train.json
+    learning_rate, weight_decay, nesterov, clip_by, toss_coin, noise_decay, amsgrad = 5e-3, 1e-5, True, 1e-3, True, 1e-2, False
+
+
+def param_groups(model, weight_decay):
+    """Classification/train.py:121-137 - one group per tensor, weight decay by shape."""
+    groups = []
+    for _, p in model.named_parameters():
+        if p.dim() == 4:
+            wd = 0.0 if p.shape[1] == 1 else weight_decay
+        else:
+            wd = weight_decay * 0.01
+        groups.append({"params": [p], "weight_decay": wd})
+    return groups
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--id=%d" % index, "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        top = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(top) if top else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (port of the reference path) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_qat_images_per_s(batch, steps, warmup, threads=None):
+    import numpy as np
+    from oracle import frost_oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(1882)
+    np.random.seed(1882)
+    spec = O.net_spec("large", 1.0, 1000)
+    net = O.OracleNet(spec, O.fresh_state_dict(spec, seed=1882))
+    params = net.parameters()
+    wds = [(0.0 if p.shape[1] == 1 else Args.weight_decay) if p.dim() == 4 else Args.weight_decay * 0.01 for p in params]
+    opt = O.GradBoost("QSGD", params, Args.learning_rate, momentum=0.9, nesterov=True, clip_by=Args.clip_by,
+                      toss_coin=True, noise_decay=Args.noise_decay)
+    opt.is_warmup = False
+    crit = torch.nn.CrossEntropyLoss()
+    x = torch.randn(batch, 3, 224, 224)
+    y = torch.randint(0, 1000, (batch,))
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for p in params:
+            p.grad = None
+        loss = crit(net.forward(x, training=True, drop_rate=0.2), y)
+        loss.backward()
+        with torch.no_grad():
+            opt.step([p.grad for p in params], wds=wds)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return batch * len(times) / sum(times), threads, sum(times) / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_bs = 16
+    steps = max(1, min(args.steps, 6))
+    warm = max(1, min(args.warmup, 1))
+    ips, threads, spstep = cpu_qat_images_per_s(sample_bs, steps, warm)
+    sample = "%d timed + %d warm-up QAT steps (fwd+bwd+QSGD GradBoost) of FrostNet-L at bs=%d on %d host threads" % (
+        steps, warm, sample_bs, threads)
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "FrostNet-Large 1.0 QAT (StatAssist+GradBoost QSGD) 224x224 synthetic, CPU oracle, bs=%d sample" % sample_bs},
+            "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def algorithmic_cost(name, a):
+    """(bytes, flops) of one C-ABI call from its arguments (what the op must move / compute)."""
+    if name == "frost_pw_conv_forward":
+        M, K, co = a[5], a[6], a[7]
+        return M * K + co * K + 4 * M * co, 2 * M * K * co
+    if name == "frost_bnq_apply":
+        M, Cc = a[1], a[2]
+        return 5 * M * Cc, 0
+    if name == "frost_pw_dgrad":
+        M, K, co = a[4], a[5], a[6]
+        return 4 * M * co + co * K + 4 * M * K, 2 * M * K * co
+    if name == "frost_pw_wgrad":
+        M, K, co = a[4], a[5], a[6]
+        return 4 * M * co + M * K + 4 * co * K, 2 * M * K * co
+    return 0, 0
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    import frostnet_b200 as F
+    from frostnet_b200 import _lib as L
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (b200 arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    bs = args.batch
+    torch.manual_seed(1882)
+    model = F.frostnet_quant_large_1_0().to(dev)
+    model.train()
+    if world > 1:
+        F.parallel.broadcast_parameters(model)
+    opt = F.get_optimizer("QSGD", param_groups(model, Args.weight_decay), Args)
+    crit = torch.nn.CrossEntropyLoss()
+    g = torch.Generator().manual_seed(1882 + rank)
+    x_host = torch.randn(bs, 3, 224, 224, generator=g).pin_memory()
+    y_host = torch.randint(0, 1000, (bs,), generator=g).pin_memory()
+    x = x_host.to(dev)
+    y = y_host.to(dev)
+
+    def step(xb, yb):
+        opt.zero_grad()
+        loss = crit(model(xb), yb)
+        loss.backward()
+        opt.step()
+        return loss
+
+    # StatAssist (Classification/train.py:149-173): FP warm-up steps collect GradBoost sensitivity,
+    # then fuse + prepare_qat; the timed region is steady-state QAT.
+    for _ in range(2):
+        step(x[:64], y[:64])
+    opt.is_warmup = False
+    model.fuse_model()
+    F.prepare_qat(model)
+    if world > 1:
+        F.parallel.distribute(model)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    W, K = max(3, args.warmup), args.steps
+    for _ in range(W):
+        step(x, y)
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = L.launch_count()
+    ms = timed(lambda: step(x, y), K)
+    launches = L.launch_count() - l0
+    value = world * bs * K / (ms * 1e-3)
+
+    # end to end: pinned host batch -> device every step, loss read back every step
+    def e2e_step():
+        xb = x_host.to(dev, non_blocking=True)
+        yb = y_host.to(dev, non_blocking=True)
+        return float(step(xb, yb))
+    e2e_step()
+    ms_e2e = timed(e2e_step, K)
+    e2e_value = world * bs * K / (ms_e2e * 1e-3)
+    clocks = sampler.stop() if sampler else None
+
+    # per-entry-point CUDA-event pass (rank 0): roofline of the dominant kernel
+    roofline, breakdown = None, None
+    if rank == 0:
+        prof = {}
+        orig_call = L.call
+
+        def prof_call(name, *a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            orig_call(name, *a)
+            e1.record()
+            prof.setdefault(name, []).append((e0, e1, algorithmic_cost(name, a)))
+        pk = min(K, 5)
+        import frostnet_b200.engine as E
+        import frostnet_b200.optimizer as OP
+        E.L.call = prof_call
+        try:
+            torch.cuda.synchronize()
+            for _ in range(pk):
+                step(x, y)
+            torch.cuda.synchronize()
+        finally:
+            E.L.call = orig_call
+        agg = {}
+        for name, evs in prof.items():
+            t = sum(a.elapsed_time(b) for a, b, _ in evs) / pk
+            agg[name] = (t, sum(c[0] for _, _, c in evs) / pk, sum(c[1] for _, _, c in evs) / pk, len(evs) // pk)
+        tot = sum(v[0] for v in agg.values())
+        breakdown = {k: {"ms_per_step": round(v[0], 4), "share": round(v[0] / tot, 4), "calls_per_step": v[3]}
+                     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:8]}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        top = next((k for k, _ in sorted(agg.items(), key=lambda kv: -kv[1][0]) if agg[k][1] > 0), None)
+        if top:
+            t_ms, byt, flop, calls = agg[top]
+            ai = flop / max(byt, 1)
+            if ai > tf_peak * 1e12 / (hbm_peak * 1e9):
+                ach = flop / (t_ms * 1e-3) / 1e12
+                roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
+                            "frac": ach / tf_peak, "traffic": None}
+            else:
+                ach = byt / (t_ms * 1e-3) / 1e9
+                roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": ach / hbm_peak, "traffic": None}
+            roofline["peak_source"] = src
+            roofline["launches_per_step"] = calls
+            roofline["avg_launch_ms"] = t_ms / max(calls, 1)
+            roofline["algorithmic_bytes_per_step"] = byt
+            roofline["algorithmic_flops_per_step"] = flop
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ips, threads, spstep = cpu_qat_images_per_s(16, 3, 1)
+        cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "3 timed + 1 warm-up QAT steps (fwd+bwd+QSGD GradBoost) of FrostNet-L at bs=16, %.1f s/step" % spstep}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 activations x s8 weights -> s32 (exact), fp32 BN/grad/optimizer",
+        "data": "synthetic",
+        "config": {"workload": "FrostNet-Large 1.0 QAT (StatAssist+GradBoost QSGD) bs=%d/GPU 224x224 synthetic ImageNet" % bs,
+                   "global_batch": bs * world, "parallelism": "dp%d" % world,
+                   "l2": "per-step working set (~8 GB of activations) >> 126 MB L2; no explicit flush"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
+                "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "gpu_launches_per_step": launches / K,
+        "clocks": clocks,
+        "roofline": roofline,
+        "conv_roofline": {"algorithmic_tflops": FLOP_PER_IMG * bs * K / (ms * 1e-3) / 1e12,
+                          "note": "2.563 GFLOP/img conv fwd+bwd (SURVEY 8d) / step time; tensor peak %s" % "1407 TF/s sustained bf16"},
+        "breakdown": breakdown,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
