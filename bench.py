@@ -235,6 +235,14 @@ def run_b200(args):
     launches = L.launch_count() - l0
     value = world * bs * K / (ms * 1e-3)
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms / K, "steps": K,
+                              "gpu_launches_per_step": launches / K, "quick": True}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # end to end: pinned host batch -> device every step, loss read back every step
     def e2e_step():
         xb = x_host.to(dev, non_blocking=True)
@@ -342,6 +350,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="device-resident timing only (for ncu launch lists)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
