@@ -70,6 +70,8 @@ class OptChunk(C.Structure):
 
 
 OPT_CHUNK = 2048
+WEIGHT_CHUNK = 8192
+WEIGHT_BWD_CHANNELS = 8
 FQ_SCRATCH_FLOATS = 2048
 OPT_KINDS = {"QSGD": 0, "QRMS": 1, "QAdam": 2, "QAdamW": 3}
 
@@ -81,8 +83,8 @@ _SIGNATURES = {
     "frost_fq_forward": [c_p, i64, FQ, i32, i32, i32, i32, f32, c_p, c_p, c_p, c_p, c_p],
     "frost_fq_backward": [c_p, c_p, i64, c_p, c_p],
     "frost_input_quant": [c_p, i32, i32, i32, i32, FQ, i32, f32, c_p, c_p, c_p, c_p],
-    "frost_weight_prep_multi": [c_p, i32, c_p],
-    "frost_weight_backward_multi": [c_p, i32, c_p],
+    "frost_weight_prep_multi": [c_p, i32, c_p, i32, c_p, c_p],
+    "frost_weight_backward_multi": [c_p, i32, c_p, i32, c_p],
     "frost_pw_conv_forward": [c_p, c_p, c_p, c_p, c_p, i64, i32, i32, c_p, c_p, c_p],
     "frost_dw_conv_forward": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, c_p, c_p, c_p],
     "frost_stem_conv_forward": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, i32, c_p, c_p, c_p],
@@ -142,6 +144,15 @@ def call(name, *args):
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError("%s failed (%d): %s" % (name, rc, lib.frost_last_error().decode()))
+
+
+def chunk_table(counts, per_chunk, device):
+    """Device int32 [n,2] work list {tensor, chunk} covering counts[i] items in slices of per_chunk."""
+    rows = []
+    for t, n in enumerate(counts):
+        rows.extend((t, c) for c in range((int(n) + per_chunk - 1) // per_chunk))
+    tab = torch.tensor(rows, dtype=torch.int32).reshape(-1, 2)
+    return tab.to(device), len(rows)
 
 
 def launch_count():

@@ -8,7 +8,7 @@
 
 namespace frost {
 
-void dw_launch_shape(int C, int* cg_per_block, int* nchunks, int* threads);
+void dw_launch_shape(int C, int max_cgb, int* cg_per_block, int* nchunks, int* threads);
 
 __device__ __forceinline__ float bn_affine(int I, float A, float B) { return fmaf((float)I, A, B); }
 
@@ -240,7 +240,7 @@ extern "C" int frost_bn_backward(const FrostBnBackwardArgs* a, void* stream) {
     return FROST_ECUDA;
   }
   int cgb, chunks, threads;
-  dw_launch_shape(a->C, &cgb, &chunks, &threads);
+  dw_launch_shape(a->C, 256, &cgb, &chunks, &threads);
   const int rows_per_block = threads / cgb;
   int gx = (int)std::min<int64_t>(ceil_div(a->M, (int64_t)rows_per_block * 4), (int64_t)kNumSMs * 8);
   bn_bwd_reduce_kernel<<<dim3(gx, chunks), threads, sizeof(double) * cgb * 8, st>>>(*a, cgb);

@@ -7,7 +7,6 @@
 
 namespace frost {
 
-void dw_launch_shape(int C, int* cg_per_block, int* nchunks, int* threads);
 
 constexpr int GB_T = 64;    // output tile edge
 constexpr int GB_RC = 16;   // reduction chunk
@@ -156,114 +155,6 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__
       if (k < K) atomicAdd(dwq + (int64_t)co * K + k, acc[i][j] * s_a);
     }
   }
-}
-
-// ---------------------------------------------------------------- depthwise dgrad
-// dx[n][ih][iw][c] (+)= s_w * sum_{r,s} dz[n][oh][ow][c] * (w[r][s][c]-zp_w),  oh*S-pad+r == ih
-template <int KS, int S>
-__global__ void __launch_bounds__(256) dw_dgrad_kernel(const float* __restrict__ dz, const int8_t* __restrict__ wq,
-                                                      const float* __restrict__ w_scale_p, const int32_t* __restrict__ w_zp_p,
-                                                      int N, int H, int W, int C, int Ho, int Wo, int cg_per_block,
-                                                      float* __restrict__ dx, int accumulate) {
-  constexpr int PAD = (KS - 1) / 2;
-  const int CG = C >> 2;
-  const int cg_local = threadIdx.x % cg_per_block;
-  const int cg = blockIdx.y * cg_per_block + cg_local;
-  const int pix_per_block = blockDim.x / cg_per_block;
-  const int pix_local = threadIdx.x / cg_per_block;
-  if (cg >= CG) return;
-  const float zp_w = (float)*w_zp_p, s_w = *w_scale_p;
-  float w[KS * KS][4];
-#pragma unroll
-  for (int t = 0; t < KS * KS; ++t) {
-    const unsigned pk = __ldg(reinterpret_cast<const unsigned*>(wq + (int64_t)t * C + cg * 4));
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) w[t][ch] = ((float)(int8_t)((pk >> (8 * ch)) & 0xff) - zp_w) * s_w;
-  }
-  const int64_t total = (int64_t)N * H * W;
-  for (int64_t p = (int64_t)blockIdx.x * pix_per_block + pix_local; p < total; p += (int64_t)gridDim.x * pix_per_block) {
-    const int iw = (int)(p % W);
-    const int64_t t1 = p / W;
-    const int ih = (int)(t1 % H);
-    const int n = (int)(t1 / H);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int r = 0; r < KS; ++r) {
-      const int th = ih + PAD - r;
-      if (th < 0 || (th % S) != 0) continue;
-      const int oh = th / S;
-      if (oh >= Ho) continue;
-#pragma unroll
-      for (int s = 0; s < KS; ++s) {
-        const int tw = iw + PAD - s;
-        if (tw < 0 || (tw % S) != 0) continue;
-        const int ow = tw / S;
-        if (ow >= Wo) continue;
-        const float4 d = __ldg(reinterpret_cast<const float4*>(dz + (((int64_t)n * Ho + oh) * Wo + ow) * C) + cg);
-        acc[0] = fmaf(d.x, w[r * KS + s][0], acc[0]);
-        acc[1] = fmaf(d.y, w[r * KS + s][1], acc[1]);
-        acc[2] = fmaf(d.z, w[r * KS + s][2], acc[2]);
-        acc[3] = fmaf(d.w, w[r * KS + s][3], acc[3]);
-      }
-    }
-    float4* o = reinterpret_cast<float4*>(dx + p * C) + cg;
-    float4 v = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    if (accumulate) {
-      const float4 old = *o;
-      v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
-    }
-    *o = v;
-  }
-}
-
-// ---------------------------------------------------------------- depthwise wgrad
-// dwq[t][c] += s_a * sum_{n,oh,ow} dz[n][oh][ow][c] * (x[n][oh*S-pad+r][ow*S-pad+s][c] - zp_a)
-template <int KS, int S>
-__global__ void __launch_bounds__(256) dw_wgrad_kernel(const float* __restrict__ dz, const uint8_t* __restrict__ xq,
-                                                      const float* __restrict__ x_scale_p, const int32_t* __restrict__ x_zp_p,
-                                                      int N, int H, int W, int C, int Ho, int Wo, int cg_per_block,
-                                                      float* __restrict__ dwq) {
-  constexpr int PAD = (KS - 1) / 2;
-  const int CG = C >> 2;
-  const int cg_local = threadIdx.x % cg_per_block;
-  const int cg = blockIdx.y * cg_per_block + cg_local;
-  const int pix_per_block = blockDim.x / cg_per_block;
-  const int pix_local = threadIdx.x / cg_per_block;
-  if (cg >= CG) return;
-  const float zp_a = (float)*x_zp_p;
-  float acc[KS * KS][4];
-#pragma unroll
-  for (int t = 0; t < KS * KS; ++t)
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) acc[t][ch] = 0.0f;
-  const int64_t total = (int64_t)N * Ho * Wo;
-  for (int64_t p = (int64_t)blockIdx.x * pix_per_block + pix_local; p < total; p += (int64_t)gridDim.x * pix_per_block) {
-    const int ow = (int)(p % Wo);
-    const int64_t t1 = p / Wo;
-    const int oh = (int)(t1 % Ho);
-    const int n = (int)(t1 / Ho);
-    const float4 d = __ldg(reinterpret_cast<const float4*>(dz + p * C) + cg);
-#pragma unroll
-    for (int r = 0; r < KS; ++r) {
-      const int ih = oh * S - PAD + r;
-      if (ih < 0 || ih >= H) continue;
-#pragma unroll
-      for (int s = 0; s < KS; ++s) {
-        const int iw = ow * S - PAD + s;
-        if (iw < 0 || iw >= W) continue;
-        const unsigned pk = __ldg(reinterpret_cast<const unsigned*>(xq + (((int64_t)n * H + ih) * W + iw) * C + cg * 4));
-        acc[r * KS + s][0] = fmaf(d.x, (float)(pk & 0xff) - zp_a, acc[r * KS + s][0]);
-        acc[r * KS + s][1] = fmaf(d.y, (float)((pk >> 8) & 0xff) - zp_a, acc[r * KS + s][1]);
-        acc[r * KS + s][2] = fmaf(d.z, (float)((pk >> 16) & 0xff) - zp_a, acc[r * KS + s][2]);
-        acc[r * KS + s][3] = fmaf(d.w, (float)((pk >> 24) & 0xff) - zp_a, acc[r * KS + s][3]);
-      }
-    }
-  }
-  const float s_a = *x_scale_p;
-#pragma unroll
-  for (int t = 0; t < KS * KS; ++t)
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) atomicAdd(dwq + (int64_t)t * C + cg * 4 + ch, acc[t][ch] * s_a);
 }
 
 // ---------------------------------------------------------------- stem wgrad
@@ -431,54 +322,6 @@ extern "C" int frost_pw_wgrad(const float* dz, const uint8_t* xq, const float* x
   }
   launch_pw_wgrad_u8(dz, xq, x_scale, x_zp, M, K, cout, dwq, st);
   FROST_LAUNCH_CHECK("pw_wgrad");
-  return FROST_OK;
-}
-
-extern "C" int frost_dw_dgrad(const float* dz, const int8_t* wq, const float* w_scale, const int32_t* w_zp, int N, int H,
-                              int W, int C, int k, int stride, float* dx, int accumulate, void* stream) {
-  FROST_REQUIRE(dz && wq && w_scale && w_zp && dx, "frost_dw_dgrad: null pointer");
-  FROST_REQUIRE(C > 0 && C % 4 == 0 && (k == 3 || k == 5) && (stride == 1 || stride == 2), "frost_dw_dgrad: bad shape");
-  cudaStream_t st = (cudaStream_t)stream;
-  const int pad = (k - 1) / 2;
-  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
-  int cgb, chunks, threads;
-  dw_launch_shape(C, &cgb, &chunks, &threads);
-  const int ppb = threads / cgb;
-  int gx = (int)std::min<int64_t>(ceil_div((int64_t)N * H * W, ppb), (int64_t)kNumSMs * 8);
-  dim3 grid(gx, chunks);
-#define L(KS, S) dw_dgrad_kernel<KS, S><<<grid, threads, 0, st>>>(dz, wq, w_scale, w_zp, N, H, W, C, Ho, Wo, cgb, dx, accumulate)
-  if (k == 3 && stride == 1) L(3, 1);
-  else if (k == 3 && stride == 2) L(3, 2);
-  else if (k == 5 && stride == 1) L(5, 1);
-  else L(5, 2);
-#undef L
-  FROST_LAUNCH_CHECK("dw_dgrad");
-  return FROST_OK;
-}
-
-extern "C" int frost_dw_wgrad(const float* dz, const uint8_t* xq, const float* x_scale, const int32_t* x_zp, int N, int H,
-                              int W, int C, int k, int stride, float* dwq, void* stream) {
-  FROST_REQUIRE(dz && xq && x_scale && x_zp && dwq, "frost_dw_wgrad: null pointer");
-  FROST_REQUIRE(C > 0 && C % 4 == 0 && (k == 3 || k == 5) && (stride == 1 || stride == 2), "frost_dw_wgrad: bad shape");
-  cudaStream_t st = (cudaStream_t)stream;
-  const int pad = (k - 1) / 2;
-  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
-  if (cudaMemsetAsync(dwq, 0, sizeof(float) * (size_t)k * k * C, st) != cudaSuccess) {
-    set_error("frost_dw_wgrad: memset failed");
-    return FROST_ECUDA;
-  }
-  int cgb, chunks, threads;
-  dw_launch_shape(C, &cgb, &chunks, &threads);
-  const int ppb = threads / cgb;
-  int gx = (int)std::min<int64_t>(ceil_div((int64_t)N * Ho * Wo, (int64_t)ppb * 16), (int64_t)kNumSMs * 4);
-  dim3 grid(gx, chunks);
-#define L(KS, S) dw_wgrad_kernel<KS, S><<<grid, threads, 0, st>>>(dz, xq, x_scale, x_zp, N, H, W, C, Ho, Wo, cgb, dwq)
-  if (k == 3 && stride == 1) L(3, 1);
-  else if (k == 3 && stride == 2) L(3, 2);
-  else if (k == 5 && stride == 1) L(5, 1);
-  else L(5, 2);
-#undef L
-  FROST_LAUNCH_CHECK("dw_wgrad");
   return FROST_OK;
 }
 

@@ -187,111 +187,6 @@ __global__ void __launch_bounds__(256) pw_conv_fwd_kernel(const uint8_t* __restr
   if (tid < BN && n0 + tid < cout) global_stat_flush(stats + n0 + tid, s_stat[tid]);
 }
 
-// ================================================================= depthwise kxk (SIMT int)
-// NHWC, 4 channels per thread (one 32-bit load per pixel), a strip of TW output pixels along W
-// per work item; weights live unpacked in registers for the thread's lifetime (its channel group
-// is constant across the grid-stride loop).  Zero padding == index zp_a, i.e. (q - zp_a) = 0.
-constexpr int DW_TW = 4;
-
-template <int KS, int S>
-__global__ void __launch_bounds__(256) dw_conv_fwd_kernel(const uint8_t* __restrict__ xq, const int32_t* __restrict__ x_zp_p,
-                                                         const int8_t* __restrict__ wq, const int32_t* __restrict__ w_zp_p,
-                                                         int N, int H, int W, int C, int Ho, int Wo, int cg_per_block,
-                                                         int32_t* __restrict__ acc_out, FrostChanStats* __restrict__ stats) {
-  extern __shared__ SmemStat s_stat[];  // [cg_per_block*4]
-  constexpr int PAD = (KS - 1) / 2;
-  constexpr int IW = (DW_TW - 1) * S + KS;
-  const int zp_a = *x_zp_p, zp_w = *w_zp_p;
-  const int CG = C >> 2;
-  const int cg_local = threadIdx.x % cg_per_block;
-  const int cg = blockIdx.y * cg_per_block + cg_local;
-  const int strips_per_block = blockDim.x / cg_per_block;
-  const int strip_local = threadIdx.x / cg_per_block;
-  const bool active = (cg < CG) && (strip_local < strips_per_block);
-
-  smem_stat_init(s_stat, cg_per_block * 4);
-  __syncthreads();
-
-  int w[KS * KS][4];
-  if (active) {
-#pragma unroll
-    for (int t = 0; t < KS * KS; ++t) {
-      const unsigned pk = __ldg(reinterpret_cast<const unsigned*>(wq + (int64_t)t * C + cg * 4));
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) w[t][ch] = (int)(int8_t)((pk >> (8 * ch)) & 0xff) - zp_w;
-    }
-  }
-  long long st_sum[4] = {0, 0, 0, 0};
-  unsigned long long st_sq[4] = {0, 0, 0, 0};
-  int st_mn[4] = {INT_MAX, INT_MAX, INT_MAX, INT_MAX};
-  int st_mx[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};
-
-  const int strips_w = (Wo + DW_TW - 1) / DW_TW;
-  const int64_t total_strips = (int64_t)N * Ho * strips_w;
-  if (active) {
-    for (int64_t sidx = (int64_t)blockIdx.x * strips_per_block + strip_local; sidx < total_strips;
-         sidx += (int64_t)gridDim.x * strips_per_block) {
-      const int sw = (int)(sidx % strips_w);
-      const int64_t t1 = sidx / strips_w;
-      const int oh = (int)(t1 % Ho);
-      const int n = (int)(t1 / Ho);
-      const int ow0 = sw * DW_TW;
-      int acc[DW_TW][4];
-#pragma unroll
-      for (int t = 0; t < DW_TW; ++t)
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) acc[t][ch] = 0;
-#pragma unroll
-      for (int r = 0; r < KS; ++r) {
-        const int ih = oh * S - PAD + r;
-        if (ih < 0 || ih >= H) continue;
-        const uint8_t* row = xq + (((int64_t)n * H + ih) * W) * C + cg * 4;
-#pragma unroll
-        for (int j = 0; j < IW; ++j) {
-          const int iw = ow0 * S - PAD + j;
-          if (iw < 0 || iw >= W) continue;
-          const unsigned pk = __ldg(reinterpret_cast<const unsigned*>(row + (int64_t)iw * C));
-          int xa[4];
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) xa[ch] = (int)((pk >> (8 * ch)) & 0xff) - zp_a;
-#pragma unroll
-          for (int t = 0; t < DW_TW; ++t) {
-            const int dx = j - t * S;
-            if (dx >= 0 && dx < KS) {
-#pragma unroll
-              for (int ch = 0; ch < 4; ++ch) acc[t][ch] += xa[ch] * w[r * KS + dx][ch];
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int t = 0; t < DW_TW; ++t) {
-        const int ow = ow0 + t;
-        if (ow < Wo) {
-          int4 v = make_int4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
-          *reinterpret_cast<int4*>(acc_out + (((int64_t)n * Ho + oh) * Wo + ow) * C + cg * 4) = v;
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            const int I = acc[t][ch];
-            st_sum[ch] += I;
-            st_sq[ch] += (unsigned long long)((long long)I * (long long)I);
-            st_mn[ch] = min(st_mn[ch], I);
-            st_mx[ch] = max(st_mx[ch], I);
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch)
-      if (st_mn[ch] <= st_mx[ch]) smem_stat_add(&s_stat[cg_local * 4 + ch], st_sum[ch], st_sq[ch], st_mn[ch], st_mx[ch]);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < cg_per_block * 4; i += blockDim.x) {
-    const int c = blockIdx.y * cg_per_block * 4 + i;
-    if (c < C) global_stat_flush(stats + c, s_stat[i]);
-  }
-}
-
 // ================================================================= dense kxk stem (SIMT int)
 // One thread per output pixel, all couts (<=32) in registers; weights broadcast from smem.
 constexpr int STEM_MAXC = 32;
@@ -391,47 +286,6 @@ extern "C" int frost_pw_conv_forward(const uint8_t* xq, const int32_t* x_zp, con
     pw_conv_fwd_kernel<64><<<grid, 256, 0, st>>>(xq, x_zp, wq, w_zp, wsum, M, K, cout, acc, stats);
   }
   FROST_LAUNCH_CHECK("pw_conv_fwd");
-  return FROST_OK;
-}
-
-namespace frost {
-// channel-group chunking shared by the depthwise kernels: threads per block is a multiple of the
-// number of 4-channel groups handled by the block, so a thread's channel group never changes.
-void dw_launch_shape(int C, int* cg_per_block, int* nchunks, int* threads) {
-  const int CG = C / 4;
-  int chunks = (CG + 255) / 256;
-  while (CG % chunks != 0 && chunks < CG) ++chunks;
-  const int cgb = CG / chunks;
-  *cg_per_block = cgb;
-  *nchunks = chunks;
-  *threads = cgb * (256 / cgb);
-}
-}  // namespace frost
-
-extern "C" int frost_dw_conv_forward(const uint8_t* xq, const int32_t* x_zp, const int8_t* wq, const int32_t* w_zp,
-                                     int N, int H, int W, int C, int k, int stride, int32_t* acc,
-                                     FrostChanStats* stats, void* stream) {
-  FROST_REQUIRE(xq && x_zp && wq && w_zp && acc && stats, "frost_dw_conv_forward: null pointer");
-  FROST_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "frost_dw_conv_forward: bad shape (C%%4 must be 0)");
-  FROST_REQUIRE((k == 3 || k == 5) && (stride == 1 || stride == 2), "frost_dw_conv_forward: k in {3,5}, stride in {1,2}");
-  cudaStream_t st = (cudaStream_t)stream;
-  const int pad = (k - 1) / 2;
-  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
-  int cgb, chunks, threads;
-  dw_launch_shape(C, &cgb, &chunks, &threads);
-  const int strips_per_block = threads / cgb;
-  const int64_t total_strips = (int64_t)N * Ho * ((Wo + DW_TW - 1) / DW_TW);
-  int gx = (int)std::min<int64_t>(ceil_div(total_strips, strips_per_block), (int64_t)kNumSMs * 8);
-  dim3 grid(gx, chunks);
-  const size_t smem = sizeof(SmemStat) * cgb * 4;
-#define DW_LAUNCH(KS, S)                                                                                   \
-  dw_conv_fwd_kernel<KS, S><<<grid, threads, smem, st>>>(xq, x_zp, wq, w_zp, N, H, W, C, Ho, Wo, cgb, acc, stats)
-  if (k == 3 && stride == 1) DW_LAUNCH(3, 1);
-  else if (k == 3 && stride == 2) DW_LAUNCH(3, 2);
-  else if (k == 5 && stride == 1) DW_LAUNCH(5, 1);
-  else DW_LAUNCH(5, 2);
-#undef DW_LAUNCH
-  FROST_LAUNCH_CHECK("dw_conv_fwd");
   return FROST_OK;
 }
 

@@ -1,0 +1,418 @@
+// dw_conv.cu - depthwise kxk convolution (k in {3,5}, stride in {1,2}) forward / dgrad / wgrad on NHWC
+// quantize indices: frostnet.py:116-118 (conv2 of the Frost bottleneck) after fuse + prepare_qat, i.e. the
+// F.conv2d(groups=C) at conv_fused.py:155 and its aten::convolution_backward.
+//
+// Common shape: a thread owns ONE 4-channel group (one 32-bit word of uint8 indices / one float4 of
+// gradient per pixel) for its whole lifetime and walks strips of 4 pixels along W.  A block covers
+// `cgb` channel groups (<= 64) x several strips; the per-channel-group weights live in shared memory.
+// Per kernel row the thread issues all (predicated, coalesced) loads of the input window first, then
+// the MACs - out-of-image taps read the zero-point index, i.e. contribute (q - zp_a) = 0 exactly like
+// the reference's zero padding of the dequantised tensor.
+#include "common.cuh"
+
+namespace frost {
+
+struct SmemStat {
+  long long sum;
+  unsigned long long sq;
+  int mn, mx;
+};
+
+constexpr int DW_TW = 4;
+constexpr int DW_MAX_CGB = 64;
+
+// channel-group chunking shared by the per-channel kernels: threads per block is a multiple of the number
+// of 4-channel groups handled by the block, so a thread's channel group never changes.
+void dw_launch_shape(int C, int max_cgb, int* cg_per_block, int* nchunks, int* threads) {
+  const int CG = C / 4;
+  int chunks = (CG + max_cgb - 1) / max_cgb;
+  while (CG % chunks != 0 && chunks < CG) ++chunks;
+  const int cgb = CG / chunks;
+  *cg_per_block = cgb;
+  *nchunks = chunks;
+  *threads = cgb * (256 / cgb);
+}
+
+__device__ __forceinline__ int sext_byte(unsigned w, int ch) {
+  // PRMT with the sign-replicate bit: byte `ch` sign-extended to 32 bits in one instruction
+  // (inline PTX: __byte_perm documents only 3 selector bits per nibble)
+  const unsigned sel = (unsigned)ch | ((8u | ch) << 4) | ((8u | ch) << 8) | ((8u | ch) << 12);
+  int d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(0u), "r"(sel));
+  return d;
+}
+__device__ __forceinline__ int zext_byte(unsigned w, int ch) { return (int)((w >> (8 * ch)) & 0xffu); }
+
+// ================================================================= forward
+template <int KS, int S>
+__global__ void __launch_bounds__(256, 2) dw_conv_fwd_kernel(const uint8_t* __restrict__ xq, const int32_t* __restrict__ x_zp_p,
+                                                            const int8_t* __restrict__ wq, const int32_t* __restrict__ w_zp_p,
+                                                            int N, int H, int W, int C, int Ho, int Wo, int cgb,
+                                                            int32_t* __restrict__ acc_out, FrostChanStats* __restrict__ stats) {
+  extern __shared__ __align__(16) unsigned char dw_smem[];
+  unsigned* s_w = reinterpret_cast<unsigned*>(dw_smem);                               // [KS*KS][cgb] packed int8x4
+  SmemStat* s_stat = reinterpret_cast<SmemStat*>(dw_smem + sizeof(unsigned) * KS * KS * DW_MAX_CGB);  // [cgb*4]
+  constexpr int PAD = (KS - 1) / 2;
+  constexpr int IW = (DW_TW - 1) * S + KS;
+  const int zp_a = *x_zp_p, zp_w = *w_zp_p;
+  const unsigned zp4 = (unsigned)zp_a * 0x01010101u;
+  const int cg_local = threadIdx.x % cgb;
+  const int cg = blockIdx.y * cgb + cg_local;
+  const int spb = blockDim.x / cgb;
+  const int strip_local = threadIdx.x / cgb;
+
+  for (int i = threadIdx.x; i < KS * KS * cgb; i += blockDim.x) {
+    const int t = i / cgb, g = i % cgb;
+    s_w[t * cgb + g] = __ldg(reinterpret_cast<const unsigned*>(wq + (int64_t)t * C + (blockIdx.y * cgb + g) * 4));
+  }
+  for (int i = threadIdx.x; i < cgb * 4; i += blockDim.x) {
+    s_stat[i].sum = 0; s_stat[i].sq = 0; s_stat[i].mn = INT_MAX; s_stat[i].mx = INT_MIN;
+  }
+  __syncthreads();
+
+  long long st_sum[4] = {0, 0, 0, 0};
+  unsigned long long st_sq[4] = {0, 0, 0, 0};
+  int st_mn[4] = {INT_MAX, INT_MAX, INT_MAX, INT_MAX};
+  int st_mx[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};
+
+  const int strips_w = (Wo + DW_TW - 1) / DW_TW;
+  const int64_t total_strips = (int64_t)N * Ho * strips_w;
+  for (int64_t sidx = (int64_t)blockIdx.x * spb + strip_local; sidx < total_strips; sidx += (int64_t)gridDim.x * spb) {
+    const int sw = (int)(sidx % strips_w);
+    const int64_t t1 = sidx / strips_w;
+    const int oh = (int)(t1 % Ho);
+    const int n = (int)(t1 / Ho);
+    const int ow0 = sw * DW_TW;
+    int acc[DW_TW][4];
+#pragma unroll
+    for (int t = 0; t < DW_TW; ++t)
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) acc[t][ch] = 0;
+#pragma unroll
+    for (int r = 0; r < KS; ++r) {
+      const int ih = oh * S - PAD + r;
+      const bool rok = (unsigned)ih < (unsigned)H;
+      const uint8_t* row = xq + (((int64_t)n * H + (rok ? ih : 0)) * W) * C + cg * 4;
+      unsigned xw[IW];
+#pragma unroll
+      for (int j = 0; j < IW; ++j) {
+        const int iw = ow0 * S - PAD + j;
+        const bool ok = rok && ((unsigned)iw < (unsigned)W);
+        xw[j] = ok ? __ldg(reinterpret_cast<const unsigned*>(row + (int64_t)iw * C)) : zp4;
+      }
+      int wr[KS][4];
+#pragma unroll
+      for (int dx = 0; dx < KS; ++dx) {
+        const unsigned pk = s_w[(r * KS + dx) * cgb + cg_local];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) wr[dx][ch] = sext_byte(pk, ch) - zp_w;
+      }
+#pragma unroll
+      for (int j = 0; j < IW; ++j) {
+        int xa[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) xa[ch] = zext_byte(xw[j], ch) - zp_a;
+#pragma unroll
+        for (int t = 0; t < DW_TW; ++t) {
+          const int dx = j - t * S;
+          if (dx >= 0 && dx < KS) {
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) acc[t][ch] += xa[ch] * wr[dx][ch];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < DW_TW; ++t) {
+      const int ow = ow0 + t;
+      if (ow < Wo) {
+        *reinterpret_cast<int4*>(acc_out + (((int64_t)n * Ho + oh) * Wo + ow) * C + cg * 4) =
+            make_int4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int I = acc[t][ch];
+          st_sum[ch] += I;
+          st_sq[ch] += (unsigned long long)((long long)I * (long long)I);
+          st_mn[ch] = min(st_mn[ch], I);
+          st_mx[ch] = max(st_mx[ch], I);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    if (st_mn[ch] <= st_mx[ch]) {
+      SmemStat* s = &s_stat[cg_local * 4 + ch];
+      atomicAdd(reinterpret_cast<unsigned long long*>(&s->sum), (unsigned long long)st_sum[ch]);
+      atomicAdd(&s->sq, st_sq[ch]);
+      atomicMin(&s->mn, st_mn[ch]);
+      atomicMax(&s->mx, st_mx[ch]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cgb * 4; i += blockDim.x) {
+    const SmemStat s = s_stat[i];
+    if (s.mn == INT_MAX && s.mx == INT_MIN) continue;
+    FrostChanStats* g = stats + blockIdx.y * cgb * 4 + i;
+    atomicAdd(reinterpret_cast<unsigned long long*>(&g->sum), (unsigned long long)s.sum);
+    atomicAdd(&g->sq_lo, s.sq & 0xffffffffull);
+    atomicAdd(&g->sq_hi, s.sq >> 32);
+    atomicMin(&g->min, s.mn);
+    atomicMax(&g->max, s.mx);
+  }
+}
+
+// ================================================================= dgrad
+// dx[n][ih][iw][c] (+)= sum_{r,s} dz[n][oh][ow][c] * wf[r][s][c],  oh*S - PAD + r == ih, ow*S - PAD + s == iw.
+// Strips start at multiples of 4 along W, so for stride 2 the set of (pixel, tap) pairs that hit an
+// output column is known at compile time; valid kernel rows are a run-time (per-thread) stride-S loop.
+template <int KS, int S>
+__global__ void __launch_bounds__(256, 2) dw_dgrad_kernel(const float* __restrict__ dz, const int8_t* __restrict__ wq,
+                                                         const float* __restrict__ w_scale_p, const int32_t* __restrict__ w_zp_p,
+                                                         int N, int H, int W, int C, int Ho, int Wo, int cgb,
+                                                         float* __restrict__ dx, int accumulate) {
+  extern __shared__ __align__(16) unsigned char dw_smem[];
+  float4* s_w = reinterpret_cast<float4*>(dw_smem);  // [KS*KS][cgb] dequantised weights
+  constexpr int PAD = (KS - 1) / 2;
+  // window of output columns touched by a 4-pixel input strip starting at iw0 (iw0 % 4 == 0):
+  //   ow = (iw0 + t + PAD - s) / S  for the (t, s) with (t + PAD - s) % S == 0
+  constexpr int JLO = -(PAD / S);                 // min of (t+PAD-s)/S over the valid pairs
+  constexpr int JHI = (DW_TW - 1 + PAD) / S;      // max
+  constexpr int NJ = JHI - JLO + 1;
+  const int cg_local = threadIdx.x % cgb;
+  const int cg = blockIdx.y * cgb + cg_local;
+  const int spb = blockDim.x / cgb;
+  const int strip_local = threadIdx.x / cgb;
+  {
+    const float zp_w = (float)*w_zp_p, s_wt = *w_scale_p;
+    for (int i = threadIdx.x; i < KS * KS * cgb; i += blockDim.x) {
+      const int t = i / cgb, g = i % cgb;
+      const unsigned pk = __ldg(reinterpret_cast<const unsigned*>(wq + (int64_t)t * C + (blockIdx.y * cgb + g) * 4));
+      s_w[t * cgb + g] = make_float4(((float)sext_byte(pk, 0) - zp_w) * s_wt, ((float)sext_byte(pk, 1) - zp_w) * s_wt,
+                                     ((float)sext_byte(pk, 2) - zp_w) * s_wt, ((float)sext_byte(pk, 3) - zp_w) * s_wt);
+    }
+  }
+  __syncthreads();
+  const int strips_w = (W + DW_TW - 1) / DW_TW;
+  const int64_t total_strips = (int64_t)N * H * strips_w;
+  for (int64_t sidx = (int64_t)blockIdx.x * spb + strip_local; sidx < total_strips; sidx += (int64_t)gridDim.x * spb) {
+    const int sw = (int)(sidx % strips_w);
+    const int64_t t1 = sidx / strips_w;
+    const int ih = (int)(t1 % H);
+    const int n = (int)(t1 / H);
+    const int iw0 = sw * DW_TW;
+    const int ow_base = iw0 / S;          // iw0 % 4 == 0 -> exact
+    float acc[DW_TW][4];
+#pragma unroll
+    for (int t = 0; t < DW_TW; ++t)
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) acc[t][ch] = 0.0f;
+    const int r0 = (ih + PAD) % S;
+    for (int r = r0; r < KS; r += S) {
+      const int th = ih + PAD - r;
+      if (th < 0) break;
+      const int oh = th / S;
+      if (oh >= Ho) continue;
+      const float* row = dz + (((int64_t)n * Ho + oh) * Wo) * C + cg * 4;
+      float4 d[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int ow = ow_base + JLO + j;
+        d[j] = ((unsigned)ow < (unsigned)Wo) ? __ldg(reinterpret_cast<const float4*>(row + (int64_t)ow * C))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int s = 0; s < KS; ++s) {
+        const float4 w = s_w[(r * KS + s) * cgb + cg_local];
+#pragma unroll
+        for (int t = 0; t < DW_TW; ++t) {
+          if ((t + PAD - s) % S == 0) {                       // compile-time
+            const int jj = (t + PAD - s) / S - JLO;           // compile-time; exact because S divides (t+PAD-s)
+            acc[t][0] = fmaf(d[jj].x, w.x, acc[t][0]);
+            acc[t][1] = fmaf(d[jj].y, w.y, acc[t][1]);
+            acc[t][2] = fmaf(d[jj].z, w.z, acc[t][2]);
+            acc[t][3] = fmaf(d[jj].w, w.w, acc[t][3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < DW_TW; ++t) {
+      const int iw = iw0 + t;
+      if (iw < W) {
+        float4* o = reinterpret_cast<float4*>(dx + (((int64_t)n * H + ih) * W + iw) * C) + cg;
+        float4 v = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+        if (accumulate) {
+          const float4 old = *o;
+          v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+        }
+        *o = v;
+      }
+    }
+  }
+}
+
+// ================================================================= wgrad
+// dwq[r*KS+s][c] += s_a * sum_{n,oh,ow} dz[n][oh][ow][c] * (x[n][oh*S-PAD+r][ow*S-PAD+s][c] - zp_a)
+// One thread: one channel group, all KS*KS taps in registers, strips of 4 output pixels.
+template <int KS, int S>
+__global__ void __launch_bounds__(256) dw_wgrad_kernel(const float* __restrict__ dz, const uint8_t* __restrict__ xq,
+                                                      const float* __restrict__ x_scale_p, const int32_t* __restrict__ x_zp_p,
+                                                      int N, int H, int W, int C, int Ho, int Wo, int cgb,
+                                                      float* __restrict__ dwq) {
+  extern __shared__ __align__(16) unsigned char dw_smem[];
+  float* s_acc = reinterpret_cast<float*>(dw_smem);  // [KS*KS][cgb*4]
+  constexpr int PAD = (KS - 1) / 2;
+  constexpr int IW = (DW_TW - 1) * S + KS;
+  const int zp_a = *x_zp_p;
+  const unsigned zp4 = (unsigned)zp_a * 0x01010101u;
+  const float zpf = (float)zp_a;
+  const int cg_local = threadIdx.x % cgb;
+  const int cg = blockIdx.y * cgb + cg_local;
+  const int spb = blockDim.x / cgb;
+  const int strip_local = threadIdx.x / cgb;
+  for (int i = threadIdx.x; i < KS * KS * cgb * 4; i += blockDim.x) s_acc[i] = 0.0f;
+  __syncthreads();
+  float acc[KS * KS][4];
+#pragma unroll
+  for (int t = 0; t < KS * KS; ++t)
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) acc[t][ch] = 0.0f;
+  const int strips_w = (Wo + DW_TW - 1) / DW_TW;
+  const int64_t total_strips = (int64_t)N * Ho * strips_w;
+  for (int64_t sidx = (int64_t)blockIdx.x * spb + strip_local; sidx < total_strips; sidx += (int64_t)gridDim.x * spb) {
+    const int sw = (int)(sidx % strips_w);
+    const int64_t t1 = sidx / strips_w;
+    const int oh = (int)(t1 % Ho);
+    const int n = (int)(t1 / Ho);
+    const int ow0 = sw * DW_TW;
+    float4 d[DW_TW];
+    const float* drow = dz + (((int64_t)n * Ho + oh) * Wo) * C + cg * 4;
+#pragma unroll
+    for (int t = 0; t < DW_TW; ++t)
+      d[t] = (ow0 + t < Wo) ? __ldg(reinterpret_cast<const float4*>(drow + (int64_t)(ow0 + t) * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < KS; ++r) {
+      const int ih = oh * S - PAD + r;
+      if ((unsigned)ih >= (unsigned)H) continue;
+      const uint8_t* row = xq + (((int64_t)n * H + ih) * W) * C + cg * 4;
+      unsigned xw[IW];
+#pragma unroll
+      for (int j = 0; j < IW; ++j) {
+        const int iw = ow0 * S - PAD + j;
+        xw[j] = ((unsigned)iw < (unsigned)W) ? __ldg(reinterpret_cast<const unsigned*>(row + (int64_t)iw * C)) : zp4;
+      }
+#pragma unroll
+      for (int j = 0; j < IW; ++j) {
+        float xa[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) xa[ch] = (float)zext_byte(xw[j], ch) - zpf;
+#pragma unroll
+        for (int t = 0; t < DW_TW; ++t) {
+          const int s = j - t * S;
+          if (s >= 0 && s < KS) {
+            acc[r * KS + s][0] = fmaf(d[t].x, xa[0], acc[r * KS + s][0]);
+            acc[r * KS + s][1] = fmaf(d[t].y, xa[1], acc[r * KS + s][1]);
+            acc[r * KS + s][2] = fmaf(d[t].z, xa[2], acc[r * KS + s][2]);
+            acc[r * KS + s][3] = fmaf(d[t].w, xa[3], acc[r * KS + s][3]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < KS * KS; ++t)
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) atomicAdd(&s_acc[(t * cgb + cg_local) * 4 + ch], acc[t][ch]);
+  __syncthreads();
+  const float s_a = *x_scale_p;
+  for (int i = threadIdx.x; i < KS * KS * cgb * 4; i += blockDim.x) {
+    const int t = i / (cgb * 4), c = i % (cgb * 4);
+    atomicAdd(dwq + (int64_t)t * C + blockIdx.y * cgb * 4 + c, s_acc[i] * s_a);
+  }
+}
+
+}  // namespace frost
+
+using namespace frost;
+
+static bool dw_shape_ok(int C, int k, int stride) { return C > 0 && C % 4 == 0 && (k == 3 || k == 5) && (stride == 1 || stride == 2); }
+
+extern "C" int frost_dw_conv_forward(const uint8_t* xq, const int32_t* x_zp, const int8_t* wq, const int32_t* w_zp,
+                                     int N, int H, int W, int C, int k, int stride, int32_t* acc,
+                                     FrostChanStats* stats, void* stream) {
+  FROST_REQUIRE(xq && x_zp && wq && w_zp && acc && stats, "frost_dw_conv_forward: null pointer");
+  FROST_REQUIRE(N > 0 && H > 0 && W > 0 && dw_shape_ok(C, k, stride),
+                "frost_dw_conv_forward: bad shape (C%%4==0, k in {3,5}, stride in {1,2})");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int pad = (k - 1) / 2;
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  int cgb, chunks, threads;
+  dw_launch_shape(C, DW_MAX_CGB, &cgb, &chunks, &threads);
+  const int spb = threads / cgb;
+  const int64_t total_strips = (int64_t)N * Ho * ((Wo + DW_TW - 1) / DW_TW);
+  const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total_strips, (int64_t)spb * 2), (int64_t)kNumSMs * 16 / chunks + 1));
+  dim3 grid(gx, chunks);
+  const size_t smem = sizeof(unsigned) * k * k * DW_MAX_CGB + sizeof(SmemStat) * cgb * 4;
+#define L(KS, S) dw_conv_fwd_kernel<KS, S><<<grid, threads, smem, st>>>(xq, x_zp, wq, w_zp, N, H, W, C, Ho, Wo, cgb, acc, stats)
+  if (k == 3 && stride == 1) L(3, 1);
+  else if (k == 3 && stride == 2) L(3, 2);
+  else if (k == 5 && stride == 1) L(5, 1);
+  else L(5, 2);
+#undef L
+  FROST_LAUNCH_CHECK("dw_conv_fwd");
+  return FROST_OK;
+}
+
+extern "C" int frost_dw_dgrad(const float* dz, const int8_t* wq, const float* w_scale, const int32_t* w_zp, int N, int H,
+                              int W, int C, int k, int stride, float* dx, int accumulate, void* stream) {
+  FROST_REQUIRE(dz && wq && w_scale && w_zp && dx, "frost_dw_dgrad: null pointer");
+  FROST_REQUIRE(N > 0 && H > 0 && W > 0 && dw_shape_ok(C, k, stride), "frost_dw_dgrad: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int pad = (k - 1) / 2;
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  int cgb, chunks, threads;
+  dw_launch_shape(C, DW_MAX_CGB, &cgb, &chunks, &threads);
+  const int spb = threads / cgb;
+  const int64_t total_strips = (int64_t)N * H * ((W + DW_TW - 1) / DW_TW);
+  const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total_strips, (int64_t)spb * 2), (int64_t)kNumSMs * 16 / chunks + 1));
+  dim3 grid(gx, chunks);
+  const size_t smem = sizeof(float4) * k * k * cgb;
+#define L(KS, S) dw_dgrad_kernel<KS, S><<<grid, threads, smem, st>>>(dz, wq, w_scale, w_zp, N, H, W, C, Ho, Wo, cgb, dx, accumulate)
+  if (k == 3 && stride == 1) L(3, 1);
+  else if (k == 3 && stride == 2) L(3, 2);
+  else if (k == 5 && stride == 1) L(5, 1);
+  else L(5, 2);
+#undef L
+  FROST_LAUNCH_CHECK("dw_dgrad");
+  return FROST_OK;
+}
+
+extern "C" int frost_dw_wgrad(const float* dz, const uint8_t* xq, const float* x_scale, const int32_t* x_zp, int N, int H,
+                              int W, int C, int k, int stride, float* dwq, void* stream) {
+  FROST_REQUIRE(dz && xq && x_scale && x_zp && dwq, "frost_dw_wgrad: null pointer");
+  FROST_REQUIRE(N > 0 && H > 0 && W > 0 && dw_shape_ok(C, k, stride), "frost_dw_wgrad: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int pad = (k - 1) / 2;
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  if (cudaMemsetAsync(dwq, 0, sizeof(float) * (size_t)k * k * C, st) != cudaSuccess) {
+    set_error("frost_dw_wgrad: memset failed");
+    return FROST_ECUDA;
+  }
+  int cgb, chunks, threads;
+  dw_launch_shape(C, DW_MAX_CGB, &cgb, &chunks, &threads);
+  const int spb = threads / cgb;
+  const int64_t total_strips = (int64_t)N * Ho * ((Wo + DW_TW - 1) / DW_TW);
+  // every thread should see >= 8 strips so that the final smem/global reduction is amortised
+  const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total_strips, (int64_t)spb * 8), (int64_t)kNumSMs * 4 / chunks + 1));
+  dim3 grid(gx, chunks);
+  const size_t smem = sizeof(float) * k * k * cgb * 4;
+#define L(KS, S) dw_wgrad_kernel<KS, S><<<grid, threads, smem, st>>>(dz, xq, x_scale, x_zp, N, H, W, C, Ho, Wo, cgb, dwq)
+  if (k == 3 && stride == 1) L(3, 1);
+  else if (k == 3 && stride == 2) L(3, 2);
+  else if (k == 5 && stride == 1) L(5, 1);
+  else L(5, 2);
+#undef L
+  FROST_LAUNCH_CHECK("dw_wgrad");
+  return FROST_OK;
+}

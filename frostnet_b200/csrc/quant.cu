@@ -86,44 +86,75 @@ __device__ __forceinline__ int64_t wq_index(const FrostWeightDesc& d, int c, int
   }
 }
 
-constexpr int kWeightThreads = 1024;
+constexpr int kWeightThreads = 256;
 
-__global__ void __launch_bounds__(kWeightThreads) weight_prep_kernel(const FrostWeightDesc* __restrict__ descs) {
-  const FrostWeightDesc d = descs[blockIdx.x];
+__device__ __forceinline__ float weight_sf(const FrostWeightDesc& d, int c, float* rstd_out) {
+  // scale_factor = gamma / sqrt(running_var + eps)      (conv_fused.py:138-139)
+  float sf = 1.0f, rstd = 1.0f;
+  if (d.bn_weight) {
+    const float std_run = __fsqrt_rn(__fadd_rn(d.bn_var[c], d.bn_eps));
+    sf = __fdiv_rn(d.bn_weight[c], std_run);
+    rstd = __fdiv_rn(1.0f, std_run);
+  }
+  if (rstd_out) *rstd_out = rstd;
+  return sf;
+}
+
+// pass 1 (one CTA per FROST_WEIGHT_CHUNK elements): min/max of Ws = W * scale_factor
+__global__ void __launch_bounds__(kWeightThreads) weight_minmax_kernel(const FrostWeightDesc* __restrict__ descs,
+                                                                      const FrostOptChunk* __restrict__ chunks,
+                                                                      float* __restrict__ scratch) {
+  const FrostOptChunk ck = chunks[blockIdx.x];
+  const FrostWeightDesc& d = descs[ck.tensor];
+  if (!d.observe) return;
   const int K = d.cin_g * d.kh * d.kw;
   const int64_t total = (int64_t)d.cout * K;
-  // phase 0: scale_factor = gamma / sqrt(running_var + eps)      (conv_fused.py:138-139)
+  const int64_t e0 = (int64_t)ck.chunk * FROST_WEIGHT_CHUNK;
+  const int64_t e1 = min(total, e0 + FROST_WEIGHT_CHUNK);
+  float mn = INFINITY, mx = -INFINITY;
+  for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+    const int c = (int)(e / K);
+    const float ws = __fmul_rn(d.weight[e], weight_sf(d, c, nullptr));
+    mn = fminf(mn, ws);
+    mx = fmaxf(mx, ws);
+  }
+  block_minmax(mn, mx);
+  if (threadIdx.x == 0) {
+    atomic_min_float(scratch + 2 * ck.tensor, mn);
+    atomic_max_float(scratch + 2 * ck.tensor + 1, mx);
+  }
+}
+
+// pass 2 (one CTA per layer): scale_factor arrays, observer EMA + qparams, reset of the scratch slot
+__global__ void __launch_bounds__(kWeightThreads) weight_finalize_kernel(const FrostWeightDesc* __restrict__ descs,
+                                                                        float* __restrict__ scratch) {
+  const FrostWeightDesc& d = descs[blockIdx.x];
   for (int c = threadIdx.x; c < d.cout; c += blockDim.x) {
-    float sf = 1.0f, rstd = 1.0f;
-    if (d.bn_weight) {
-      const float std_run = __fsqrt_rn(__fadd_rn(d.bn_var[c], d.bn_eps));
-      sf = __fdiv_rn(d.bn_weight[c], std_run);
-      rstd = __fdiv_rn(1.0f, std_run);
-    }
-    d.sf[c] = sf;
+    float rstd;
+    d.sf[c] = weight_sf(d, c, &rstd);
     d.rstd_run[c] = rstd;
     d.wsum[c] = 0;
   }
-  __syncthreads();
-  // phase 1: observer over Ws = W * scale_factor
-  if (d.observe) {
-    float mn = INFINITY, mx = -INFINITY;
-    for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
-      const int c = (int)(e / K);
-      const float ws = __fmul_rn(d.weight[e], d.sf[c]);
-      mn = fminf(mn, ws);
-      mx = fmaxf(mx, ws);
-    }
-    block_minmax(mn, mx);
-    if (threadIdx.x == 0) observer_update(d.wfq, mn, mx, -128, 127, true, d.averaging_const);
+  if (threadIdx.x == 0) {
+    if (d.observe) observer_update(d.wfq, scratch[2 * blockIdx.x], scratch[2 * blockIdx.x + 1], -128, 127, true, d.averaging_const);
+    scratch[2 * blockIdx.x] = INFINITY;
+    scratch[2 * blockIdx.x + 1] = -INFINITY;
   }
-  __syncthreads();
-  __threadfence_block();
-  // phase 2: quantise
+}
+
+// pass 3 (one CTA per chunk): int8 indices in the kernel layout, STE mask, per-cout index sums
+__global__ void __launch_bounds__(kWeightThreads) weight_quant_kernel(const FrostWeightDesc* __restrict__ descs,
+                                                                     const FrostOptChunk* __restrict__ chunks) {
+  const FrostOptChunk ck = chunks[blockIdx.x];
+  const FrostWeightDesc& d = descs[ck.tensor];
+  const int K = d.cin_g * d.kh * d.kw;
+  const int64_t total = (int64_t)d.cout * K;
+  const int64_t e0 = (int64_t)ck.chunk * FROST_WEIGHT_CHUNK;
+  const int64_t e1 = min(total, e0 + FROST_WEIGHT_CHUNK);
   const float s = *d.wfq.scale, zp = (float)*d.wfq.zero_point;
   const float inv = __fdiv_rn(1.0f, s);
   const int khw = d.kh * d.kw;
-  for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
+  for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
     const int c = (int)(e / K);
     const int r = (int)(e - (int64_t)c * K);
     const int ci = r / khw, yx = r - ci * khw;
@@ -138,25 +169,28 @@ __global__ void __launch_bounds__(kWeightThreads) weight_prep_kernel(const Frost
 }
 
 // dW = dWq*mask*sf ; dgamma = dgamma_bn + (dsf_bn + sum_k dWq*mask*W) * rstd_run   (SURVEY 8a' 5-6)
-__global__ void __launch_bounds__(kWeightThreads) weight_backward_kernel(const FrostWeightDesc* __restrict__ descs) {
-  const FrostWeightDesc d = descs[blockIdx.x];
+// one CTA (8 warps) per 8 output channels of one layer: chunks[i] = {layer, first channel / 8}
+__global__ void __launch_bounds__(kWeightThreads) weight_backward_kernel(const FrostWeightDesc* __restrict__ descs,
+                                                                        const FrostOptChunk* __restrict__ chunks) {
+  const FrostOptChunk ck = chunks[blockIdx.x];
+  const FrostWeightDesc& d = descs[ck.tensor];
   const int K = d.cin_g * d.kh * d.kw;
   const int khw = d.kh * d.kw;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int c = warp; c < d.cout; c += nwarps) {
-    const float sf = d.sf[c];
-    float acc = 0.0f;
-    for (int r = lane; r < K; r += 32) {
-      const int64_t e = (int64_t)c * K + r;
-      const int ci = r / khw, yx = r - ci * khw;
-      const int y = yx / d.kw, x = yx - y * d.kw;
-      const float dws = d.wmask[e] ? d.dwq[wq_index(d, c, ci, y, x)] : 0.0f;
-      d.dweight[e] = dws * sf;
-      acc = fmaf(dws, d.weight[e], acc);
-    }
-    acc = warp_sum(acc);
-    if (lane == 0 && d.dgamma) d.dgamma[c] = d.dgamma_bn[c] + (d.dsf_bn[c] + acc) * d.rstd_run[c];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = ck.chunk * (kWeightThreads / 32) + warp;
+  if (c >= d.cout) return;
+  const float sf = d.sf[c];
+  float acc = 0.0f;
+  for (int r = lane; r < K; r += 32) {
+    const int64_t e = (int64_t)c * K + r;
+    const int ci = r / khw, yx = r - ci * khw;
+    const int y = yx / d.kw, x = yx - y * d.kw;
+    const float dws = d.wmask[e] ? d.dwq[wq_index(d, c, ci, y, x)] : 0.0f;
+    d.dweight[e] = dws * sf;
+    acc = fmaf(dws, d.weight[e], acc);
   }
+  acc = warp_sum(acc);
+  if (lane == 0 && d.dgamma) d.dgamma[c] = d.dgamma_bn[c] + (d.dsf_bn[c] + acc) * d.rstd_run[c];
 }
 
 __global__ void stats_reset_kernel(FrostChanStats* s, int64_t n) {
@@ -238,16 +272,23 @@ extern "C" int frost_input_quant(const float* x_nchw, int N, int C, int H, int W
   return FROST_OK;
 }
 
-extern "C" int frost_weight_prep_multi(const FrostWeightDesc* descs, int n, void* stream) {
-  FROST_REQUIRE(descs && n > 0, "frost_weight_prep_multi: bad args");
-  weight_prep_kernel<<<n, kWeightThreads, 0, (cudaStream_t)stream>>>(descs);
-  FROST_LAUNCH_CHECK("weight_prep");
+extern "C" int frost_weight_prep_multi(const FrostWeightDesc* descs, int n, const FrostOptChunk* chunks, int n_chunks,
+                                       float* scratch, void* stream) {
+  FROST_REQUIRE(descs && n > 0 && chunks && n_chunks > 0 && scratch, "frost_weight_prep_multi: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  weight_minmax_kernel<<<n_chunks, kWeightThreads, 0, st>>>(descs, chunks, scratch);
+  FROST_LAUNCH_CHECK("weight_minmax");
+  weight_finalize_kernel<<<n, kWeightThreads, 0, st>>>(descs, scratch);
+  FROST_LAUNCH_CHECK("weight_finalize");
+  weight_quant_kernel<<<n_chunks, kWeightThreads, 0, st>>>(descs, chunks);
+  FROST_LAUNCH_CHECK("weight_quant");
   return FROST_OK;
 }
 
-extern "C" int frost_weight_backward_multi(const FrostWeightDesc* descs, int n, void* stream) {
-  FROST_REQUIRE(descs && n > 0, "frost_weight_backward_multi: bad args");
-  weight_backward_kernel<<<n, kWeightThreads, 0, (cudaStream_t)stream>>>(descs);
+extern "C" int frost_weight_backward_multi(const FrostWeightDesc* descs, int n, const FrostOptChunk* chunks, int n_chunks,
+                                           void* stream) {
+  FROST_REQUIRE(descs && n > 0 && chunks && n_chunks > 0, "frost_weight_backward_multi: bad args");
+  weight_backward_kernel<<<n_chunks, kWeightThreads, 0, (cudaStream_t)stream>>>(descs, chunks);
   FROST_LAUNCH_CHECK("weight_backward");
   return FROST_OK;
 }

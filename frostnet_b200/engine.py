@@ -164,6 +164,9 @@ class QATEngine:
         self.n_stat_chan = tot_c
         self.scratch = torch.zeros(L.FQ_SCRATCH_FLOATS, dtype=torch.float32, device=dev)
         self._wdesc_dev = [self._build_wdesc(i) for i in range(2)]
+        self._wchunks, self._n_wchunks = L.chunk_table([ly.wq.numel() for ly in self.layers], L.WEIGHT_CHUNK, dev)
+        self._wbchunks, self._n_wbchunks = L.chunk_table([ly.cout for ly in self.layers], L.WEIGHT_BWD_CHANNELS, dev)
+        self._wscratch = torch.tensor([float("inf"), float("-inf")] * len(self.layers), dtype=torch.float32, device=dev)
         self._built = True
 
     def _build_wdesc(self, which):
@@ -267,7 +270,8 @@ class QATEngine:
         if self.record_taps:
             self.last_taps = {}
         # all weights: scale_factor, observer, int8 indices - one launch
-        L.call("frost_weight_prep_multi", self._wdesc_dev[0].data_ptr(), len(self.layers), st)
+        L.call("frost_weight_prep_multi", self._wdesc_dev[0].data_ptr(), len(self.layers), self._wchunks.data_ptr(),
+               self._n_wchunks, self._wscratch.data_ptr(), st)
         L.call("frost_stats_reset", self.stats.data_ptr(), self.n_stat_chan, st)
         # QuantStub
         qfq = m.quant.activation_post_process
@@ -467,7 +471,8 @@ class QATEngine:
                 gx_written = True
             g = gx
         self._conv_bn_bwd(self.stem, g, saved, gbase, None, False, st)
-        L.call("frost_weight_backward_multi", self._wdesc_dev[which].data_ptr(), len(self.layers), st)
+        L.call("frost_weight_backward_multi", self._wdesc_dev[which].data_ptr(), len(self.layers),
+               self._wbchunks.data_ptr(), self._n_wbchunks, st)
         if self.grad_sync is not None:
             self.grad_sync(gflat)
         grads = []

@@ -87,7 +87,7 @@ int frost_input_quant(const float* x_nchw, int N, int C, int H, int W, FrostFQ f
  * (torch/ao/nn/intrinsic/qat/modules/conv_fused.py:131-146; frostnet.py:14-28,46-60 after
  * fuse_model): scale_factor = gamma/sqrt(running_var+eps); Ws = W*scale_factor;
  * observer+qparams (qint8, per_tensor_symmetric); q_w = clamp(rint(Ws/s_w)+zp_w).
- * One CTA per descriptor; `descs` lives in DEVICE memory (n of them). */
+ * `descs` lives in DEVICE memory (n of them). */
 typedef struct {
   const float* weight;      /* [cout][cin_g][kh][kw] fp32, PyTorch layout                     */
   const float* bn_weight;   /* gamma[cout], or NULL (classifier: scale_factor = 1)            */
@@ -112,8 +112,17 @@ typedef struct {
   float* dweight;           /* out: grad of weight, PyTorch layout                             */
   float* dgamma;            /* out: grad of bn.weight [cout] (NULL for classifier)             */
 } FrostWeightDesc;
-int frost_weight_prep_multi(const FrostWeightDesc* descs, int n, void* stream);
-int frost_weight_backward_multi(const FrostWeightDesc* descs, int n, void* stream);
+/* Work list entry shared by the multi-tensor kernels: {tensor/layer index, chunk index within it}. */
+typedef struct { int32_t tensor; int32_t chunk; } FrostOptChunk;
+/* prep: `chunks` (device) lists every FROST_WEIGHT_CHUNK-element slice of every layer; `scratch` is
+ * 2*n floats initialised to (+inf,-inf) pairs once by the caller (the kernels re-arm it).
+ * backward: `chunks` lists every group of FROST_WEIGHT_BWD_CHANNELS output channels of every layer. */
+#define FROST_WEIGHT_CHUNK 8192
+#define FROST_WEIGHT_BWD_CHANNELS 8
+int frost_weight_prep_multi(const FrostWeightDesc* descs, int n, const FrostOptChunk* chunks,
+                            int n_chunks, float* scratch, void* stream);
+int frost_weight_backward_multi(const FrostWeightDesc* descs, int n, const FrostOptChunk* chunks,
+                                int n_chunks, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Convolutions on quantize indices (the F.conv2d at conv_fused.py:155, restated exactly in
@@ -301,7 +310,6 @@ typedef struct {
  * chunks[i] = {tensor index, chunk index within the tensor}; a chunk is FROST_OPT_CHUNK
  * consecutive elements, one CTA each, so no CTA is launched without work. */
 #define FROST_OPT_CHUNK 2048
-typedef struct { int32_t tensor; int32_t chunk; } FrostOptChunk;
 int frost_gradboost_multi(const FrostOptTensor* tensors, int n, const FrostOptChunk* chunks,
                           int n_chunks, const FrostOptHyper* hyper, void* stream);
 

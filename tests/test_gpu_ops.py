@@ -180,9 +180,13 @@ def test_weight_prep_and_backward_vs_oracle(shape, layout):
         items.append((w, gamma, var, fq, bufs, wd, gd, vd))
     arr = (L().WeightDesc * len(descs))(*descs)
     tab = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(DEV)
+    n_el = int(np.prod(shape))
+    chunks, n_chunks = L().chunk_table([n_el] * len(descs), L().WEIGHT_CHUNK, DEV)
+    bchunks, n_bchunks = L().chunk_table([shape[0]] * len(descs), L().WEIGHT_BWD_CHANNELS, DEV)
+    wscratch = torch.tensor([float("inf"), float("-inf")] * len(descs), device=DEV)
     for it in range(2):
-        L().call("frost_weight_prep_multi", tab.data_ptr(), len(descs), stream())
-        L().call("frost_weight_backward_multi", tab.data_ptr(), len(descs), stream())
+        L().call("frost_weight_prep_multi", tab.data_ptr(), len(descs), chunks.data_ptr(), n_chunks, wscratch.data_ptr(), stream())
+        L().call("frost_weight_backward_multi", tab.data_ptr(), len(descs), bchunks.data_ptr(), n_bchunks, stream())
         for (w, gamma, var, fq, bufs, *_rest) in items:
             wl = w.clone().requires_grad_(True)
             if gamma is not None:
