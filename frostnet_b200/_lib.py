@@ -86,6 +86,7 @@ _SIGNATURES = {
     "frost_weight_prep_multi": [c_p, i32, c_p, i32, c_p, c_p],
     "frost_weight_backward_multi": [c_p, i32, c_p, i32, c_p],
     "frost_pw_conv_forward": [c_p, c_p, c_p, c_p, c_p, i64, i32, i32, c_p, c_p, c_p],
+    "frost_pw_conv_forward_simt": [c_p, c_p, c_p, c_p, c_p, i64, i32, i32, c_p, c_p, c_p],
     "frost_dw_conv_forward": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, c_p, c_p, c_p],
     "frost_stem_conv_forward": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, i32, c_p, c_p, c_p],
     "frost_bn_finalize": [C.POINTER(BnFinalizeArgs), c_p],

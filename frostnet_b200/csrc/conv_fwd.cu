@@ -268,14 +268,14 @@ __global__ void __launch_bounds__(STEM_THREADS) stem_conv_fwd_kernel(
 
 using namespace frost;
 
-extern "C" int frost_pw_conv_forward(const uint8_t* xq, const int32_t* x_zp, const int8_t* wq, const int32_t* w_zp,
+extern "C" int frost_pw_conv_forward_simt(const uint8_t* xq, const int32_t* x_zp, const int8_t* wq, const int32_t* w_zp,
                                      const int32_t* wsum, int64_t M, int K, int cout, int32_t* acc,
                                      FrostChanStats* stats, void* stream) {
-  FROST_REQUIRE(xq && x_zp && wq && w_zp && wsum && acc && stats, "frost_pw_conv_forward: null pointer");
-  FROST_REQUIRE(M > 0 && K > 0 && cout > 0, "frost_pw_conv_forward: empty problem M=%lld K=%d cout=%d", (long long)M, K, cout);
-  FROST_REQUIRE(K % 8 == 0, "frost_pw_conv_forward: K=%d must be a multiple of 8", K);
+  FROST_REQUIRE(xq && x_zp && wq && w_zp && wsum && acc && stats, "frost_pw_conv_forward_simt: null pointer");
+  FROST_REQUIRE(M > 0 && K > 0 && cout > 0, "frost_pw_conv_forward_simt: empty problem M=%lld K=%d cout=%d", (long long)M, K, cout);
+  FROST_REQUIRE(K % 8 == 0, "frost_pw_conv_forward_simt: K=%d must be a multiple of 8", K);
   FROST_REQUIRE((reinterpret_cast<uintptr_t>(xq) & 7) == 0 && (reinterpret_cast<uintptr_t>(wq) & 7) == 0,
-                "frost_pw_conv_forward: operands must be 8-byte aligned");
+                "frost_pw_conv_forward_simt: operands must be 8-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned gx = (unsigned)ceil_div(M, PW_BM);
   if (cout <= 32 || (cout % 64 != 0 && cout % 64 <= 32 && cout < 128)) {

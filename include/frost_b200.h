@@ -127,10 +127,15 @@ int frost_weight_backward_multi(const FrostWeightDesc* descs, int n, const Frost
 /* ---------------------------------------------------------------------------------------------
  * Convolutions on quantize indices (the F.conv2d at conv_fused.py:155, restated exactly in
  * integers: conv = s_a*s_w*I).  All write I (int32 NHWC) and accumulate FrostChanStats. */
-/* 1x1 pointwise: xq[M][K] u8, wq[cout][K] s8 -> acc[M][cout]. K%8==0, cout%4==0. */
+/* 1x1 pointwise: xq[M][K] u8, wq[cout][K] s8 -> acc[M][cout]. K%8==0, cout%4==0, 16-byte aligned.
+ * tcgen05.mma kind::i8 with TMEM accumulators (pw_conv_tc.cu); wsum[co] = sum_k q_w[co][k]. */
 int frost_pw_conv_forward(const uint8_t* xq, const int32_t* x_zp, const int8_t* wq,
                           const int32_t* w_zp, const int32_t* wsum, int64_t M, int K, int cout,
                           int32_t* acc, FrostChanStats* stats, void* stream);
+/* Same contract on CUDA cores (dp4a); kept as the cross-check of the tensor-core kernel. */
+int frost_pw_conv_forward_simt(const uint8_t* xq, const int32_t* x_zp, const int8_t* wq,
+                               const int32_t* w_zp, const int32_t* wsum, int64_t M, int K, int cout,
+                               int32_t* acc, FrostChanStats* stats, void* stream);
 /* depthwise kxk (k in {3,5}), stride in {1,2}, pad=(k-1)/2: xq[N][H][W][C] -> acc[N][Ho][Wo][C]. C%4==0 */
 int frost_dw_conv_forward(const uint8_t* xq, const int32_t* x_zp, const int8_t* wq,
                           const int32_t* w_zp, int N, int H, int W, int C, int k, int stride,

@@ -235,9 +235,11 @@ def _check_stats(buf, I):
         assert int(raw["mn"][c]) == int(col.min()) and int(raw["mx"][c]) == int(col.max()), c
 
 
+@pytest.mark.parametrize("entry", ["frost_pw_conv_forward", "frost_pw_conv_forward_simt"])
 @pytest.mark.parametrize("M,K,cout,zpw", [(1, 16, 16, 0), (130, 24, 24, 0), (257, 104, 312, 0), (1000, 1728, 320, 0),
-                                          (300, 56, 40, -128), (64, 320, 1280, 0), (513, 96, 16, 127)])
-def test_pw_conv_forward_exact(M, K, cout, zpw):
+                                          (300, 56, 40, -128), (64, 320, 1280, 0), (513, 96, 16, 127), (40000, 16, 96, 0),
+                                          (12544, 288, 1728, 0), (5000, 168, 40, 127), (777, 1440, 192, -128)])
+def test_pw_conv_forward_exact(M, K, cout, zpw, entry):
     g = torch.Generator().manual_seed(M + K)
     xq = torch.randint(0, 256, (M, K), generator=g, dtype=torch.int64)
     wq = torch.randint(-128, 128, (cout, K), generator=g, dtype=torch.int64)
@@ -248,8 +250,9 @@ def test_pw_conv_forward_exact(M, K, cout, zpw):
     wsum = wq.sum(1).int().to(DEV)
     acc = torch.empty(M, cout, dtype=torch.int32, device=DEV)
     st = _stats_buf(cout)
-    L().call("frost_pw_conv_forward", xd.data_ptr(), za.data_ptr(), wd.data_ptr(), zw.data_ptr(), wsum.data_ptr(), M, K,
+    L().call(entry, xd.data_ptr(), za.data_ptr(), wd.data_ptr(), zw.data_ptr(), wsum.data_ptr(), M, K,
              cout, acc.data_ptr(), st.data_ptr(), stream())
+    torch.cuda.synchronize()
     assert torch.equal(acc.cpu().long(), I)
     _check_stats(st, I)
 
