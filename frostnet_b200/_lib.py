@@ -26,7 +26,7 @@ class WeightDesc(C.Structure):
     _fields_ = [("weight", c_p), ("bn_weight", c_p), ("bn_var", c_p), ("bn_eps", C.c_float),
                 ("cout", C.c_int32), ("cin_g", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
                 ("layout", C.c_int32), ("observe", C.c_int32), ("averaging_const", C.c_float),
-                ("wfq", FQ), ("wq", c_p), ("wmask", c_p), ("sf", c_p), ("rstd_run", c_p), ("wsum", c_p),
+                ("wfq", FQ), ("wq", c_p), ("wq_t", c_p), ("wmask", c_p), ("sf", c_p), ("rstd_run", c_p), ("wsum", c_p),
                 ("dwq", c_p), ("dgamma_bn", c_p), ("dsf_bn", c_p), ("dweight", c_p), ("dgamma", c_p)]
 
 
@@ -102,7 +102,9 @@ _SIGNATURES = {
     "frost_linear_forward": [c_p, c_p, c_p, c_p, c_p, i32, i32, i32, c_p, c_p],
     "frost_linear_backward": [c_p, c_p, c_p, c_p, c_p, i32, i32, i32, c_p, c_p, c_p, c_p],
     "frost_pw_dgrad": [c_p, c_p, c_p, c_p, i64, i32, i32, c_p, i32, c_p],
+    "frost_pw_dgrad_tc": [c_p, c_p, c_p, c_p, i64, i32, i32, c_p, i32, c_p],
     "frost_pw_wgrad": [c_p, c_p, c_p, c_p, i64, i32, i32, c_p, c_p],
+    "frost_pw_wgrad_tc": [c_p, c_p, c_p, c_p, i64, i32, i32, c_p, c_p],
     "frost_dw_dgrad": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, c_p, i32, c_p],
     "frost_dw_wgrad": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, c_p, c_p],
     "frost_stem_wgrad": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, i32, c_p, c_p],

@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(kWeightThreads) weight_quant_kernel(const Fros
     const float idx = fq_index(ws, inv, zp);
     const float qc = fminf(fmaxf(idx, -128.0f), 127.0f);
     d.wq[wq_index(d, c, ci, y, x)] = (int8_t)qc;
+    if (d.wq_t) d.wq_t[(int64_t)r * d.cout + c] = (int8_t)qc;   // 1x1: r == ci
     d.wmask[e] = (idx >= -128.0f && idx <= 127.0f) ? 1 : 0;
     atomicAdd(d.wsum + c, (int)qc);
   }

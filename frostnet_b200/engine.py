@@ -61,6 +61,7 @@ class _Layer:
         f32 = dict(dtype=torch.float32, device=dev)
         n = self.cout * self.cin_g * self.kh * self.kw
         self.wq = torch.zeros(n, dtype=torch.int8, device=dev)
+        self.wq_t = torch.zeros(n, dtype=torch.int8, device=dev) if self.kind == "pw" else None
         self.wmask = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.sf = torch.ones(self.cout, **f32)
         self.rstd = torch.ones(self.cout, **f32)
@@ -187,6 +188,7 @@ class QATEngine:
             d.wfq = _fq_struct(mod.weight_fake_quant)
             d.wq, d.wmask, d.sf, d.rstd_run, d.wsum = (ly.wq.data_ptr(), ly.wmask.data_ptr(), ly.sf.data_ptr(),
                                                        ly.rstd.data_ptr(), ly.wsum.data_ptr())
+            d.wq_t = ly.wq_t.data_ptr() if ly.wq_t is not None else None
             d.dwq = ly.dwq.data_ptr()
             d.dweight = g.data_ptr() + 4 * self.param_off[id(mod.weight)]
             if ly.has_bn:
@@ -390,10 +392,10 @@ class QATEngine:
         L.call("frost_bn_backward", C.byref(a), st)
         wfq = mod.weight_fake_quant
         if ly.kind == "pw":
-            L.call("frost_pw_wgrad", dz.data_ptr(), xin.q.data_ptr(), xin.scale.data_ptr(), xin.zp.data_ptr(), M, ly.cin,
+            L.call("frost_pw_wgrad_tc", dz.data_ptr(), xin.q.data_ptr(), xin.scale.data_ptr(), xin.zp.data_ptr(), M, ly.cin,
                    ly.cout, ly.dwq.data_ptr(), st)
             if dx is not None:
-                L.call("frost_pw_dgrad", dz.data_ptr(), ly.wq.data_ptr(), wfq.scale.data_ptr(), wfq.zero_point.data_ptr(),
+                L.call("frost_pw_dgrad_tc", dz.data_ptr(), ly.wq_t.data_ptr(), wfq.scale.data_ptr(), wfq.zero_point.data_ptr(),
                        M, ly.cin, ly.cout, dx.data_ptr(), 1 if accumulate else 0, st)
         elif ly.kind == "dw":
             L.call("frost_dw_wgrad", dz.data_ptr(), xin.q.data_ptr(), xin.scale.data_ptr(), xin.zp.data_ptr(), xin.N,

@@ -101,6 +101,7 @@ typedef struct {
   float averaging_const;
   FrostFQ wfq;
   int8_t* wq;               /* out: int8 indices in `layout`                                   */
+  int8_t* wq_t;             /* out (layout 0, 1x1 only; may be NULL): transposed copy [cin][cout] for dgrad */
   uint8_t* wmask;           /* out: STE mask, PyTorch layout                                   */
   float* sf;               /* out: scale_factor[cout]                                         */
   float* rstd_run;          /* out: 1/sqrt(running_var+eps)[cout] as seen by this forward       */
@@ -258,10 +259,17 @@ int frost_linear_backward(const float* dout, const float* x, const int8_t* wq,
 
 /* ---------------------------------------------------------------------------------------------
  * dgrad / wgrad of the convolutions (aten::convolution_backward in the reference). */
-/* dx[M][K] (+)= s_w * sum_co dz[M][co]*(wq[co][K]-zp_w) */
+/* dx[M][K] (+)= s_w * sum_co dz[M][co]*(wq[co][K]-zp_w)      (CUDA-core fp32 version) */
 int frost_pw_dgrad(const float* dz, const int8_t* wq, const float* w_scale, const int32_t* w_zp,
                    int64_t M, int K, int cout, float* dx, int accumulate, void* stream);
-/* dwq[cout][K] = s_a * sum_m dz[m][co]*(xq[m][K]-zp_a)     (dwq zeroed by callee) */
+/* Same result on tensor cores: tcgen05.mma kind::f16 with dz split into bf16 hi+lo (16 mantissa bits) and
+ * the integer weights exact in bf16; wq_t = transposed weight indices [K][cout] from weight prep. */
+int frost_pw_dgrad_tc(const float* dz, const int8_t* wq_t, const float* w_scale, const int32_t* w_zp,
+                      int64_t M, int K, int cout, float* dx, int accumulate, void* stream);
+/* Tensor-core wgrad: reduction over the rows m with MN-major bf16 operands (dz hi/lo split), fp32 atomics. */
+int frost_pw_wgrad_tc(const float* dz, const uint8_t* xq, const float* x_scale, const int32_t* x_zp,
+                      int64_t M, int K, int cout, float* dwq, void* stream);
+/* dwq[cout][K] = s_a * sum_m dz[m][co]*(xq[m][K]-zp_a)     (dwq zeroed by callee; CUDA-core fp32 version) */
 int frost_pw_wgrad(const float* dz, const uint8_t* xq, const float* x_scale, const int32_t* x_zp,
                    int64_t M, int K, int cout, float* dwq, void* stream);
 int frost_dw_dgrad(const float* dz, const int8_t* wq, const float* w_scale, const int32_t* w_zp,

@@ -132,14 +132,15 @@ def _weight_desc(w, gamma, var, eps, layout, fq, bufs):
     d.cout, d.cin_g, d.kh, d.kw = w.shape
     d.layout, d.observe, d.averaging_const = layout, 1, 0.01
     d.wfq = fq.c()
-    for k in ("wq", "wmask", "sf", "rstd_run", "wsum", "dwq", "dgamma_bn", "dsf_bn", "dweight", "dgamma"):
+    for k in ("wq", "wq_t", "wmask", "sf", "rstd_run", "wsum", "dwq", "dgamma_bn", "dsf_bn", "dweight", "dgamma"):
         setattr(d, k, bufs[k].data_ptr() if bufs.get(k) is not None else None)
     return d
 
 
 def _alloc_wbufs(w, with_bn=True):
     n, co = w.numel(), w.shape[0]
-    b = dict(wq=torch.zeros(n, dtype=torch.int8, device=DEV), wmask=torch.zeros(n, dtype=torch.uint8, device=DEV),
+    b = dict(wq=torch.zeros(n, dtype=torch.int8, device=DEV),
+             wq_t=torch.zeros(n, dtype=torch.int8, device=DEV) if (w.shape[2] == 1 and w.shape[1] > 1) else None, wmask=torch.zeros(n, dtype=torch.uint8, device=DEV),
              sf=torch.zeros(co, device=DEV), rstd_run=torch.zeros(co, device=DEV),
              wsum=torch.zeros(co, dtype=torch.int32, device=DEV), dwq=torch.zeros(n, device=DEV),
              dweight=torch.zeros(n, device=DEV))
@@ -199,6 +200,8 @@ def test_weight_prep_and_backward_vs_oracle(shape, layout):
             fq.assert_state_equal()
             idx = fq.oracle.last_idx
             assert torch.equal(bufs["wq"].cpu(), _to_layout(idx.clamp(-128, 127).to(torch.int8), layout))
+            if bufs["wq_t"] is not None:
+                assert torch.equal(bufs["wq_t"].cpu().reshape(shape[1], shape[0]), bufs["wq"].cpu().reshape(shape[0], shape[1]).t())
             # ATen's vectorised CPU sqrt/div may differ from IEEE scalar code in the last ulp of a vector tail
             torch.testing.assert_close(bufs["sf"].cpu(), sf.detach(), rtol=2.5e-7, atol=0)
             assert torch.equal(bufs["wsum"].cpu(), idx.clamp(-128, 127).reshape(shape[0], -1).sum(1).int())
@@ -469,7 +472,8 @@ def test_add_forward_backward_bit_exact():
 
 
 # ------------------------------------------------------------------------------------------ dgrad / wgrad
-@pytest.mark.parametrize("M,K,cout", [(70, 16, 24), (1000, 104, 312), (333, 1728, 320), (64, 320, 1280)])
+@pytest.mark.parametrize("M,K,cout", [(70, 16, 24), (1000, 104, 312), (333, 1728, 320), (64, 320, 1280), (20000, 56, 168),
+                                      (5000, 288, 1728)])
 def test_pw_dgrad_wgrad(M, K, cout):
     g = torch.Generator().manual_seed(M)
     dz = torch.randn(M, cout, generator=g)
@@ -487,10 +491,42 @@ def test_pw_dgrad_wgrad(M, K, cout):
     L().call("frost_pw_dgrad", dzd.data_ptr(), wd.data_ptr(), sw_t.data_ptr(), zw_t.data_ptr(), M, K, cout,
              dx.data_ptr(), 1, stream())
     torch.testing.assert_close(dx.cpu().double(), dx_ref + 1.0, rtol=1e-4, atol=1e-4 * float(dx_ref.abs().max()))
+    # tensor-core version (bf16 hi/lo split of dz, exact integer weights) from the transposed weights
+    wtd = wq.t().contiguous().to(torch.int8).to(DEV)
+    for accumulate in (0, 1):
+        dx2 = torch.ones(M, K, device=DEV)
+        L().call("frost_pw_dgrad_tc", dzd.data_ptr(), wtd.data_ptr(), sw_t.data_ptr(), zw_t.data_ptr(), M, K, cout,
+                 dx2.data_ptr(), accumulate, stream())
+        torch.cuda.synchronize()
+        ref2 = dx_ref + (1.0 if accumulate else 0.0)
+        err = float((dx2.cpu().double() - ref2).abs().max()) / float(dx_ref.abs().max())
+        assert err < 5e-5, (accumulate, err)
+    # integer-valued dz: products and sums are exact in the tensor-core path
+    dzi = torch.randint(-64, 65, (M, cout), generator=g).float()
+    dx3 = torch.empty(M, K, device=DEV)
+    one = torch.ones(1, device=DEV)
+    L().call("frost_pw_dgrad_tc", dzi.to(DEV).data_ptr(), wtd.data_ptr(), one.data_ptr(), zw_t.data_ptr(), M, K, cout,
+             dx3.data_ptr(), 0, stream())
+    torch.cuda.synchronize()
+    assert torch.equal(dx3.cpu().double(), dzi.double() @ (wq - zp_w).double())
     dwq = torch.empty(cout, K, device=DEV)
     L().call("frost_pw_wgrad", dzd.data_ptr(), xd.data_ptr(), sa_t.data_ptr(), za_t.data_ptr(), M, K, cout,
              dwq.data_ptr(), stream())
     torch.testing.assert_close(dwq.cpu().double(), dw_ref, rtol=1e-4, atol=1e-4 * float(dw_ref.abs().max()))
+    dwq2 = torch.empty(cout, K, device=DEV)
+    L().call("frost_pw_wgrad_tc", dzd.data_ptr(), xd.data_ptr(), sa_t.data_ptr(), za_t.data_ptr(), M, K, cout,
+             dwq2.data_ptr(), stream())
+    torch.cuda.synchronize()
+    errw = float((dwq2.cpu().double() - dw_ref).abs().max()) / float(dw_ref.abs().max())
+    assert errw < 5e-5, errw
+    if M <= 1000:      # integer-valued dz: exact
+        dzs = torch.randint(-8, 9, (M, cout), generator=g).float()
+        one_w = torch.ones(1, device=DEV)
+        dzsd = dzs.to(DEV)
+        L().call("frost_pw_wgrad_tc", dzsd.data_ptr(), xd.data_ptr(), one_w.data_ptr(), za_t.data_ptr(), M, K, cout,
+                 dwq2.data_ptr(), stream())
+        torch.cuda.synchronize()
+        assert torch.equal(dwq2.cpu().double(), dzs.double().t() @ (xq - zp_a).double())
 
 
 @pytest.mark.parametrize("N,H,W,Cc,k,s", [(2, 9, 11, 32, 3, 1), (1, 14, 14, 96, 5, 2), (2, 7, 7, 1728, 5, 1), (2, 16, 15, 72, 3, 2)])
