@@ -94,6 +94,18 @@ __global__ void __launch_bounds__(DG_THREADS, 1) pw_dgrad_tc_kernel(const float*
             f[i][1] = __ldg(p + 1);
           }
         }
+        // weights: all loads first (BN*8/128 <= 16 per thread), then convert + store
+        constexpr int WL = BN * 8 / 128;
+        uint2 wpk[WL];
+#pragma unroll
+        for (int q = 0; q < WL; ++q) {
+          const int idx = tp + 128 * q;
+          const int r = idx >> 3, c = idx & 7;
+          const int cc = kb * DG_KE + c * 8;
+          wpk[q] = make_uint2(0u, 0u);
+          if (idx < n_eff * 8 && r < n_valid && cc < cout)
+            wpk[q] = __ldg(reinterpret_cast<const uint2*>(wq_t + (int64_t)(n0 + r) * cout + cc));
+        }
         mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -106,20 +118,21 @@ __global__ void __launch_bounds__(DG_THREADS, 1) pw_dgrad_tc_kernel(const float*
           *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
           *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]), pack_bf16(l[4], l[5]), pack_bf16(l[6], l[7]));
         }
-        for (int idx = tp; idx < n_eff * 8; idx += 128) {
-          const int r = idx >> 3, c = idx & 7;
-          const int cc = kb * DG_KE + c * 8;
-          uint2 pk = make_uint2(0u, 0u);
-          const bool v = (r < n_valid) && (cc < cout);
-          if (v) pk = __ldg(reinterpret_cast<const uint2*>(wq_t + (int64_t)(n0 + r) * cout + cc));
-          float w[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const unsigned word = e < 4 ? pk.x : pk.y;
-            w[e] = v ? (float)(int)(int8_t)((word >> (8 * (e & 3))) & 0xff) - zp_w : 0.0f;
+        for (int q = 0; q < WL; ++q) {
+          const int idx = tp + 128 * q;
+          if (idx < n_eff * 8) {
+            const int r = idx >> 3, c = idx & 7;
+            const bool v = (r < n_valid) && (kb * DG_KE + c * 8 < cout);
+            float w[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const unsigned word = e < 4 ? wpk[q].x : wpk[q].y;
+              w[e] = v ? (float)(int)(int8_t)((word >> (8 * (e & 3))) & 0xff) - zp_w : 0.0f;
+            }
+            *reinterpret_cast<uint4*>(b_s + sw128_offset(r, c)) =
+                make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
           }
-          *reinterpret_cast<uint4*>(b_s + sw128_offset(r, c)) =
-              make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
         }
         fence_proxy_async();
         mbar_arrive(&full_bar[s]);
@@ -309,6 +322,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const float*
             f[i][1] = __ldg(p + 1);
           }
         }
+        // activations: all loads first (64 rows x 256/8 chunks / 128 threads <= 16 per thread)
+        constexpr int XL = WG_ROWS * (WG_BN / 8) / 128;
+        uint2 xpk[XL];
+#pragma unroll
+        for (int q = 0; q < XL; ++q) {
+          const int idx = tp + 128 * q;
+          const int r = idx / cpr, kc = idx - r * cpr;
+          xpk[q] = make_uint2(0u, 0u);
+          if (idx < WG_ROWS * cpr && mb + r < m_end && k0 + kc * 8 < K)
+            xpk[q] = __ldg(reinterpret_cast<const uint2*>(xq + (mb + r) * K + k0 + kc * 8));
+        }
         mbar_wait(&empty_bar[s], ((kb / WG_STAGES) & 1) ^ 1);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -321,21 +345,21 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const float*
           *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
           *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]), pack_bf16(l[4], l[5]), pack_bf16(l[6], l[7]));
         }
-        for (int idx = tp; idx < WG_ROWS * cpr; idx += 128) {
-          const int r = idx / cpr, kc = idx - r * cpr;
-          const int64_t m = mb + r;
-          const int k = k0 + kc * 8;
-          uint2 pk = make_uint2(0u, 0u);
-          const bool v = (m < m_end) && (k < K);
-          if (v) pk = __ldg(reinterpret_cast<const uint2*>(xq + m * K + k));
-          float w[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const unsigned word = e < 4 ? pk.x : pk.y;
-            w[e] = v ? (float)((word >> (8 * (e & 3))) & 0xff) - zp_a : 0.0f;
+        for (int q = 0; q < XL; ++q) {
+          const int idx = tp + 128 * q;
+          if (idx < WG_ROWS * cpr) {
+            const int r = idx / cpr, kc = idx - r * cpr;
+            const bool v = (mb + r < m_end) && (k0 + kc * 8 < K);
+            float w[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const unsigned word = e < 4 ? xpk[q].x : xpk[q].y;
+              w[e] = v ? (float)((word >> (8 * (e & 3))) & 0xff) - zp_a : 0.0f;
+            }
+            *reinterpret_cast<uint4*>(b_s + (uint32_t)(kc >> 3) * WG_BLK + sw128_offset(r, kc & 7)) =
+                make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
           }
-          *reinterpret_cast<uint4*>(b_s + (uint32_t)(kc >> 3) * WG_BLK + sw128_offset(r, kc & 7)) =
-              make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
         }
         fence_proxy_async();
         mbar_arrive(&full_bar[s]);
