@@ -148,19 +148,35 @@ def run_reference(args):
 # B200 arm
 # ------------------------------------------------------------------------------------------------
 def algorithmic_cost(name, a):
-    """(bytes, flops) of one C-ABI call from its arguments (what the op must move / compute)."""
-    if name == "frost_pw_conv_forward":
+    """(bytes, flops) of one C-ABI call from its arguments: what the op must move / compute."""
+    if name in ("frost_pw_conv_forward", "frost_pw_conv_forward_simt"):
         M, K, co = a[5], a[6], a[7]
         return M * K + co * K + 4 * M * co, 2 * M * K * co
     if name == "frost_bnq_apply":
         M, Cc = a[1], a[2]
         return 5 * M * Cc, 0
-    if name == "frost_pw_dgrad":
+    if name in ("frost_pw_dgrad", "frost_pw_dgrad_tc"):
         M, K, co = a[4], a[5], a[6]
         return 4 * M * co + co * K + 4 * M * K, 2 * M * K * co
-    if name == "frost_pw_wgrad":
+    if name in ("frost_pw_wgrad", "frost_pw_wgrad_tc"):
         M, K, co = a[4], a[5], a[6]
         return 4 * M * co + M * K + 4 * co * K, 2 * M * K * co
+    if name == "frost_bn_backward":
+        args = getattr(a[0], "_obj", None)          # ctypes.byref(struct) keeps the struct in _obj
+        if args is not None:
+            return 20 * args.M * args.C, 0        # reduce: dy+I (8 B); apply: dy+I+dz (12 B)
+    if name == "frost_dw_conv_forward":
+        N, H, W, Cc, k, s = a[4], a[5], a[6], a[7], a[8], a[9]
+        Ho, Wo = (H + s - 1) // s, (W + s - 1) // s
+        return N * H * W * Cc + 4 * N * Ho * Wo * Cc, 2 * N * Ho * Wo * Cc * k * k
+    if name == "frost_dw_dgrad":
+        N, H, W, Cc, k, s = a[4], a[5], a[6], a[7], a[8], a[9]
+        Ho, Wo = (H + s - 1) // s, (W + s - 1) // s
+        return 4 * N * H * W * Cc + 4 * N * Ho * Wo * Cc, 2 * N * Ho * Wo * Cc * k * k
+    if name == "frost_dw_wgrad":
+        N, H, W, Cc, k, s = a[4], a[5], a[6], a[7], a[8], a[9]
+        Ho, Wo = (H + s - 1) // s, (W + s - 1) // s
+        return N * H * W * Cc + 4 * N * Ho * Wo * Cc, 2 * N * Ho * Wo * Cc * k * k
     return 0, 0
 
 

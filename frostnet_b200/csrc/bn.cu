@@ -123,17 +123,36 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(FrostBnBackwardArgs 
     const float4 A = __ldg(reinterpret_cast<const float4*>(a.A) + cg);
     const float4 B = __ldg(reinterpret_cast<const float4*>(a.B) + cg);
     double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-    for (int64_t m = (int64_t)blockIdx.x * rows_per_block + row_local; m < a.M; m += (int64_t)gridDim.x * rows_per_block) {
-      const float4 dy = __ldg(reinterpret_cast<const float4*>(a.dy + m * C) + cg);
-      const int4 I = __ldg(reinterpret_cast<const int4*>(a.acc + m * C) + cg);
-      const float d0 = bn_dv(dy.x, I.x, A.x, B.x, a.relu, inv, zp);
-      const float d1 = bn_dv(dy.y, I.y, A.y, B.y, a.relu, inv, zp);
-      const float d2 = bn_dv(dy.z, I.z, A.z, B.z, a.relu, inv, zp);
-      const float d3 = bn_dv(dy.w, I.w, A.w, B.w, a.relu, inv, zp);
-      s1[0] += d0; s2[0] += (double)d0 * (double)I.x;
-      s1[1] += d1; s2[1] += (double)d1 * (double)I.y;
-      s1[2] += d2; s2[2] += (double)d2 * (double)I.z;
-      s1[3] += d3; s2[3] += (double)d3 * (double)I.w;
+    const int64_t stride = (int64_t)gridDim.x * rows_per_block;
+    constexpr int U = 4;   // rows in flight per thread: 8 independent 16-byte loads
+    for (int64_t m = (int64_t)blockIdx.x * rows_per_block + row_local; m < a.M; m += U * stride) {
+      float4 dy[U];
+      int4 I[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t mm = m + u * stride;
+        dy[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        I[u] = make_int4(0, 0, 0, 0);
+        if (mm < a.M) {
+          dy[u] = __ldg(reinterpret_cast<const float4*>(a.dy + mm * C) + cg);
+          I[u] = __ldg(reinterpret_cast<const int4*>(a.acc + mm * C) + cg);
+        }
+      }
+      float p1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float d0 = bn_dv(dy[u].x, I[u].x, A.x, B.x, a.relu, inv, zp);
+        const float d1 = bn_dv(dy[u].y, I[u].y, A.y, B.y, a.relu, inv, zp);
+        const float d2 = bn_dv(dy[u].z, I[u].z, A.z, B.z, a.relu, inv, zp);
+        const float d3 = bn_dv(dy[u].w, I[u].w, A.w, B.w, a.relu, inv, zp);
+        p1[0] += d0; p1[1] += d1; p1[2] += d2; p1[3] += d3;
+        s2[0] += (double)d0 * (double)I[u].x;
+        s2[1] += (double)d1 * (double)I[u].y;
+        s2[2] += (double)d2 * (double)I[u].z;
+        s2[3] += (double)d3 * (double)I[u].w;
+      }
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) s1[ch] += (double)p1[ch];
     }
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
@@ -242,7 +261,7 @@ extern "C" int frost_bn_backward(const FrostBnBackwardArgs* a, void* stream) {
   int cgb, chunks, threads;
   dw_launch_shape(a->C, 256, &cgb, &chunks, &threads);
   const int rows_per_block = threads / cgb;
-  int gx = (int)std::min<int64_t>(ceil_div(a->M, (int64_t)rows_per_block * 4), (int64_t)kNumSMs * 8);
+  int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(a->M, (int64_t)rows_per_block * 8), (int64_t)kNumSMs * 8 / chunks));
   bn_bwd_reduce_kernel<<<dim3(gx, chunks), threads, sizeof(double) * cgb * 8, st>>>(*a, cgb);
   FROST_LAUNCH_CHECK("bn_bwd_reduce");
   bn_bwd_coef_kernel<<<1, 256, 0, st>>>(*a);
