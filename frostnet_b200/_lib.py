@@ -26,7 +26,7 @@ class WeightDesc(C.Structure):
     _fields_ = [("weight", c_p), ("bn_weight", c_p), ("bn_var", c_p), ("bn_eps", C.c_float),
                 ("cout", C.c_int32), ("cin_g", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
                 ("layout", C.c_int32), ("observe", C.c_int32), ("averaging_const", C.c_float),
-                ("wfq", FQ), ("wq", c_p), ("wq_t", c_p), ("wmask", c_p), ("sf", c_p), ("rstd_run", c_p), ("wsum", c_p),
+                ("wfq", FQ), ("wq", c_p), ("wt_bf16", c_p), ("wmask", c_p), ("sf", c_p), ("rstd_run", c_p), ("wsum", c_p),
                 ("dwq", c_p), ("dgamma_bn", c_p), ("dsf_bn", c_p), ("dweight", c_p), ("dgamma", c_p)]
 
 
@@ -43,7 +43,7 @@ class BnBackwardArgs(C.Structure):
     _fields_ = [("dy", c_p), ("acc", c_p), ("M", C.c_int64), ("C", C.c_int32), ("relu", C.c_int32),
                 ("A", c_p), ("B", c_p), ("mean_I", c_p), ("kfac", c_p), ("gamma", c_p), ("sf", c_p),
                 ("x_scale", c_p), ("w_scale", c_p), ("out_scale", c_p), ("out_zp", c_p), ("eps", C.c_float),
-                ("sums", c_p), ("coef", c_p), ("dz", c_p), ("dgamma_bn", c_p), ("dbeta", c_p), ("dsf_bn", c_p)]
+                ("sums", c_p), ("coef", c_p), ("dz", c_p), ("dz_lo", c_p), ("dz_format", C.c_int32), ("dgamma_bn", c_p), ("dbeta", c_p), ("dsf_bn", c_p)]
 
 
 class QTensor(C.Structure):
@@ -104,7 +104,7 @@ _SIGNATURES = {
     "frost_pw_dgrad": [c_p, c_p, c_p, c_p, i64, i32, i32, c_p, i32, c_p],
     "frost_pw_dgrad_tc": [c_p, c_p, c_p, c_p, i64, i32, i32, c_p, i32, c_p],
     "frost_pw_wgrad": [c_p, c_p, c_p, c_p, i64, i32, i32, c_p, c_p],
-    "frost_pw_wgrad_tc": [c_p, c_p, c_p, c_p, i64, i32, i32, c_p, c_p],
+    "frost_pw_wgrad_tc": [c_p, c_p, c_p, c_p, c_p, i64, i32, i32, c_p, c_p],
     "frost_dw_dgrad": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, c_p, i32, c_p],
     "frost_dw_wgrad": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, c_p, c_p],
     "frost_stem_wgrad": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, i32, c_p, c_p],

@@ -4,6 +4,7 @@
 //   conv_orig = conv/scale_factor = I * m_c,  m_c = s_a*s_w/scale_factor_c
 //   v = bn(conv_orig) = A_c*I + B_c          (training: batch statistics from exact integer sums)
 //   y = FQ_a(relu(v))
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace frost {
@@ -217,7 +218,24 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(FrostBnBackwardArgs a
       const float dv = bn_dv(dyv[e], Iv[e], s_c[c], s_c[C + c], a.relu, inv, zp);
       o[e] = s_c[3 * C + c] * (dv - s_c[4 * C + c] - s_c[5 * C + c] * ((float)Iv[e] - s_c[2 * C + c]));
     }
-    reinterpret_cast<float4*>(a.dz)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    if (a.dz_format == 0) {
+      reinterpret_cast<float4*>(a.dz)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+      // bf16 hi + lo planes: hi = bf16(dz), lo = bf16(dz - hi)  (dz - hi is exact in fp32)
+      __nv_bfloat16 h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        h[e] = __float2bfloat16_rn(o[e]);
+        l[e] = __float2bfloat16_rn(o[e] - __bfloat162float(h[e]));
+      }
+      uint2 hv, lv;
+      hv.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+      hv.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+      lv.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+      lv.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+      reinterpret_cast<uint2*>(a.dz)[i] = hv;
+      reinterpret_cast<uint2*>(a.dz_lo)[i] = lv;
+    }
   }
 }
 
@@ -253,6 +271,7 @@ extern "C" int frost_bn_backward(const FrostBnBackwardArgs* a, void* stream) {
                     a->dbeta && a->dsf_bn,
                 "frost_bn_backward: null pointer");
   FROST_REQUIRE(a->M > 0 && a->C > 0 && a->C % 4 == 0, "frost_bn_backward: C=%d must be a positive multiple of 4", a->C);
+  FROST_REQUIRE(a->dz_format == 0 || (a->dz_format == 1 && a->dz_lo), "frost_bn_backward: dz_format 1 needs dz_lo");
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(a->sums, 0, sizeof(double) * 2 * a->C, st) != cudaSuccess) {
     set_error("frost_bn_backward: memset failed");

@@ -1,11 +1,13 @@
-// pw_bwd_tc.cu - dgrad of the 1x1 convolutions on 5th-gen tensor cores (aten::convolution_backward's
-// input gradient for the squeeze / expand / reduce / last_layer convs of frostnet.py:98-119,293).
-//   dx[m][k] (+)= s_w * sum_co dz[m][co] * (q_w[co][k] - zp_w)
-// dz is fp32 (it is not on a quantisation grid), the weights are small integers.  tcgen05.mma kind::f16
-// with bf16 operands and fp32 accumulation in TMEM: the integer weights are exact in bf16, dz is split into
-// bf16 hi + bf16 lo (16 mantissa bits, relative error 2^-17) and both halves are accumulated, i.e. 2 MMAs
-// per k-step.  Same warp-specialised persistent structure as pw_conv_tc.cu; the producer warps convert
-// (fp32 -> hi/lo bf16, int8 -> bf16) in registers and store straight into the SWIZZLE_128B operand tiles.
+// pw_bwd_tc.cu - dgrad and wgrad of the 1x1 convolutions on 5th-gen tensor cores
+// (aten::convolution_backward for the squeeze / expand / reduce / last_layer convs of frostnet.py:98-119,293).
+//   dgrad: dx[m][k]    (+)= s_w * sum_co dz[m][co] * (q_w[co][k] - zp_w)
+//   wgrad: dwq[co][k]   +=  s_a * sum_m  dz[m][co] * (q_a[m][k]  - zp_a)
+// dz is fp32-valued (it is not on a quantisation grid); frost_bn_backward hands it over as two bf16 planes
+// hi + lo (16 mantissa bits, relative error 2^-17).  The integer operands are exact in bf16.  tcgen05.mma
+// kind::f16 with fp32 accumulation in TMEM, 2 MMAs (hi, lo) per k-step.
+// Because dz already sits in HBM in operand format, the producers are pure cp.async (LDGSTS) into the
+// SWIZZLE_128B tiles - the same bytes serve as the K-major A operand of dgrad and, untouched, as the MN-major
+// A operand of wgrad (the transposes of the reference's wgrad are done by the UMMA descriptors).
 #include <cuda_bf16.h>
 #include "tc_common.cuh"
 
@@ -13,38 +15,38 @@ namespace frost {
 
 using namespace tc;
 
-constexpr int DG_BM = 128;
-constexpr int DG_KE = 64;        // reduction elements per stage (64 bf16 = one 128-byte swizzle span)
-constexpr int DG_THREADS = 288;
-constexpr int DG_SCR = 32 * 36;
-
-template <int BN>
-__host__ __device__ constexpr int dg_stages() { return BN >= 256 ? 3 : 4; }
-template <int BN>
-constexpr size_t dg_smem_bytes() {
-  return 1024 + (size_t)dg_stages<BN>() * (2 * DG_BM * 128 + BN * 128) + 4 * DG_SCR * 4 + (2 * dg_stages<BN>() + 4) * 8 + 16;
-}
+constexpr int BW_SCR = 32 * 36;
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&v);
 }
-__device__ __forceinline__ void split_bf16(float x, float& hi, float& lo) {
-  hi = __bfloat162float(__float2bfloat16_rn(x));
-  lo = x - hi;
+
+// ================================================================= dgrad
+constexpr int DG_BM = 128;
+constexpr int DG_KE = 64;          // reduction elements (cout) per stage: 64 bf16 = one 128-byte swizzle span
+constexpr int DG_THREADS = 416;    // warps 0-7 epilogue (2 groups), 8-11 producer, 12 MMA
+
+template <int BN>
+__host__ __device__ constexpr int dg_stages() { return BN >= 256 ? 2 : (BN >= 128 ? 3 : 4); }
+template <int BN>
+constexpr size_t dg_smem_bytes() {
+  return 1024 + (size_t)dg_stages<BN>() * (2 * DG_BM * 128 + BN * 128) + 8 * BW_SCR * 4 + (2 * dg_stages<BN>() + 4) * 8 + 16;
 }
 
 template <int BN>
-__global__ void __launch_bounds__(DG_THREADS, 1) pw_dgrad_tc_kernel(const float* __restrict__ dz, const int8_t* __restrict__ wq_t,
-                                                                   const float* __restrict__ w_scale_p,
-                                                                   const int32_t* __restrict__ w_zp_p, int64_t M, int K,
+__global__ void __launch_bounds__(DG_THREADS, 1) pw_dgrad_tc_kernel(const uint16_t* __restrict__ dz_hi,
+                                                                   const uint16_t* __restrict__ dz_lo,
+                                                                   const uint16_t* __restrict__ wt,
+                                                                   const float* __restrict__ w_scale_p, int64_t M, int K,
                                                                    int cout, float* __restrict__ dx, int accumulate) {
   constexpr int STAGES = dg_stages<BN>();
+  constexpr int BW_LAG = STAGES > 2 ? 2 : 1;   // cp.async groups in flight per producer thread (< STAGES)
   constexpr int A_BYTES = DG_BM * 128, B_BYTES = BN * 128, STAGE = 2 * A_BYTES + B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* scratch = reinterpret_cast<float*>(smem + STAGES * STAGE);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(scratch + 4 * DG_SCR);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(scratch + 8 * BW_SCR);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -62,83 +64,53 @@ __global__ void __launch_bounds__(DG_THREADS, 1) pw_dgrad_tc_kernel(const float*
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
     mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc<2 * BN>(tmem_slot);
+  if (warp == 12) tmem_alloc<2 * BN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 4 && warp < 8) {
-    // ================================================================= producer: load + convert + swizzled store
-    const int tp = threadIdx.x - 128;
+  if (warp >= 8 && warp < 12) {
+    // ================================================================= producer (pure cp.async)
+    const int tp = threadIdx.x - 256;
     const int c16 = tp & 7, r0 = tp >> 3;
-    const float zp_w = (float)*w_zp_p;
     uint32_t it = 0;
     for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
       const int64_t m0 = mt * DG_BM;
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % STAGES;
-        uint8_t* a_hi = smem + s * STAGE;
-        uint8_t* a_lo = a_hi + A_BYTES;
-        uint8_t* b_s = a_lo + A_BYTES;
-        const int co = kb * DG_KE + c16 * 8;         // first of this thread's 8 reduction elements
-        // issue all global loads of the stage before touching shared memory (memory-level parallelism)
-        float4 f[8][2];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int64_t m = m0 + r0 + 16 * i;
-          f[i][0] = f[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m < M && co < cout) {                  // cout % 8 == 0: the 8-element chunk is in or out
-            const float4* p = reinterpret_cast<const float4*>(dz + m * cout + co);
-            f[i][0] = __ldg(p);
-            f[i][1] = __ldg(p + 1);
-          }
-        }
-        // weights: all loads first (BN*8/128 <= 16 per thread), then convert + store
-        constexpr int WL = BN * 8 / 128;
-        uint2 wpk[WL];
-#pragma unroll
-        for (int q = 0; q < WL; ++q) {
-          const int idx = tp + 128 * q;
-          const int r = idx >> 3, c = idx & 7;
-          const int cc = kb * DG_KE + c * 8;
-          wpk[q] = make_uint2(0u, 0u);
-          if (idx < n_eff * 8 && r < n_valid && cc < cout)
-            wpk[q] = __ldg(reinterpret_cast<const uint2*>(wq_t + (int64_t)(n0 + r) * cout + cc));
-        }
         mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        const uint32_t a_hi = smem_u32(smem + s * STAGE);
+        const uint32_t a_lo = a_hi + A_BYTES, b_s = a_lo + A_BYTES;
+        const int co = kb * DG_KE + c16 * 8;           // 8 bf16 = 16 bytes; cout % 8 == 0
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = r0 + 16 * i;
-          const float x[8] = {f[i][0].x, f[i][0].y, f[i][0].z, f[i][0].w, f[i][1].x, f[i][1].y, f[i][1].z, f[i][1].w};
-          float h[8], l[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) split_bf16(x[e], h[e], l[e]);
-          const uint32_t off = sw128_offset(r, c16);
-          *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
-          *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]), pack_bf16(l[4], l[5]), pack_bf16(l[6], l[7]));
+          const int64_t m = m0 + r;
+          const bool v = (m < M) && (co < cout);
+          const int64_t off = v ? m * cout + co : 0;
+          const uint32_t d = sw128_offset(r, c16);
+          cp_async_zfill<16>(a_hi + d, dz_hi + off, v);
+          cp_async_zfill<16>(a_lo + d, dz_lo + off, v);
         }
-#pragma unroll
-        for (int q = 0; q < WL; ++q) {
-          const int idx = tp + 128 * q;
-          if (idx < n_eff * 8) {
-            const int r = idx >> 3, c = idx & 7;
-            const bool v = (r < n_valid) && (kb * DG_KE + c * 8 < cout);
-            float w[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const unsigned word = e < 4 ? wpk[q].x : wpk[q].y;
-              w[e] = v ? (float)(int)(int8_t)((word >> (8 * (e & 3))) & 0xff) - zp_w : 0.0f;
-            }
-            *reinterpret_cast<uint4*>(b_s + sw128_offset(r, c)) =
-                make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
-          }
+        for (int idx = tp; idx < n_eff * 8; idx += 128) {
+          const int r = idx >> 3, c = idx & 7;
+          const int cc = kb * DG_KE + c * 8;
+          const bool v = (r < n_valid) && (cc < cout);
+          cp_async_zfill<16>(b_s + sw128_offset(r, c), wt + (v ? (int64_t)(n0 + r) * cout + cc : 0), v);
         }
-        fence_proxy_async();
-        mbar_arrive(&full_bar[s]);
+        cp_async_commit();
+        if (it >= (uint32_t)BW_LAG) {
+          cp_async_wait<BW_LAG>();
+          fence_proxy_async();
+          mbar_arrive(&full_bar[(it - BW_LAG) % STAGES]);
+        }
       }
     }
-  } else if (warp == 8) {
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (uint32_t j = (it > (uint32_t)BW_LAG ? it - BW_LAG : 0u); j < it; ++j) mbar_arrive(&full_bar[j % STAGES]);
+  } else if (warp == 12) {
     // ================================================================= MMA issuer
     const uint32_t idesc = umma_idesc(1 /*F32*/, 1 /*BF16*/, 1 /*BF16*/, DG_BM, n_eff);
     uint32_t it = 0, tile_i = 0;
@@ -166,18 +138,20 @@ __global__ void __launch_bounds__(DG_THREADS, 1) pw_dgrad_tc_kernel(const float*
       }
     }
   } else {
-    // ================================================================= epilogue
-    float* my = scratch + warp * DG_SCR;
+    // ================================================================= epilogue: two groups, one per TMEM buffer
+    const int grp = warp >> 2, wq4 = warp & 3;
+    float* my = scratch + warp * BW_SCR;
     const float s_w = *w_scale_p;
     uint32_t tile_i = 0;
     for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++tile_i) {
       const uint32_t acc = tile_i & 1;
-      const int64_t m0 = mt * DG_BM + warp * 32;
+      if ((int)acc != grp) continue;
+      const int64_t m0 = mt * DG_BM + wq4 * 32;
       mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1);
       tc_fence_after();
       for (int chunk = 0; chunk * 32 < n_valid; ++chunk) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + acc * BN + chunk * 32 + ((uint32_t)(warp * 32) << 16), v);
+        tmem_ld_32x32(tmem_base + acc * BN + chunk * 32 + ((uint32_t)(wq4 * 32) << 16), v);
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj)
           *reinterpret_cast<float4*>(my + lane * 36 + 4 * jj) =
@@ -211,21 +185,22 @@ __global__ void __launch_bounds__(DG_THREADS, 1) pw_dgrad_tc_kernel(const float*
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     tc_fence_after();
     tmem_dealloc<2 * BN>(tmem_base);
   }
 }
 
 template <int BN>
-static int launch_dgrad_tc(const float* dz, const int8_t* wq_t, const float* w_scale, const int32_t* w_zp, int64_t M, int K,
-                           int cout, float* dx, int accumulate, cudaStream_t st) {
+static int launch_dgrad_tc(const uint16_t* dz_hi, const uint16_t* dz_lo, const uint16_t* wt, const float* w_scale, int64_t M,
+                           int K, int cout, float* dx, int accumulate, cudaStream_t st) {
   constexpr size_t smem = dg_smem_bytes<BN>();
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(pw_dgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("pw_dgrad_tc: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
+      (void)cudaGetLastError();
       return FROST_ECUDA;
     }
     attr_done = true;
@@ -233,24 +208,24 @@ static int launch_dgrad_tc(const float* dz, const int8_t* wq_t, const float* w_s
   const int n_tiles = (K + BN - 1) / BN;
   const int64_t m_tiles = ceil_div(M, DG_BM);
   const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(m_tiles, kNumSMs / n_tiles));
-  pw_dgrad_tc_kernel<BN><<<dim3(gx, n_tiles), DG_THREADS, smem, st>>>(dz, wq_t, w_scale, w_zp, M, K, cout, dx, accumulate);
+  pw_dgrad_tc_kernel<BN><<<dim3(gx, n_tiles), DG_THREADS, smem, st>>>(dz_hi, dz_lo, wt, w_scale, M, K, cout, dx, accumulate);
   return FROST_OK;
 }
 
-
 // ================================================================= wgrad
-//   dwq[co][k] += s_a * sum_m dz[m][co] * (q_a[m][k] - zp_a)
 // GEMM with the reduction over the rows m: D[co][k] = sum_m A[co][m] * B[k][m].  Both operands are stored
 // exactly as they sit in HBM (row m = 128-byte lines of co resp. k), which is the canonical MN-MAJOR
 // SWIZZLE_128B layout: 8 (m) x 64 (co|k) bf16 atoms of 1024 B, the next 8 rows 1024 B further (SBO), the next
-// 64 columns 8192 B further (LBO).  The transposes the reference's wgrad needs are done by the descriptors.
+// 64 columns one block further (LBO).
 constexpr int WG_ROWS = 64;       // reduction rows (m) per stage
-constexpr int WG_STAGES = 3;
 constexpr int WG_BLK = 64 * 128;  // one 64-column block of a stage: 64 rows x 128 B
-constexpr int WG_THREADS = 288;
-constexpr int WG_BN = 256;
+constexpr int WG_THREADS = 288;   // warps 0-3 epilogue, 4-7 producer, 8 MMA
+
+template <int BN>
+__host__ __device__ constexpr int wg_stages() { return BN >= 256 ? 3 : 4; }
+template <int BN>
 constexpr size_t wg_smem_bytes() {
-  return 1024 + (size_t)WG_STAGES * (2 * 2 * WG_BLK + 4 * WG_BLK) + 4 * DG_SCR * 4 + (2 * WG_STAGES + 2) * 8 + 16;
+  return 1024 + (size_t)wg_stages<BN>() * (4 * WG_BLK + (BN / 64) * WG_BLK) + 4 * BW_SCR * 4 + (2 * wg_stages<BN>() + 2) * 8 + 16;
 }
 
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
@@ -263,35 +238,40 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
   return d;
 }
 
-__global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const float* __restrict__ dz, const uint8_t* __restrict__ xq,
+template <int BN>
+__global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16_t* __restrict__ dz_hi,
+                                                                   const uint16_t* __restrict__ dz_lo,
+                                                                   const uint8_t* __restrict__ xq,
                                                                    const float* __restrict__ x_scale_p,
                                                                    const int32_t* __restrict__ x_zp_p, int64_t M, int K,
                                                                    int cout, int64_t rows_per_split, float* __restrict__ dwq) {
-  constexpr int A_BYTES = 2 * WG_BLK;                   // 128 co x 64 rows, one of (hi, lo)
-  constexpr int STAGE = 2 * A_BYTES + 4 * WG_BLK;       // hi, lo, up to 256 k
+  constexpr int STAGES = wg_stages<BN>();
+  constexpr int BW_LAG = 2;
+  constexpr int A_BYTES = 2 * WG_BLK;                       // 128 co x 64 rows, one of (hi, lo)
+  constexpr int STAGE = 2 * A_BYTES + (BN / 64) * WG_BLK;   // hi, lo, BN k-columns
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* scratch = reinterpret_cast<float*>(smem + WG_STAGES * STAGE);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(scratch + 4 * DG_SCR);
-  uint64_t* empty_bar = full_bar + WG_STAGES;
-  uint64_t* tfull_bar = empty_bar + WG_STAGES;
+  float* scratch = reinterpret_cast<float*>(smem + STAGES * STAGE);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(scratch + 4 * BW_SCR);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int co0 = blockIdx.x * 128;
-  const int k0 = blockIdx.y * WG_BN;
-  const int n_valid = min(WG_BN, K - k0);
+  const int k0 = blockIdx.y * BN;
+  const int n_valid = min(BN, K - k0);
   const int n_eff = (n_valid + 15) & ~15;
   const int64_t m_begin = (int64_t)blockIdx.z * rows_per_split;
   const int64_t m_end = min(M, m_begin + rows_per_split);
   const int num_kb = (int)((m_end - m_begin + WG_ROWS - 1) / WG_ROWS);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tfull_bar[0], 1);
     mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc<WG_BN>(tmem_slot);
+  if (warp == 8) tmem_alloc<BN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -304,26 +284,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const float*
       const int cidx = tp & 15, r0 = tp >> 4;          // 16 chunks of 8 co per row, 8 rows per pass
       const float zp_a = (float)*x_zp_p;
       const int cpr = n_eff >> 3;                      // 8-channel chunks per row of x
+      constexpr int XL = WG_ROWS * (BN / 8) / 128;     // x chunks per thread (<= 16)
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % WG_STAGES;
-        uint8_t* a_hi = smem + s * STAGE;
-        uint8_t* a_lo = a_hi + A_BYTES;
-        uint8_t* b_s = a_lo + A_BYTES;
+        const int s = kb % STAGES;
+        uint8_t* stage = smem + s * STAGE;
+        const uint32_t a_hi = smem_u32(stage), a_lo = a_hi + A_BYTES;
+        uint8_t* b_s = stage + 2 * A_BYTES;
         const int64_t mb = m_begin + (int64_t)kb * WG_ROWS;
-        const int co = co0 + cidx * 8;
-        float4 f[8][2];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int64_t m = mb + r0 + 8 * i;
-          f[i][0] = f[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m < m_end && co < cout) {
-            const float4* p = reinterpret_cast<const float4*>(dz + m * cout + co);
-            f[i][0] = __ldg(p);
-            f[i][1] = __ldg(p + 1);
-          }
-        }
-        // activations: all loads first (64 rows x 256/8 chunks / 128 threads <= 16 per thread)
-        constexpr int XL = WG_ROWS * (WG_BN / 8) / 128;
+        // x: all loads first (registers), so their latency overlaps the wait for the stage
         uint2 xpk[XL];
 #pragma unroll
         for (int q = 0; q < XL; ++q) {
@@ -333,18 +301,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const float*
           if (idx < WG_ROWS * cpr && mb + r < m_end && k0 + kc * 8 < K)
             xpk[q] = __ldg(reinterpret_cast<const uint2*>(xq + (mb + r) * K + k0 + kc * 8));
         }
-        mbar_wait(&empty_bar[s], ((kb / WG_STAGES) & 1) ^ 1);
+        mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+        // dz hi/lo: cp.async straight into the MN-major tiles
+        const int co = co0 + cidx * 8;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = r0 + 8 * i;
-          const float x[8] = {f[i][0].x, f[i][0].y, f[i][0].z, f[i][0].w, f[i][1].x, f[i][1].y, f[i][1].z, f[i][1].w};
-          float h[8], l[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) split_bf16(x[e], h[e], l[e]);
-          const uint32_t off = (uint32_t)(cidx >> 3) * WG_BLK + sw128_offset(r, cidx & 7);
-          *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
-          *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]), pack_bf16(l[4], l[5]), pack_bf16(l[6], l[7]));
+          const int64_t m = mb + r;
+          const bool v = (m < m_end) && (co < cout);
+          const int64_t off = v ? m * cout + co : 0;
+          const uint32_t d = (uint32_t)(cidx >> 3) * WG_BLK + sw128_offset(r, cidx & 7);
+          cp_async_zfill<16>(a_hi + d, dz_hi + off, v);
+          cp_async_zfill<16>(a_lo + d, dz_lo + off, v);
         }
+        cp_async_commit();
 #pragma unroll
         for (int q = 0; q < XL; ++q) {
           const int idx = tp + 128 * q;
@@ -361,15 +331,21 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const float*
                 make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
           }
         }
-        fence_proxy_async();
-        mbar_arrive(&full_bar[s]);
+        if (kb >= BW_LAG) {
+          cp_async_wait<BW_LAG>();
+          fence_proxy_async();
+          mbar_arrive(&full_bar[(kb - BW_LAG) % STAGES]);
+        }
       }
+      cp_async_wait<0>();
+      fence_proxy_async();
+      for (int j = (num_kb > BW_LAG ? num_kb - BW_LAG : 0); j < num_kb; ++j) mbar_arrive(&full_bar[j % STAGES]);
     } else if (warp == 8) {
       // ================================================================= MMA issuer (A and B MN-major)
       const uint32_t idesc = umma_idesc(1, 1, 1, 128, n_eff) | (1u << 15) | (1u << 16);
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % WG_STAGES;
-        mbar_wait(&full_bar[s], (kb / WG_STAGES) & 1);
+        const int s = kb % STAGES;
+        mbar_wait(&full_bar[s], (kb / STAGES) & 1);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_s = smem_u32(smem + s * STAGE);
@@ -388,7 +364,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const float*
       }
     } else {
       // ================================================================= epilogue: fp32 atomics into dwq[co][k]
-      float* my = scratch + warp * DG_SCR;
+      float* my = scratch + warp * BW_SCR;
       const float s_a = *x_scale_p;
       mbar_wait(&tfull_bar[0], 0);
       tc_fence_after();
@@ -422,58 +398,75 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const float*
   __syncthreads();
   if (warp == 8) {
     tc_fence_after();
-    tmem_dealloc<WG_BN>(tmem_base);
+    tmem_dealloc<BN>(tmem_base);
   }
 }
 
-}  // namespace frost
-
-using namespace frost;
-
-extern "C" int frost_pw_dgrad_tc(const float* dz, const int8_t* wq_t, const float* w_scale, const int32_t* w_zp, int64_t M,
-                                 int K, int cout, float* dx, int accumulate, void* stream) {
-  FROST_REQUIRE(dz && wq_t && w_scale && w_zp && dx, "frost_pw_dgrad_tc: null pointer");
-  FROST_REQUIRE(M > 0 && K > 0 && cout > 0 && K % 4 == 0 && cout % 8 == 0,
-                "frost_pw_dgrad_tc: K=%d must be a multiple of 4 and cout=%d of 8", K, cout);
-  FROST_REQUIRE((reinterpret_cast<uintptr_t>(dz) & 15) == 0 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(wq_t) & 7) == 0,
-                "frost_pw_dgrad_tc: operands must be 16-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
-  int rc;
-  if (K <= 64) rc = launch_dgrad_tc<64>(dz, wq_t, w_scale, w_zp, M, K, cout, dx, accumulate, st);
-  else if (K <= 128) rc = launch_dgrad_tc<128>(dz, wq_t, w_scale, w_zp, M, K, cout, dx, accumulate, st);
-  else rc = launch_dgrad_tc<256>(dz, wq_t, w_scale, w_zp, M, K, cout, dx, accumulate, st);
-  if (rc) return rc;
-  FROST_LAUNCH_CHECK("pw_dgrad_tc");
-  return FROST_OK;
-}
-
-extern "C" int frost_pw_wgrad_tc(const float* dz, const uint8_t* xq, const float* x_scale, const int32_t* x_zp, int64_t M,
-                                 int K, int cout, float* dwq, void* stream) {
-  FROST_REQUIRE(dz && xq && x_scale && x_zp && dwq, "frost_pw_wgrad_tc: null pointer");
-  FROST_REQUIRE(M > 0 && K > 0 && cout > 0 && K % 8 == 0 && cout % 8 == 0, "frost_pw_wgrad_tc: K and cout must be multiples of 8");
-  FROST_REQUIRE((reinterpret_cast<uintptr_t>(dz) & 15) == 0 && (reinterpret_cast<uintptr_t>(dwq) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(xq) & 7) == 0,
-                "frost_pw_wgrad_tc: operands must be 16-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
-  if (cudaMemsetAsync(dwq, 0, sizeof(float) * (size_t)K * cout, st) != cudaSuccess) {
-    set_error("frost_pw_wgrad_tc: memset failed");
-    return FROST_ECUDA;
-  }
+template <int BN>
+static int launch_wgrad_tc(const uint16_t* dz_hi, const uint16_t* dz_lo, const uint8_t* xq, const float* x_scale,
+                           const int32_t* x_zp, int64_t M, int K, int cout, float* dwq, cudaStream_t st) {
+  constexpr size_t smem = wg_smem_bytes<BN>();
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem_bytes());
+    cudaError_t e = cudaFuncSetAttribute(pw_wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("pw_wgrad_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return FROST_ECUDA;
     }
     attr_done = true;
   }
-  const int ct = (int)ceil_div(cout, 128), kt = (int)ceil_div(K, WG_BN);
+  const int ct = (int)ceil_div(cout, 128), kt = (int)ceil_div(K, BN);
   int64_t splits = std::max<int64_t>(1, std::min<int64_t>(ceil_div(M, WG_ROWS * 4), (int64_t)kNumSMs / ((int64_t)ct * kt)));
   int64_t rows = ceil_div(ceil_div(M, splits), WG_ROWS) * WG_ROWS;
   splits = ceil_div(M, rows);
-  pw_wgrad_tc_kernel<<<dim3(ct, kt, (unsigned)splits), WG_THREADS, wg_smem_bytes(), st>>>(dz, xq, x_scale, x_zp, M, K, cout, rows, dwq);
+  pw_wgrad_tc_kernel<BN><<<dim3(ct, kt, (unsigned)splits), WG_THREADS, smem, st>>>(dz_hi, dz_lo, xq, x_scale, x_zp, M, K, cout, rows, dwq);
+  return FROST_OK;
+}
+
+}  // namespace frost
+
+using namespace frost;
+
+extern "C" int frost_pw_dgrad_tc(const void* dz_hi, const void* dz_lo, const void* wt_bf16, const float* w_scale, int64_t M,
+                                 int K, int cout, float* dx, int accumulate, void* stream) {
+  FROST_REQUIRE(dz_hi && dz_lo && wt_bf16 && w_scale && dx, "frost_pw_dgrad_tc: null pointer");
+  FROST_REQUIRE(M > 0 && K > 0 && cout > 0 && K % 4 == 0 && cout % 8 == 0,
+                "frost_pw_dgrad_tc: K=%d must be a multiple of 4 and cout=%d of 8", K, cout);
+  FROST_REQUIRE((reinterpret_cast<uintptr_t>(dz_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(dz_lo) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(dx) & 15) == 0 && (reinterpret_cast<uintptr_t>(wt_bf16) & 15) == 0,
+                "frost_pw_dgrad_tc: operands must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint16_t* hi = static_cast<const uint16_t*>(dz_hi);
+  const uint16_t* lo = static_cast<const uint16_t*>(dz_lo);
+  const uint16_t* wt = static_cast<const uint16_t*>(wt_bf16);
+  int rc;
+  if (K <= 64) rc = launch_dgrad_tc<64>(hi, lo, wt, w_scale, M, K, cout, dx, accumulate, st);
+  else if (K <= 128) rc = launch_dgrad_tc<128>(hi, lo, wt, w_scale, M, K, cout, dx, accumulate, st);
+  else rc = launch_dgrad_tc<256>(hi, lo, wt, w_scale, M, K, cout, dx, accumulate, st);
+  if (rc) return rc;
+  FROST_LAUNCH_CHECK("pw_dgrad_tc");
+  return FROST_OK;
+}
+
+extern "C" int frost_pw_wgrad_tc(const void* dz_hi, const void* dz_lo, const uint8_t* xq, const float* x_scale,
+                                 const int32_t* x_zp, int64_t M, int K, int cout, float* dwq, void* stream) {
+  FROST_REQUIRE(dz_hi && dz_lo && xq && x_scale && x_zp && dwq, "frost_pw_wgrad_tc: null pointer");
+  FROST_REQUIRE(M > 0 && K > 0 && cout > 0 && K % 8 == 0 && cout % 8 == 0, "frost_pw_wgrad_tc: K and cout must be multiples of 8");
+  FROST_REQUIRE((reinterpret_cast<uintptr_t>(dz_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(dz_lo) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(dwq) & 15) == 0 && (reinterpret_cast<uintptr_t>(xq) & 7) == 0,
+                "frost_pw_wgrad_tc: operands must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(dwq, 0, sizeof(float) * (size_t)K * cout, st) != cudaSuccess) {
+    set_error("frost_pw_wgrad_tc: memset failed");
+    return FROST_ECUDA;
+  }
+  const uint16_t* hi = static_cast<const uint16_t*>(dz_hi);
+  const uint16_t* lo = static_cast<const uint16_t*>(dz_lo);
+  int rc;
+  if (K <= 64) rc = launch_wgrad_tc<64>(hi, lo, xq, x_scale, x_zp, M, K, cout, dwq, st);
+  else if (K <= 128) rc = launch_wgrad_tc<128>(hi, lo, xq, x_scale, x_zp, M, K, cout, dwq, st);
+  else rc = launch_wgrad_tc<256>(hi, lo, xq, x_scale, x_zp, M, K, cout, dwq, st);
+  if (rc) return rc;
   FROST_LAUNCH_CHECK("pw_wgrad_tc");
   return FROST_OK;
 }

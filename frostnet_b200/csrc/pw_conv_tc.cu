@@ -29,15 +29,16 @@ struct TcStat {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 128;  // bytes of K per stage (= one swizzle span)
-constexpr int TC_STAGES = 4;
+template <int BN>
+__host__ __device__ constexpr int tc_stages() { return BN >= 256 ? 3 : 4; }
 constexpr int TC_LAG = 2;   // cp.async groups in flight per producer thread
-constexpr int TC_THREADS = 288;
+constexpr int TC_THREADS = 416;   // warps 0-7 epilogue (2 groups), 8-11 producer, 12 MMA
 constexpr int TC_SCR = 32 * 36;  // ints of transpose scratch per epilogue warp
 
 template <int BN>
 constexpr size_t tc_smem_bytes() {
-  return 1024 + (size_t)TC_STAGES * (TC_BM * TC_BK + BN * TC_BK) + 4 * TC_SCR * 4 + BN * 4 + BN * sizeof(TcStat) +
-         (2 * TC_STAGES + 4) * 8 + 16;
+  return 1024 + (size_t)tc_stages<BN>() * (TC_BM * TC_BK + BN * TC_BK) + 8 * TC_SCR * 4 + BN * 4 + BN * sizeof(TcStat) +
+         (2 * tc_stages<BN>() + 4) * 8 + 16;
 }
 
 template <int BN, bool VEC16>
@@ -47,9 +48,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
     int32_t* __restrict__ acc_out, FrostChanStats* __restrict__ stats) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int TC_STAGES = tc_stages<BN>();
   constexpr int A_BYTES = TC_BM * TC_BK, B_BYTES = BN * TC_BK, STAGE = A_BYTES + B_BYTES;
   int* scratch = reinterpret_cast<int*>(smem + TC_STAGES * STAGE);
-  int* s_corr = scratch + 4 * TC_SCR;
+  int* s_corr = scratch + 8 * TC_SCR;
   TcStat* s_stat = reinterpret_cast<TcStat*>(s_corr + BN);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stat + BN);
   uint64_t* empty_bar = full_bar + TC_STAGES;
@@ -84,15 +86,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
     mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc<2 * BN>(tmem_slot);
+  if (warp == 12) tmem_alloc<2 * BN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 8 && warp < 12) {
     // ================================================================= producer
-    const int tp = threadIdx.x - 128;
+    const int tp = threadIdx.x - 256;
     const int c16 = tp & 7, r0 = tp >> 3;  // 16 rows per pass
     uint32_t it = 0;
     for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
     cp_async_wait<0>();
     fence_proxy_async();
     for (uint32_t j = (it > (uint32_t)TC_LAG ? it - TC_LAG : 0u); j < it; ++j) mbar_arrive(&full_bar[j % TC_STAGES]);
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // ================================================================= MMA issuer
     const uint32_t idesc = umma_idesc(2 /*S32*/, 0 /*A: u8*/, zp_w == 0 ? 1 : 0 /*B: s8 | u8*/, TC_BM, n_eff);
     uint32_t it = 0, tile_i = 0;
@@ -185,17 +187,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
       }
     }
   } else {
-    // ================================================================= epilogue (warps 0-3 <-> TMEM lanes 32*warp..)
+    // ================================================================= epilogue
+    // two groups of 4 warps; group g drains accumulator buffer g (tiles g, g+2, ...); warp w of a group owns
+    // TMEM lanes 32*(w%4).. (the hardware restricts a warp to the lane quarter warp_id % 4)
+    const int grp = warp >> 2, wq4 = warp & 3;
     int* my = scratch + warp * TC_SCR;
     uint32_t tile_i = 0;
     for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++tile_i) {
       const uint32_t acc = tile_i & 1;
-      const int64_t m0 = mt * TC_BM + warp * 32;
+      if ((int)acc != grp) continue;
+      const int64_t m0 = mt * TC_BM + wq4 * 32;
       mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1);
       tc_fence_after();
       for (int chunk = 0; chunk * 32 < n_valid; ++chunk) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + acc * BN + chunk * 32 + ((uint32_t)(warp * 32) << 16), v);
+        tmem_ld_32x32(tmem_base + acc * BN + chunk * 32 + ((uint32_t)(wq4 * 32) << 16), v);
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
           int4 o;
@@ -268,7 +274,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
     atomicMin(&g->min, s.mn);
     atomicMax(&g->max, s.mx);
   }
-  if (warp == 8) {
+  if (warp == 12) {
     tc_fence_after();
     tmem_dealloc<2 * BN>(tmem_base);
   }

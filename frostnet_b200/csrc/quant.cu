@@ -1,6 +1,7 @@
 // quant.cu - per-tensor fake-quant (observer + qparams + quantise), QuantStub, weight prep/backward.
 // Restates torch.fused_moving_avg_obs_fake_quant (torch/ao/quantization/fake_quantize.py:423-438)
 // and the weight side of nniqat.ConvBn2d (torch/ao/nn/intrinsic/qat/modules/conv_fused.py:131-146).
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace frost {
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(kWeightThreads) weight_quant_kernel(const Fros
     const float idx = fq_index(ws, inv, zp);
     const float qc = fminf(fmaxf(idx, -128.0f), 127.0f);
     d.wq[wq_index(d, c, ci, y, x)] = (int8_t)qc;
-    if (d.wq_t) d.wq_t[(int64_t)r * d.cout + c] = (int8_t)qc;   // 1x1: r == ci
+    if (d.wt_bf16) d.wt_bf16[(int64_t)r * d.cout + c] = __bfloat16_as_ushort(__float2bfloat16_rn(qc - zp));  // 1x1: r == ci; exact
     d.wmask[e] = (idx >= -128.0f && idx <= 127.0f) ? 1 : 0;
     atomicAdd(d.wsum + c, (int)qc);
   }

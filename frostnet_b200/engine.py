@@ -61,7 +61,7 @@ class _Layer:
         f32 = dict(dtype=torch.float32, device=dev)
         n = self.cout * self.cin_g * self.kh * self.kw
         self.wq = torch.zeros(n, dtype=torch.int8, device=dev)
-        self.wq_t = torch.zeros(n, dtype=torch.int8, device=dev) if self.kind == "pw" else None
+        self.wt_bf16 = torch.zeros(n, dtype=torch.bfloat16, device=dev) if self.kind == "pw" else None
         self.wmask = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.sf = torch.ones(self.cout, **f32)
         self.rstd = torch.ones(self.cout, **f32)
@@ -188,7 +188,7 @@ class QATEngine:
             d.wfq = _fq_struct(mod.weight_fake_quant)
             d.wq, d.wmask, d.sf, d.rstd_run, d.wsum = (ly.wq.data_ptr(), ly.wmask.data_ptr(), ly.sf.data_ptr(),
                                                        ly.rstd.data_ptr(), ly.wsum.data_ptr())
-            d.wq_t = ly.wq_t.data_ptr() if ly.wq_t is not None else None
+            d.wt_bf16 = ly.wt_bf16.data_ptr() if ly.wt_bf16 is not None else None
             d.dwq = ly.dwq.data_ptr()
             d.dweight = g.data_ptr() + 4 * self.param_off[id(mod.weight)]
             if ly.has_bn:
@@ -378,7 +378,15 @@ class QATEngine:
             raise RuntimeError("frostnet_b200: backward through eval-mode BatchNorm is not supported")
         mod, dev = ly.mod, self.dev
         M = acc.shape[0]
-        dz = torch.empty((M, ly.cout), dtype=torch.float32, device=dev)
+        # pointwise layers get dz as two bf16 planes (the operand format of the tensor-core dgrad/wgrad);
+        # depthwise / stem consumers read fp32
+        tc_fmt = ly.kind == "pw"
+        if tc_fmt:
+            dz = torch.empty((M, ly.cout), dtype=torch.bfloat16, device=dev)
+            dz_lo = torch.empty((M, ly.cout), dtype=torch.bfloat16, device=dev)
+        else:
+            dz = torch.empty((M, ly.cout), dtype=torch.float32, device=dev)
+            dz_lo = None
         a = L.BnBackwardArgs()
         a.dy, a.acc, a.M, a.C, a.relu = dy.data_ptr(), acc.data_ptr(), M, ly.cout, 1 if ly.relu else 0
         a.A, a.B, a.mean_I, a.kfac = ly.A.data_ptr(), ly.B.data_ptr(), ly.mean_I.data_ptr(), ly.kfac.data_ptr()
@@ -387,15 +395,16 @@ class QATEngine:
         a.out_scale, a.out_zp = out.scale.data_ptr(), out.zp.data_ptr()
         a.eps = mod.bn.eps
         a.sums, a.coef, a.dz = ly.sums.data_ptr(), ly.coef.data_ptr(), dz.data_ptr()
+        a.dz_lo, a.dz_format = L.ptr(dz_lo), 1 if tc_fmt else 0
         a.dgamma_bn, a.dsf_bn = ly.dgamma_bn.data_ptr(), ly.dsf_bn.data_ptr()
         a.dbeta = gbase + 4 * self.param_off[id(mod.bn.bias)]
         L.call("frost_bn_backward", C.byref(a), st)
         wfq = mod.weight_fake_quant
         if ly.kind == "pw":
-            L.call("frost_pw_wgrad_tc", dz.data_ptr(), xin.q.data_ptr(), xin.scale.data_ptr(), xin.zp.data_ptr(), M, ly.cin,
-                   ly.cout, ly.dwq.data_ptr(), st)
+            L.call("frost_pw_wgrad_tc", dz.data_ptr(), dz_lo.data_ptr(), xin.q.data_ptr(), xin.scale.data_ptr(),
+                   xin.zp.data_ptr(), M, ly.cin, ly.cout, ly.dwq.data_ptr(), st)
             if dx is not None:
-                L.call("frost_pw_dgrad_tc", dz.data_ptr(), ly.wq_t.data_ptr(), wfq.scale.data_ptr(), wfq.zero_point.data_ptr(),
+                L.call("frost_pw_dgrad_tc", dz.data_ptr(), dz_lo.data_ptr(), ly.wt_bf16.data_ptr(), wfq.scale.data_ptr(),
                        M, ly.cin, ly.cout, dx.data_ptr(), 1 if accumulate else 0, st)
         elif ly.kind == "dw":
             L.call("frost_dw_wgrad", dz.data_ptr(), xin.q.data_ptr(), xin.scale.data_ptr(), xin.zp.data_ptr(), xin.N,

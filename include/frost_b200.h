@@ -101,7 +101,8 @@ typedef struct {
   float averaging_const;
   FrostFQ wfq;
   int8_t* wq;               /* out: int8 indices in `layout`                                   */
-  int8_t* wq_t;             /* out (layout 0, 1x1 only; may be NULL): transposed copy [cin][cout] for dgrad */
+  uint16_t* wt_bf16;        /* out (layout 0, 1x1 only; may be NULL): (q_w - zp_w) as bf16, transposed [cin][cout],
+                               the B operand of the tensor-core dgrad                          */
   uint8_t* wmask;           /* out: STE mask, PyTorch layout                                   */
   float* sf;               /* out: scale_factor[cout]                                         */
   float* rstd_run;          /* out: 1/sqrt(running_var+eps)[cout] as seen by this forward       */
@@ -204,7 +205,9 @@ typedef struct {
   float eps;
   double* sums;                /* scratch [2*C]                                               */
   float* coef;                 /* scratch [3*C]                                               */
-  float* dz;                   /* out [M][C]                                                  */
+  float* dz;                   /* out [M][C] fp32 (dz_format 0)  |  bf16 hi plane [M][C] (dz_format 1)  */
+  void* dz_lo;                 /* out bf16 lo plane [M][C] (dz_format 1): dz == hi + lo to 16 mantissa bits */
+  int32_t dz_format;           /* 0: fp32 (depthwise / stem consumers); 1: bf16 hi+lo planes (tensor-core dgrad/wgrad) */
   float* dgamma_bn;            /* out [C]                                                     */
   float* dbeta;                /* out [C]                                                     */
   float* dsf_bn;               /* out [C]                                                     */
@@ -262,13 +265,14 @@ int frost_linear_backward(const float* dout, const float* x, const int8_t* wq,
 /* dx[M][K] (+)= s_w * sum_co dz[M][co]*(wq[co][K]-zp_w)      (CUDA-core fp32 version) */
 int frost_pw_dgrad(const float* dz, const int8_t* wq, const float* w_scale, const int32_t* w_zp,
                    int64_t M, int K, int cout, float* dx, int accumulate, void* stream);
-/* Same result on tensor cores: tcgen05.mma kind::f16 with dz split into bf16 hi+lo (16 mantissa bits) and
- * the integer weights exact in bf16; wq_t = transposed weight indices [K][cout] from weight prep. */
-int frost_pw_dgrad_tc(const float* dz, const int8_t* wq_t, const float* w_scale, const int32_t* w_zp,
+/* Same result on tensor cores: tcgen05.mma kind::f16, bf16 operands, fp32 accumulation in TMEM.
+ * dz comes as two bf16 planes (hi, lo; written by frost_bn_backward with dz_format 1), the integer weights
+ * are exact in bf16 (wt_bf16 [K][cout] from weight prep); 2 MMAs per k-step. */
+int frost_pw_dgrad_tc(const void* dz_hi, const void* dz_lo, const void* wt_bf16, const float* w_scale,
                       int64_t M, int K, int cout, float* dx, int accumulate, void* stream);
-/* Tensor-core wgrad: reduction over the rows m with MN-major bf16 operands (dz hi/lo split), fp32 atomics. */
-int frost_pw_wgrad_tc(const float* dz, const uint8_t* xq, const float* x_scale, const int32_t* x_zp,
-                      int64_t M, int K, int cout, float* dwq, void* stream);
+/* Tensor-core wgrad: reduction over the rows m with MN-major bf16 operands (dz hi/lo planes), fp32 atomics. */
+int frost_pw_wgrad_tc(const void* dz_hi, const void* dz_lo, const uint8_t* xq, const float* x_scale,
+                      const int32_t* x_zp, int64_t M, int K, int cout, float* dwq, void* stream);
 /* dwq[cout][K] = s_a * sum_m dz[m][co]*(xq[m][K]-zp_a)     (dwq zeroed by callee; CUDA-core fp32 version) */
 int frost_pw_wgrad(const float* dz, const uint8_t* xq, const float* x_scale, const int32_t* x_zp,
                    int64_t M, int K, int cout, float* dwq, void* stream);

@@ -132,7 +132,7 @@ def _weight_desc(w, gamma, var, eps, layout, fq, bufs):
     d.cout, d.cin_g, d.kh, d.kw = w.shape
     d.layout, d.observe, d.averaging_const = layout, 1, 0.01
     d.wfq = fq.c()
-    for k in ("wq", "wq_t", "wmask", "sf", "rstd_run", "wsum", "dwq", "dgamma_bn", "dsf_bn", "dweight", "dgamma"):
+    for k in ("wq", "wt_bf16", "wmask", "sf", "rstd_run", "wsum", "dwq", "dgamma_bn", "dsf_bn", "dweight", "dgamma"):
         setattr(d, k, bufs[k].data_ptr() if bufs.get(k) is not None else None)
     return d
 
@@ -140,7 +140,7 @@ def _weight_desc(w, gamma, var, eps, layout, fq, bufs):
 def _alloc_wbufs(w, with_bn=True):
     n, co = w.numel(), w.shape[0]
     b = dict(wq=torch.zeros(n, dtype=torch.int8, device=DEV),
-             wq_t=torch.zeros(n, dtype=torch.int8, device=DEV) if (w.shape[2] == 1 and w.shape[1] > 1) else None, wmask=torch.zeros(n, dtype=torch.uint8, device=DEV),
+             wt_bf16=torch.zeros(n, dtype=torch.bfloat16, device=DEV) if (w.shape[2] == 1 and w.shape[1] > 1) else None, wmask=torch.zeros(n, dtype=torch.uint8, device=DEV),
              sf=torch.zeros(co, device=DEV), rstd_run=torch.zeros(co, device=DEV),
              wsum=torch.zeros(co, dtype=torch.int32, device=DEV), dwq=torch.zeros(n, device=DEV),
              dweight=torch.zeros(n, device=DEV))
@@ -200,8 +200,9 @@ def test_weight_prep_and_backward_vs_oracle(shape, layout):
             fq.assert_state_equal()
             idx = fq.oracle.last_idx
             assert torch.equal(bufs["wq"].cpu(), _to_layout(idx.clamp(-128, 127).to(torch.int8), layout))
-            if bufs["wq_t"] is not None:
-                assert torch.equal(bufs["wq_t"].cpu().reshape(shape[1], shape[0]), bufs["wq"].cpu().reshape(shape[0], shape[1]).t())
+            if bufs["wt_bf16"] is not None:
+                exp_t = (bufs["wq"].cpu().reshape(shape[0], shape[1]).float() - float(int(fq.zp))).t()
+                assert torch.equal(bufs["wt_bf16"].cpu().float().reshape(shape[1], shape[0]), exp_t)
             # ATen's vectorised CPU sqrt/div may differ from IEEE scalar code in the last ulp of a vector tail
             torch.testing.assert_close(bufs["sf"].cpu(), sf.detach(), rtol=2.5e-7, atol=0)
             assert torch.equal(bufs["wsum"].cpu(), idx.clamp(-128, 127).reshape(shape[0], -1).sum(1).int())
@@ -402,6 +403,14 @@ def test_bn_finalize_apply_and_backward(M, Cc, relu, training):
     scale = float(conv.grad.abs().max())
     err = float((dz.cpu().double() - conv.grad).abs().max())
     assert err <= 2e-4 * scale, (err, scale)
+    # bf16 hi/lo plane format (operand format of the tensor-core dgrad / wgrad)
+    p_hi = torch.empty(M, Cc, dtype=torch.bfloat16, device=DEV)
+    p_lo = torch.empty(M, Cc, dtype=torch.bfloat16, device=DEV)
+    b.dz, b.dz_lo, b.dz_format = p_hi.data_ptr(), p_lo.data_ptr(), 1
+    L().call("frost_bn_backward", C.byref(b), stream())
+    rec = p_hi.float() + p_lo.float()
+    assert float((rec - dz).abs().max()) <= 2.0 ** -16 * float(dz.abs().max())
+    assert torch.equal(p_hi, dz.to(torch.bfloat16))
     torch.testing.assert_close(dbeta.cpu().double(), b64.grad, rtol=1e-4, atol=1e-4 * float(b64.grad.abs().max()))
     torch.testing.assert_close(dgb.cpu().double(), g64.grad, rtol=1e-3, atol=2e-4 * float(g64.grad.abs().max()))
 
@@ -471,6 +480,12 @@ def test_add_forward_backward_bit_exact():
         assert torch.equal(dsum.cpu(), x.grad) and torch.equal(da.cpu(), x.grad)
 
 
+def _split_bf16(x):
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return hi.contiguous(), lo.contiguous()
+
+
 # ------------------------------------------------------------------------------------------ dgrad / wgrad
 @pytest.mark.parametrize("M,K,cout", [(70, 16, 24), (1000, 104, 312), (333, 1728, 320), (64, 320, 1280), (20000, 56, 168),
                                       (5000, 288, 1728)])
@@ -487,15 +502,16 @@ def test_pw_dgrad_wgrad(M, K, cout):
     sw_t, sa_t = torch.tensor([s_w], device=DEV), torch.tensor([s_a], device=DEV)
     zw_t, za_t = torch.tensor([zp_w], dtype=torch.int32, device=DEV), torch.tensor([zp_a], dtype=torch.int32, device=DEV)
     dzd, wd, xd = dz.to(DEV), wq.to(torch.int8).to(DEV), xq.to(torch.uint8).to(DEV)
+    dz_hi, dz_lo = _split_bf16(dzd)
     dx = torch.ones(M, K, device=DEV)
     L().call("frost_pw_dgrad", dzd.data_ptr(), wd.data_ptr(), sw_t.data_ptr(), zw_t.data_ptr(), M, K, cout,
              dx.data_ptr(), 1, stream())
     torch.testing.assert_close(dx.cpu().double(), dx_ref + 1.0, rtol=1e-4, atol=1e-4 * float(dx_ref.abs().max()))
     # tensor-core version (bf16 hi/lo split of dz, exact integer weights) from the transposed weights
-    wtd = wq.t().contiguous().to(torch.int8).to(DEV)
+    wtd = (wq - zp_w).t().contiguous().to(torch.bfloat16).to(DEV)
     for accumulate in (0, 1):
         dx2 = torch.ones(M, K, device=DEV)
-        L().call("frost_pw_dgrad_tc", dzd.data_ptr(), wtd.data_ptr(), sw_t.data_ptr(), zw_t.data_ptr(), M, K, cout,
+        L().call("frost_pw_dgrad_tc", dz_hi.data_ptr(), dz_lo.data_ptr(), wtd.data_ptr(), sw_t.data_ptr(), M, K, cout,
                  dx2.data_ptr(), accumulate, stream())
         torch.cuda.synchronize()
         ref2 = dx_ref + (1.0 if accumulate else 0.0)
@@ -505,7 +521,8 @@ def test_pw_dgrad_wgrad(M, K, cout):
     dzi = torch.randint(-64, 65, (M, cout), generator=g).float()
     dx3 = torch.empty(M, K, device=DEV)
     one = torch.ones(1, device=DEV)
-    L().call("frost_pw_dgrad_tc", dzi.to(DEV).data_ptr(), wtd.data_ptr(), one.data_ptr(), zw_t.data_ptr(), M, K, cout,
+    i_hi, i_lo = _split_bf16(dzi.to(DEV))
+    L().call("frost_pw_dgrad_tc", i_hi.data_ptr(), i_lo.data_ptr(), wtd.data_ptr(), one.data_ptr(), M, K, cout,
              dx3.data_ptr(), 0, stream())
     torch.cuda.synchronize()
     assert torch.equal(dx3.cpu().double(), dzi.double() @ (wq - zp_w).double())
@@ -514,17 +531,17 @@ def test_pw_dgrad_wgrad(M, K, cout):
              dwq.data_ptr(), stream())
     torch.testing.assert_close(dwq.cpu().double(), dw_ref, rtol=1e-4, atol=1e-4 * float(dw_ref.abs().max()))
     dwq2 = torch.empty(cout, K, device=DEV)
-    L().call("frost_pw_wgrad_tc", dzd.data_ptr(), xd.data_ptr(), sa_t.data_ptr(), za_t.data_ptr(), M, K, cout,
-             dwq2.data_ptr(), stream())
+    L().call("frost_pw_wgrad_tc", dz_hi.data_ptr(), dz_lo.data_ptr(), xd.data_ptr(), sa_t.data_ptr(), za_t.data_ptr(), M, K,
+             cout, dwq2.data_ptr(), stream())
     torch.cuda.synchronize()
     errw = float((dwq2.cpu().double() - dw_ref).abs().max()) / float(dw_ref.abs().max())
     assert errw < 5e-5, errw
     if M <= 1000:      # integer-valued dz: exact
         dzs = torch.randint(-8, 9, (M, cout), generator=g).float()
         one_w = torch.ones(1, device=DEV)
-        dzsd = dzs.to(DEV)
-        L().call("frost_pw_wgrad_tc", dzsd.data_ptr(), xd.data_ptr(), one_w.data_ptr(), za_t.data_ptr(), M, K, cout,
-                 dwq2.data_ptr(), stream())
+        s_hi, s_lo = _split_bf16(dzs.to(DEV))
+        L().call("frost_pw_wgrad_tc", s_hi.data_ptr(), s_lo.data_ptr(), xd.data_ptr(), one_w.data_ptr(), za_t.data_ptr(), M, K,
+                 cout, dwq2.data_ptr(), stream())
         torch.cuda.synchronize()
         assert torch.equal(dwq2.cpu().double(), dzs.double().t() @ (xq - zp_a).double())
 
