@@ -14,8 +14,8 @@ void dw_launch_shape(int C, int max_cgb, int* cg_per_block, int* nchunks, int* t
 __device__ __forceinline__ float bn_affine(int I, float A, float B) { return fmaf((float)I, A, B); }
 
 // ---------------------------------------------------------------- finalize (1 CTA)
-__global__ void __launch_bounds__(256) bn_finalize_kernel(FrostBnFinalizeArgs a) {
-  __shared__ float s_mn[8], s_mx[8];
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(FrostBnFinalizeArgs a) {
+  __shared__ float s_mn[32], s_mx[32];
   const double M = (double)a.count;
   const double sa_sw = (double)(*a.x_scale) * (double)(*a.w_scale);
   float gmn = INFINITY, gmx = -INFINITY;
@@ -172,35 +172,34 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(FrostBnBackwardArgs 
 }
 
 // Per-channel coefficients of  dz = c1*(dv - a0 - a1*(I - mean_I))  plus the BN parameter grads.
-__global__ void __launch_bounds__(256) bn_bwd_coef_kernel(FrostBnBackwardArgs a) {
-  const double M = (double)a.M;
-  const double sa_sw = (double)(*a.x_scale) * (double)(*a.w_scale);
-  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-    const double S1 = a.sums[2 * c], S2 = a.sums[2 * c + 1];
-    const double k = (double)a.kfac[c];
-    const double T = k * (S2 - (double)a.mean_I[c] * S1);  // sum dv*xhat
-    const double g = (double)a.gamma[c];
-    const double sf = (double)a.sf[c];
-    const double invstd = k * sf / sa_sw;                  // k = m_c*invstd, m_c = sa_sw/sf
-    a.coef[3 * c + 0] = (float)((double)a.A[c] / sa_sw);   // c1 = gamma*invstd/sf
-    a.coef[3 * c + 1] = (float)(S1 / M);                   // a0
-    a.coef[3 * c + 2] = (float)(k * T / M);                // a1
-    a.dgamma_bn[c] = (float)T;
-    a.dbeta[c] = (float)S1;
-    a.dsf_bn[c] = (float)(-g * T * (double)a.eps * invstd * invstd / sf);
-  }
-}
-
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(FrostBnBackwardArgs a, int64_t n4) {
   extern __shared__ float s_c[];  // A,B,mean_I,c1,a0,a1 : 6*C
   const int C = a.C;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    s_c[c] = a.A[c];
-    s_c[C + c] = a.B[c];
-    s_c[2 * C + c] = a.mean_I[c];
-    s_c[3 * C + c] = a.coef[3 * c];
-    s_c[4 * C + c] = a.coef[3 * c + 1];
-    s_c[5 * C + c] = a.coef[3 * c + 2];
+  {
+    // per-channel coefficients of dz = c1*(dv - a0 - a1*(I - mean_I)) from the reduced sums; every block
+    // recomputes them (C <= a few thousand, a handful of double flops each); block 0 also emits the BN grads
+    const double M = (double)a.M;
+    const double sa_sw = (double)(*a.x_scale) * (double)(*a.w_scale);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const double S1 = a.sums[2 * c], S2 = a.sums[2 * c + 1];
+      const double k = (double)a.kfac[c];
+      const float mean_I = a.mean_I[c];
+      const double T = k * (S2 - (double)mean_I * S1);      // sum dv*xhat
+      const float A = a.A[c];
+      s_c[c] = A;
+      s_c[C + c] = a.B[c];
+      s_c[2 * C + c] = mean_I;
+      s_c[3 * C + c] = (float)((double)A / sa_sw);          // c1 = gamma*invstd/sf
+      s_c[4 * C + c] = (float)(S1 / M);                     // a0
+      s_c[5 * C + c] = (float)(k * T / M);                  // a1
+      if (blockIdx.x == 0) {
+        const double g = (double)a.gamma[c], sf = (double)a.sf[c];
+        const double invstd = k * sf / sa_sw;               // k = m_c*invstd, m_c = sa_sw/sf
+        a.dgamma_bn[c] = (float)T;
+        a.dbeta[c] = (float)S1;
+        a.dsf_bn[c] = (float)(-g * T * (double)a.eps * invstd * invstd / sf);
+      }
+    }
   }
   __syncthreads();
   const float inv = __fdiv_rn(1.0f, *a.out_scale), zp = (float)*a.out_zp;
@@ -249,7 +248,7 @@ extern "C" int frost_bn_finalize(const FrostBnFinalizeArgs* a, void* stream) {
                     a->afq.zero_point && a->afq.min_val && a->afq.max_val,
                 "frost_bn_finalize: null pointer");
   FROST_REQUIRE(a->C > 0 && a->count > 0, "frost_bn_finalize: empty tensor");
-  bn_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*a);
+  bn_finalize_kernel<<<1, a->C >= 512 ? 1024 : (a->C >= 128 ? 256 : 64), 0, (cudaStream_t)stream>>>(*a);
   FROST_LAUNCH_CHECK("bn_finalize");
   return FROST_OK;
 }
@@ -283,12 +282,10 @@ extern "C" int frost_bn_backward(const FrostBnBackwardArgs* a, void* stream) {
   int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(a->M, (int64_t)rows_per_block * 8), (int64_t)kNumSMs * 8 / chunks));
   bn_bwd_reduce_kernel<<<dim3(gx, chunks), threads, sizeof(double) * cgb * 8, st>>>(*a, cgb);
   FROST_LAUNCH_CHECK("bn_bwd_reduce");
-  bn_bwd_coef_kernel<<<1, 256, 0, st>>>(*a);
-  FROST_LAUNCH_CHECK("bn_bwd_coef");
   const int64_t n4 = a->M * a->C / 4;
   const size_t smem = 6 * (size_t)a->C * sizeof(float);
   FROST_REQUIRE(smem <= 48 * 1024, "frost_bn_backward: C=%d too large for the coefficient tile", a->C);
-  bn_bwd_apply_kernel<<<grid_for(n4, 256 * 4), 256, smem, st>>>(*a, n4);
+  bn_bwd_apply_kernel<<<grid_for(n4, 256 * 8, kNumSMs * 8), 256, smem, st>>>(*a, n4);
   FROST_LAUNCH_CHECK("bn_bwd_apply");
   return FROST_OK;
 }

@@ -159,52 +159,64 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__
 
 // ---------------------------------------------------------------- stem wgrad
 // dwq[co][r][s][ci] += s_a * sum_pix dz[pix][co] * (x[patch(pix)][r][s][ci] - zp_a)
-constexpr int STEMW_PIX = 32;
+// Batches of 64 pixels: the (pixel, tap) patch values and the dz rows are staged in shared memory by
+// threads that keep their pixel coordinates in registers (one div/mod per pixel, not per element);
+// thread (co, tap-group) then accumulates its <= 4 taps over the batch.
+constexpr int STEMW_PIX = 64;
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ dz, const uint8_t* __restrict__ xq,
                                                         const float* __restrict__ x_scale_p, const int32_t* __restrict__ x_zp_p,
                                                         int N, int H, int W, int cin, int cout, int k, int stride, int pad,
                                                         int Ho, int Wo, int64_t pix_per_block, float* __restrict__ dwq) {
   extern __shared__ float s_buf[];
   const int KK = k * k * cin;
-  float* s_patch = s_buf;                      // [STEMW_PIX][KK]
-  float* s_dz = s_buf + STEMW_PIX * KK;        // [STEMW_PIX][32]
+  const int KP = KK | 1;                       // odd pitch: conflict-free column reads
+  float* s_patch = s_buf;                      // [STEMW_PIX][KP]
+  float* s_dz = s_buf + STEMW_PIX * KP;        // [STEMW_PIX][32]
   const int co = threadIdx.x & 31, j = threadIdx.x >> 5;  // 8 tap groups
   const float zp_a = (float)*x_zp_p;
   const int64_t total = (int64_t)N * Ho * Wo;
   const int64_t p_begin = (int64_t)blockIdx.x * pix_per_block;
   const int64_t p_end = min(total, p_begin + pix_per_block);
+  // fill role: 4 threads per pixel, each takes taps f, f+4, ...
+  const int fp = threadIdx.x >> 2, ff = threadIdx.x & 3;
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
   for (int64_t pb = p_begin; pb < p_end; pb += STEMW_PIX) {
     const int np = (int)min((int64_t)STEMW_PIX, p_end - pb);
-    for (int i = threadIdx.x; i < STEMW_PIX * KK; i += blockDim.x) {
-      const int pl = i / KK, t = i % KK;
-      float v = 0.0f;
-      if (pl < np) {
-        const int64_t p = pb + pl;
-        const int ow = (int)(p % Wo);
+    {
+      const int64_t p = pb + fp;
+      const bool pv = fp < np;
+      int ow = 0, oh = 0, n = 0;
+      if (pv) {
+        ow = (int)(p % Wo);
         const int64_t t1 = p / Wo;
-        const int oh = (int)(t1 % Ho);
-        const int n = (int)(t1 / Ho);
-        const int ci = t % cin, rs = t / cin, r = rs / k, s = rs % k;
-        const int ih = oh * stride - pad + r, iw = ow * stride - pad + s;
-        if (ih >= 0 && ih < H && iw >= 0 && iw < W)
-          v = (float)__ldg(xq + (((int64_t)n * H + ih) * W + iw) * cin + ci) - zp_a;
+        oh = (int)(t1 % Ho);
+        n = (int)(t1 / Ho);
       }
-      s_patch[i] = v;
+      const int ih0 = oh * stride - pad, iw0 = ow * stride - pad;
+      const uint8_t* img = xq + (int64_t)n * H * W * cin;
+      for (int t = ff; t < KK; t += 4) {
+        const int ci = t % cin, rs = t / cin, r = rs / k, sx = rs - r * k;
+        const int ih = ih0 + r, iw = iw0 + sx;
+        float v = 0.0f;
+        if (pv && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
+          v = (float)__ldg(img + ((int64_t)ih * W + iw) * cin + ci) - zp_a;
+        s_patch[fp * KP + t] = v;
+      }
     }
     for (int i = threadIdx.x; i < STEMW_PIX * 32; i += blockDim.x) {
       const int pl = i >> 5, c = i & 31;
       s_dz[i] = (pl < np && c < cout) ? __ldg(dz + (pb + pl) * cout + c) : 0.0f;
     }
     __syncthreads();
-    for (int pl = 0; pl < np; ++pl) {
+#pragma unroll 4
+    for (int pl = 0; pl < STEMW_PIX; ++pl) {
       const float d = s_dz[pl * 32 + co];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         const int t = j + 8 * i;
-        if (t < KK) acc[i] = fmaf(d, s_patch[pl * KK + t], acc[i]);
+        if (t < KK) acc[i] = fmaf(d, s_patch[pl * KP + t], acc[i]);
       }
     }
     __syncthreads();
@@ -212,7 +224,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
   if (co < cout) {
     const float s_a = *x_scale_p;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 4; ++i) {
       const int t = j + 8 * i;
       if (t < KK) atomicAdd(dwq + (int64_t)co * KK + t, acc[i] * s_a);
     }
@@ -328,7 +340,7 @@ extern "C" int frost_pw_wgrad(const float* dz, const uint8_t* xq, const float* x
 extern "C" int frost_stem_wgrad(const float* dz, const uint8_t* xq, const float* x_scale, const int32_t* x_zp, int N,
                                 int H, int W, int cin, int cout, int k, int stride, int pad, float* dwq, void* stream) {
   FROST_REQUIRE(dz && xq && x_scale && x_zp && dwq, "frost_stem_wgrad: null pointer");
-  FROST_REQUIRE(cout > 0 && cout <= 32 && cin > 0 && k > 0 && k * k * cin <= 64, "frost_stem_wgrad: cout<=32, k*k*cin<=64");
+  FROST_REQUIRE(cout > 0 && cout <= 32 && cin > 0 && k > 0 && k * k * cin <= 32, "frost_stem_wgrad: cout<=32, k*k*cin<=32");
   cudaStream_t st = (cudaStream_t)stream;
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   const int KK = k * k * cin;
@@ -337,9 +349,9 @@ extern "C" int frost_stem_wgrad(const float* dz, const uint8_t* xq, const float*
     return FROST_ECUDA;
   }
   const int64_t total = (int64_t)N * Ho * Wo;
-  const int64_t nblk = std::min<int64_t>(ceil_div(total, STEMW_PIX), (int64_t)kNumSMs * 8);
+  const int64_t nblk = std::min<int64_t>(ceil_div(total, STEMW_PIX), (int64_t)kNumSMs * 6);
   const int64_t ppb = ceil_div(ceil_div(total, nblk), STEMW_PIX) * STEMW_PIX;
-  const size_t smem = sizeof(float) * (STEMW_PIX * KK + STEMW_PIX * 32);
+  const size_t smem = sizeof(float) * (STEMW_PIX * (KK | 1) + STEMW_PIX * 32);
   stem_wgrad_kernel<<<(unsigned)ceil_div(total, ppb), 256, smem, st>>>(dz, xq, x_scale, x_zp, N, H, W, cin, cout, k, stride,
                                                                       pad, Ho, Wo, ppb, dwq);
   FROST_LAUNCH_CHECK("stem_wgrad");

@@ -254,12 +254,14 @@ __global__ void __launch_bounds__(256, 2) dw_dgrad_kernel(const float* __restric
 
 // ================================================================= wgrad
 // dwq[r*KS+s][c] += s_a * sum_{n,oh,ow} dz[n][oh][ow][c] * (x[n][oh*S-PAD+r][ow*S-PAD+s][c] - zp_a)
-// One thread: one channel group, all KS*KS taps in registers, strips of 4 output pixels.
+// One thread: one channel group and ONE kernel row r (KS taps x 4 channels = 20 accumulators, so three
+// CTAs fit per SM), strips of 4 output pixels.  The KS threads that share a strip read the same dz words
+// (L1 hits); each reads its own input row.
 template <int KS, int S>
-__global__ void __launch_bounds__(256) dw_wgrad_kernel(const float* __restrict__ dz, const uint8_t* __restrict__ xq,
-                                                      const float* __restrict__ x_scale_p, const int32_t* __restrict__ x_zp_p,
-                                                      int N, int H, int W, int C, int Ho, int Wo, int cgb,
-                                                      float* __restrict__ dwq) {
+__global__ void __launch_bounds__(256, 3) dw_wgrad_kernel(const float* __restrict__ dz, const uint8_t* __restrict__ xq,
+                                                         const float* __restrict__ x_scale_p, const int32_t* __restrict__ x_zp_p,
+                                                         int N, int H, int W, int C, int Ho, int Wo, int cgb,
+                                                         float* __restrict__ dwq) {
   extern __shared__ __align__(16) unsigned char dw_smem[];
   float* s_acc = reinterpret_cast<float*>(dw_smem);  // [KS*KS][cgb*4]
   constexpr int PAD = (KS - 1) / 2;
@@ -268,14 +270,15 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const float* __restrict__
   const unsigned zp4 = (unsigned)zp_a * 0x01010101u;
   const float zpf = (float)zp_a;
   const int cg_local = threadIdx.x % cgb;
+  const int r = (threadIdx.x / cgb) % KS;
+  const int strip_local = threadIdx.x / (cgb * KS);
+  const int spb = blockDim.x / (cgb * KS);
   const int cg = blockIdx.y * cgb + cg_local;
-  const int spb = blockDim.x / cgb;
-  const int strip_local = threadIdx.x / cgb;
   for (int i = threadIdx.x; i < KS * KS * cgb * 4; i += blockDim.x) s_acc[i] = 0.0f;
   __syncthreads();
-  float acc[KS * KS][4];
+  float acc[KS][4];
 #pragma unroll
-  for (int t = 0; t < KS * KS; ++t)
+  for (int t = 0; t < KS; ++t)
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) acc[t][ch] = 0.0f;
   const int strips_w = (Wo + DW_TW - 1) / DW_TW;
@@ -286,44 +289,41 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const float* __restrict__
     const int oh = (int)(t1 % Ho);
     const int n = (int)(t1 / Ho);
     const int ow0 = sw * DW_TW;
-    float4 d[DW_TW];
+    const int ih = oh * S - PAD + r;
+    if ((unsigned)ih >= (unsigned)H) continue;       // this kernel row falls outside the image for this strip
     const float* drow = dz + (((int64_t)n * Ho + oh) * Wo) * C + cg * 4;
+    const uint8_t* row = xq + (((int64_t)n * H + ih) * W) * C + cg * 4;
+    float4 d[DW_TW];
+    unsigned xw[IW];
 #pragma unroll
     for (int t = 0; t < DW_TW; ++t)
       d[t] = (ow0 + t < Wo) ? __ldg(reinterpret_cast<const float4*>(drow + (int64_t)(ow0 + t) * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int r = 0; r < KS; ++r) {
-      const int ih = oh * S - PAD + r;
-      if ((unsigned)ih >= (unsigned)H) continue;
-      const uint8_t* row = xq + (((int64_t)n * H + ih) * W) * C + cg * 4;
-      unsigned xw[IW];
+    for (int j = 0; j < IW; ++j) {
+      const int iw = ow0 * S - PAD + j;
+      xw[j] = ((unsigned)iw < (unsigned)W) ? __ldg(reinterpret_cast<const unsigned*>(row + (int64_t)iw * C)) : zp4;
+    }
 #pragma unroll
-      for (int j = 0; j < IW; ++j) {
-        const int iw = ow0 * S - PAD + j;
-        xw[j] = ((unsigned)iw < (unsigned)W) ? __ldg(reinterpret_cast<const unsigned*>(row + (int64_t)iw * C)) : zp4;
-      }
+    for (int j = 0; j < IW; ++j) {
+      float xa[4];
 #pragma unroll
-      for (int j = 0; j < IW; ++j) {
-        float xa[4];
+      for (int ch = 0; ch < 4; ++ch) xa[ch] = (float)zext_byte(xw[j], ch) - zpf;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) xa[ch] = (float)zext_byte(xw[j], ch) - zpf;
-#pragma unroll
-        for (int t = 0; t < DW_TW; ++t) {
-          const int s = j - t * S;
-          if (s >= 0 && s < KS) {
-            acc[r * KS + s][0] = fmaf(d[t].x, xa[0], acc[r * KS + s][0]);
-            acc[r * KS + s][1] = fmaf(d[t].y, xa[1], acc[r * KS + s][1]);
-            acc[r * KS + s][2] = fmaf(d[t].z, xa[2], acc[r * KS + s][2]);
-            acc[r * KS + s][3] = fmaf(d[t].w, xa[3], acc[r * KS + s][3]);
-          }
+      for (int t = 0; t < DW_TW; ++t) {
+        const int s = j - t * S;
+        if (s >= 0 && s < KS) {
+          acc[s][0] = fmaf(d[t].x, xa[0], acc[s][0]);
+          acc[s][1] = fmaf(d[t].y, xa[1], acc[s][1]);
+          acc[s][2] = fmaf(d[t].z, xa[2], acc[s][2]);
+          acc[s][3] = fmaf(d[t].w, xa[3], acc[s][3]);
         }
       }
     }
   }
 #pragma unroll
-  for (int t = 0; t < KS * KS; ++t)
+  for (int t = 0; t < KS; ++t)
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) atomicAdd(&s_acc[(t * cgb + cg_local) * 4 + ch], acc[t][ch]);
+    for (int ch = 0; ch < 4; ++ch) atomicAdd(&s_acc[((r * KS + t) * cgb + cg_local) * 4 + ch], acc[t][ch]);
   __syncthreads();
   const float s_a = *x_scale_p;
   for (int i = threadIdx.x; i < KS * KS * cgb * 4; i += blockDim.x) {
@@ -400,11 +400,12 @@ extern "C" int frost_dw_wgrad(const float* dz, const uint8_t* xq, const float* x
     return FROST_ECUDA;
   }
   int cgb, chunks, threads;
-  dw_launch_shape(C, DW_MAX_CGB, &cgb, &chunks, &threads);
-  const int spb = threads / cgb;
+  dw_launch_shape(C, 256 / (k * 2) > 48 ? 48 : 256 / k, &cgb, &chunks, &threads);   // cgb * k <= 256
+  const int spb = 256 / (cgb * k);
+  threads = cgb * k * spb;
   const int64_t total_strips = (int64_t)N * Ho * ((Wo + DW_TW - 1) / DW_TW);
   // every thread should see >= 8 strips so that the final smem/global reduction is amortised
-  const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total_strips, (int64_t)spb * 8), (int64_t)kNumSMs * 4 / chunks + 1));
+  const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total_strips, (int64_t)spb * 8), (int64_t)kNumSMs * 6 / chunks + 1));
   dim3 grid(gx, chunks);
   const size_t smem = sizeof(float) * k * k * cgb * 4;
 #define L(KS, S) dw_wgrad_kernel<KS, S><<<grid, threads, smem, st>>>(dz, xq, x_scale, x_zp, N, H, W, C, Ho, Wo, cgb, dwq)
