@@ -70,33 +70,46 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(FrostBnFinalizeArgs a
 }
 
 // ---------------------------------------------------------------- apply: I -> uint8 index
-// 8 consecutive elements per thread-iteration (2x 16-byte loads, one 8-byte store).
-__global__ void __launch_bounds__(256) bnq_apply_kernel(const int32_t* __restrict__ acc, int64_t n8, int C,
+// 4 consecutive channels per thread-iteration (one 16-byte load, one 4-byte store; the per-channel affine
+// is read from shared memory as float4 - consecutive lanes hit consecutive banks), two iterations in flight.
+__device__ __forceinline__ unsigned bnq4(const int4 v, const float4 A, const float4 B, int relu, float inv, float zp) {
+  float r0 = bn_affine(v.x, A.x, B.x), r1 = bn_affine(v.y, A.y, B.y), r2 = bn_affine(v.z, A.z, B.z), r3 = bn_affine(v.w, A.w, B.w);
+  if (relu) { r0 = fmaxf(r0, 0.0f); r1 = fmaxf(r1, 0.0f); r2 = fmaxf(r2, 0.0f); r3 = fmaxf(r3, 0.0f); }
+  const unsigned q0 = (unsigned)fminf(fmaxf(fq_index(r0, inv, zp), 0.0f), 255.0f);
+  const unsigned q1 = (unsigned)fminf(fmaxf(fq_index(r1, inv, zp), 0.0f), 255.0f);
+  const unsigned q2 = (unsigned)fminf(fmaxf(fq_index(r2, inv, zp), 0.0f), 255.0f);
+  const unsigned q3 = (unsigned)fminf(fmaxf(fq_index(r3, inv, zp), 0.0f), 255.0f);
+  return q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+}
+
+__global__ void __launch_bounds__(256) bnq_apply_kernel(const int32_t* __restrict__ acc, int64_t n4, int C,
                                                        const float* __restrict__ A, const float* __restrict__ B,
                                                        int relu, const float* __restrict__ scale_p,
                                                        const int32_t* __restrict__ zp_p, uint8_t* __restrict__ q) {
-  extern __shared__ float s_ab[];  // A[C], B[C]
+  extern __shared__ __align__(16) float s_ab[];  // A[C], B[C]
   for (int c = threadIdx.x; c < C; c += blockDim.x) { s_ab[c] = A[c]; s_ab[C + c] = B[c]; }
   __syncthreads();
   const float s = *scale_p, zp = (float)*zp_p;
   const float inv = __fdiv_rn(1.0f, s);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
-    const int4 v0 = __ldg(reinterpret_cast<const int4*>(acc) + 2 * i);
-    const int4 v1 = __ldg(reinterpret_cast<const int4*>(acc) + 2 * i + 1);
-    const int I[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-    int c = (int)((i * 8) % C);
-    unsigned out[2] = {0u, 0u};
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float v = bn_affine(I[e], s_ab[c], s_ab[C + c]);
-      if (relu) v = fmaxf(v, 0.0f);
-      const float qc = fminf(fmaxf(fq_index(v, inv, zp), 0.0f), 255.0f);
-      out[e >> 2] |= ((unsigned)qc) << (8 * (e & 3));
-      if (++c == C) c = 0;
-    }
-    reinterpret_cast<uint2*>(q)[i] = make_uint2(out[0], out[1]);
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int C4 = C >> 2;
+  int cg = (int)(i0 % C4);                       // 4-channel group of this thread's element, no division in the loop
+  const int cstep = (int)(stride % C4);
+  const int4* in = reinterpret_cast<const int4*>(acc);
+  unsigned* out = reinterpret_cast<unsigned*>(q);
+  const float4* sA = reinterpret_cast<const float4*>(s_ab);
+  const float4* sB = reinterpret_cast<const float4*>(s_ab + C);
+  int64_t i = i0;
+  for (; i + stride < n4; i += 2 * stride) {
+    const int4 v0 = __ldg(in + i);
+    const int4 v1 = __ldg(in + i + stride);
+    int cg1 = cg + cstep; if (cg1 >= C4) cg1 -= C4;
+    out[i] = bnq4(v0, sA[cg], sB[cg], relu, inv, zp);
+    out[i + stride] = bnq4(v1, sA[cg1], sB[cg1], relu, inv, zp);
+    cg = cg1 + cstep; if (cg >= C4) cg -= C4;
   }
+  if (i < n4) out[i] = bnq4(__ldg(in + i), sA[cg], sB[cg], relu, inv, zp);
 }
 
 // ---------------------------------------------------------------- backward
@@ -109,7 +122,7 @@ __device__ __forceinline__ float bn_dv(float dy, int I, float A, float B, int re
   return pass ? dy : 0.0f;
 }
 
-// Per-channel S1 = sum dv, S2 = sum dv*I.  Thread -> fixed 4-channel group, strided rows.
+// Per-channel S1 = sum dv, S2 = sum dv*(I - mean_I).  Thread -> fixed 4-channel group, strided rows.
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(FrostBnBackwardArgs a, int cg_per_block) {
   extern __shared__ double s_sum[];  // [cg_per_block*4][2]
   const int C = a.C, CG = C >> 2;
@@ -124,8 +137,11 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(FrostBnBackwardArgs 
     const float4 A = __ldg(reinterpret_cast<const float4*>(a.A) + cg);
     const float4 B = __ldg(reinterpret_cast<const float4*>(a.B) + cg);
     double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(a.mean_I) + cg);
     const int64_t stride = (int64_t)gridDim.x * rows_per_block;
     constexpr int U = 4;   // rows in flight per thread: 8 independent 16-byte loads
+    int batches = 0;
+    float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
     for (int64_t m = (int64_t)blockIdx.x * rows_per_block + row_local; m < a.M; m += U * stride) {
       float4 dy[U];
       int4 I[U];
@@ -139,7 +155,6 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(FrostBnBackwardArgs 
           I[u] = __ldg(reinterpret_cast<const int4*>(a.acc + mm * C) + cg);
         }
       }
-      float p1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const float d0 = bn_dv(dy[u].x, I[u].x, A.x, B.x, a.relu, inv, zp);
@@ -147,14 +162,20 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(FrostBnBackwardArgs 
         const float d2 = bn_dv(dy[u].z, I[u].z, A.z, B.z, a.relu, inv, zp);
         const float d3 = bn_dv(dy[u].w, I[u].w, A.w, B.w, a.relu, inv, zp);
         p1[0] += d0; p1[1] += d1; p1[2] += d2; p1[3] += d3;
-        s2[0] += (double)d0 * (double)I[u].x;
-        s2[1] += (double)d1 * (double)I[u].y;
-        s2[2] += (double)d2 * (double)I[u].z;
-        s2[3] += (double)d3 * (double)I[u].w;
+        // centred: no cancellation between sum dv*I and mean*sum dv, so fp32 partial sums suffice
+        p2[0] = fmaf(d0, (float)I[u].x - mu.x, p2[0]);
+        p2[1] = fmaf(d1, (float)I[u].y - mu.y, p2[1]);
+        p2[2] = fmaf(d2, (float)I[u].z - mu.z, p2[2]);
+        p2[3] = fmaf(d3, (float)I[u].w - mu.w, p2[3]);
       }
+      if (++batches == 16) {      // flush the fp32 partials (<= 64 terms) into the fp64 accumulators
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) s1[ch] += (double)p1[ch];
+        for (int ch = 0; ch < 4; ++ch) { s1[ch] += (double)p1[ch]; s2[ch] += (double)p2[ch]; p1[ch] = 0.f; p2[ch] = 0.f; }
+        batches = 0;
+      }
     }
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) { s1[ch] += (double)p1[ch]; s2[ch] += (double)p2[ch]; }
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
       atomicAdd(&s_sum[(cg_local * 4 + ch) * 2], s1[ch]);
@@ -173,7 +194,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(FrostBnBackwardArgs 
 
 // Per-channel coefficients of  dz = c1*(dv - a0 - a1*(I - mean_I))  plus the BN parameter grads.
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(FrostBnBackwardArgs a, int64_t n4) {
-  extern __shared__ float s_c[];  // A,B,mean_I,c1,a0,a1 : 6*C
+  extern __shared__ __align__(16) float s_c[];  // A,B,mean_I,c1,a0,a1 : 6*C
   const int C = a.C;
   {
     // per-channel coefficients of dz = c1*(dv - a0 - a1*(I - mean_I)) from the reduced sums; every block
@@ -184,7 +205,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(FrostBnBackwardArgs a
       const double S1 = a.sums[2 * c], S2 = a.sums[2 * c + 1];
       const double k = (double)a.kfac[c];
       const float mean_I = a.mean_I[c];
-      const double T = k * (S2 - (double)mean_I * S1);      // sum dv*xhat
+      const double T = k * S2;                              // sum dv*xhat (S2 is already centred)
       const float A = a.A[c];
       s_c[c] = A;
       s_c[C + c] = a.B[c];
@@ -204,18 +225,25 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(FrostBnBackwardArgs a
   __syncthreads();
   const float inv = __fdiv_rn(1.0f, *a.out_scale), zp = (float)*a.out_zp;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int C4 = C >> 2;
+  int cg = (int)(i0 % C4);              // C % 4 == 0: a float4 never straddles a row
+  const int cstep = (int)(stride % C4);
+  const float4* s4 = reinterpret_cast<const float4*>(s_c);
+  for (int64_t i = i0; i < n4; i += stride) {
     const float4 dy = __ldg(reinterpret_cast<const float4*>(a.dy) + i);
     const int4 I4 = __ldg(reinterpret_cast<const int4*>(a.acc) + i);
-    const float dyv[4] = {dy.x, dy.y, dy.z, dy.w};
-    const int Iv[4] = {I4.x, I4.y, I4.z, I4.w};
+    const float4 cA = s4[cg], cB = s4[C4 + cg], cM = s4[2 * C4 + cg], c1 = s4[3 * C4 + cg], a0 = s4[4 * C4 + cg], a1 = s4[5 * C4 + cg];
+    cg += cstep;
+    if (cg >= C4) cg -= C4;
     float o[4];
-    const int c0 = (int)((i * 4) % C);  // C % 4 == 0: a float4 never straddles a row
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int c = c0 + e;
-      const float dv = bn_dv(dyv[e], Iv[e], s_c[c], s_c[C + c], a.relu, inv, zp);
-      o[e] = s_c[3 * C + c] * (dv - s_c[4 * C + c] - s_c[5 * C + c] * ((float)Iv[e] - s_c[2 * C + c]));
+    {
+      const float dv0 = bn_dv(dy.x, I4.x, cA.x, cB.x, a.relu, inv, zp), dv1 = bn_dv(dy.y, I4.y, cA.y, cB.y, a.relu, inv, zp);
+      const float dv2 = bn_dv(dy.z, I4.z, cA.z, cB.z, a.relu, inv, zp), dv3 = bn_dv(dy.w, I4.w, cA.w, cB.w, a.relu, inv, zp);
+      o[0] = c1.x * (dv0 - a0.x - a1.x * ((float)I4.x - cM.x));
+      o[1] = c1.y * (dv1 - a0.y - a1.y * ((float)I4.y - cM.y));
+      o[2] = c1.z * (dv2 - a0.z - a1.z * ((float)I4.z - cM.z));
+      o[3] = c1.w * (dv3 - a0.w - a1.w * ((float)I4.w - cM.w));
     }
     if (a.dz_format == 0) {
       reinterpret_cast<float4*>(a.dz)[i] = make_float4(o[0], o[1], o[2], o[3]);
@@ -256,10 +284,10 @@ extern "C" int frost_bn_finalize(const FrostBnFinalizeArgs* a, void* stream) {
 extern "C" int frost_bnq_apply(const int32_t* acc, int64_t M, int C, const float* A, const float* B, int relu,
                                const float* out_scale, const int32_t* out_zp, uint8_t* q, void* stream) {
   FROST_REQUIRE(acc && A && B && out_scale && out_zp && q, "frost_bnq_apply: null pointer");
-  FROST_REQUIRE(M > 0 && C > 0 && C % 8 == 0, "frost_bnq_apply: C=%d must be a positive multiple of 8", C);
-  const int64_t n8 = M * C / 8;
-  bnq_apply_kernel<<<grid_for(n8, 256 * 2), 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(acc, n8, C, A, B, relu,
-                                                                                              out_scale, out_zp, q);
+  FROST_REQUIRE(M > 0 && C > 0 && C % 4 == 0, "frost_bnq_apply: C=%d must be a positive multiple of 4", C);
+  const int64_t n4 = M * C / 4;
+  bnq_apply_kernel<<<grid_for(n4, 256 * 8, kNumSMs * 8), 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(acc, n4, C, A, B, relu,
+                                                                                                          out_scale, out_zp, q);
   FROST_LAUNCH_CHECK("bnq_apply");
   return FROST_OK;
 }
@@ -279,7 +307,7 @@ extern "C" int frost_bn_backward(const FrostBnBackwardArgs* a, void* stream) {
   int cgb, chunks, threads;
   dw_launch_shape(a->C, 256, &cgb, &chunks, &threads);
   const int rows_per_block = threads / cgb;
-  int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(a->M, (int64_t)rows_per_block * 8), (int64_t)kNumSMs * 8 / chunks));
+  int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(a->M, (int64_t)rows_per_block * 16), (int64_t)kNumSMs * 8 / chunks));
   bn_bwd_reduce_kernel<<<dim3(gx, chunks), threads, sizeof(double) * cgb * 8, st>>>(*a, cgb);
   FROST_LAUNCH_CHECK("bn_bwd_reduce");
   const int64_t n4 = a->M * a->C / 4;

@@ -183,7 +183,7 @@ int frost_bnq_apply(const int32_t* acc, int64_t M, int C, const float* A, const 
                     const float* out_scale, const int32_t* out_zp, uint8_t* q, void* stream);
 
 /* Backward of the same chain (SURVEY.md 8a'): dy = grad wrt the fake-quantised output.
- * reduce: S1_c = sum dv, S2_c = sum dv*I  with dv = dy*[0<=idx<=255]*[v>0]   (double[2*C], zeroed by callee)
+ * reduce: S1_c = sum dv, S2_c = sum dv*(I-mean_I)  with dv = dy*[0<=idx<=255]*[v>0]   (double[2*C], zeroed by callee)
  * apply : dz = grad wrt the real-valued conv output (what dgrad/wgrad consume), and
  *         dgamma_bn = sum dv*xhat, dbeta = S1, dsf_bn (see FrostWeightDesc). */
 typedef struct {
