@@ -138,7 +138,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "FrostNet-Large 1.0 QAT (StatAssist+GradBoost QSGD) 224x224 synthetic, CPU oracle, bs=%d sample" % sample_bs},
+            "config": {"workload": "FrostNet-Large 1.0 QAT (StatAssist+GradBoost QSGD) bs=256/GPU 224x224 synthetic ImageNet",
+                       "global_batch": 256 * max(1, args.gpus), "parallelism": "dp%d" % max(1, args.gpus),
+                       "reference_sample": "CPU path, bs=%d per step (bounded sample of the same workload)" % sample_bs},
             "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -192,6 +194,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     bs = args.batch
     torch.manual_seed(1882)
@@ -269,29 +273,30 @@ def run_b200(args):
     e2e_value = world * bs * K / (ms_e2e * 1e-3)
     clocks = sampler.stop() if sampler else None
 
-    # per-entry-point CUDA-event pass (rank 0): roofline of the dominant kernel
+    # per-entry-point CUDA-event pass: roofline of the dominant kernel.  Every rank runs the same steps (the
+    # gradient all-reduce inside backward is a collective); only rank 0 records events.
     roofline, breakdown = None, None
-    if rank == 0:
-        prof = {}
-        orig_call = L.call
+    pk = min(K, 5)
+    prof = {}
+    import frostnet_b200.engine as E
+    orig_call = L.call
 
-        def prof_call(name, *a):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            orig_call(name, *a)
-            e1.record()
-            prof.setdefault(name, []).append((e0, e1, algorithmic_cost(name, a)))
-        pk = min(K, 5)
-        import frostnet_b200.engine as E
-        import frostnet_b200.optimizer as OP
+    def prof_call(name, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_call(name, *a)
+        e1.record()
+        prof.setdefault(name, []).append((e0, e1, algorithmic_cost(name, a)))
+    if rank == 0:
         E.L.call = prof_call
-        try:
-            torch.cuda.synchronize()
-            for _ in range(pk):
-                step(x, y)
-            torch.cuda.synchronize()
-        finally:
-            E.L.call = orig_call
+    try:
+        torch.cuda.synchronize()
+        for _ in range(pk):
+            step(x, y)
+        torch.cuda.synchronize()
+    finally:
+        E.L.call = orig_call
+    if rank == 0:
         agg = {}
         for name, evs in prof.items():
             t = sum(a.elapsed_time(b) for a, b, _ in evs) / pk
