@@ -8,5 +8,6 @@ from .frostnet import FrostNet, CascadePreExBottleneck, ConvBNReLU, ConvBN
 from .qat import prepare_qat, patch_torch_quantization, FrostFakeQuantize
 from .optimizer import QSGD, QRMSprop, QAdam, QAdamW, get_optimizer
 from . import parallel
+from . import frostnet_features
 
 __version__ = "0.1.0"

@@ -34,13 +34,13 @@ class BnFinalizeArgs(C.Structure):
     _fields_ = [("stats", c_p), ("C", C.c_int32), ("count", C.c_int64), ("x_scale", c_p), ("w_scale", c_p),
                 ("sf", c_p), ("gamma", c_p), ("beta", c_p), ("running_mean", c_p), ("running_var", c_p),
                 ("num_batches_tracked", c_p), ("momentum", C.c_float), ("eps", C.c_float),
-                ("training", C.c_int32), ("relu", C.c_int32), ("observe", C.c_int32),
+                ("stats_format", C.c_int32), ("training", C.c_int32), ("relu", C.c_int32), ("observe", C.c_int32),
                 ("averaging_const", C.c_float), ("afq", FQ), ("A", c_p), ("B", c_p), ("mean_I", c_p),
                 ("kfac", c_p), ("cur_minmax", c_p)]
 
 
 class BnBackwardArgs(C.Structure):
-    _fields_ = [("dy", c_p), ("acc", c_p), ("M", C.c_int64), ("C", C.c_int32), ("relu", C.c_int32),
+    _fields_ = [("dy", c_p), ("acc", c_p), ("acc_format", C.c_int32), ("M", C.c_int64), ("C", C.c_int32), ("relu", C.c_int32),
                 ("A", c_p), ("B", c_p), ("mean_I", c_p), ("kfac", c_p), ("gamma", c_p), ("sf", c_p),
                 ("x_scale", c_p), ("w_scale", c_p), ("out_scale", c_p), ("out_zp", c_p), ("eps", C.c_float),
                 ("sums", c_p), ("coef", c_p), ("dz", c_p), ("dz_lo", c_p), ("dz_format", C.c_int32), ("dgamma_bn", c_p), ("dbeta", c_p), ("dsf_bn", c_p)]
@@ -80,6 +80,11 @@ i32, i64, f32 = C.c_int, C.c_int64, C.c_float
 # name -> argtypes ; every function returns int.  Mirrors include/frost_b200.h one to one.
 _SIGNATURES = {
     "frost_stats_reset": [c_p, i64, c_p],
+    "frost_stats_reset_f32": [c_p, i64, c_p],
+    "frost_stem_conv_forward_f32": [c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, i32, c_p, c_p, c_p],
+    "frost_stem_wgrad_f32": [c_p, c_p, i32, i32, i32, i32, i32, i32, i32, i32, c_p, c_p],
+    "frost_dequant_to_nchw": [c_p, c_p, c_p, i32, i32, i32, i32, c_p, c_p],
+    "frost_nchw_to_nhwc": [c_p, i32, i32, i32, i32, c_p, i32, c_p],
     "frost_fq_forward": [c_p, i64, FQ, i32, i32, i32, i32, f32, c_p, c_p, c_p, c_p, c_p],
     "frost_fq_backward": [c_p, c_p, i64, c_p, c_p],
     "frost_input_quant": [c_p, i32, i32, i32, i32, FQ, i32, f32, c_p, c_p, c_p, c_p],
@@ -90,7 +95,7 @@ _SIGNATURES = {
     "frost_dw_conv_forward": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, c_p, c_p, c_p],
     "frost_stem_conv_forward": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, i32, c_p, c_p, c_p],
     "frost_bn_finalize": [C.POINTER(BnFinalizeArgs), c_p],
-    "frost_bnq_apply": [c_p, i64, i32, c_p, c_p, i32, c_p, c_p, c_p, c_p],
+    "frost_bnq_apply": [c_p, i32, i64, i32, c_p, c_p, i32, c_p, c_p, c_p, c_p],
     "frost_bn_backward": [C.POINTER(BnBackwardArgs), c_p],
     "frost_cat_forward": [QTensor, QTensor, i64, FQ, i32, f32, c_p, c_p, c_p],
     "frost_cat_backward": [c_p, QTensor, QTensor, i64, c_p, c_p, c_p, c_p, i32, c_p],

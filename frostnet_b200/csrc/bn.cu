@@ -11,7 +11,9 @@ namespace frost {
 
 void dw_launch_shape(int C, int max_cgb, int* cg_per_block, int* nchunks, int* threads);
 
-__device__ __forceinline__ float bn_affine(int I, float A, float B) { return fmaf((float)I, A, B); }
+// raw conv output of one element as a float: int32 accumulator (format 0) or fp32 bits (format 1)
+__device__ __forceinline__ float acc_val(int raw, int fmt) { return fmt ? __int_as_float(raw) : (float)raw; }
+__device__ __forceinline__ float bn_affine(float I, float A, float B) { return fmaf(I, A, B); }
 
 // ---------------------------------------------------------------- finalize (1 CTA)
 __global__ void __launch_bounds__(1024) bn_finalize_kernel(FrostBnFinalizeArgs a) {
@@ -21,8 +23,9 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(FrostBnFinalizeArgs a
   float gmn = INFINITY, gmx = -INFINITY;
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
     const FrostChanStats st = a.stats[c];
-    const double sum = (double)st.sum;
-    const double sq = (double)st.sq_hi * 4294967296.0 + (double)st.sq_lo;
+    const double sum = a.stats_format ? __longlong_as_double(st.sum) : (double)st.sum;
+    const double sq = a.stats_format ? __longlong_as_double((long long)st.sq_lo)
+                                     : (double)st.sq_hi * 4294967296.0 + (double)st.sq_lo;
     const double mean_I = sum / M;
     double var_I = sq / M - mean_I * mean_I;
     if (var_I < 0.0) var_I = 0.0;
@@ -47,7 +50,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(FrostBnFinalizeArgs a
     a.mean_I[c] = (float)mean_I;
     a.kfac[c] = (float)(m_c * invstd);
     // v is monotone in I for fixed (A,B): the channel extrema of v sit at the integer extrema.
-    float v0 = bn_affine(st.min, A, B), v1 = bn_affine(st.max, A, B);
+    float v0 = bn_affine(acc_val(st.min, a.stats_format), A, B), v1 = bn_affine(acc_val(st.max, a.stats_format), A, B);
     if (a.relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
     gmn = fminf(gmn, fminf(v0, v1));
     gmx = fmaxf(gmx, fmaxf(v0, v1));
@@ -72,8 +75,9 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(FrostBnFinalizeArgs a
 // ---------------------------------------------------------------- apply: I -> uint8 index
 // 4 consecutive channels per thread-iteration (one 16-byte load, one 4-byte store; the per-channel affine
 // is read from shared memory as float4 - consecutive lanes hit consecutive banks), two iterations in flight.
-__device__ __forceinline__ unsigned bnq4(const int4 v, const float4 A, const float4 B, int relu, float inv, float zp) {
-  float r0 = bn_affine(v.x, A.x, B.x), r1 = bn_affine(v.y, A.y, B.y), r2 = bn_affine(v.z, A.z, B.z), r3 = bn_affine(v.w, A.w, B.w);
+__device__ __forceinline__ unsigned bnq4(const int4 v, int fmt, const float4 A, const float4 B, int relu, float inv, float zp) {
+  float r0 = bn_affine(acc_val(v.x, fmt), A.x, B.x), r1 = bn_affine(acc_val(v.y, fmt), A.y, B.y);
+  float r2 = bn_affine(acc_val(v.z, fmt), A.z, B.z), r3 = bn_affine(acc_val(v.w, fmt), A.w, B.w);
   if (relu) { r0 = fmaxf(r0, 0.0f); r1 = fmaxf(r1, 0.0f); r2 = fmaxf(r2, 0.0f); r3 = fmaxf(r3, 0.0f); }
   const unsigned q0 = (unsigned)fminf(fmaxf(fq_index(r0, inv, zp), 0.0f), 255.0f);
   const unsigned q1 = (unsigned)fminf(fmaxf(fq_index(r1, inv, zp), 0.0f), 255.0f);
@@ -82,7 +86,7 @@ __device__ __forceinline__ unsigned bnq4(const int4 v, const float4 A, const flo
   return q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
 }
 
-__global__ void __launch_bounds__(256) bnq_apply_kernel(const int32_t* __restrict__ acc, int64_t n4, int C,
+__global__ void __launch_bounds__(256) bnq_apply_kernel(const int32_t* __restrict__ acc, int fmt, int64_t n4, int C,
                                                        const float* __restrict__ A, const float* __restrict__ B,
                                                        int relu, const float* __restrict__ scale_p,
                                                        const int32_t* __restrict__ zp_p, uint8_t* __restrict__ q) {
@@ -105,16 +109,16 @@ __global__ void __launch_bounds__(256) bnq_apply_kernel(const int32_t* __restric
     const int4 v0 = __ldg(in + i);
     const int4 v1 = __ldg(in + i + stride);
     int cg1 = cg + cstep; if (cg1 >= C4) cg1 -= C4;
-    out[i] = bnq4(v0, sA[cg], sB[cg], relu, inv, zp);
-    out[i + stride] = bnq4(v1, sA[cg1], sB[cg1], relu, inv, zp);
+    out[i] = bnq4(v0, fmt, sA[cg], sB[cg], relu, inv, zp);
+    out[i + stride] = bnq4(v1, fmt, sA[cg1], sB[cg1], relu, inv, zp);
     cg = cg1 + cstep; if (cg >= C4) cg -= C4;
   }
-  if (i < n4) out[i] = bnq4(__ldg(in + i), sA[cg], sB[cg], relu, inv, zp);
+  if (i < n4) out[i] = bnq4(__ldg(in + i), fmt, sA[cg], sB[cg], relu, inv, zp);
 }
 
 // ---------------------------------------------------------------- backward
 // dv = dy * [0 <= idx <= 255] * [v > 0 if relu]
-__device__ __forceinline__ float bn_dv(float dy, int I, float A, float B, int relu, float inv, float zp) {
+__device__ __forceinline__ float bn_dv(float dy, float I, float A, float B, int relu, float inv, float zp) {
   const float v = bn_affine(I, A, B);
   const float r = relu ? fmaxf(v, 0.0f) : v;
   const float idx = fq_index(r, inv, zp);
@@ -157,16 +161,18 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(FrostBnBackwardArgs 
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const float d0 = bn_dv(dy[u].x, I[u].x, A.x, B.x, a.relu, inv, zp);
-        const float d1 = bn_dv(dy[u].y, I[u].y, A.y, B.y, a.relu, inv, zp);
-        const float d2 = bn_dv(dy[u].z, I[u].z, A.z, B.z, a.relu, inv, zp);
-        const float d3 = bn_dv(dy[u].w, I[u].w, A.w, B.w, a.relu, inv, zp);
+        const float i0 = acc_val(I[u].x, a.acc_format), i1 = acc_val(I[u].y, a.acc_format);
+        const float i2 = acc_val(I[u].z, a.acc_format), i3 = acc_val(I[u].w, a.acc_format);
+        const float d0 = bn_dv(dy[u].x, i0, A.x, B.x, a.relu, inv, zp);
+        const float d1 = bn_dv(dy[u].y, i1, A.y, B.y, a.relu, inv, zp);
+        const float d2 = bn_dv(dy[u].z, i2, A.z, B.z, a.relu, inv, zp);
+        const float d3 = bn_dv(dy[u].w, i3, A.w, B.w, a.relu, inv, zp);
         p1[0] += d0; p1[1] += d1; p1[2] += d2; p1[3] += d3;
         // centred: no cancellation between sum dv*I and mean*sum dv, so fp32 partial sums suffice
-        p2[0] = fmaf(d0, (float)I[u].x - mu.x, p2[0]);
-        p2[1] = fmaf(d1, (float)I[u].y - mu.y, p2[1]);
-        p2[2] = fmaf(d2, (float)I[u].z - mu.z, p2[2]);
-        p2[3] = fmaf(d3, (float)I[u].w - mu.w, p2[3]);
+        p2[0] = fmaf(d0, i0 - mu.x, p2[0]);
+        p2[1] = fmaf(d1, i1 - mu.y, p2[1]);
+        p2[2] = fmaf(d2, i2 - mu.z, p2[2]);
+        p2[3] = fmaf(d3, i3 - mu.w, p2[3]);
       }
       if (++batches == 16) {      // flush the fp32 partials (<= 64 terms) into the fp64 accumulators
 #pragma unroll
@@ -238,12 +244,14 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(FrostBnBackwardArgs a
     if (cg >= C4) cg -= C4;
     float o[4];
     {
-      const float dv0 = bn_dv(dy.x, I4.x, cA.x, cB.x, a.relu, inv, zp), dv1 = bn_dv(dy.y, I4.y, cA.y, cB.y, a.relu, inv, zp);
-      const float dv2 = bn_dv(dy.z, I4.z, cA.z, cB.z, a.relu, inv, zp), dv3 = bn_dv(dy.w, I4.w, cA.w, cB.w, a.relu, inv, zp);
-      o[0] = c1.x * (dv0 - a0.x - a1.x * ((float)I4.x - cM.x));
-      o[1] = c1.y * (dv1 - a0.y - a1.y * ((float)I4.y - cM.y));
-      o[2] = c1.z * (dv2 - a0.z - a1.z * ((float)I4.z - cM.z));
-      o[3] = c1.w * (dv3 - a0.w - a1.w * ((float)I4.w - cM.w));
+      const float i0 = acc_val(I4.x, a.acc_format), i1 = acc_val(I4.y, a.acc_format);
+      const float i2 = acc_val(I4.z, a.acc_format), i3 = acc_val(I4.w, a.acc_format);
+      const float dv0 = bn_dv(dy.x, i0, cA.x, cB.x, a.relu, inv, zp), dv1 = bn_dv(dy.y, i1, cA.y, cB.y, a.relu, inv, zp);
+      const float dv2 = bn_dv(dy.z, i2, cA.z, cB.z, a.relu, inv, zp), dv3 = bn_dv(dy.w, i3, cA.w, cB.w, a.relu, inv, zp);
+      o[0] = c1.x * (dv0 - a0.x - a1.x * (i0 - cM.x));
+      o[1] = c1.y * (dv1 - a0.y - a1.y * (i1 - cM.y));
+      o[2] = c1.z * (dv2 - a0.z - a1.z * (i2 - cM.z));
+      o[3] = c1.w * (dv3 - a0.w - a1.w * (i3 - cM.w));
     }
     if (a.dz_format == 0) {
       reinterpret_cast<float4*>(a.dz)[i] = make_float4(o[0], o[1], o[2], o[3]);
@@ -281,12 +289,12 @@ extern "C" int frost_bn_finalize(const FrostBnFinalizeArgs* a, void* stream) {
   return FROST_OK;
 }
 
-extern "C" int frost_bnq_apply(const int32_t* acc, int64_t M, int C, const float* A, const float* B, int relu,
+extern "C" int frost_bnq_apply(const int32_t* acc, int acc_format, int64_t M, int C, const float* A, const float* B, int relu,
                                const float* out_scale, const int32_t* out_zp, uint8_t* q, void* stream) {
   FROST_REQUIRE(acc && A && B && out_scale && out_zp && q, "frost_bnq_apply: null pointer");
   FROST_REQUIRE(M > 0 && C > 0 && C % 4 == 0, "frost_bnq_apply: C=%d must be a positive multiple of 4", C);
   const int64_t n4 = M * C / 4;
-  bnq_apply_kernel<<<grid_for(n4, 256 * 8, kNumSMs * 8), 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(acc, n4, C, A, B, relu,
+  bnq_apply_kernel<<<grid_for(n4, 256 * 8, kNumSMs * 8), 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(acc, acc_format, n4, C, A, B, relu,
                                                                                                           out_scale, out_zp, q);
   FROST_LAUNCH_CHECK("bnq_apply");
   return FROST_OK;

@@ -36,6 +36,15 @@ class _QT:
         return L.QTensor(self.q.data_ptr(), self.scale.data_ptr(), self.zp.data_ptr(), self.mm.data_ptr(), self.C)
 
 
+class _RawInput:
+    """fp32 NCHW image fed straight to the stem (feature backbone: no QuantStub); scale == 1."""
+    __slots__ = ("x", "N", "H", "W", "C", "scale")
+
+    def __init__(self, x, scale_one):
+        self.x, self.scale = x, scale_one
+        self.N, self.C, self.H, self.W = x.shape
+
+
 def _fq_struct(f):
     return L.FQ(f.activation_post_process.min_val.data_ptr(), f.activation_post_process.max_val.data_ptr(),
                 f.scale.data_ptr(), f.zero_point.data_ptr())
@@ -164,6 +173,7 @@ class QATEngine:
                 o += ly.cout
         self.n_stat_chan = tot_c
         self.scratch = torch.zeros(L.FQ_SCRATCH_FLOATS, dtype=torch.float32, device=dev)
+        self.one = torch.ones(1, dtype=torch.float32, device=dev)
         self._wdesc_dev = [self._build_wdesc(i) for i in range(2)]
         self._wchunks, self._n_wchunks = L.chunk_table([ly.wq.numel() for ly in self.layers], L.WEIGHT_CHUNK, dev)
         self._wbchunks, self._n_wbchunks = L.chunk_table([ly.cout for ly in self.layers], L.WEIGHT_BWD_CHANNELS, dev)
@@ -215,7 +225,12 @@ class QATEngine:
         M = N * Ho * Wo
         acc = torch.empty((M, ly.cout), dtype=torch.int32, device=dev)
         wzp = mod.weight_fake_quant.zero_point
-        if ly.kind == "pw":
+        raw = isinstance(xin, _RawInput)          # feature backbone stem: fp32 image, fp32 raw conv output
+        if raw:
+            L.call("frost_stats_reset_f32", ly.stats_ptr, ly.cout, st)
+            L.call("frost_stem_conv_forward_f32", xin.x.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(), N, xin.H, xin.W, xin.C,
+                   ly.cout, ly.kh, ly.stride, ly.pad, acc.data_ptr(), ly.stats_ptr, st)
+        elif ly.kind == "pw":
             if xin.C != ly.cin:
                 raise RuntimeError("%s: input has %d channels, expected %d" % (ly.name, xin.C, ly.cin))
             L.call("frost_pw_conv_forward", xin.q.data_ptr(), xin.zp.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(),
@@ -230,6 +245,7 @@ class QATEngine:
         bn = mod.bn
         a = L.BnFinalizeArgs()
         a.stats, a.C, a.count = ly.stats_ptr, ly.cout, M
+        a.stats_format = 1 if raw else 0
         a.x_scale, a.w_scale, a.sf = xin.scale.data_ptr(), mod.weight_fake_quant.scale.data_ptr(), ly.sf.data_ptr()
         a.gamma, a.beta = bn.weight.data_ptr(), bn.bias.data_ptr()
         a.running_mean, a.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
@@ -245,7 +261,7 @@ class QATEngine:
         a.cur_minmax = ly.mm.data_ptr()
         L.call("frost_bn_finalize", C.byref(a), st)
         q = torch.empty((M, ly.cout), dtype=torch.uint8, device=dev)
-        L.call("frost_bnq_apply", acc.data_ptr(), M, ly.cout, ly.A.data_ptr(), ly.B.data_ptr(), a.relu,
+        L.call("frost_bnq_apply", acc.data_ptr(), 1 if raw else 0, M, ly.cout, ly.A.data_ptr(), ly.B.data_ptr(), a.relu,
                afq.scale.data_ptr(), afq.zero_point.data_ptr(), q.data_ptr(), st)
         self._maybe_force(ly.name, q)
         out = _QT(q, N, Ho, Wo, ly.cout, afq.scale, afq.zero_point, ly.mm)
@@ -262,8 +278,6 @@ class QATEngine:
         training = m.training
         if x.device != dev:
             raise RuntimeError("frostnet_b200: input on %s, model on %s" % (x.device, dev))
-        if self.features:
-            raise NotImplementedError("frostnet_b200: the feature backbone's QAT path needs an fp32-input stem kernel")
         x = x.detach()
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
@@ -275,16 +289,20 @@ class QATEngine:
         L.call("frost_weight_prep_multi", self._wdesc_dev[0].data_ptr(), len(self.layers), self._wchunks.data_ptr(),
                self._n_wchunks, self._wscratch.data_ptr(), st)
         L.call("frost_stats_reset", self.stats.data_ptr(), self.n_stat_chan, st)
-        # QuantStub
-        qfq = m.quant.activation_post_process
-        xq = torch.empty((N, H, W, Cin), dtype=torch.uint8, device=dev)
-        mm_in = torch.empty(2, dtype=torch.float32, device=dev)
-        L.call("frost_input_quant", x.data_ptr(), N, Cin, H, W, _fq_struct(qfq), 1 if qfq._observe else 0,
-               Q.AVERAGING_CONSTANT, xq.data_ptr(), mm_in.data_ptr(), self.scratch.data_ptr(), st)
-        self._maybe_force("quant", xq)
-        t = _QT(xq, N, H, W, Cin, qfq.scale, qfq.zero_point, mm_in)
-        if self.record_taps:
-            self.last_taps["quant.q"] = xq
+        if self.features:
+            t = _RawInput(x, self.one)           # frostnet_features.py:342-343: conv1 sees the raw image
+        else:
+            # QuantStub
+            qfq = m.quant.activation_post_process
+            xq = torch.empty((N, H, W, Cin), dtype=torch.uint8, device=dev)
+            mm_in = torch.empty(2, dtype=torch.float32, device=dev)
+            L.call("frost_input_quant", x.data_ptr(), N, Cin, H, W, _fq_struct(qfq), 1 if qfq._observe else 0,
+                   Q.AVERAGING_CONSTANT, xq.data_ptr(), mm_in.data_ptr(), self.scratch.data_ptr(), st)
+            self._maybe_force("quant", xq)
+            t = _QT(xq, N, H, W, Cin, qfq.scale, qfq.zero_point, mm_in)
+            if self.record_taps:
+                self.last_taps["quant.q"] = xq
+        feats = []
         t = self._conv_bn(self.stem, t, training, st, saved)
         for b in self.blocks:
             blk = b["mod"]
@@ -327,6 +345,17 @@ class QATEngine:
                     self.last_taps[b["name"] + ".add_q"] = qa
                 o = s
             t = o
+            if self.features and b["stage_end"] and b["stage"] != 3:     # [x1, x2, x3, x5]
+                y = torch.empty((t.N, t.C, t.H, t.W), dtype=torch.float32, device=dev)
+                L.call("frost_dequant_to_nchw", t.q.data_ptr(), t.scale.data_ptr(), t.zp.data_ptr(), t.N, t.H, t.W, t.C,
+                       y.data_ptr(), st)
+                feats.append(y)
+                if saved is not None:
+                    saved.setdefault("taps", []).append((b["name"], t))
+        if self.features:
+            if saved is not None:
+                saved["N"] = N
+            return feats, saved
         t = self._conv_bn(self.last, t, training, st, saved)
         # head: avg-pool -> dropout -> classifier conv (+bias) -> FQ
         HW = t.H * t.W
@@ -388,7 +417,9 @@ class QATEngine:
             dz = torch.empty((M, ly.cout), dtype=torch.float32, device=dev)
             dz_lo = None
         a = L.BnBackwardArgs()
+        raw = isinstance(xin, _RawInput)
         a.dy, a.acc, a.M, a.C, a.relu = dy.data_ptr(), acc.data_ptr(), M, ly.cout, 1 if ly.relu else 0
+        a.acc_format = 1 if raw else 0
         a.A, a.B, a.mean_I, a.kfac = ly.A.data_ptr(), ly.B.data_ptr(), ly.mean_I.data_ptr(), ly.kfac.data_ptr()
         a.gamma, a.sf = mod.bn.weight.data_ptr(), ly.sf.data_ptr()
         a.x_scale, a.w_scale = xin.scale.data_ptr(), mod.weight_fake_quant.scale.data_ptr()
@@ -412,34 +443,55 @@ class QATEngine:
             if dx is not None:
                 L.call("frost_dw_dgrad", dz.data_ptr(), ly.wq.data_ptr(), wfq.scale.data_ptr(), wfq.zero_point.data_ptr(),
                        xin.N, xin.H, xin.W, xin.C, ly.kh, ly.stride, dx.data_ptr(), 1 if accumulate else 0, st)
+        elif raw:
+            L.call("frost_stem_wgrad_f32", dz.data_ptr(), xin.x.data_ptr(), xin.N, xin.H, xin.W, xin.C, ly.cout, ly.kh,
+                   ly.stride, ly.pad, ly.dwq.data_ptr(), st)
         else:
             L.call("frost_stem_wgrad", dz.data_ptr(), xin.q.data_ptr(), xin.scale.data_ptr(), xin.zp.data_ptr(), xin.N,
                    xin.H, xin.W, xin.C, ly.cout, ly.kh, ly.stride, ly.pad, ly.dwq.data_ptr(), st)
 
     def backward(self, saved, dlogits):
+        """dlogits: grad of the logits (classifier) or the list of 4 NCHW feature-map grads (feature backbone)."""
         dev, st = self.dev, L.stream()
         which = self._pick_gflat()
         gflat = self.gflat[which]
         gbase = gflat.data_ptr()
         f32 = dict(dtype=torch.float32, device=dev)
         N = saved["N"]
-        t_last, pooled, keep, keep_scale, lmask, HW = saved["head"]
-        cls, cmod = self.cls, self.cls.mod
-        dlogits = dlogits.contiguous().float()
-        dpre = torch.empty_like(dlogits)
-        L.call("frost_fq_backward", dlogits.data_ptr(), lmask.data_ptr(), dlogits.numel(), dpre.data_ptr(), st)
-        dpooled = torch.empty((N, cls.cin), **f32)
-        L.call("frost_linear_backward", dpre.data_ptr(), pooled.data_ptr(), cls.wq.data_ptr(),
-               cmod.weight_fake_quant.scale.data_ptr(), cmod.weight_fake_quant.zero_point.data_ptr(), N, cls.cin, cls.cout,
-               dpooled.data_ptr(), cls.dwq.data_ptr(), gbase + 4 * self.param_off[id(cmod.bias)], st)
-        dy = torch.empty((N * HW, t_last.C), **f32)
-        L.call("frost_pool_dropout_backward", dpooled.data_ptr(), N, HW, t_last.C, L.ptr(keep), keep_scale,
-               dy.data_ptr(), st)
-        xin_last = saved[self.last.name][0]
-        g = torch.empty((xin_last.M, xin_last.C), **f32)
-        self._conv_bn_bwd(self.last, dy, saved, gbase, g, False, st)
-        del dy
+        tap_grads = {}
+        if self.features:
+            for (name, qt), gr in zip(saved["taps"], dlogits):
+                if gr is not None:
+                    tap_grads[name] = (qt, gr.contiguous().float())
+            g = None
+        else:
+            t_last, pooled, keep, keep_scale, lmask, HW = saved["head"]
+            cls, cmod = self.cls, self.cls.mod
+            dlogits = dlogits.contiguous().float()
+            dpre = torch.empty_like(dlogits)
+            L.call("frost_fq_backward", dlogits.data_ptr(), lmask.data_ptr(), dlogits.numel(), dpre.data_ptr(), st)
+            dpooled = torch.empty((N, cls.cin), **f32)
+            L.call("frost_linear_backward", dpre.data_ptr(), pooled.data_ptr(), cls.wq.data_ptr(),
+                   cmod.weight_fake_quant.scale.data_ptr(), cmod.weight_fake_quant.zero_point.data_ptr(), N, cls.cin,
+                   cls.cout, dpooled.data_ptr(), cls.dwq.data_ptr(), gbase + 4 * self.param_off[id(cmod.bias)], st)
+            dy = torch.empty((N * HW, t_last.C), **f32)
+            L.call("frost_pool_dropout_backward", dpooled.data_ptr(), N, HW, t_last.C, L.ptr(keep), keep_scale,
+                   dy.data_ptr(), st)
+            xin_last = saved[self.last.name][0]
+            g = torch.empty((xin_last.M, xin_last.C), **f32)
+            self._conv_bn_bwd(self.last, dy, saved, gbase, g, False, st)
+            del dy
         for b in reversed(self.blocks):
+            if b["name"] in tap_grads:                 # a returned feature map: its NCHW grad joins the chain
+                qt, gr = tap_grads[b["name"]]
+                if g is None:
+                    g = torch.empty((qt.M, qt.C), **f32)
+                    L.call("frost_nchw_to_nhwc", gr.data_ptr(), qt.N, qt.C, qt.H, qt.W, g.data_ptr(), 0, st)
+                else:
+                    L.call("frost_nchw_to_nhwc", gr.data_ptr(), qt.N, qt.C, qt.H, qt.W, g.data_ptr(), 1, st)
+            if g is None:                              # no gradient reaches this block's output
+                xo = saved[b["reduce"].name][2] if not b["skip"] else saved[b["name"] + ".add"][2]
+                g = torch.zeros((xo.M, xo.C), **f32)
             dout = g                                   # grad wrt the block output
             conv2, reduce = b["conv2"], b["reduce"]
             xin = saved[b["name"] + ".in"]
@@ -499,20 +551,21 @@ class QATEngine:
             raise RuntimeError("frostnet_b200: the QAT path runs on a CUDA device (B200) only; got a CPU tensor")
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.params)
         if need_grad:
-            return _QATFunction.apply(self, x, *self.params)
-        logits, _ = self.forward(x, save=False)
-        return logits
+            out = _QATFunction.apply(self, x, *self.params)
+            return list(out) if self.features else out
+        out, _ = self.forward(x, save=False)
+        return out
 
 
 class _QATFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, x, *params):
-        logits, saved = engine.forward(x, save=True)
+        out, saved = engine.forward(x, save=True)
         ctx.engine, ctx.saved = engine, saved
-        return logits
+        return tuple(out) if engine.features else out
 
     @staticmethod
-    def backward(ctx, dlogits):
-        grads = ctx.engine.backward(ctx.saved, dlogits)
+    def backward(ctx, *douts):
+        grads = ctx.engine.backward(ctx.saved, list(douts) if ctx.engine.features else douts[0])
         ctx.saved = None
         return (None, None) + tuple(grads)

@@ -58,6 +58,10 @@ typedef struct {
 
 /* Reset `n` channel-stat records (sum=0, min=INT_MAX, max=INT_MIN). */
 int frost_stats_reset(FrostChanStats* stats, int64_t n, void* stream);
+/* Same record reused for a conv whose raw output is fp32 (the feature backbone's stem, which has no QuantStub
+ * in front of it - frostnet_features.py:342-343): sum / sq_lo hold doubles (sum z, sum z^2), min / max hold
+ * float bits.  Reset: sums 0, min +inf, max -inf. */
+int frost_stats_reset_f32(FrostChanStats* stats, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Generic per-tensor fake-quant on fp32 data (logits of classifier.2, unit tests).
@@ -167,6 +171,7 @@ typedef struct {
   float* running_var;
   int64_t* num_batches_tracked;
   float momentum, eps;
+  int32_t stats_format;        /* 0: integer statistics of int32 accumulators; 1: fp32 raw conv output (see above) */
   int32_t training;            /* 1: batch statistics + running-stat update; 0: running stats */
   int32_t relu;
   int32_t observe;
@@ -179,7 +184,8 @@ typedef struct {
   float* cur_minmax;           /* out [2] dequantised min/max of the produced tensor          */
 } FrostBnFinalizeArgs;
 int frost_bn_finalize(const FrostBnFinalizeArgs* a, void* stream);
-int frost_bnq_apply(const int32_t* acc, int64_t M, int C, const float* A, const float* B, int relu,
+/* acc_format: 0 = int32 accumulators, 1 = fp32 raw conv output (bit pattern in the same buffer). */
+int frost_bnq_apply(const int32_t* acc, int acc_format, int64_t M, int C, const float* A, const float* B, int relu,
                     const float* out_scale, const int32_t* out_zp, uint8_t* q, void* stream);
 
 /* Backward of the same chain (SURVEY.md 8a'): dy = grad wrt the fake-quantised output.
@@ -188,7 +194,8 @@ int frost_bnq_apply(const int32_t* acc, int64_t M, int C, const float* A, const 
  *         dgamma_bn = sum dv*xhat, dbeta = S1, dsf_bn (see FrostWeightDesc). */
 typedef struct {
   const float* dy;             /* [M][C] fp32                                                 */
-  const int32_t* acc;          /* [M][C] int32 I saved by the forward                         */
+  const int32_t* acc;          /* [M][C] int32 I saved by the forward (fp32 bits if acc_format 1) */
+  int32_t acc_format;
   int64_t M;
   int32_t C;
   int32_t relu;
@@ -282,6 +289,17 @@ int frost_dw_dgrad(const float* dz, const int8_t* wq, const float* w_scale, cons
 /* dwq[k*k][C] */
 int frost_dw_wgrad(const float* dz, const uint8_t* xq, const float* x_scale, const int32_t* x_zp,
                    int N, int H, int W, int C, int k, int stride, float* dwq, void* stream);
+/* Feature backbone (frostnet_features.py:342-352): the stem convolves the raw fp32 NCHW image with the
+ * fake-quantised weights: z[m][co] = sum x * (q_w - zp_w)   (conv == s_w * z), fp32 statistics. */
+int frost_stem_conv_forward_f32(const float* x_nchw, const int8_t* wq, const int32_t* w_zp, int N, int H, int W,
+                                int cin, int cout, int k, int stride, int pad, float* z, FrostChanStats* stats,
+                                void* stream);
+int frost_stem_wgrad_f32(const float* dz, const float* x_nchw, int N, int H, int W, int cin, int cout, int k,
+                         int stride, int pad, float* dwq, void* stream);
+/* feature taps: y_nchw = (q - zp) * s ; and the way back: g_nhwc (+)= transpose(g_nchw) */
+int frost_dequant_to_nchw(const uint8_t* q, const float* scale, const int32_t* zp, int N, int H, int W, int C,
+                          float* y_nchw, void* stream);
+int frost_nchw_to_nhwc(const float* g_nchw, int N, int C, int H, int W, float* g_nhwc, int accumulate, void* stream);
 /* dwq[cout][k][k][cin] (the stem has no dgrad: its input is the image) */
 int frost_stem_wgrad(const float* dz, const uint8_t* xq, const float* x_scale, const int32_t* x_zp,
                      int N, int H, int W, int cin, int cout, int k, int stride, int pad, float* dwq,

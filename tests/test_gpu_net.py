@@ -246,3 +246,49 @@ def test_cpu_input_fails_loudly():
     model = build_model_from_golden(g, torch.device("cuda:0"))
     with pytest.raises(RuntimeError):
         model(g["xs"][0])
+
+
+def test_feature_backbone_matches_reference_golden_and_oracle():
+    """frostnet_features.FrostNet after prepare: forward (4 NCHW maps) vs the golden file made by the REAL
+    reference, and forward + backward vs the oracle (teacher-forced), incl. the fp32-input stem."""
+    import frostnet_b200 as F
+    from frostnet_b200 import frostnet_features as FF
+    from oracle import frost_oracle as O
+    g = load_golden("features_small035.pt")
+    dev = torch.device("cuda:0")
+    model = FF.FrostNet(mode=g["mode"], width_mult=g["width_mult"], quantized=True)
+    model.train()
+    model.fuse_model()
+    F.prepare_qat(model)
+    model.load_state_dict(g["sd0"], strict=True)
+    model.to(dev)
+    onet = O.OracleNet(O.net_spec(g["mode"], g["width_mult"]), g["sd0"], features=True)
+    onet.record = True
+    x = g["x"]
+    ofeats = onet.forward(x, training=True)
+    for a, b in zip(ofeats, g["feats"]):
+        assert rel_l2(a.detach(), b) < 1e-2          # oracle here vs reference there (different CPUs)
+    gen = torch.Generator().manual_seed(3)
+    douts = [torch.randn(f.shape, generator=gen) for f in ofeats]
+    douts[1] = None                                      # an unused tap must be tolerated
+    sum((f * d).sum() for f, d in zip(ofeats, douts) if d is not None).backward()
+    eng = model._frost_engine
+    eng.force, eng.force_report = _force_dict(onet, dev), {}
+    feats = model(x.to(dev))
+    assert isinstance(feats, list) and len(feats) == 4
+    for f, of in zip(feats, ofeats):
+        assert f.shape == of.shape
+        assert rel_l2(f.detach().cpu(), of.detach()) < LOGIT_REL_L2
+    sum((f * d.to(dev)).sum() for f, d in zip(feats, douts) if d is not None).backward()
+    rep = eng.force_report
+    assert all(mx <= 1 and r <= max(LAYER_MISMATCH_RATE, 1.0 / 64) for r, mx in rep.values()), rep
+    e_grad, worst = _grad_rel_l2(model, onet)
+    print("features: grad rel-L2 %.3g (worst %s), max layer mismatch %.3g" % (e_grad, worst, max(r for r, _ in rep.values())))
+    assert e_grad < GRAD_REL_L2
+    _check_state(model, onet, [k for k in g["sd0"] if "running_" in k or k.endswith("min_val") or k.endswith("max_val")
+                               or k.endswith("scale") or k.endswith("zero_point")])
+    # eval / no-grad path
+    model.eval()
+    with torch.no_grad():
+        f2 = model(x.to(dev))
+    assert len(f2) == 4 and all(torch.isfinite(t).all() for t in f2)

@@ -359,7 +359,7 @@ def test_bn_finalize_apply_and_backward(M, Cc, relu, training):
     a.A, a.B, a.mean_I, a.kfac, a.cur_minmax = A.data_ptr(), B.data_ptr(), meanI.data_ptr(), kfac.data_ptr(), mm.data_ptr()
     L().call("frost_bn_finalize", C.byref(a), stream())
     q = torch.empty(M, Cc, dtype=torch.uint8, device=DEV)
-    L().call("frost_bnq_apply", Id.data_ptr(), M, Cc, A.data_ptr(), B.data_ptr(), int(relu), fq.scale.data_ptr(),
+    L().call("frost_bnq_apply", Id.data_ptr(), 0, M, Cc, A.data_ptr(), B.data_ptr(), int(relu), fq.scale.data_ptr(),
              fq.zp.data_ptr(), q.data_ptr(), stream())
     conv, g64, b64, v, r, y, rm64, rv64 = _bn_reference(I, gamma, beta, rm, rv, sf, s_a, s_w, relu, training, fq.oracle)
     # observer state: min/max of the pre-quant tensor agree to fp32 rounding; qparams follow

@@ -78,7 +78,7 @@ def test_large_structure_known_answers():
 
 def test_factories_and_errors():
     import frostnet_b200 as F
-    names = [n for n in dir(F) if n.startswith("frostnet_")]
+    names = [n for n in dir(F) if n.startswith("frostnet_") and n != "frostnet_features"]
     assert len(names) == 30
     assert sum(p.numel() for p in F.frostnet_small_1_0().parameters()) == 4858776
     assert sum(p.numel() for p in F.frostnet_base_1_0().parameters()) == 5001712
@@ -132,3 +132,27 @@ def test_optimizer_surface():
     p[0].grad = torch.ones(3)
     with pytest.raises(RuntimeError):
         opt.step()                                            # CPU tensors: no fallback
+
+
+def test_feature_backbone_surface_and_state_dict():
+    import frostnet_b200 as F
+    from frostnet_b200 import frostnet_features as FF
+    g = load_golden("features_small035.pt")
+    model = FF.FrostNet(mode=g["mode"], width_mult=g["width_mult"], quantized=True)
+    model.init_weights('')
+    feats = model(torch.randn(1, 3, 64, 64))
+    assert [tuple(f.shape[1:]) for f in feats] == [tuple(f.shape[1:]) for f in g["feats"]]
+    model.train()
+    model.fuse_model()
+    F.prepare_qat(model)
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(g["sd0"].keys())
+    for k, v in g["sd0"].items():
+        assert sd[k].dtype == v.dtype and sd[k].shape == v.shape, k
+    model.load_state_dict(g["sd0"], strict=True)
+    with pytest.raises(RuntimeError):
+        model(g["x"])                                   # prepared model on CPU tensors: no fallback
+    large = FF.FrostNet(mode="large", width_mult=1.0)
+    assert [f.shape[1] for f in large(torch.randn(1, 3, 64, 64))] == [24, 40, 96, 320]
+    with pytest.raises(ValueError):
+        FF.FrostNet(mode="tiny")

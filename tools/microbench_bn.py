@@ -40,7 +40,7 @@ for (M, Cc) in [(50176, 312), (12544, 1440), (200704, 168), (802816, 96), (32112
     b.dgamma_bn, b.dbeta, b.dsf_bn = o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr()
     t_bn = timeit(lambda: L.call("frost_bn_backward", C.byref(b), st))
     q = torch.empty(M, Cc, dtype=torch.uint8, device=dev)
-    t_q = timeit(lambda: L.call("frost_bnq_apply", acc.data_ptr(), M, Cc, A.data_ptr(), B.data_ptr(), 1, sc.data_ptr(), zp.data_ptr(), q.data_ptr(), st))
+    t_q = timeit(lambda: L.call("frost_bnq_apply", acc.data_ptr(), 0, M, Cc, A.data_ptr(), B.data_ptr(), 1, sc.data_ptr(), zp.data_ptr(), q.data_ptr(), st))
     t_copy = timeit(lambda: dz.copy_(dy))
     n = M * Cc
     print("M=%d C=%d  elems %.1fM | bn_backward %.1f us (%.0f GB/s of 20B/elt) | bnq %.1f us (%.0f GB/s of 5B/elt) | torch copy %.1f us (%.0f GB/s)" % (
