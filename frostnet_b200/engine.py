@@ -175,6 +175,7 @@ class QATEngine:
         self.scratch = torch.zeros(L.FQ_SCRATCH_FLOATS, dtype=torch.float32, device=dev)
         self.one = torch.ones(1, dtype=torch.float32, device=dev)
         self._wdesc_dev = [self._build_wdesc(i) for i in range(2)]
+        self._flag_epoch = Q.FrostFakeQuantize.flag_epoch
         self._wchunks, self._n_wchunks = L.chunk_table([ly.wq.numel() for ly in self.layers], L.WEIGHT_CHUNK, dev)
         self._wbchunks, self._n_wbchunks = L.chunk_table([ly.cout for ly in self.layers], L.WEIGHT_BWD_CHANNELS, dev)
         self._wscratch = torch.tensor([float("inf"), float("-inf")] * len(self.layers), dtype=torch.float32, device=dev)
@@ -209,9 +210,12 @@ class QATEngine:
         host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
         return host.to(self.dev)
 
-    def _observer_flags_changed(self):
-        # cheap re-encode when someone toggled observers (rare): rebuild descriptor tables
-        self._wdesc_dev = [self._build_wdesc(i) for i in range(2)]
+    def _refresh_flags(self):
+        # someone toggled an observer (torch.ao.quantization.disable_observer / load_state_dict): the weight
+        # descriptor tables carry the per-layer `observe` flag, re-encode them (rare)
+        if self._flag_epoch != Q.FrostFakeQuantize.flag_epoch:
+            self._wdesc_dev = [self._build_wdesc(i) for i in range(2)]
+            self._flag_epoch = Q.FrostFakeQuantize.flag_epoch
 
     # ------------------------------------------------------------------ forward pieces
     def _conv_bn(self, ly, xin, training, st, saved):
@@ -274,6 +278,7 @@ class QATEngine:
 
     def forward(self, x, save):
         self._ensure_built()
+        self._refresh_flags()
         m, dev, st = self.model, self.dev, L.stream()
         training = m.training
         if x.device != dev:

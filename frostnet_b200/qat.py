@@ -36,13 +36,20 @@ class FrostObserverState(nn.Module):
         self.averaging_constant = AVERAGING_CONSTANT
 
 
-class FrostFakeQuantize(nn.Module):
-    """State of one FusedMovingAvgObsFakeQuantize (per-tensor).  K1 in SURVEY.md 8c."""
+class FrostFakeQuantize(torch.ao.quantization.FakeQuantizeBase):
+    """State of one FusedMovingAvgObsFakeQuantize (per-tensor).  K1 in SURVEY.md 8c.
+
+    Derives from torch's FakeQuantizeBase so that ``model.apply(torch.ao.quantization.disable_observer)``
+    (Classification/train.py:27-33 defines exactly that helper) reaches it."""
+
+    flag_epoch = 0      # bumped whenever any instance toggles a flag; the engine re-encodes its tables
 
     def __init__(self, quant_min, quant_max, symmetric):
         super().__init__()
         self.quant_min, self.quant_max, self.is_symmetric_quant = quant_min, quant_max, symmetric
         self.activation_post_process = FrostObserverState()
+        # FusedMovingAvgObsFakeQuantize keeps these two as int64 (state_dict compatibility)
+        del self._buffers["fake_quant_enabled"], self._buffers["observer_enabled"]
         self.register_buffer("fake_quant_enabled", torch.tensor([1], dtype=torch.long))
         self.register_buffer("observer_enabled", torch.tensor([1], dtype=torch.long))
         self.register_buffer("scale", torch.tensor([1.0], dtype=torch.float))
@@ -63,6 +70,10 @@ class FrostFakeQuantize(nn.Module):
     def enable_observer(self, enabled=True):
         self._observe = bool(enabled)
         self.observer_enabled[0] = 1 if enabled else 0
+        FrostFakeQuantize.flag_epoch += 1
+
+    def calculate_qparams(self, **kwargs):
+        return self.scale, self.zero_point
 
     def disable_observer(self):
         self.enable_observer(False)
@@ -82,6 +93,7 @@ class FrostFakeQuantize(nn.Module):
         k = prefix + "observer_enabled"
         if k in state_dict:
             self._observe = bool(int(state_dict[k].reshape(-1)[0]))
+            FrostFakeQuantize.flag_epoch += 1
 
     def forward(self, x):
         raise RuntimeError("frostnet_b200: FrostFakeQuantize is state only; it runs inside the QAT engine")

@@ -156,3 +156,18 @@ def test_feature_backbone_surface_and_state_dict():
     assert [f.shape[1] for f in large(torch.randn(1, 3, 64, 64))] == [24, 40, 96, 320]
     with pytest.raises(ValueError):
         FF.FrostNet(mode="tiny")
+
+
+def test_observer_toggle_protocol():
+    """torch.ao.quantization.disable_observer / enable_observer reach the fake-quant state modules."""
+    import torch.ao.quantization as taq
+    from frostnet_b200 import qat
+    g = load_golden("net_small035.pt")
+    model = build_model_from_golden(g, torch.device("cpu"))
+    model.apply(taq.disable_observer)
+    fqs = [m for m in model.modules() if isinstance(m, qat.FrostFakeQuantize)]
+    assert fqs and all(not f._observe and int(f.observer_enabled) == 0 for f in fqs)
+    model.apply(taq.enable_observer)
+    assert all(f._observe and int(f.observer_enabled) == 1 for f in fqs)
+    with pytest.raises(RuntimeError):
+        model.apply(taq.disable_fake_quant)              # the engine computes on indices: cannot be disabled
