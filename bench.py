@@ -303,7 +303,8 @@ def run_b200(args):
             agg[name] = (t, sum(c[0] for _, _, c in evs) / pk, sum(c[1] for _, _, c in evs) / pk, len(evs) // pk)
         tot = sum(v[0] for v in agg.values())
         breakdown = {k: {"ms_per_step": round(v[0], 4), "share": round(v[0] / tot, 4), "calls_per_step": v[3]}
-                     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:8]}
+                     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:12]}
+        breakdown["all_entry_points_ms"] = round(tot, 3)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
