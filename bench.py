@@ -163,10 +163,11 @@ def algorithmic_cost(name, a):
     if name in ("frost_pw_wgrad", "frost_pw_wgrad_tc"):
         M, K, co = a[4], a[5], a[6]
         return 4 * M * co + M * K + 4 * co * K, 2 * M * K * co
-    if name == "frost_bn_backward":
+    if name in ("frost_bn_backward", "frost_bn_backward_reduce", "frost_bn_backward_apply"):
         args = getattr(a[0], "_obj", None)          # ctypes.byref(struct) keeps the struct in _obj
-        if args is not None:
-            return 20 * args.M * args.C, 0        # reduce: dy+I (8 B); apply: dy+I+dz (12 B)
+        if args is not None:                        # reduce: dy+I (8 B); apply: dy+I+dz (12 B)
+            per = {"frost_bn_backward": 20, "frost_bn_backward_reduce": 8, "frost_bn_backward_apply": 12}[name]
+            return per * args.M * args.C, 0
     if name == "frost_dw_conv_forward":
         N, H, W, Cc, k, s = a[4], a[5], a[6], a[7], a[8], a[9]
         Ho, Wo = (H + s - 1) // s, (W + s - 1) // s
@@ -325,6 +326,22 @@ def run_b200(args):
                 ach = byt / (t_ms * 1e-3) / 1e9
                 roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                             "frac": ach / hbm_peak, "traffic": None}
+            kernel_of = {"frost_bn_backward_apply": "bn_bwd_apply_kernel", "frost_bn_backward_reduce": "bn_bwd_reduce_kernel",
+                         "frost_pw_conv_forward": "pw_conv_fwd_tc_kernel", "frost_pw_wgrad_tc": "pw_wgrad_tc_kernel",
+                         "frost_pw_dgrad_tc": "pw_dgrad_tc_kernel", "frost_bnq_apply": "bnq_apply_kernel",
+                         "frost_dw_conv_forward": "dw_conv_fwd_kernel", "frost_dw_wgrad": "dw_wgrad_kernel",
+                         "frost_dw_dgrad": "dw_dgrad_kernel"}
+            roofline["cuda_kernel"] = kernel_of.get(top)
+            # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture, if there is one
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                ent = tr.get(roofline["cuda_kernel"])
+                if ent:
+                    roofline["traffic"] = ent["dram_bytes_per_launch"]
+                    roofline["traffic_source"] = ent["source"]
+            except Exception:
+                pass
+            roofline["algorithmic_bytes_per_launch"] = byt / max(calls, 1)
             roofline["peak_source"] = src
             roofline["launches_per_step"] = calls
             roofline["avg_launch_ms"] = t_ms / max(calls, 1)

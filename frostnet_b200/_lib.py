@@ -97,6 +97,8 @@ _SIGNATURES = {
     "frost_bn_finalize": [C.POINTER(BnFinalizeArgs), c_p],
     "frost_bnq_apply": [c_p, i32, i64, i32, c_p, c_p, i32, c_p, c_p, c_p, c_p],
     "frost_bn_backward": [C.POINTER(BnBackwardArgs), c_p],
+    "frost_bn_backward_reduce": [C.POINTER(BnBackwardArgs), c_p],
+    "frost_bn_backward_apply": [C.POINTER(BnBackwardArgs), c_p],
     "frost_cat_forward": [QTensor, QTensor, i64, FQ, i32, f32, c_p, c_p, c_p],
     "frost_cat_backward": [c_p, QTensor, QTensor, i64, c_p, c_p, c_p, c_p, i32, c_p],
     "frost_add_forward": [QTensor, QTensor, i64, FQ, i32, f32, c_p, c_p, c_p, c_p],

@@ -300,13 +300,20 @@ extern "C" int frost_bnq_apply(const int32_t* acc, int acc_format, int64_t M, in
   return FROST_OK;
 }
 
-extern "C" int frost_bn_backward(const FrostBnBackwardArgs* a, void* stream) {
+static int bn_backward_check(const FrostBnBackwardArgs* a) {
   FROST_REQUIRE(a && a->dy && a->acc && a->A && a->B && a->mean_I && a->kfac && a->gamma && a->sf && a->x_scale &&
                     a->w_scale && a->out_scale && a->out_zp && a->sums && a->coef && a->dz && a->dgamma_bn &&
                     a->dbeta && a->dsf_bn,
                 "frost_bn_backward: null pointer");
   FROST_REQUIRE(a->M > 0 && a->C > 0 && a->C % 4 == 0, "frost_bn_backward: C=%d must be a positive multiple of 4", a->C);
   FROST_REQUIRE(a->dz_format == 0 || (a->dz_format == 1 && a->dz_lo), "frost_bn_backward: dz_format 1 needs dz_lo");
+  FROST_REQUIRE(6 * (size_t)a->C * sizeof(float) <= 96 * 1024, "frost_bn_backward: C=%d too large for the coefficient tile", a->C);
+  return FROST_OK;
+}
+
+extern "C" int frost_bn_backward_reduce(const FrostBnBackwardArgs* a, void* stream) {
+  int rc = bn_backward_check(a);
+  if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(a->sums, 0, sizeof(double) * 2 * a->C, st) != cudaSuccess) {
     set_error("frost_bn_backward: memset failed");
@@ -318,10 +325,26 @@ extern "C" int frost_bn_backward(const FrostBnBackwardArgs* a, void* stream) {
   int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(a->M, (int64_t)rows_per_block * 16), (int64_t)kNumSMs * 8 / chunks));
   bn_bwd_reduce_kernel<<<dim3(gx, chunks), threads, sizeof(double) * cgb * 8, st>>>(*a, cgb);
   FROST_LAUNCH_CHECK("bn_bwd_reduce");
+  return FROST_OK;
+}
+
+extern "C" int frost_bn_backward_apply(const FrostBnBackwardArgs* a, void* stream) {
+  int rc = bn_backward_check(a);
+  if (rc) return rc;
   const int64_t n4 = a->M * a->C / 4;
   const size_t smem = 6 * (size_t)a->C * sizeof(float);
-  FROST_REQUIRE(smem <= 48 * 1024, "frost_bn_backward: C=%d too large for the coefficient tile", a->C);
-  bn_bwd_apply_kernel<<<grid_for(n4, 256 * 8, kNumSMs * 8), 256, smem, st>>>(*a, n4);
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    cudaFuncSetAttribute(bn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set = true;
+  }
+  bn_bwd_apply_kernel<<<grid_for(n4, 256 * 8, kNumSMs * 8), 256, smem, (cudaStream_t)stream>>>(*a, n4);
   FROST_LAUNCH_CHECK("bn_bwd_apply");
   return FROST_OK;
+}
+
+extern "C" int frost_bn_backward(const FrostBnBackwardArgs* a, void* stream) {
+  int rc = frost_bn_backward_reduce(a, stream);
+  if (rc) return rc;
+  return frost_bn_backward_apply(a, stream);
 }

@@ -434,7 +434,8 @@ class QATEngine:
         a.dz_lo, a.dz_format = L.ptr(dz_lo), 1 if tc_fmt else 0
         a.dgamma_bn, a.dsf_bn = ly.dgamma_bn.data_ptr(), ly.dsf_bn.data_ptr()
         a.dbeta = gbase + 4 * self.param_off[id(mod.bn.bias)]
-        L.call("frost_bn_backward", C.byref(a), st)
+        L.call("frost_bn_backward_reduce", C.byref(a), st)
+        L.call("frost_bn_backward_apply", C.byref(a), st)
         wfq = mod.weight_fake_quant
         if ly.kind == "pw":
             L.call("frost_pw_wgrad_tc", dz.data_ptr(), dz_lo.data_ptr(), xin.q.data_ptr(), xin.scale.data_ptr(),

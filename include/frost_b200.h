@@ -219,7 +219,9 @@ typedef struct {
   float* dbeta;                /* out [C]                                                     */
   float* dsf_bn;               /* out [C]                                                     */
 } FrostBnBackwardArgs;
-int frost_bn_backward(const FrostBnBackwardArgs* a, void* stream);
+int frost_bn_backward(const FrostBnBackwardArgs* a, void* stream);          /* reduce, then apply */
+int frost_bn_backward_reduce(const FrostBnBackwardArgs* a, void* stream);   /* pass 1: the two per-channel sums */
+int frost_bn_backward_apply(const FrostBnBackwardArgs* a, void* stream);    /* pass 2: dz + BN parameter grads  */
 
 /* ---------------------------------------------------------------------------------------------
  * FloatFunctional.cat / .add (frostnet.py:129,142;
