@@ -303,7 +303,9 @@ def run_b200(args):
             t = sum(a.elapsed_time(b) for a, b, _ in evs) / pk
             agg[name] = (t, sum(c[0] for _, _, c in evs) / pk, sum(c[1] for _, _, c in evs) / pk, len(evs) // pk)
         tot = sum(v[0] for v in agg.values())
-        breakdown = {k: {"ms_per_step": round(v[0], 4), "share": round(v[0] / tot, 4), "calls_per_step": v[3]}
+        breakdown = {k: {"ms_per_step": round(v[0], 4), "share": round(v[0] / tot, 4), "calls_per_step": v[3],
+                         "algorithmic_GBps": round(v[1] / (v[0] * 1e-3) / 1e9, 1) if v[1] else None,
+                         "algorithmic_TFLOPps": round(v[2] / (v[0] * 1e-3) / 1e12, 2) if v[2] else None}
                      for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:12]}
         breakdown["all_entry_points_ms"] = round(tot, 3)
         peaks = {}
