@@ -8,6 +8,7 @@ from .frostnet import FrostNet, CascadePreExBottleneck, ConvBNReLU, ConvBN
 from .qat import prepare_qat, patch_torch_quantization, FrostFakeQuantize
 from .optimizer import QSGD, QRMSprop, QAdam, QAdamW, get_optimizer
 from . import parallel
+from .prefetch import DevicePrefetcher
 from . import frostnet_features
 
 __version__ = "0.1.0"

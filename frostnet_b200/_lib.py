@@ -116,6 +116,8 @@ _SIGNATURES = {
     "frost_dw_wgrad": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, c_p, c_p],
     "frost_stem_wgrad": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, i32, c_p, c_p],
     "frost_gradboost_multi": [c_p, i32, c_p, i32, C.POINTER(OptHyper), c_p],
+    "frost_set_tunable": [i32, i32],
+    "frost_get_tunable": [i32],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["frost_abi_version", "frost_last_error", "frost_launch_count"])
 

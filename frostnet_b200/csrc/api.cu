@@ -15,7 +15,30 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// launch-shape knobs (FROST_TUNE_*): defaults are the values measured best on B200 (tools/microbench_ops.py)
+static std::atomic<int> g_tune[FROST_TUNE_COUNT] = {};
+static const int g_tune_default[FROST_TUNE_COUNT] = {
+    /* DW_FWD_CTAS_PER_SM */ 2, /* DW_WGRAD_CTAS_PER_SM */ 3, /* BN_RED_CTAS_PER_SM */ 3, /* BN_RED_MAX_CGB */ 16,
+    /* STEM_FWD_CTAS_PER_SM */ 2, /* STEM_WGRAD_CTAS_PER_SM */ 4, /* DW_DGRAD_CTAS_PER_SM */ 16};
+int tunable(int which) {
+  const int v = g_tune[which].load(std::memory_order_relaxed);
+  return v > 0 ? v : g_tune_default[which];
+}
 }  // namespace frost
+
+extern "C" int frost_set_tunable(int which, int value) {
+  if (which < 0 || which >= FROST_TUNE_COUNT || value < 0) {
+    frost::set_error("frost_set_tunable: unknown knob %d or negative value %d", which, value);
+    return FROST_EINVAL;
+  }
+  frost::g_tune[which].store(value, std::memory_order_relaxed);
+  return FROST_OK;
+}
+extern "C" int frost_get_tunable(int which) {
+  if (which < 0 || which >= FROST_TUNE_COUNT) return FROST_EINVAL;
+  return frost::tunable(which);
+}
 
 extern "C" int frost_abi_version(void) { return 1; }
 extern "C" const char* frost_last_error(void) { return frost::g_err; }

@@ -127,20 +127,26 @@ __device__ __forceinline__ float bn_dv(float dy, float I, float A, float B, int 
 }
 
 // Per-channel S1 = sum dv, S2 = sum dv*(I - mean_I).  Thread -> fixed 4-channel group, strided rows.
+// A CTA owns a narrow slice of channels (cg_per_block <= 16 groups: 256-byte row segments) and many rows, so
+// that few CTAs contribute to any one channel: the partials are combined through shared memory (no atomics)
+// and each CTA issues ONE fp64 atomic per (channel, sum) - same-sector L2 atomics serialise (~12 ns each), and
+// with all-channel CTAs that tail was longer than the streaming pass for most layers.
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(FrostBnBackwardArgs a, int cg_per_block) {
-  extern __shared__ double s_sum[];  // [cg_per_block*4][2]
-  const int C = a.C, CG = C >> 2;
+  extern __shared__ double s_part[];  // [rows_per_block][cg_per_block][4 channels][2 sums]
+  const int C = a.C;
   const int cg_local = threadIdx.x % cg_per_block;
   const int cg = blockIdx.y * cg_per_block + cg_local;
   const int rows_per_block = blockDim.x / cg_per_block;
   const int row_local = threadIdx.x / cg_per_block;
-  for (int i = threadIdx.x; i < cg_per_block * 8; i += blockDim.x) s_sum[i] = 0.0;
-  __syncthreads();
-  if (cg < CG) {
+  // this thread's fp64 accumulators live in its own shared-memory slot [row_local][cg_local*8 + 2*ch + {0,1}]
+  // (column t of the CTA's slice is the global sum index blockIdx.y*cg_per_block*8 + t; sums is [C][2])
+  double* mine = s_part + ((size_t)row_local * cg_per_block + cg_local) * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mine[j] = 0.0;
+  {
     const float inv = __fdiv_rn(1.0f, *a.out_scale), zp = (float)*a.out_zp;
     const float4 A = __ldg(reinterpret_cast<const float4*>(a.A) + cg);
     const float4 B = __ldg(reinterpret_cast<const float4*>(a.B) + cg);
-    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
     const float4 mu = __ldg(reinterpret_cast<const float4*>(a.mean_I) + cg);
     const int64_t stride = (int64_t)gridDim.x * rows_per_block;
     constexpr int U = 4;   // rows in flight per thread: 8 independent 16-byte loads
@@ -176,25 +182,19 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(FrostBnBackwardArgs 
       }
       if (++batches == 16) {      // flush the fp32 partials (<= 64 terms) into the fp64 accumulators
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) { s1[ch] += (double)p1[ch]; s2[ch] += (double)p2[ch]; p1[ch] = 0.f; p2[ch] = 0.f; }
+        for (int ch = 0; ch < 4; ++ch) { mine[2 * ch] += (double)p1[ch]; mine[2 * ch + 1] += (double)p2[ch]; p1[ch] = 0.f; p2[ch] = 0.f; }
         batches = 0;
       }
     }
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) { s1[ch] += (double)p1[ch]; s2[ch] += (double)p2[ch]; }
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      atomicAdd(&s_sum[(cg_local * 4 + ch) * 2], s1[ch]);
-      atomicAdd(&s_sum[(cg_local * 4 + ch) * 2 + 1], s2[ch]);
-    }
+    for (int ch = 0; ch < 4; ++ch) { mine[2 * ch] += (double)p1[ch]; mine[2 * ch + 1] += (double)p2[ch]; }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < cg_per_block * 4; i += blockDim.x) {
-    const int c = blockIdx.y * cg_per_block * 4 + i;
-    if (c < C) {
-      atomicAdd(a.sums + 2 * c, s_sum[2 * i]);
-      atomicAdd(a.sums + 2 * c + 1, s_sum[2 * i + 1]);
-    }
+  const int cols = cg_per_block * 8;
+  for (int t = threadIdx.x; t < cols; t += blockDim.x) {
+    double tot = 0.0;
+    for (int r = 0; r < rows_per_block; ++r) tot += s_part[(size_t)r * cols + t];
+    atomicAdd(a.sums + (size_t)blockIdx.y * cols + t, tot);
   }
 }
 
@@ -320,10 +320,11 @@ extern "C" int frost_bn_backward_reduce(const FrostBnBackwardArgs* a, void* stre
     return FROST_ECUDA;
   }
   int cgb, chunks, threads;
-  dw_launch_shape(a->C, 256, &cgb, &chunks, &threads);
+  dw_launch_shape(a->C, std::min(64, tunable(FROST_TUNE_BN_RED_MAX_CGB)), &cgb, &chunks, &threads);
   const int rows_per_block = threads / cgb;
-  int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(a->M, (int64_t)rows_per_block * 16), (int64_t)kNumSMs * 8 / chunks));
-  bn_bwd_reduce_kernel<<<dim3(gx, chunks), threads, sizeof(double) * cgb * 8, st>>>(*a, cgb);
+  const int64_t wave = std::max<int64_t>(1, (int64_t)kNumSMs * tunable(FROST_TUNE_BN_RED_CTAS_PER_SM) / chunks);
+  int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(a->M, (int64_t)rows_per_block * 8), wave));
+  bn_bwd_reduce_kernel<<<dim3(gx, chunks), threads, sizeof(double) * threads * 8, st>>>(*a, cgb);
   FROST_LAUNCH_CHECK("bn_bwd_reduce");
   return FROST_OK;
 }

@@ -14,6 +14,7 @@ namespace frost {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+int tunable(int which);  // FROST_TUNE_* launch-shape knob (api.cu)
 
 #define FROST_REQUIRE(cond, ...)            \
   do {                                      \
@@ -74,6 +75,22 @@ __device__ __forceinline__ void atomic_min_float(float* addr, float v) {
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
   else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+// One CTA's contribution to a channel's integer statistics.  Hundreds of CTAs hit the same 32-byte record at
+// the end of a kernel and same-sector atomics serialise in L2 (measured ~12 ns each), so the min/max atomics
+// are skipped when a (possibly stale, hence only ever too large / too small) read shows they cannot win.
+__device__ __forceinline__ void chan_stats_flush(FrostChanStats* g, long long sum, unsigned long long sq, int mn, int mx) {
+  if (mn > mx) return;  // nothing accumulated
+  atomicAdd(reinterpret_cast<unsigned long long*>(&g->sum), (unsigned long long)sum);
+  if (sq >> 32) {
+    atomicAdd(&g->sq_lo, sq & 0xffffffffull);
+    atomicAdd(&g->sq_hi, sq >> 32);
+  } else {
+    atomicAdd(&g->sq_lo, sq);
+  }
+  if (mn < __ldcg(&g->min)) atomicMin(&g->min, mn);
+  if (mx > __ldcg(&g->max)) atomicMax(&g->max, mx);
 }
 
 // ---------------------------------------------------------------- quantisation parameters

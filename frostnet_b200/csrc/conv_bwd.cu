@@ -159,50 +159,55 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__
 
 // ---------------------------------------------------------------- stem wgrad
 // dwq[co][r][s][ci] += s_a * sum_pix dz[pix][co] * (x[patch(pix)][r][s][ci] - zp_a)
-// Batches of 64 pixels: the (pixel, tap) patch values and the dz rows are staged in shared memory by
-// threads that keep their pixel coordinates in registers (one div/mod per pixel, not per element);
-// thread (co, tap-group) then accumulates its <= 4 taps over the batch.
+// Batches of 64 pixels: the (pixel, tap) patch values and the dz rows are staged in shared memory (pitch 32,
+// taps >= k*k*cin stay zero).  Compute role: thread = (4 couts, 4 taps, pixel subset of 4): two 16-byte
+// shared loads feed 16 FMAs (the previous one-cout thread needed 5 loads per 4 FMAs and was LDS-bound).
+// The four pixel subsets are summed through shared memory, then one scalar atomic per (co, tap) per CTA;
+// the grid is one resident wave (frost::tunable).
 constexpr int STEMW_PIX = 64;
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ dz, const uint8_t* __restrict__ xq,
                                                         const float* __restrict__ x_scale_p, const int32_t* __restrict__ x_zp_p,
                                                         int N, int H, int W, int cin, int cout, int k, int stride, int pad,
                                                         int Ho, int Wo, int64_t pix_per_block, float* __restrict__ dwq) {
-  extern __shared__ float s_buf[];
+  constexpr int PP = 36;                       // patch pitch: 16-byte aligned rows, fill stores spread over banks
+  __shared__ __align__(16) float s_buf[STEMW_PIX * PP + STEMW_PIX * 32];
   const int KK = k * k * cin;
-  const int KP = KK | 1;                       // odd pitch: conflict-free column reads
-  float* s_patch = s_buf;                      // [STEMW_PIX][KP]
-  float* s_dz = s_buf + STEMW_PIX * KP;        // [STEMW_PIX][32]
-  const int co = threadIdx.x & 31, j = threadIdx.x >> 5;  // 8 tap groups
+  float* s_patch = s_buf;                      // [STEMW_PIX][PP]
+  float* s_dz = s_buf + STEMW_PIX * PP;        // [STEMW_PIX][32]
+  const int co4 = threadIdx.x & 7, tg = (threadIdx.x >> 3) & 7, psub = threadIdx.x >> 6;
   const float zp_a = (float)*x_zp_p;
   const int64_t total = (int64_t)N * Ho * Wo;
   const int64_t p_begin = (int64_t)blockIdx.x * pix_per_block;
   const int64_t p_end = min(total, p_begin + pix_per_block);
-  // fill role: 4 threads per pixel, each takes taps f, f+4, ...
+  // fill role: 4 threads per pixel, each takes kernel positions (r, s) = ff, ff+4, ... with all input channels
   const int fp = threadIdx.x >> 2, ff = threadIdx.x & 3;
-  float acc[8];
+  for (int i = threadIdx.x; i < STEMW_PIX * PP; i += blockDim.x) s_patch[i] = 0.0f;
+  float acc[4][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  __syncthreads();
   for (int64_t pb = p_begin; pb < p_end; pb += STEMW_PIX) {
     const int np = (int)min((int64_t)STEMW_PIX, p_end - pb);
     {
-      const int64_t p = pb + fp;
       const bool pv = fp < np;
       int ow = 0, oh = 0, n = 0;
       if (pv) {
-        ow = (int)(p % Wo);
-        const int64_t t1 = p / Wo;
-        oh = (int)(t1 % Ho);
-        n = (int)(t1 / Ho);
+        const unsigned p = (unsigned)(pb + fp);          // total < 2^31 (checked on the host)
+        ow = (int)(p % (unsigned)Wo);
+        const unsigned t1 = p / (unsigned)Wo;
+        oh = (int)(t1 % (unsigned)Ho);
+        n = (int)(t1 / (unsigned)Ho);
       }
       const int ih0 = oh * stride - pad, iw0 = ow * stride - pad;
       const uint8_t* img = xq + (int64_t)n * H * W * cin;
-      for (int t = ff; t < KK; t += 4) {
-        const int ci = t % cin, rs = t / cin, r = rs / k, sx = rs - r * k;
+      for (int rs = ff; rs < k * k; rs += 4) {
+        const int r = rs / k, sx = rs - r * k;
         const int ih = ih0 + r, iw = iw0 + sx;
-        float v = 0.0f;
-        if (pv && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
-          v = (float)__ldg(img + ((int64_t)ih * W + iw) * cin + ci) - zp_a;
-        s_patch[fp * KP + t] = v;
+        const bool ok = pv && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W;
+        const uint8_t* px = img + ((int64_t)ih * W + iw) * cin;
+        for (int ci = 0; ci < cin; ++ci) s_patch[fp * PP + rs * cin + ci] = ok ? (float)__ldg(px + ci) - zp_a : 0.0f;
       }
     }
     for (int i = threadIdx.x; i < STEMW_PIX * 32; i += blockDim.x) {
@@ -211,22 +216,29 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
     }
     __syncthreads();
 #pragma unroll 4
-    for (int pl = 0; pl < STEMW_PIX; ++pl) {
-      const float d = s_dz[pl * 32 + co];
+    for (int pl = psub; pl < STEMW_PIX; pl += 4) {
+      const float4 d = *reinterpret_cast<const float4*>(s_dz + pl * 32 + 4 * co4);
+      const float4 x = *reinterpret_cast<const float4*>(s_patch + pl * PP + 4 * tg);
+      const float dv[4] = {d.x, d.y, d.z, d.w}, xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int t = j + 8 * i;
-        if (t < KK) acc[i] = fmaf(d, s_patch[pl * KP + t], acc[i]);
-      }
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], dv[j], acc[i][j]);
     }
     __syncthreads();
   }
-  if (co < cout) {
-    const float s_a = *x_scale_p;
+  // combine the 4 pixel subsets: s_buf reused as [psub][tap 32][co 32]
+  float* s_red = s_buf;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int t = j + 8 * i;
-      if (t < KK) atomicAdd(dwq + (int64_t)co * KK + t, acc[i] * s_a);
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(s_red + (psub * 32 + 4 * tg + i) * 32 + 4 * co4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  __syncthreads();
+  const float s_a = *x_scale_p;
+  for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+    const int t = i >> 5, co = i & 31;
+    if (t < KK && co < cout) {
+      const float v = s_red[i] + s_red[1024 + i] + s_red[2048 + i] + s_red[3072 + i];
+      atomicAdd(dwq + (int64_t)co * KK + t, v * s_a);
     }
   }
 }
@@ -349,10 +361,10 @@ extern "C" int frost_stem_wgrad(const float* dz, const uint8_t* xq, const float*
     return FROST_ECUDA;
   }
   const int64_t total = (int64_t)N * Ho * Wo;
-  const int64_t nblk = std::min<int64_t>(ceil_div(total, STEMW_PIX), (int64_t)kNumSMs * 6);
+  const int64_t nblk = std::min<int64_t>(ceil_div(total, STEMW_PIX), (int64_t)kNumSMs * tunable(FROST_TUNE_STEM_WGRAD_CTAS_PER_SM));
   const int64_t ppb = ceil_div(ceil_div(total, nblk), STEMW_PIX) * STEMW_PIX;
-  const size_t smem = sizeof(float) * (STEMW_PIX * (KK | 1) + STEMW_PIX * 32);
-  stem_wgrad_kernel<<<(unsigned)ceil_div(total, ppb), 256, smem, st>>>(dz, xq, x_scale, x_zp, N, H, W, cin, cout, k, stride,
+  FROST_REQUIRE(total < (int64_t)1 << 31, "frost_stem_wgrad: more than 2^31 output pixels");
+  stem_wgrad_kernel<<<(unsigned)ceil_div(total, ppb), 256, 0, st>>>(dz, xq, x_scale, x_zp, N, H, W, cin, cout, k, stride,
                                                                       pad, Ho, Wo, ppb, dwq);
   FROST_LAUNCH_CHECK("stem_wgrad");
   return FROST_OK;

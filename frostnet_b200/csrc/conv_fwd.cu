@@ -40,12 +40,7 @@ __device__ __forceinline__ void smem_stat_add(SmemStat* s, long long sum, unsign
   atomicMax(&s->mx, mx);
 }
 __device__ __forceinline__ void global_stat_flush(FrostChanStats* g, const SmemStat& s) {
-  if (s.mn == INT_MAX && s.mx == INT_MIN) return;  // nothing accumulated
-  atomicAdd(reinterpret_cast<unsigned long long*>(&g->sum), (unsigned long long)s.sum);
-  atomicAdd(&g->sq_lo, s.sq & 0xffffffffull);
-  atomicAdd(&g->sq_hi, s.sq >> 32);
-  atomicMin(&g->min, s.mn);
-  atomicMax(&g->max, s.mx);
+  chan_stats_flush(g, s.sum, s.sq, s.mn, s.mx);
 }
 
 // ================================================================= 1x1 pointwise (dp4a, SIMT)
@@ -210,58 +205,67 @@ __global__ void __launch_bounds__(STEM_THREADS) stem_conv_fwd_kernel(
   __syncthreads();
 
   const int64_t total = (int64_t)N * Ho * Wo;
-  const int64_t p0 = (int64_t)blockIdx.x * STEM_THREADS;
-  const int64_t p = p0 + threadIdx.x;
-  int acc[STEM_MAXC];
+  const int64_t tiles = (total + STEM_THREADS - 1) / STEM_THREADS;
+  // statistics role: thread -> (pixel group g, channel c), fixed for the CTA's lifetime; the CTA is persistent
+  // over pixel tiles so that only gridDim.x (one resident wave) sets of atomics reach each channel's record
+  const int sc = threadIdx.x % STEM_MAXC;
+  const int sg = threadIdx.x / STEM_MAXC;      // 0..7
+  constexpr int G = STEM_THREADS / STEM_MAXC;  // 8
+  long long st_s = 0;
+  unsigned long long st_sq = 0;
+  int st_mn = INT_MAX, st_mx = INT_MIN;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t p0 = tile * STEM_THREADS;
+    const int64_t p = p0 + threadIdx.x;
+    int acc[STEM_MAXC];
 #pragma unroll
-  for (int c = 0; c < STEM_MAXC; ++c) acc[c] = 0;
-  if (p < total) {
-    const int ow = (int)(p % Wo);
-    const int64_t t1 = p / Wo;
-    const int oh = (int)(t1 % Ho);
-    const int n = (int)(t1 / Ho);
-    for (int r = 0; r < k; ++r) {
-      const int ih = oh * stride - pad + r;
-      if (ih < 0 || ih >= H) continue;
-      for (int s = 0; s < k; ++s) {
-        const int iw = ow * stride - pad + s;
-        if (iw < 0 || iw >= W) continue;
-        const uint8_t* px = xq + (((int64_t)n * H + ih) * W + iw) * cin;
-        for (int ci = 0; ci < cin; ++ci) {
-          const int xa = (int)__ldg(px + ci) - zp_a;
-          const int* wrow = s_w + ((r * k + s) * cin + ci) * STEM_MAXC;
+    for (int c = 0; c < STEM_MAXC; ++c) acc[c] = 0;
+    if (p < total) {
+      const int ow = (int)(p % Wo);
+      const int64_t t1 = p / Wo;
+      const int oh = (int)(t1 % Ho);
+      const int n = (int)(t1 / Ho);
+      for (int r = 0; r < k; ++r) {
+        const int ih = oh * stride - pad + r;
+        if (ih < 0 || ih >= H) continue;
+        for (int s = 0; s < k; ++s) {
+          const int iw = ow * stride - pad + s;
+          if (iw < 0 || iw >= W) continue;
+          const uint8_t* px = xq + (((int64_t)n * H + ih) * W + iw) * cin;
+          for (int ci = 0; ci < cin; ++ci) {
+            const int xa = (int)__ldg(px + ci) - zp_a;
+            const int* wrow = s_w + ((r * k + s) * cin + ci) * STEM_MAXC;
 #pragma unroll
-          for (int c = 0; c < STEM_MAXC; ++c) acc[c] += xa * wrow[c];
+            for (int c = 0; c < STEM_MAXC; ++c) acc[c] += xa * wrow[c];
+          }
         }
       }
     }
-  }
 #pragma unroll
-  for (int c = 0; c < STEM_MAXC; ++c) s_tile[threadIdx.x * (STEM_MAXC + 1) + c] = acc[c];
-  __syncthreads();
-  // coalesced store + per-channel statistics: thread -> (pixel group, channel)
-  const int npix = (int)min((int64_t)STEM_THREADS, total - p0);
-  {
-    const int c = threadIdx.x % STEM_MAXC;
-    const int g = threadIdx.x / STEM_MAXC;       // 0..7
-    constexpr int G = STEM_THREADS / STEM_MAXC;  // 8
-    if (c < cout) {
-      long long s = 0;
-      unsigned long long sq = 0;
-      int mn = INT_MAX, mx = INT_MIN;
-      for (int px = g; px < npix; px += G) {
-        const int I = s_tile[px * (STEM_MAXC + 1) + c];
-        acc_out[(p0 + px) * cout + c] = I;
-        s += I;
-        sq += (unsigned long long)((long long)I * (long long)I);
-        mn = min(mn, I);
-        mx = max(mx, I);
+    for (int c = 0; c < STEM_MAXC; ++c) s_tile[threadIdx.x * (STEM_MAXC + 1) + c] = acc[c];
+    __syncthreads();
+    // coalesced store + per-channel statistics
+    const int npix = (int)min((int64_t)STEM_THREADS, total - p0);
+    if (sc < cout) {
+      int s32 = 0;   // |I| <= 27*255*128 < 2^20 and <= 32 pixels per thread and tile: no overflow
+      for (int px = sg; px < npix; px += G) {
+        const int I = s_tile[px * (STEM_MAXC + 1) + sc];
+        acc_out[(p0 + px) * cout + sc] = I;
+        s32 += I;
+        st_sq += (unsigned long long)((long long)I * (long long)I);
+        st_mn = min(st_mn, I);
+        st_mx = max(st_mx, I);
       }
-      if (mn <= mx) smem_stat_add(&s_stat[c], s, sq, mn, mx);
+      st_s += s32;
     }
+    __syncthreads();
   }
+  if (sc < cout && st_mn <= st_mx) smem_stat_add(&s_stat[sc], st_s, st_sq, st_mn, st_mx);
   __syncthreads();
-  if (threadIdx.x < cout) global_stat_flush(stats + threadIdx.x, s_stat[threadIdx.x]);
+  if (threadIdx.x < cout) {
+    const SmemStat t = s_stat[threadIdx.x];
+    chan_stats_flush(stats + threadIdx.x, t.sum, t.sq, t.mn, t.mx);
+  }
 }
 
 }  // namespace frost
@@ -304,7 +308,8 @@ extern "C" int frost_stem_conv_forward(const uint8_t* xq, const int32_t* x_zp, c
     cudaFuncSetAttribute(stem_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr_set = true;
   }
-  stem_conv_fwd_kernel<<<(unsigned)ceil_div(total, STEM_THREADS), STEM_THREADS, smem, st>>>(
+  const int64_t wave = (int64_t)kNumSMs * tunable(FROST_TUNE_STEM_FWD_CTAS_PER_SM);
+  stem_conv_fwd_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, STEM_THREADS), wave), STEM_THREADS, smem, st>>>(
       xq, x_zp, wq, w_zp, N, H, W, cin, cout, k, stride, pad, Ho, Wo, acc, stats);
   FROST_LAUNCH_CHECK("stem_conv_fwd");
   return FROST_OK;

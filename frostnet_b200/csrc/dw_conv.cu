@@ -43,6 +43,35 @@ __device__ __forceinline__ int sext_byte(unsigned w, int ch) {
 }
 __device__ __forceinline__ int zext_byte(unsigned w, int ch) { return (int)((w >> (8 * ch)) & 0xffu); }
 
+// Strip walker: strip index -> (strip column sw, row oh, image n) advanced by a fixed step with adds and
+// carries only (a 64-bit div/mod pair per strip costs more instructions than a 3x3 strip's arithmetic).
+struct StripWalker {
+  int sw, oh, n;
+  int d_sw, d_oh, d_n;
+  int strips_w, rows;
+  __device__ __forceinline__ void init(int64_t first, int64_t step, int strips_w_, int rows_) {
+    strips_w = strips_w_;
+    rows = rows_;
+    sw = (int)(first % strips_w);
+    const int64_t t1 = first / strips_w;
+    oh = (int)(t1 % rows);
+    n = (int)(t1 / rows);
+    d_sw = (int)(step % strips_w);
+    const int64_t s1 = step / strips_w;
+    d_oh = (int)(s1 % rows);
+    d_n = (int)(s1 / rows);
+  }
+  __device__ __forceinline__ void next() {
+    sw += d_sw;
+    int carry = 0;
+    if (sw >= strips_w) { sw -= strips_w; carry = 1; }
+    oh += d_oh + carry;
+    carry = 0;
+    if (oh >= rows) { oh -= rows; carry = 1; }
+    n += d_n + carry;
+  }
+};
+
 // ================================================================= forward (dp4a)
 // Per kernel row the thread loads the strip's input window (one 32-bit word = 4 channels per pixel),
 // transposes 4x4 byte blocks in registers (8 PRMT) so that one word holds 4 CONSECUTIVE PIXELS of one channel,
@@ -121,13 +150,11 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_kernel(const uint8_t* __re
   int st_mx[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};
 
   const int strips_w = (Wo + DW_TW - 1) / DW_TW;
-  const int64_t total_strips = (int64_t)N * Ho * strips_w;
-  for (int64_t sidx = (int64_t)blockIdx.x * spb + strip_local; sidx < total_strips; sidx += (int64_t)gridDim.x * spb) {
-    const int sw = (int)(sidx % strips_w);
-    const int64_t t1 = sidx / strips_w;
-    const int oh = (int)(t1 % Ho);
-    const int n = (int)(t1 / Ho);
-    const int ow0 = sw * DW_TW;
+  StripWalker wk;
+  wk.init((int64_t)blockIdx.x * spb + strip_local, (int64_t)gridDim.x * spb, strips_w, Ho);
+  for (; wk.n < N; wk.next()) {
+    const int oh = wk.oh, n = wk.n;
+    const int ow0 = wk.sw * DW_TW;
     int acc[DW_TW][4];
 #pragma unroll
     for (int t = 0; t < DW_TW; ++t)
@@ -206,13 +233,7 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_kernel(const uint8_t* __re
   __syncthreads();
   for (int i = threadIdx.x; i < cgb * 4; i += blockDim.x) {
     const SmemStat s = s_stat[i];
-    if (s.mn == INT_MAX && s.mx == INT_MIN) continue;
-    FrostChanStats* g = stats + blockIdx.y * cgb * 4 + i;
-    atomicAdd(reinterpret_cast<unsigned long long*>(&g->sum), (unsigned long long)s.sum);
-    atomicAdd(&g->sq_lo, s.sq & 0xffffffffull);
-    atomicAdd(&g->sq_hi, s.sq >> 32);
-    atomicMin(&g->min, s.mn);
-    atomicMax(&g->max, s.mx);
+    chan_stats_flush(stats + blockIdx.y * cgb * 4 + i, s.sum, s.sq, s.mn, s.mx);
   }
 }
 
@@ -251,13 +272,11 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_generic_kernel(const uint8
   int st_mx[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};
 
   const int strips_w = (Wo + DW_TW - 1) / DW_TW;
-  const int64_t total_strips = (int64_t)N * Ho * strips_w;
-  for (int64_t sidx = (int64_t)blockIdx.x * spb + strip_local; sidx < total_strips; sidx += (int64_t)gridDim.x * spb) {
-    const int sw = (int)(sidx % strips_w);
-    const int64_t t1 = sidx / strips_w;
-    const int oh = (int)(t1 % Ho);
-    const int n = (int)(t1 / Ho);
-    const int ow0 = sw * DW_TW;
+  StripWalker wk;
+  wk.init((int64_t)blockIdx.x * spb + strip_local, (int64_t)gridDim.x * spb, strips_w, Ho);
+  for (; wk.n < N; wk.next()) {
+    const int oh = wk.oh, n = wk.n;
+    const int ow0 = wk.sw * DW_TW;
     int acc[DW_TW][4];
 #pragma unroll
     for (int t = 0; t < DW_TW; ++t)
@@ -327,13 +346,7 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_generic_kernel(const uint8
   __syncthreads();
   for (int i = threadIdx.x; i < cgb * 4; i += blockDim.x) {
     const SmemStat s = s_stat[i];
-    if (s.mn == INT_MAX && s.mx == INT_MIN) continue;
-    FrostChanStats* g = stats + blockIdx.y * cgb * 4 + i;
-    atomicAdd(reinterpret_cast<unsigned long long*>(&g->sum), (unsigned long long)s.sum);
-    atomicAdd(&g->sq_lo, s.sq & 0xffffffffull);
-    atomicAdd(&g->sq_hi, s.sq >> 32);
-    atomicMin(&g->min, s.mn);
-    atomicMax(&g->max, s.mx);
+    chan_stats_flush(stats + blockIdx.y * cgb * 4 + i, s.sum, s.sq, s.mn, s.mx);
   }
 }
 
@@ -369,13 +382,11 @@ __global__ void __launch_bounds__(256, 3) dw_dgrad_kernel(const float* __restric
   }
   __syncthreads();
   const int strips_w = (W + DW_TW - 1) / DW_TW;
-  const int64_t total_strips = (int64_t)N * H * strips_w;
-  for (int64_t sidx = (int64_t)blockIdx.x * spb + strip_local; sidx < total_strips; sidx += (int64_t)gridDim.x * spb) {
-    const int sw = (int)(sidx % strips_w);
-    const int64_t t1 = sidx / strips_w;
-    const int ih = (int)(t1 % H);
-    const int n = (int)(t1 / H);
-    const int iw0 = sw * DW_TW;
+  StripWalker wk;
+  wk.init((int64_t)blockIdx.x * spb + strip_local, (int64_t)gridDim.x * spb, strips_w, H);
+  for (; wk.n < N; wk.next()) {
+    const int ih = wk.oh, n = wk.n;
+    const int iw0 = wk.sw * DW_TW;
     const int ow_base = iw0 / S;          // iw0 % 4 == 0 -> exact
     float acc[DW_TW][4];
 #pragma unroll
@@ -443,7 +454,7 @@ __global__ void __launch_bounds__(256, 3) dw_wgrad_kernel(const float* __restric
   constexpr int IW = (DW_TW - 1) * S + KS;
   const int zp_a = *x_zp_p;
   const unsigned zp4 = (unsigned)zp_a * 0x01010101u;
-  const float zpf = (float)zp_a;
+  const float zpf_magic = 8388608.0f + (float)zp_a;
   const int cg_local = threadIdx.x % cgb;
   const int r = (threadIdx.x / cgb) % KS;
   const int strip_local = threadIdx.x / (cgb * KS);
@@ -457,13 +468,11 @@ __global__ void __launch_bounds__(256, 3) dw_wgrad_kernel(const float* __restric
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) acc[t][ch] = 0.0f;
   const int strips_w = (Wo + DW_TW - 1) / DW_TW;
-  const int64_t total_strips = (int64_t)N * Ho * strips_w;
-  for (int64_t sidx = (int64_t)blockIdx.x * spb + strip_local; sidx < total_strips; sidx += (int64_t)gridDim.x * spb) {
-    const int sw = (int)(sidx % strips_w);
-    const int64_t t1 = sidx / strips_w;
-    const int oh = (int)(t1 % Ho);
-    const int n = (int)(t1 / Ho);
-    const int ow0 = sw * DW_TW;
+  StripWalker wk;
+  wk.init((int64_t)blockIdx.x * spb + strip_local, (int64_t)gridDim.x * spb, strips_w, Ho);
+  for (; wk.n < N; wk.next()) {
+    const int oh = wk.oh, n = wk.n;
+    const int ow0 = wk.sw * DW_TW;
     const int ih = oh * S - PAD + r;
     if ((unsigned)ih >= (unsigned)H) continue;       // this kernel row falls outside the image for this strip
     const float* drow = dz + (((int64_t)n * Ho + oh) * Wo) * C + cg * 4;
@@ -481,8 +490,9 @@ __global__ void __launch_bounds__(256, 3) dw_wgrad_kernel(const float* __restric
 #pragma unroll
     for (int j = 0; j < IW; ++j) {
       float xa[4];
+      // byte -> float without I2F: 0x4B0000bb is the float 2^23 + bb; subtracting 2^23 + zp is exact
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) xa[ch] = (float)zext_byte(xw[j], ch) - zpf;
+      for (int ch = 0; ch < 4; ++ch) xa[ch] = __uint_as_float(__byte_perm(xw[j], 0x4B000000u, 0x7650u + ch)) - zpf_magic;
 #pragma unroll
       for (int t = 0; t < DW_TW; ++t) {
         const int s = j - t * S;
@@ -501,9 +511,12 @@ __global__ void __launch_bounds__(256, 3) dw_wgrad_kernel(const float* __restric
     for (int ch = 0; ch < 4; ++ch) atomicAdd(&s_acc[((r * KS + t) * cgb + cg_local) * 4 + ch], acc[t][ch]);
   __syncthreads();
   const float s_a = *x_scale_p;
-  for (int i = threadIdx.x; i < KS * KS * cgb * 4; i += blockDim.x) {
-    const int t = i / (cgb * 4), c = i % (cgb * 4);
-    atomicAdd(dwq + (int64_t)t * C + blockIdx.y * cgb * 4 + c, s_acc[i] * s_a);
+  // one 16-byte vector atomic per (tap, channel group): 4x fewer same-sector L2 atomics than scalar adds
+  for (int i = threadIdx.x; i < KS * KS * cgb; i += blockDim.x) {
+    const int t = i / cgb, g = i % cgb;
+    const float4 v = *reinterpret_cast<const float4*>(s_acc + (size_t)i * 4);
+    atomicAdd(reinterpret_cast<float4*>(dwq + (int64_t)t * C + (blockIdx.y * cgb + g) * 4),
+              make_float4(v.x * s_a, v.y * s_a, v.z * s_a, v.w * s_a));
   }
 }
 
@@ -526,7 +539,10 @@ extern "C" int frost_dw_conv_forward(const uint8_t* xq, const int32_t* x_zp, con
   dw_launch_shape(C, DW_MAX_CGB, &cgb, &chunks, &threads);
   const int spb = threads / cgb;
   const int64_t total_strips = (int64_t)N * Ho * ((Wo + DW_TW - 1) / DW_TW);
-  const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total_strips, (int64_t)spb * 2), (int64_t)kNumSMs * 16 / chunks + 1));
+  // one resident wave: every CTA ends with one set of atomics per channel on the same 32-byte records, and
+  // same-sector atomics serialise in L2 - 16 waves of CTAs cost more in that tail than the convolution itself
+  const int64_t wave = std::max<int64_t>(1, (int64_t)kNumSMs * tunable(FROST_TUNE_DW_FWD_CTAS_PER_SM) / chunks);
+  const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total_strips, (int64_t)spb * 2), wave));
   dim3 grid(gx, chunks);
   const size_t smem = sizeof(unsigned) * (2 * k * 4 * DW_MAX_CGB + DW_MAX_CGB * 4) + sizeof(SmemStat) * cgb * 4;
   const size_t smem_g = sizeof(unsigned) * k * k * DW_MAX_CGB + sizeof(SmemStat) * cgb * 4;
@@ -555,7 +571,8 @@ extern "C" int frost_dw_dgrad(const float* dz, const int8_t* wq, const float* w_
   dw_launch_shape(C, DW_MAX_CGB, &cgb, &chunks, &threads);
   const int spb = threads / cgb;
   const int64_t total_strips = (int64_t)N * H * ((W + DW_TW - 1) / DW_TW);
-  const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total_strips, (int64_t)spb * 2), (int64_t)kNumSMs * 16 / chunks + 1));
+  const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total_strips, (int64_t)spb * 2),
+                                                              (int64_t)kNumSMs * tunable(FROST_TUNE_DW_DGRAD_CTAS_PER_SM) / chunks + 1));
   dim3 grid(gx, chunks);
   const size_t smem = sizeof(float4) * k * k * cgb;
 #define L(KS, S) dw_dgrad_kernel<KS, S><<<grid, threads, smem, st>>>(dz, wq, w_scale, w_zp, N, H, W, C, Ho, Wo, cgb, dx, accumulate)
@@ -572,6 +589,7 @@ extern "C" int frost_dw_wgrad(const float* dz, const uint8_t* xq, const float* x
                               int W, int C, int k, int stride, float* dwq, void* stream) {
   FROST_REQUIRE(dz && xq && x_scale && x_zp && dwq, "frost_dw_wgrad: null pointer");
   FROST_REQUIRE(N > 0 && H > 0 && W > 0 && dw_shape_ok(C, k, stride), "frost_dw_wgrad: bad shape");
+  FROST_REQUIRE((reinterpret_cast<uintptr_t>(dwq) & 15) == 0, "frost_dw_wgrad: dwq must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const int pad = (k - 1) / 2;
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
@@ -585,7 +603,8 @@ extern "C" int frost_dw_wgrad(const float* dz, const uint8_t* xq, const float* x
   threads = cgb * k * spb;
   const int64_t total_strips = (int64_t)N * Ho * ((Wo + DW_TW - 1) / DW_TW);
   // every thread should see >= 8 strips so that the final smem/global reduction is amortised
-  const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total_strips, (int64_t)spb * 8), (int64_t)kNumSMs * 6 / chunks + 1));
+  const int64_t wave = std::max<int64_t>(1, (int64_t)kNumSMs * tunable(FROST_TUNE_DW_WGRAD_CTAS_PER_SM) / chunks);
+  const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total_strips, (int64_t)spb * 8), wave));
   dim3 grid(gx, chunks);
   const size_t smem = sizeof(float) * k * k * cgb * 4;
 #define L(KS, S) dw_wgrad_kernel<KS, S><<<grid, threads, smem, st>>>(dz, xq, x_scale, x_zp, N, H, W, C, Ho, Wo, cgb, dwq)

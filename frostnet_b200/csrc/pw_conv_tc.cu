@@ -266,13 +266,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
   __syncthreads();
   for (int j = threadIdx.x; j < n_valid; j += blockDim.x) {
     const TcStat s = s_stat[j];
-    if (s.mn == INT_MAX && s.mx == INT_MIN) continue;
-    FrostChanStats* g = stats + n0 + j;
-    atomicAdd(reinterpret_cast<unsigned long long*>(&g->sum), (unsigned long long)s.sum);
-    atomicAdd(&g->sq_lo, s.sq & 0xffffffffull);
-    atomicAdd(&g->sq_hi, s.sq >> 32);
-    atomicMin(&g->min, s.mn);
-    atomicMax(&g->max, s.mx);
+    chan_stats_flush(stats + n0 + j, s.sum, s.sq, s.mn, s.mx);
   }
   if (warp == 12) {
     tc_fence_after();

@@ -36,6 +36,21 @@ const char* frost_last_error(void);
 /* Number of kernels this library has launched since load (all threads); bench.py's gpu_launches. */
 int64_t frost_launch_count(void);
 
+/* Launch-shape knobs for measurement (tools/microbench_ops.py sweeps them on the device; results never depend
+ * on them).  value 0 restores the built-in default.  Not part of the reference-facing surface. */
+enum {
+  FROST_TUNE_DW_FWD_CTAS_PER_SM = 0,   /* depthwise forward: resident CTAs per SM (grid = 148 * value)      */
+  FROST_TUNE_DW_WGRAD_CTAS_PER_SM = 1, /* depthwise wgrad                                                    */
+  FROST_TUNE_BN_RED_CTAS_PER_SM = 2,   /* bn_backward_reduce                                                 */
+  FROST_TUNE_BN_RED_MAX_CGB = 3,       /* bn_backward_reduce: max 4-channel groups per CTA (channel chunking) */
+  FROST_TUNE_STEM_FWD_CTAS_PER_SM = 4, /* stem forward (persistent over pixel tiles)                         */
+  FROST_TUNE_STEM_WGRAD_CTAS_PER_SM = 5,
+  FROST_TUNE_DW_DGRAD_CTAS_PER_SM = 6,
+  FROST_TUNE_COUNT = 7
+};
+int frost_set_tunable(int which, int value);
+int frost_get_tunable(int which);
+
 /* One FusedMovingAvgObsFakeQuantize instance (torch/ao/quantization/fake_quantize.py:423-438):
  * the four state buffers of the module, on the device.  Kernels read AND update them in place
  * (observer EMA, then qparams), exactly the side effects of torch.fused_moving_avg_obs_fake_quant. */

@@ -269,7 +269,8 @@ def _conv_int_ref(xq, zpa, w, zpw, stride, pad, groups):
 
 
 @pytest.mark.parametrize("N,H,W,Cc,k,s,zpw", [(2, 9, 11, 32, 3, 1, 0), (1, 14, 14, 96, 5, 2, 0), (3, 7, 7, 1728, 5, 1, 0),
-                                              (2, 16, 15, 72, 3, 2, -128), (1, 5, 6, 1440, 5, 1, 0), (2, 3, 3, 16, 5, 1, 0)])
+                                              (2, 16, 15, 72, 3, 2, -128), (1, 5, 6, 1440, 5, 1, 0), (2, 3, 3, 16, 5, 1, 0),
+                                              (6, 56, 56, 144, 5, 2, 0), (40, 28, 30, 32, 3, 1, 0), (5, 33, 57, 96, 3, 2, 127)])
 def test_dw_conv_forward_exact(N, H, W, Cc, k, s, zpw):
     g = torch.Generator().manual_seed(H * W + Cc)
     xq = torch.randint(0, 256, (N, H, W, Cc), generator=g, dtype=torch.int64)
@@ -331,7 +332,7 @@ def _bn_reference(I, gamma, beta, rm, rv, sf, s_a, s_w, relu, training, fq):
 
 
 @pytest.mark.parametrize("M,Cc,relu,training", [(64, 16, True, True), (1000, 24, False, True), (513, 1728, True, True),
-                                                (200, 40, True, False)])
+                                                (200, 40, True, False), (20000, 360, True, True), (70000, 72, True, True)])
 def test_bn_finalize_apply_and_backward(M, Cc, relu, training):
     I, gamma, beta, rm, rv, sf, s_a, s_w = _bn_setup(M, Cc, M + Cc)
     Id = I.int().to(DEV)
@@ -546,7 +547,8 @@ def test_pw_dgrad_wgrad(M, K, cout):
         assert torch.equal(dwq2.cpu().double(), dzs.double().t() @ (xq - zp_a).double())
 
 
-@pytest.mark.parametrize("N,H,W,Cc,k,s", [(2, 9, 11, 32, 3, 1), (1, 14, 14, 96, 5, 2), (2, 7, 7, 1728, 5, 1), (2, 16, 15, 72, 3, 2)])
+@pytest.mark.parametrize("N,H,W,Cc,k,s", [(2, 9, 11, 32, 3, 1), (1, 14, 14, 96, 5, 2), (2, 7, 7, 1728, 5, 1), (2, 16, 15, 72, 3, 2),
+                                          (6, 56, 56, 144, 5, 2), (40, 28, 30, 32, 3, 1), (5, 33, 57, 96, 3, 1)])
 def test_dw_dgrad_wgrad(N, H, W, Cc, k, s):
     g = torch.Generator().manual_seed(H + Cc)
     pad = (k - 1) // 2
@@ -575,8 +577,8 @@ def test_dw_dgrad_wgrad(N, H, W, Cc, k, s):
     torch.testing.assert_close(dwq.cpu().double(), refw, rtol=1e-4, atol=1e-4 * float(refw.abs().max()))
 
 
-def test_stem_wgrad():
-    N, H, W, cout = 2, 33, 31, 16
+@pytest.mark.parametrize("N,H,W,cout", [(2, 33, 31, 16), (5, 224, 224, 32), (1, 8, 8, 24)])
+def test_stem_wgrad(N, H, W, cout):
     g = torch.Generator().manual_seed(5)
     xq = torch.randint(0, 256, (N, H, W, 3), generator=g)
     s_a, zp_a = 0.02, 120
@@ -644,3 +646,36 @@ def test_bad_arguments_are_reported_not_crashed():
         L().call("frost_pw_conv_forward", 8, 8, 8, 8, 8, 4, 12, 16, 8, 8, None)
     with pytest.raises(RuntimeError):
         L().call("frost_dw_conv_forward", 8, 8, 8, 8, 1, 4, 4, 16, 7, 1, 8, 8, None)
+
+
+# ------------------------------------------------------------------------------------------ launch-shape knobs
+@pytest.mark.parametrize("knob,values", [(0, [1, 16]), (4, [1, 8])])
+def test_results_do_not_depend_on_launch_knobs(knob, values):
+    """FROST_TUNE_* only reshape grids: integer outputs and statistics must be identical for every value."""
+    lib = L().load()
+    outs = []
+    try:
+        for v in values:
+            assert lib.frost_set_tunable(knob, v) == 0 and lib.frost_get_tunable(knob) == v
+            if knob == 0:
+                test_dw_conv_forward_exact(3, 7, 7, 1728, 5, 1, 0)
+                test_dw_conv_forward_exact(2, 9, 11, 32, 3, 1, 0)
+            else:
+                test_stem_conv_forward_exact(2, 224, 224, 32)
+            outs.append(v)
+    finally:
+        lib.frost_set_tunable(knob, 0)
+    assert lib.frost_set_tunable(99, 1) != 0 and b"unknown knob" in lib.frost_last_error()
+
+
+def test_device_prefetcher_yields_every_batch_in_order():
+    import frostnet_b200 as F
+    batches = [(torch.full((4, 3, 8, 8), float(i)).pin_memory(), torch.full((4,), i, dtype=torch.int64).pin_memory())
+               for i in range(5)]
+    seen = []
+    for x, y in F.DevicePrefetcher(batches, DEV):
+        assert x.is_cuda and y.is_cuda
+        seen.append((float(x.mean()), int(y[0])))
+        x.mul_(2.0)       # the consumer may scribble on the buffer; the next copy waits for it
+    assert seen == [(float(i), i) for i in range(5)]
+    assert list(F.DevicePrefetcher([], DEV)) == []
