@@ -155,13 +155,13 @@ def algorithmic_cost(name, a):
         M, K, co = a[5], a[6], a[7]
         return M * K + co * K + 4 * M * co, 2 * M * K * co
     if name == "frost_bnq_apply":
-        M, Cc = a[1], a[2]
+        M, Cc = a[2], a[3]
         return 5 * M * Cc, 0
     if name in ("frost_pw_dgrad", "frost_pw_dgrad_tc"):
         M, K, co = a[4], a[5], a[6]
         return 4 * M * co + co * K + 4 * M * K, 2 * M * K * co
     if name in ("frost_pw_wgrad", "frost_pw_wgrad_tc"):
-        M, K, co = a[4], a[5], a[6]
+        M, K, co = (a[5], a[6], a[7]) if name.endswith("_tc") else (a[4], a[5], a[6])
         return 4 * M * co + M * K + 4 * co * K, 2 * M * K * co
     if name in ("frost_bn_backward", "frost_bn_backward_reduce", "frost_bn_backward_apply"):
         args = getattr(a[0], "_obj", None)          # ctypes.byref(struct) keeps the struct in _obj
@@ -303,6 +303,7 @@ def run_b200(args):
     roofline, breakdown = None, None
     pk = min(K, 5)
     prof = {}
+    call_log = []
     import frostnet_b200.engine as E
     orig_call = L.call
 
@@ -312,6 +313,12 @@ def run_b200(args):
         orig_call(name, *a)
         e1.record()
         prof.setdefault(name, []).append((e0, e1, algorithmic_cost(name, a)))
+        if args.dump_calls:
+            if name.startswith("frost_bn_backward"):
+                sig = [a[0]._obj.M, a[0]._obj.C]
+            else:
+                sig = [v for v in a[:-1] if isinstance(v, int) and 0 <= v < (1 << 40)]
+            call_log.append((name, sig, e0, e1, algorithmic_cost(name, a)[0]))
     if rank == 0:
         E.L.call = prof_call
     try:
@@ -321,6 +328,12 @@ def run_b200(args):
         torch.cuda.synchronize()
     finally:
         E.L.call = orig_call
+    if rank == 0 and args.dump_calls:
+        per = len(call_log) // pk
+        rows = [{"name": n, "sig": sig, "us": round(a.elapsed_time(b) * 1e3, 1), "bytes": byt}
+                for n, sig, a, b, byt in call_log[(pk - 1) * per:]]
+        with open(args.dump_calls, "w") as fh:
+            json.dump(rows, fh)
     if rank == 0:
         agg = {}
         for name, evs in prof.items():
@@ -417,6 +430,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (for ncu launch lists)")
+    ap.add_argument("--dump-calls", default="", help="write the per-call CUDA-event times of one profiled step to this JSON file")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -146,6 +146,11 @@ def load():
         fn.restype = C.c_int
     if lib.frost_abi_version() != 1:
         raise RuntimeError("libfrost_b200.so ABI mismatch; rebuild with python -m frostnet_b200.build --force")
+    # measurement aid: FROST_TUNE="knob=value,knob=value" presets the launch-shape knobs (include/frost_b200.h)
+    for item in filter(None, os.environ.get("FROST_TUNE", "").split(",")):
+        k, v = item.split("=")
+        if lib.frost_set_tunable(int(k), int(v)) != 0:
+            raise RuntimeError("FROST_TUNE: " + lib.frost_last_error().decode())
     _lib = lib
     return lib
 

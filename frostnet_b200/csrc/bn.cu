@@ -18,6 +18,7 @@ __device__ __forceinline__ float bn_affine(float I, float A, float B) { return f
 // ---------------------------------------------------------------- finalize (1 CTA)
 __global__ void __launch_bounds__(1024) bn_finalize_kernel(FrostBnFinalizeArgs a) {
   __shared__ float s_mn[32], s_mx[32];
+  pdl_enter();
   const double M = (double)a.count;
   const double sa_sw = (double)(*a.x_scale) * (double)(*a.w_scale);
   float gmn = INFINITY, gmx = -INFINITY;
@@ -86,11 +87,13 @@ __device__ __forceinline__ unsigned bnq4(const int4 v, int fmt, const float4 A, 
   return q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
 }
 
+template <int U>   // 16-byte loads in flight per thread
 __global__ void __launch_bounds__(256) bnq_apply_kernel(const int32_t* __restrict__ acc, int fmt, int64_t n4, int C,
                                                        const float* __restrict__ A, const float* __restrict__ B,
                                                        int relu, const float* __restrict__ scale_p,
                                                        const int32_t* __restrict__ zp_p, uint8_t* __restrict__ q) {
   extern __shared__ __align__(16) float s_ab[];  // A[C], B[C]
+  pdl_enter();
   for (int c = threadIdx.x; c < C; c += blockDim.x) { s_ab[c] = A[c]; s_ab[C + c] = B[c]; }
   __syncthreads();
   const float s = *scale_p, zp = (float)*zp_p;
@@ -104,16 +107,18 @@ __global__ void __launch_bounds__(256) bnq_apply_kernel(const int32_t* __restric
   unsigned* out = reinterpret_cast<unsigned*>(q);
   const float4* sA = reinterpret_cast<const float4*>(s_ab);
   const float4* sB = reinterpret_cast<const float4*>(s_ab + C);
-  int64_t i = i0;
-  for (; i + stride < n4; i += 2 * stride) {
-    const int4 v0 = __ldg(in + i);
-    const int4 v1 = __ldg(in + i + stride);
-    int cg1 = cg + cstep; if (cg1 >= C4) cg1 -= C4;
-    out[i] = bnq4(v0, fmt, sA[cg], sB[cg], relu, inv, zp);
-    out[i + stride] = bnq4(v1, fmt, sA[cg1], sB[cg1], relu, inv, zp);
-    cg = cg1 + cstep; if (cg >= C4) cg -= C4;
+  for (int64_t i = i0; i < n4; i += U * stride) {
+    int4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i + u * stride < n4) v[u] = __ldg(in + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i + u * stride < n4) out[i + u * stride] = bnq4(v[u], fmt, sA[cg], sB[cg], relu, inv, zp);
+      cg += cstep;
+      if (cg >= C4) cg -= C4;
+    }
   }
-  if (i < n4) out[i] = bnq4(__ldg(in + i), fmt, sA[cg], sB[cg], relu, inv, zp);
 }
 
 // ---------------------------------------------------------------- backward
@@ -131,8 +136,10 @@ __device__ __forceinline__ float bn_dv(float dy, float I, float A, float B, int 
 // that few CTAs contribute to any one channel: the partials are combined through shared memory (no atomics)
 // and each CTA issues ONE fp64 atomic per (channel, sum) - same-sector L2 atomics serialise (~12 ns each), and
 // with all-channel CTAs that tail was longer than the streaming pass for most layers.
+template <int U>   // rows in flight per thread: 2*U independent 16-byte loads
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(FrostBnBackwardArgs a, int cg_per_block) {
   extern __shared__ double s_part[];  // [rows_per_block][cg_per_block][4 channels][2 sums]
+  pdl_enter();
   const int C = a.C;
   const int cg_local = threadIdx.x % cg_per_block;
   const int cg = blockIdx.y * cg_per_block + cg_local;
@@ -149,7 +156,6 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(FrostBnBackwardArgs 
     const float4 B = __ldg(reinterpret_cast<const float4*>(a.B) + cg);
     const float4 mu = __ldg(reinterpret_cast<const float4*>(a.mean_I) + cg);
     const int64_t stride = (int64_t)gridDim.x * rows_per_block;
-    constexpr int U = 4;   // rows in flight per thread: 8 independent 16-byte loads
     int batches = 0;
     float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
     for (int64_t m = (int64_t)blockIdx.x * rows_per_block + row_local; m < a.M; m += U * stride) {
@@ -180,7 +186,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(FrostBnBackwardArgs 
         p2[2] = fmaf(d2, i2 - mu.z, p2[2]);
         p2[3] = fmaf(d3, i3 - mu.w, p2[3]);
       }
-      if (++batches == 16) {      // flush the fp32 partials (<= 64 terms) into the fp64 accumulators
+      if (++batches == 64 / U) {  // flush the fp32 partials (<= 64 terms) into the fp64 accumulators
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) { mine[2 * ch] += (double)p1[ch]; mine[2 * ch + 1] += (double)p2[ch]; p1[ch] = 0.f; p2[ch] = 0.f; }
         batches = 0;
@@ -199,8 +205,10 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(FrostBnBackwardArgs 
 }
 
 // Per-channel coefficients of  dz = c1*(dv - a0 - a1*(I - mean_I))  plus the BN parameter grads.
+template <int U>   // elements (2 x 16-byte loads each) in flight per thread
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(FrostBnBackwardArgs a, int64_t n4) {
   extern __shared__ __align__(16) float s_c[];  // A,B,mean_I,c1,a0,a1 : 6*C
+  pdl_enter();
   const int C = a.C;
   {
     // per-channel coefficients of dz = c1*(dv - a0 - a1*(I - mean_I)) from the reduced sums; every block
@@ -236,40 +244,54 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(FrostBnBackwardArgs a
   int cg = (int)(i0 % C4);              // C % 4 == 0: a float4 never straddles a row
   const int cstep = (int)(stride % C4);
   const float4* s4 = reinterpret_cast<const float4*>(s_c);
-  for (int64_t i = i0; i < n4; i += stride) {
-    const float4 dy = __ldg(reinterpret_cast<const float4*>(a.dy) + i);
-    const int4 I4 = __ldg(reinterpret_cast<const int4*>(a.acc) + i);
-    const float4 cA = s4[cg], cB = s4[C4 + cg], cM = s4[2 * C4 + cg], c1 = s4[3 * C4 + cg], a0 = s4[4 * C4 + cg], a1 = s4[5 * C4 + cg];
-    cg += cstep;
-    if (cg >= C4) cg -= C4;
-    float o[4];
-    {
-      const float i0 = acc_val(I4.x, a.acc_format), i1 = acc_val(I4.y, a.acc_format);
-      const float i2 = acc_val(I4.z, a.acc_format), i3 = acc_val(I4.w, a.acc_format);
-      const float dv0 = bn_dv(dy.x, i0, cA.x, cB.x, a.relu, inv, zp), dv1 = bn_dv(dy.y, i1, cA.y, cB.y, a.relu, inv, zp);
-      const float dv2 = bn_dv(dy.z, i2, cA.z, cB.z, a.relu, inv, zp), dv3 = bn_dv(dy.w, i3, cA.w, cB.w, a.relu, inv, zp);
-      o[0] = c1.x * (dv0 - a0.x - a1.x * (i0 - cM.x));
-      o[1] = c1.y * (dv1 - a0.y - a1.y * (i1 - cM.y));
-      o[2] = c1.z * (dv2 - a0.z - a1.z * (i2 - cM.z));
-      o[3] = c1.w * (dv3 - a0.w - a1.w * (i3 - cM.w));
-    }
-    if (a.dz_format == 0) {
-      reinterpret_cast<float4*>(a.dz)[i] = make_float4(o[0], o[1], o[2], o[3]);
-    } else {
-      // bf16 hi + lo planes: hi = bf16(dz), lo = bf16(dz - hi)  (dz - hi is exact in fp32)
-      __nv_bfloat16 h[4], l[4];
+  for (int64_t ib = i0; ib < n4; ib += U * stride) {
+    float4 dyv[U];
+    int4 Iv[U];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        h[e] = __float2bfloat16_rn(o[e]);
-        l[e] = __float2bfloat16_rn(o[e] - __bfloat162float(h[e]));
+    for (int u = 0; u < U; ++u) {
+      if (ib + u * stride < n4) {
+        dyv[u] = __ldg(reinterpret_cast<const float4*>(a.dy) + ib + u * stride);
+        Iv[u] = __ldg(reinterpret_cast<const int4*>(a.acc) + ib + u * stride);
       }
-      uint2 hv, lv;
-      hv.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
-      hv.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
-      lv.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
-      lv.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
-      reinterpret_cast<uint2*>(a.dz)[i] = hv;
-      reinterpret_cast<uint2*>(a.dz_lo)[i] = lv;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = ib + u * stride;
+      const float4 cA = s4[cg], cB = s4[C4 + cg], cM = s4[2 * C4 + cg], c1 = s4[3 * C4 + cg], a0 = s4[4 * C4 + cg], a1 = s4[5 * C4 + cg];
+      cg += cstep;
+      if (cg >= C4) cg -= C4;
+      if (i >= n4) continue;
+      const float4 dy = dyv[u];
+      const int4 I4 = Iv[u];
+      float o[4];
+      {
+        const float i0 = acc_val(I4.x, a.acc_format), i1 = acc_val(I4.y, a.acc_format);
+        const float i2 = acc_val(I4.z, a.acc_format), i3 = acc_val(I4.w, a.acc_format);
+        const float dv0 = bn_dv(dy.x, i0, cA.x, cB.x, a.relu, inv, zp), dv1 = bn_dv(dy.y, i1, cA.y, cB.y, a.relu, inv, zp);
+        const float dv2 = bn_dv(dy.z, i2, cA.z, cB.z, a.relu, inv, zp), dv3 = bn_dv(dy.w, i3, cA.w, cB.w, a.relu, inv, zp);
+        o[0] = c1.x * (dv0 - a0.x - a1.x * (i0 - cM.x));
+        o[1] = c1.y * (dv1 - a0.y - a1.y * (i1 - cM.y));
+        o[2] = c1.z * (dv2 - a0.z - a1.z * (i2 - cM.z));
+        o[3] = c1.w * (dv3 - a0.w - a1.w * (i3 - cM.w));
+      }
+      if (a.dz_format == 0) {
+        reinterpret_cast<float4*>(a.dz)[i] = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+        // bf16 hi + lo planes: hi = bf16(dz), lo = bf16(dz - hi)  (dz - hi is exact in fp32)
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          h[e] = __float2bfloat16_rn(o[e]);
+          l[e] = __float2bfloat16_rn(o[e] - __bfloat162float(h[e]));
+        }
+        uint2 hv, lv;
+        hv.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+        hv.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+        lv.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+        lv.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+        reinterpret_cast<uint2*>(a.dz)[i] = hv;
+        reinterpret_cast<uint2*>(a.dz_lo)[i] = lv;
+      }
     }
   }
 }
@@ -284,7 +306,7 @@ extern "C" int frost_bn_finalize(const FrostBnFinalizeArgs* a, void* stream) {
                     a->afq.zero_point && a->afq.min_val && a->afq.max_val,
                 "frost_bn_finalize: null pointer");
   FROST_REQUIRE(a->C > 0 && a->count > 0, "frost_bn_finalize: empty tensor");
-  bn_finalize_kernel<<<1, a->C >= 512 ? 1024 : (a->C >= 128 ? 256 : 64), 0, (cudaStream_t)stream>>>(*a);
+  launch_pdl(bn_finalize_kernel, dim3(1), dim3(a->C >= 512 ? 1024 : (a->C >= 128 ? 256 : 64)), 0, (cudaStream_t)stream, *a);
   FROST_LAUNCH_CHECK("bn_finalize");
   return FROST_OK;
 }
@@ -294,8 +316,21 @@ extern "C" int frost_bnq_apply(const int32_t* acc, int acc_format, int64_t M, in
   FROST_REQUIRE(acc && A && B && out_scale && out_zp && q, "frost_bnq_apply: null pointer");
   FROST_REQUIRE(M > 0 && C > 0 && C % 4 == 0, "frost_bnq_apply: C=%d must be a positive multiple of 4", C);
   const int64_t n4 = M * C / 4;
-  bnq_apply_kernel<<<grid_for(n4, 256 * 8, kNumSMs * 8), 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(acc, acc_format, n4, C, A, B, relu,
-                                                                                                          out_scale, out_zp, q);
+  const size_t smem = 2 * C * sizeof(float);
+  // one resident wave, U loads in flight per thread: bytes in flight per SM is what the HBM pipe needs
+  const int u = tunable(FROST_TUNE_BNQ_UNROLL);
+#define LAUNCH_BNQ(U)                                                                                                      \
+  do {                                                                                                                     \
+    static int per_sm = 0;                                                                                                 \
+    if (!per_sm && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bnq_apply_kernel<U>, 256, 16 * 1024) != cudaSuccess) \
+      per_sm = 4;                                                                                                          \
+    launch_pdl(bnq_apply_kernel<U>, dim3(grid_for(n4, 256 * U, kNumSMs * std::max(per_sm, 1))), dim3(256), smem,         \
+               (cudaStream_t)stream, acc, acc_format, n4, C, A, B, relu, out_scale, out_zp, q);                            \
+  } while (0)
+  if (u >= 8) LAUNCH_BNQ(8);
+  else if (u >= 4) LAUNCH_BNQ(4);
+  else LAUNCH_BNQ(2);
+#undef LAUNCH_BNQ
   FROST_LAUNCH_CHECK("bnq_apply");
   return FROST_OK;
 }
@@ -324,7 +359,10 @@ extern "C" int frost_bn_backward_reduce(const FrostBnBackwardArgs* a, void* stre
   const int rows_per_block = threads / cgb;
   const int64_t wave = std::max<int64_t>(1, (int64_t)kNumSMs * tunable(FROST_TUNE_BN_RED_CTAS_PER_SM) / chunks);
   int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(a->M, (int64_t)rows_per_block * 8), wave));
-  bn_bwd_reduce_kernel<<<dim3(gx, chunks), threads, sizeof(double) * threads * 8, st>>>(*a, cgb);
+  if (tunable(FROST_TUNE_BN_RED_UNROLL) >= 8)
+    launch_pdl(bn_bwd_reduce_kernel<8>, dim3(gx, chunks), dim3(threads), sizeof(double) * threads * 8, st, *a, cgb);
+  else
+    launch_pdl(bn_bwd_reduce_kernel<4>, dim3(gx, chunks), dim3(threads), sizeof(double) * threads * 8, st, *a, cgb);
   FROST_LAUNCH_CHECK("bn_bwd_reduce");
   return FROST_OK;
 }
@@ -334,12 +372,22 @@ extern "C" int frost_bn_backward_apply(const FrostBnBackwardArgs* a, void* strea
   if (rc) return rc;
   const int64_t n4 = a->M * a->C / 4;
   const size_t smem = 6 * (size_t)a->C * sizeof(float);
-  static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
-    cudaFuncSetAttribute(bn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_set = true;
-  }
-  bn_bwd_apply_kernel<<<grid_for(n4, 256 * 8, kNumSMs * 8), 256, smem, (cudaStream_t)stream>>>(*a, n4);
+  const int u = tunable(FROST_TUNE_BN_APPLY_UNROLL);
+#define LAUNCH_APPLY(U)                                                                                                    \
+  do {                                                                                                                     \
+    static int per_sm = 0;                                                                                                 \
+    if (!per_sm) {                                                                                                         \
+      cudaFuncSetAttribute(bn_bwd_apply_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                \
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_apply_kernel<U>, 256, 24 * 1024) != cudaSuccess)   \
+        per_sm = 3;                                                                                                        \
+    }                                                                                                                      \
+    launch_pdl(bn_bwd_apply_kernel<U>, dim3(grid_for(n4, 256 * U, kNumSMs * std::max(per_sm, 1))), dim3(256), smem,      \
+               (cudaStream_t)stream, *a, n4);                                                                              \
+  } while (0)
+  if (u >= 4) LAUNCH_APPLY(4);
+  else if (u >= 2) LAUNCH_APPLY(2);
+  else LAUNCH_APPLY(1);
+#undef LAUNCH_APPLY
   FROST_LAUNCH_CHECK("bn_bwd_apply");
   return FROST_OK;
 }

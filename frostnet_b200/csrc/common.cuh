@@ -36,6 +36,32 @@ int tunable(int which);  // FROST_TUNE_* launch-shape knob (api.cu)
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// A QAT step is ~590 dependent launches of 5-600 us kernels.  Kernels launched through launch_pdl() may become
+// resident while their predecessor in the stream is still draining (the predecessor's CTAs call
+// griddepcontrol.launch_dependents first thing), and block in griddepcontrol.wait until the predecessor has
+// completed and its writes are visible.  Rule for every kernel launched this way: EVERY CTA executes pdl_enter()
+// (or pdl_trigger() ... pdl_wait()) before it touches global memory and before it exits - completion of a grid
+// that skipped the wait would release its own dependents too early.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tunable(FROST_TUNE_PDL) == 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int grid_for(int64_t work_items, int per_block, int max_blocks = kNumSMs * 16) {
   int64_t b = ceil_div(work_items, per_block);
@@ -196,6 +222,7 @@ __device__ __forceinline__ void block_minmax(float& mn, float& mx) {
 static __global__ void __launch_bounds__(1024) fq_finalize_kernel(const float* __restrict__ partial, int nparts, FrostFQ fq,
                                                            int qmin, int qmax, int symmetric, float c,
                                                            int observe, float* __restrict__ cur_minmax) {
+  pdl_enter();
   float mn = INFINITY, mx = -INFINITY;
   for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
     mn = fminf(mn, partial[2 * i]);

@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
                                                         int Ho, int Wo, int64_t pix_per_block, float* __restrict__ dwq) {
   constexpr int PP = 36;                       // patch pitch: 16-byte aligned rows, fill stores spread over banks
   __shared__ __align__(16) float s_buf[STEMW_PIX * PP + STEMW_PIX * 32];
+  pdl_enter();
   const int KK = k * k * cin;
   float* s_patch = s_buf;                      // [STEMW_PIX][PP]
   float* s_dz = s_buf + STEMW_PIX * PP;        // [STEMW_PIX][32]
@@ -364,8 +365,8 @@ extern "C" int frost_stem_wgrad(const float* dz, const uint8_t* xq, const float*
   const int64_t nblk = std::min<int64_t>(ceil_div(total, STEMW_PIX), (int64_t)kNumSMs * tunable(FROST_TUNE_STEM_WGRAD_CTAS_PER_SM));
   const int64_t ppb = ceil_div(ceil_div(total, nblk), STEMW_PIX) * STEMW_PIX;
   FROST_REQUIRE(total < (int64_t)1 << 31, "frost_stem_wgrad: more than 2^31 output pixels");
-  stem_wgrad_kernel<<<(unsigned)ceil_div(total, ppb), 256, 0, st>>>(dz, xq, x_scale, x_zp, N, H, W, cin, cout, k, stride,
-                                                                      pad, Ho, Wo, ppb, dwq);
+  launch_pdl(stem_wgrad_kernel, dim3((unsigned)ceil_div(total, ppb)), dim3(256), 0, st, dz, xq, x_scale, x_zp, N, H, W, cin, cout, k,
+             stride, pad, Ho, Wo, ppb, dwq);
   FROST_LAUNCH_CHECK("stem_wgrad");
   return FROST_OK;
 }

@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(STEM_THREADS) stem_conv_fwd_kernel(
     const int32_t* __restrict__ w_zp_p, int N, int H, int W, int cin, int cout, int k, int stride, int pad, int Ho,
     int Wo, int32_t* __restrict__ acc_out, FrostChanStats* __restrict__ stats) {
   extern __shared__ int s_mem[];
+  pdl_enter();
   const int KK = k * k * cin;
   int* s_w = s_mem;                            // [KK][STEM_MAXC]
   int* s_tile = s_mem + KK * STEM_MAXC;        // [STEM_THREADS][STEM_MAXC+1]
@@ -309,8 +310,8 @@ extern "C" int frost_stem_conv_forward(const uint8_t* xq, const int32_t* x_zp, c
     attr_set = true;
   }
   const int64_t wave = (int64_t)kNumSMs * tunable(FROST_TUNE_STEM_FWD_CTAS_PER_SM);
-  stem_conv_fwd_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, STEM_THREADS), wave), STEM_THREADS, smem, st>>>(
-      xq, x_zp, wq, w_zp, N, H, W, cin, cout, k, stride, pad, Ho, Wo, acc, stats);
+  launch_pdl(stem_conv_fwd_kernel, dim3((unsigned)std::min<int64_t>(ceil_div(total, STEM_THREADS), wave)), dim3(STEM_THREADS), smem, st,
+             xq, x_zp, wq, w_zp, N, H, W, cin, cout, k, stride, pad, Ho, Wo, acc, stats);
   FROST_LAUNCH_CHECK("stem_conv_fwd");
   return FROST_OK;
 }

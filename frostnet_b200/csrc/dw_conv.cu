@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_kernel(const uint8_t* __re
                                                             int N, int H, int W, int C, int Ho, int Wo, int cgb,
                                                             int32_t* __restrict__ acc_out, FrostChanStats* __restrict__ stats) {
   extern __shared__ __align__(16) unsigned char dw_smem[];
+  pdl_enter();
   constexpr int PAD = (KS - 1) / 2;
   constexpr int IW = (DW_TW - 1) * S + KS;       // input pixels touched by a strip
   constexpr int NB = (IW + 3) / 4;               // 4-pixel blocks
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_generic_kernel(const uint8
                                                             int N, int H, int W, int C, int Ho, int Wo, int cgb,
                                                             int32_t* __restrict__ acc_out, FrostChanStats* __restrict__ stats) {
   extern __shared__ __align__(16) unsigned char dw_smem[];
+  pdl_enter();
   unsigned* s_w = reinterpret_cast<unsigned*>(dw_smem);                               // [KS*KS][cgb] packed int8x4
   SmemStat* s_stat = reinterpret_cast<SmemStat*>(dw_smem + sizeof(unsigned) * KS * KS * DW_MAX_CGB);  // [cgb*4]
   constexpr int PAD = (KS - 1) / 2;
@@ -360,6 +362,7 @@ __global__ void __launch_bounds__(256, 3) dw_dgrad_kernel(const float* __restric
                                                          int N, int H, int W, int C, int Ho, int Wo, int cgb,
                                                          float* __restrict__ dx, int accumulate) {
   extern __shared__ __align__(16) unsigned char dw_smem[];
+  pdl_enter();
   float4* s_w = reinterpret_cast<float4*>(dw_smem);  // [KS*KS][cgb] dequantised weights
   constexpr int PAD = (KS - 1) / 2;
   // window of output columns touched by a 4-pixel input strip starting at iw0 (iw0 % 4 == 0):
@@ -449,6 +452,7 @@ __global__ void __launch_bounds__(256, 3) dw_wgrad_kernel(const float* __restric
                                                          int N, int H, int W, int C, int Ho, int Wo, int cgb,
                                                          float* __restrict__ dwq) {
   extern __shared__ __align__(16) unsigned char dw_smem[];
+  pdl_enter();
   float* s_acc = reinterpret_cast<float*>(dw_smem);  // [KS*KS][cgb*4]
   constexpr int PAD = (KS - 1) / 2;
   constexpr int IW = (DW_TW - 1) * S + KS;
@@ -548,8 +552,8 @@ extern "C" int frost_dw_conv_forward(const uint8_t* xq, const int32_t* x_zp, con
   const size_t smem_g = sizeof(unsigned) * k * k * DW_MAX_CGB + sizeof(SmemStat) * cgb * 4;
 #define L(KS, S)                                                                                                        \
   do {                                                                                                                  \
-    dw_conv_fwd_kernel<KS, S><<<grid, threads, smem, st>>>(xq, x_zp, wq, w_zp, N, H, W, C, Ho, Wo, cgb, acc, stats);     \
-    dw_conv_fwd_generic_kernel<KS, S><<<grid, threads, smem_g, st>>>(xq, x_zp, wq, w_zp, N, H, W, C, Ho, Wo, cgb, acc, stats); \
+    launch_pdl(dw_conv_fwd_kernel<KS, S>, grid, dim3(threads), smem, st, xq, x_zp, wq, w_zp, N, H, W, C, Ho, Wo, cgb, acc, stats);     \
+    launch_pdl(dw_conv_fwd_generic_kernel<KS, S>, grid, dim3(threads), smem_g, st, xq, x_zp, wq, w_zp, N, H, W, C, Ho, Wo, cgb, acc, stats); \
   } while (0)
   if (k == 3 && stride == 1) L(3, 1);
   else if (k == 3 && stride == 2) L(3, 2);
@@ -575,7 +579,7 @@ extern "C" int frost_dw_dgrad(const float* dz, const int8_t* wq, const float* w_
                                                               (int64_t)kNumSMs * tunable(FROST_TUNE_DW_DGRAD_CTAS_PER_SM) / chunks + 1));
   dim3 grid(gx, chunks);
   const size_t smem = sizeof(float4) * k * k * cgb;
-#define L(KS, S) dw_dgrad_kernel<KS, S><<<grid, threads, smem, st>>>(dz, wq, w_scale, w_zp, N, H, W, C, Ho, Wo, cgb, dx, accumulate)
+#define L(KS, S) launch_pdl(dw_dgrad_kernel<KS, S>, grid, dim3(threads), smem, st, dz, wq, w_scale, w_zp, N, H, W, C, Ho, Wo, cgb, dx, accumulate)
   if (k == 3 && stride == 1) L(3, 1);
   else if (k == 3 && stride == 2) L(3, 2);
   else if (k == 5 && stride == 1) L(5, 1);
@@ -607,7 +611,7 @@ extern "C" int frost_dw_wgrad(const float* dz, const uint8_t* xq, const float* x
   const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total_strips, (int64_t)spb * 8), wave));
   dim3 grid(gx, chunks);
   const size_t smem = sizeof(float) * k * k * cgb * 4;
-#define L(KS, S) dw_wgrad_kernel<KS, S><<<grid, threads, smem, st>>>(dz, xq, x_scale, x_zp, N, H, W, C, Ho, Wo, cgb, dwq)
+#define L(KS, S) launch_pdl(dw_wgrad_kernel<KS, S>, grid, dim3(threads), smem, st, dz, xq, x_scale, x_zp, N, H, W, C, Ho, Wo, cgb, dwq)
   if (k == 3 && stride == 1) L(3, 1);
   else if (k == 3 && stride == 2) L(3, 2);
   else if (k == 5 && stride == 1) L(5, 1);

@@ -17,6 +17,7 @@ __device__ __forceinline__ float deq(unsigned byte, const QSrc& s) { return fq_d
 // (each source carries the dequantised min/max of its tensor): no reduction pass.
 __global__ void cat_finalize_kernel(FrostQTensor a, FrostQTensor b, FrostFQ fq, int observe, float c,
                                     float* cur_minmax_out) {
+  pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const float mn = fminf(a.cur_minmax[0], b.cur_minmax[0]);
   const float mx = fmaxf(a.cur_minmax[1], b.cur_minmax[1]);
@@ -32,6 +33,7 @@ __global__ void cat_finalize_kernel(FrostQTensor a, FrostQTensor b, FrostFQ fq, 
 // one thread-iteration = 8 output bytes (C1, C2 multiples of 8)
 __global__ void __launch_bounds__(256) cat_requant_kernel(FrostQTensor a, FrostQTensor b, int64_t M, const float* out_scale,
                                                          const int32_t* out_zp, uint8_t* __restrict__ q_out) {
+  pdl_enter();
   const QSrc sa = load_src(a), sb = load_src(b);
   const float so = *out_scale, zo = (float)*out_zp;
   const float inv = __fdiv_rn(1.0f, so);
@@ -62,6 +64,7 @@ __global__ void __launch_bounds__(256) cat_requant_kernel(FrostQTensor a, FrostQ
 __global__ void __launch_bounds__(256) cat_backward_kernel(const float* __restrict__ dcat, FrostQTensor a, FrostQTensor b,
                                                           int64_t M, const float* out_scale, const int32_t* out_zp,
                                                           float* __restrict__ da, float* __restrict__ db, int accumulate_b) {
+  pdl_enter();
   const QSrc sa = load_src(a), sb = load_src(b);
   const float so = *out_scale, zo = (float)*out_zp;
   const float inv = __fdiv_rn(1.0f, so);
@@ -100,6 +103,7 @@ __global__ void __launch_bounds__(256) cat_backward_kernel(const float* __restri
 
 // ---------------------------------------------------------------- add
 __global__ void __launch_bounds__(256) add_minmax_kernel(FrostQTensor a, FrostQTensor b, int64_t n4, float* __restrict__ partial) {
+  pdl_enter();
   const QSrc sa = load_src(a), sb = load_src(b);
   float mn = INFINITY, mx = -INFINITY;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -122,6 +126,7 @@ __global__ void __launch_bounds__(256) add_minmax_kernel(FrostQTensor a, FrostQT
 
 __global__ void __launch_bounds__(256) add_requant_kernel(FrostQTensor a, FrostQTensor b, int64_t n4, const float* out_scale,
                                                          const int32_t* out_zp, uint8_t* __restrict__ q_out) {
+  pdl_enter();
   const QSrc sa = load_src(a), sb = load_src(b);
   const float so = *out_scale, zo = (float)*out_zp;
   const float inv = __fdiv_rn(1.0f, so);
@@ -143,6 +148,7 @@ __global__ void __launch_bounds__(256) add_requant_kernel(FrostQTensor a, FrostQ
 __global__ void __launch_bounds__(256) add_backward_kernel(const float* __restrict__ dout, FrostQTensor a, FrostQTensor b,
                                                           int64_t n4, const float* out_scale, const int32_t* out_zp,
                                                           float* __restrict__ dsum, float* __restrict__ da, int accumulate_a) {
+  pdl_enter();
   const QSrc sa = load_src(a), sb = load_src(b);
   const float so = *out_scale, zo = (float)*out_zp;
   const float inv = __fdiv_rn(1.0f, so);
@@ -236,10 +242,10 @@ extern "C" int frost_cat_forward(FrostQTensor a, FrostQTensor b, int64_t M, Fros
                 "frost_cat_forward: null pointer");
   FROST_REQUIRE(M > 0 && a.C % 8 == 0 && b.C % 8 == 0, "frost_cat_forward: channel counts must be multiples of 8");
   cudaStream_t st = (cudaStream_t)stream;
-  cat_finalize_kernel<<<1, 32, 0, st>>>(a, b, fq, observe, averaging_const, cur_minmax_out);
+  launch_pdl(cat_finalize_kernel, dim3(1), dim3(32), 0, st, a, b, fq, observe, averaging_const, cur_minmax_out);
   FROST_LAUNCH_CHECK("cat_finalize");
   const int64_t total = M * ((a.C + b.C) / 8);
-  cat_requant_kernel<<<grid_for(total, 256 * 2), 256, 0, st>>>(a, b, M, fq.scale, fq.zero_point, q_out);
+  launch_pdl(cat_requant_kernel, dim3(grid_for(total, 256 * 2)), dim3(256), 0, st, a, b, M, fq.scale, fq.zero_point, q_out);
   FROST_LAUNCH_CHECK("cat_requant");
   return FROST_OK;
 }
@@ -249,8 +255,8 @@ extern "C" int frost_cat_backward(const float* dcat, FrostQTensor a, FrostQTenso
   FROST_REQUIRE(dcat && check_qt(a) && check_qt(b) && out_scale && out_zp && da && db, "frost_cat_backward: null pointer");
   FROST_REQUIRE(M > 0 && a.C % 4 == 0 && b.C % 4 == 0, "frost_cat_backward: channel counts must be multiples of 4");
   const int64_t total = M * ((a.C + b.C) / 4);
-  cat_backward_kernel<<<grid_for(total, 256 * 2), 256, 0, (cudaStream_t)stream>>>(dcat, a, b, M, out_scale, out_zp, da,
-                                                                                  db, accumulate_b);
+  launch_pdl(cat_backward_kernel, dim3(grid_for(total, 256 * 2)), dim3(256), 0, (cudaStream_t)stream, dcat, a, b, M, out_scale, out_zp,
+             da, db, accumulate_b);
   FROST_LAUNCH_CHECK("cat_backward");
   return FROST_OK;
 }
@@ -265,11 +271,11 @@ extern "C" int frost_add_forward(FrostQTensor a, FrostQTensor b, int64_t n, Fros
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n4 = n / 4;
   const int nblk = grid_for(n4, 256 * 4, FROST_FQ_SCRATCH_FLOATS / 2);
-  add_minmax_kernel<<<nblk, 256, 0, st>>>(a, b, n4, scratch);
+  launch_pdl(add_minmax_kernel, dim3(nblk), dim3(256), 0, st, a, b, n4, scratch);
   FROST_LAUNCH_CHECK("add_minmax");
-  fq_finalize_kernel<<<1, 1024, 0, st>>>(scratch, nblk, fq, 0, 255, 0, averaging_const, observe ? 1 : 0, cur_minmax_out);
+  launch_pdl(fq_finalize_kernel, dim3(1), dim3(1024), 0, st, scratch, nblk, fq, 0, 255, 0, averaging_const, observe ? 1 : 0, cur_minmax_out);
   FROST_LAUNCH_CHECK("add_finalize");
-  add_requant_kernel<<<grid_for(n4, 256 * 4), 256, 0, st>>>(a, b, n4, fq.scale, fq.zero_point, q_out);
+  launch_pdl(add_requant_kernel, dim3(grid_for(n4, 256 * 4)), dim3(256), 0, st, a, b, n4, fq.scale, fq.zero_point, q_out);
   FROST_LAUNCH_CHECK("add_requant");
   return FROST_OK;
 }
@@ -278,8 +284,8 @@ extern "C" int frost_add_backward(const float* dout, FrostQTensor a, FrostQTenso
                                   const int32_t* out_zp, float* dsum, float* da, int accumulate_a, void* stream) {
   FROST_REQUIRE(dout && check_qt(a) && check_qt(b) && out_scale && out_zp && dsum && da, "frost_add_backward: null pointer");
   FROST_REQUIRE(n > 0 && n % 4 == 0, "frost_add_backward: n must be a positive multiple of 4");
-  add_backward_kernel<<<grid_for(n / 4, 256 * 4), 256, 0, (cudaStream_t)stream>>>(dout, a, b, n / 4, out_scale, out_zp,
-                                                                                  dsum, da, accumulate_a);
+  launch_pdl(add_backward_kernel, dim3(grid_for(n / 4, 256 * 4)), dim3(256), 0, (cudaStream_t)stream, dout, a, b, n / 4, out_scale, out_zp,
+             dsum, da, accumulate_a);
   FROST_LAUNCH_CHECK("add_backward");
   return FROST_OK;
 }

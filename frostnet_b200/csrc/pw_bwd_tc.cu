@@ -59,15 +59,19 @@ __global__ void __launch_bounds__(DG_THREADS, 1) pw_dgrad_tc_kernel(const uint16
   const int num_kb = (cout + DG_KE - 1) / DG_KE;     // reduction blocks over cout
   const int64_t m_tiles = (M + DG_BM - 1) / DG_BM;
 
+  // barrier init and the TMEM allocation overlap the previous kernel's tail; dependents are released after the
+  // allocation is complete (see pw_conv_tc.cu)
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
     mbar_fence_init();
   }
   if (warp == 12) tmem_alloc<2 * BN>(tmem_slot);
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_trigger();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 8 && warp < 12) {
@@ -208,7 +212,7 @@ static int launch_dgrad_tc(const uint16_t* dz_hi, const uint16_t* dz_lo, const u
   const int n_tiles = (K + BN - 1) / BN;
   const int64_t m_tiles = ceil_div(M, DG_BM);
   const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(m_tiles, kNumSMs / n_tiles));
-  pw_dgrad_tc_kernel<BN><<<dim3(gx, n_tiles), DG_THREADS, smem, st>>>(dz_hi, dz_lo, wt, w_scale, M, K, cout, dx, accumulate);
+  launch_pdl(pw_dgrad_tc_kernel<BN>, dim3(gx, n_tiles), dim3(DG_THREADS), smem, st, dz_hi, dz_lo, wt, w_scale, M, K, cout, dx, accumulate);
   return FROST_OK;
 }
 
@@ -272,9 +276,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
     mbar_fence_init();
   }
   if (warp == 8) tmem_alloc<BN>(tmem_slot);
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_trigger();
   const uint32_t tmem_base = *tmem_slot;
 
   if (num_kb > 0) {
@@ -419,7 +425,7 @@ static int launch_wgrad_tc(const uint16_t* dz_hi, const uint16_t* dz_lo, const u
   int64_t splits = std::max<int64_t>(1, std::min<int64_t>(ceil_div(M, WG_ROWS * 4), (int64_t)kNumSMs / ((int64_t)ct * kt)));
   int64_t rows = ceil_div(ceil_div(M, splits), WG_ROWS) * WG_ROWS;
   splits = ceil_div(M, rows);
-  pw_wgrad_tc_kernel<BN><<<dim3(ct, kt, (unsigned)splits), WG_THREADS, smem, st>>>(dz_hi, dz_lo, xq, x_scale, x_zp, M, K, cout, rows, dwq);
+  launch_pdl(pw_wgrad_tc_kernel<BN>, dim3(ct, kt, (unsigned)splits), dim3(WG_THREADS), smem, st, dz_hi, dz_lo, xq, x_scale, x_zp, M, K, cout, rows, dwq);
   return FROST_OK;
 }
 

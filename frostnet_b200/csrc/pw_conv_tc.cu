@@ -60,6 +60,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // ---- one-time setup.  Everything up to pdl_wait() touches only this CTA's shared memory / TMEM and overlaps
+  // the tail of the previous kernel in the stream (common.cuh: programmatic dependent launch).  Dependents are
+  // released only after this CTA's TMEM allocation is complete: a dependent CTA that became resident on this SM and
+  // allocated first would block our tcgen05.alloc while waiting for our grid - a deadlock.
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    mbar_fence_init();
+  }
+  if (warp == 12) tmem_alloc<2 * BN>(tmem_slot);
+  pdl_wait();
   const int zp_a = *x_zp_p, zp_w = *w_zp_p;
   if (zp_w != 0 && zp_w != -128 && zp_w != 127) __trap();  // not reachable with ChooseQuantizationParams
   const uint32_t wxor = zp_w == 0 ? 0u : (zp_w == -128 ? 0x80808080u : 0x7f7f7f7fu);
@@ -69,8 +80,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
   const int n_eff = (n_valid + 15) & ~15;
   const int num_kb = (K + TC_BK - 1) / TC_BK;
   const int64_t m_tiles = (M + TC_BM - 1) / TC_BM;
-
-  // ---- one-time setup
   for (int j = threadIdx.x; j < BN; j += blockDim.x) {
     int corr = 0;
     if (j < n_valid) {
@@ -81,15 +90,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
     s_corr[j] = corr;
     s_stat[j].sum = 0; s_stat[j].sq = 0; s_stat[j].mn = INT_MAX; s_stat[j].mx = INT_MIN;
   }
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
-    mbar_fence_init();
-  }
-  if (warp == 12) tmem_alloc<2 * BN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_trigger();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 8 && warp < 12) {
@@ -290,7 +294,7 @@ static int launch_tc(const uint8_t* xq, const int32_t* x_zp, const int8_t* wq, c
   const int n_tiles = (cout + BN - 1) / BN;
   const int64_t m_tiles = ceil_div(M, TC_BM);
   const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(m_tiles, kNumSMs / n_tiles));
-  pw_conv_fwd_tc_kernel<BN, VEC16><<<dim3(gx, n_tiles), TC_THREADS, smem, st>>>(xq, x_zp, wq, w_zp, wsum, M, K, cout, acc, stats);
+  launch_pdl(pw_conv_fwd_tc_kernel<BN, VEC16>, dim3(gx, n_tiles), dim3(TC_THREADS), smem, st, xq, x_zp, wq, w_zp, wsum, M, K, cout, acc, stats);
   return FROST_OK;
 }
 

@@ -46,7 +46,11 @@ enum {
   FROST_TUNE_STEM_FWD_CTAS_PER_SM = 4, /* stem forward (persistent over pixel tiles)                         */
   FROST_TUNE_STEM_WGRAD_CTAS_PER_SM = 5,
   FROST_TUNE_DW_DGRAD_CTAS_PER_SM = 6,
-  FROST_TUNE_COUNT = 7
+  FROST_TUNE_PDL = 7,                  /* 1: programmatic dependent launch between the per-layer kernels, 2: off */
+  FROST_TUNE_BN_RED_UNROLL = 8,        /* bn_backward_reduce: rows in flight per thread (4 or 8)               */
+  FROST_TUNE_BN_APPLY_UNROLL = 9,      /* bn_backward_apply: elements in flight per thread (1, 2 or 4)          */
+  FROST_TUNE_BNQ_UNROLL = 10,          /* bnq_apply: 16-byte loads in flight per thread (2, 4 or 8)             */
+  FROST_TUNE_COUNT = 11
 };
 int frost_set_tunable(int which, int value);
 int frost_get_tunable(int which);

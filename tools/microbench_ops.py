@@ -15,7 +15,7 @@ from frostnet_b200 import _lib as L  # noqa: E402
 dev = "cuda:0"
 N = 256
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-T_DW_FWD, T_DW_WGRAD, T_BN_RED, T_BN_CGB, T_STEM_FWD, T_STEM_WGRAD, T_DW_DGRAD = range(7)
+T_DW_FWD, T_DW_WGRAD, T_BN_RED, T_BN_CGB, T_STEM_FWD, T_STEM_WGRAD, T_DW_DGRAD, T_PDL, T_BN_RED_UNROLL, T_BN_APPLY_UNROLL, T_BNQ_UNROLL = range(11)
 QUICK = "--quick" in sys.argv
 
 
@@ -74,18 +74,18 @@ def bench_dw(H, W, Cc, k, s):
     nin, nout = N * H * W * Cc, N * Ho * Wo * Cc
     sweep("dw_fwd", shape, lambda: L.call("frost_dw_conv_forward", xq.data_ptr(), za.data_ptr(), wq.data_ptr(), zw.data_ptr(),
                                           N, H, W, Cc, k, s, acc.data_ptr(), stats.data_ptr(), st()),
-          nin + 4 * nout, T_DW_FWD, [1, 2, 3, 4, 8, 16])
+          nin + 4 * nout, T_DW_FWD, [2, 4])
     dz = torch.randn(N, Ho, Wo, Cc, device=dev)
     dwq = torch.empty(k * k, Cc, device=dev)
     sa = f32(0.02)
     sweep("dw_wgrad", shape, lambda: L.call("frost_dw_wgrad", dz.data_ptr(), xq.data_ptr(), sa.data_ptr(), za.data_ptr(),
                                             N, H, W, Cc, k, s, dwq.data_ptr(), st()),
-          nin + 4 * nout, T_DW_WGRAD, [1, 2, 3, 6])
+          nin + 4 * nout, T_DW_WGRAD, [3, 6])
     dx = torch.empty(N, H, W, Cc, device=dev)
     sw = f32(0.01)
     sweep("dw_dgrad", shape, lambda: L.call("frost_dw_dgrad", dz.data_ptr(), wq.data_ptr(), sw.data_ptr(), zw.data_ptr(),
                                             N, H, W, Cc, k, s, dx.data_ptr(), 0, st()),
-          4 * nin + 4 * nout, T_DW_DGRAD, [3, 6, 16])
+          4 * nin + 4 * nout, T_DW_DGRAD, [8, 16, 32, 64])
 
 
 def bench_bn(M, Cc):
@@ -109,16 +109,14 @@ def bench_bn(M, Cc):
     shape = "bn M=%d C=%d" % (M, Cc)
     n = M * Cc
     red = lambda: L.call("frost_bn_backward_reduce", C.byref(b), st())  # noqa: E731
-    for cgb in ([8, 16, 32, 64] if not QUICK else [16, 64]):
-        tune(T_BN_CGB, cgb)
-        sweep("bn_red cgb<=%d" % cgb, shape, red, 8 * n, T_BN_RED, [1, 2, 3])
-    tune(T_BN_CGB, 0)
-    t = timeit(lambda: L.call("frost_bn_backward_apply", C.byref(b), st()))
-    print("%-16s %-28s %.1f us (%.0f GB/s)" % ("bn_apply", shape, t, 12 * n / t / 1e3), flush=True)
+    for unroll in (4, 8):
+        tune(T_BN_RED_UNROLL, unroll)
+        sweep("bn_red U=%d" % unroll, shape, red, 8 * n, T_BN_RED, [2, 3, 4])
+    tune(T_BN_RED_UNROLL, 0)
+    sweep("bn_apply", shape, lambda: L.call("frost_bn_backward_apply", C.byref(b), st()), 12 * n, T_BN_APPLY_UNROLL, [1, 2, 4])
     q = torch.empty(M, Cc, dtype=torch.uint8, device=dev)
-    t = timeit(lambda: L.call("frost_bnq_apply", acc.data_ptr(), 0, M, Cc, A.data_ptr(), B.data_ptr(), 1, sc.data_ptr(),
-                              zp.data_ptr(), q.data_ptr(), st()))
-    print("%-16s %-28s %.1f us (%.0f GB/s)" % ("bnq_apply", shape, t, 5 * n / t / 1e3), flush=True)
+    sweep("bnq_apply", shape, lambda: L.call("frost_bnq_apply", acc.data_ptr(), 0, M, Cc, A.data_ptr(), B.data_ptr(), 1, sc.data_ptr(),
+                                             zp.data_ptr(), q.data_ptr(), st()), 5 * n, T_BNQ_UNROLL, [2, 4, 8])
 
 
 def bench_stem():
@@ -132,13 +130,13 @@ def bench_stem():
     nb = N * H * W * 3 + 4 * N * 112 * 112 * 32
     sweep("stem_fwd", "224x224x3 -> 32", lambda: L.call("frost_stem_conv_forward", xq.data_ptr(), za.data_ptr(), wq.data_ptr(),
                                                         zw.data_ptr(), N, H, W, 3, 32, 3, 2, 1, acc.data_ptr(), stats.data_ptr(), st()),
-          nb, T_STEM_FWD, [1, 2, 3, 4, 6, 8, 16])
+          nb, T_STEM_FWD, [4, 8, 16])
     dz = torch.randn(N, 112, 112, 32, device=dev)
     dwq = torch.empty(32, 3, 3, 3, device=dev)
     sa = f32(0.02)
     sweep("stem_wgrad", "224x224x3 -> 32", lambda: L.call("frost_stem_wgrad", dz.data_ptr(), xq.data_ptr(), sa.data_ptr(), za.data_ptr(),
                                                           N, H, W, 3, 32, 3, 2, 1, dwq.data_ptr(), st()),
-          nb, T_STEM_WGRAD, [1, 2, 3, 4, 6])
+          nb, T_STEM_WGRAD, [3, 4, 5])
 
 
 def bench_pw(M, K, cout):
