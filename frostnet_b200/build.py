@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libfrost_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--use_fast_math=false"]
+EXTRA = os.environ.get("FROST_NVCC_FLAGS", "").split()      # experiments only (e.g. -DFROST_NO_NC)
 
 
 def _sources():
@@ -25,6 +26,7 @@ def _sources():
 
 def _fingerprint():
     h = hashlib.sha256()
+    h.update(" ".join(EXTRA).encode())
     for f in _sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [
             os.path.join(os.path.dirname(HERE), "include", "frost_b200.h")]:
         with open(f, "rb") as fh:
@@ -44,7 +46,7 @@ def build_library(force=False, verbose=False):
     procs = []
     for src in _sources():
         obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [NVCC] + ARCH_FLAGS + [f for f in CFLAGS if not f.startswith("--use_fast_math")] + ["-c", src, "-o", obj]
+        cmd = [NVCC] + ARCH_FLAGS + [f for f in CFLAGS if not f.startswith("--use_fast_math")] + EXTRA + ["-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))

@@ -88,10 +88,10 @@ __device__ __forceinline__ unsigned bnq4(const int4 v, int fmt, const float4 A, 
 }
 
 template <int U>   // 16-byte loads in flight per thread
-__global__ void __launch_bounds__(256) bnq_apply_kernel(const int32_t* __restrict__ acc, int fmt, int64_t n4, int C,
-                                                       const float* __restrict__ A, const float* __restrict__ B,
-                                                       int relu, const float* __restrict__ scale_p,
-                                                       const int32_t* __restrict__ zp_p, uint8_t* __restrict__ q) {
+__global__ void __launch_bounds__(256) bnq_apply_kernel(const int32_t* acc, int fmt, int64_t n4, int C,
+                                                       const float* A, const float* B,
+                                                       int relu, const float* scale_p,
+                                                       const int32_t* zp_p, uint8_t* q) {
   extern __shared__ __align__(16) float s_ab[];  // A[C], B[C]
   pdl_enter();
   for (int c = threadIdx.x; c < C; c += blockDim.x) { s_ab[c] = A[c]; s_ab[C + c] = B[c]; }
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) bnq_apply_kernel(const int32_t* __restric
     int4 v[U];
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (i + u * stride < n4) v[u] = __ldg(in + i + u * stride);
+      if (i + u * stride < n4) v[u] = ld_cg(in + i + u * stride);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (i + u * stride < n4) out[i + u * stride] = bnq4(v[u], fmt, sA[cg], sB[cg], relu, inv, zp);
@@ -152,9 +152,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(FrostBnBackwardArgs 
   for (int j = 0; j < 8; ++j) mine[j] = 0.0;
   {
     const float inv = __fdiv_rn(1.0f, *a.out_scale), zp = (float)*a.out_zp;
-    const float4 A = __ldg(reinterpret_cast<const float4*>(a.A) + cg);
-    const float4 B = __ldg(reinterpret_cast<const float4*>(a.B) + cg);
-    const float4 mu = __ldg(reinterpret_cast<const float4*>(a.mean_I) + cg);
+    const float4 A = ld_cg(reinterpret_cast<const float4*>(a.A) + cg);
+    const float4 B = ld_cg(reinterpret_cast<const float4*>(a.B) + cg);
+    const float4 mu = ld_cg(reinterpret_cast<const float4*>(a.mean_I) + cg);
     const int64_t stride = (int64_t)gridDim.x * rows_per_block;
     int batches = 0;
     float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -167,8 +167,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(FrostBnBackwardArgs 
         dy[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         I[u] = make_int4(0, 0, 0, 0);
         if (mm < a.M) {
-          dy[u] = __ldg(reinterpret_cast<const float4*>(a.dy + mm * C) + cg);
-          I[u] = __ldg(reinterpret_cast<const int4*>(a.acc + mm * C) + cg);
+          dy[u] = ld_cg(reinterpret_cast<const float4*>(a.dy + mm * C) + cg);
+          I[u] = ld_cg(reinterpret_cast<const int4*>(a.acc + mm * C) + cg);
         }
       }
 #pragma unroll
@@ -250,8 +250,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(FrostBnBackwardArgs a
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (ib + u * stride < n4) {
-        dyv[u] = __ldg(reinterpret_cast<const float4*>(a.dy) + ib + u * stride);
-        Iv[u] = __ldg(reinterpret_cast<const int4*>(a.acc) + ib + u * stride);
+        dyv[u] = ld_cg(reinterpret_cast<const float4*>(a.dy) + ib + u * stride);
+        Iv[u] = ld_cg(reinterpret_cast<const int4*>(a.acc) + ib + u * stride);
       }
     }
 #pragma unroll

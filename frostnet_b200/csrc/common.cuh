@@ -36,6 +36,17 @@ int tunable(int which);  // FROST_TUNE_* launch-shape knob (api.cu)
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---------------------------------------------------------------- global loads
+// Every load of data that another kernel of the step produced goes to L2 (ld.global.cg), and no pointer carries
+// the restrict qualifier: the NON-COHERENT path (ld.global.nc - the ldg intrinsic, or the compiler's promotion
+// of loads through const restrict pointers) is exempt from the visibility guarantee of griddepcontrol.wait.  With
+// programmatic dependent launch a CTA can be resident on an SM while an older kernel's CTA on the same SM still
+// pulls lines into L1; when the torch caching allocator hands the same address to the next layer's tensor, a
+// .nc load after the wait hit those stale lines (measured: flaky index mismatches, gone with this rule).
+// The streaming operands have no L1 reuse to lose; the depthwise windows are served by L2.
+template <typename T>
+__device__ __forceinline__ T ld_cg(const T* p) { return __ldcg(p); }
+
 // ---------------------------------------------------------------- programmatic dependent launch (PDL)
 // A QAT step is ~590 dependent launches of 5-600 us kernels.  Kernels launched through launch_pdl() may become
 // resident while their predecessor in the stream is still draining (the predecessor's CTAs call
@@ -47,8 +58,10 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
 
+// early = false: ordinary stream-ordered launch (for kernels that still load through L1, e.g. 8-byte cp.async.ca)
 template <typename... KArgs, typename... Args>
-static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+static inline cudaError_t launch_pdl_if(bool early, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                        Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -58,8 +71,13 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = tunable(FROST_TUNE_PDL) == 1 ? 1 : 0;
+  cfg.numAttrs = (early && tunable(FROST_TUNE_PDL) == 1) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  return launch_pdl_if(true, kernel, grid, block, smem, st, args...);
 }
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -219,9 +237,9 @@ __device__ __forceinline__ void block_minmax(float& mn, float& mx) {
 
 // Reduce the partials, run observer + qparams; optionally emit the dequantised min/max of the
 // tensor that the apply kernel will produce (quantisation is monotone).
-static __global__ void __launch_bounds__(1024) fq_finalize_kernel(const float* __restrict__ partial, int nparts, FrostFQ fq,
+static __global__ void __launch_bounds__(1024) fq_finalize_kernel(const float* partial, int nparts, FrostFQ fq,
                                                            int qmin, int qmax, int symmetric, float c,
-                                                           int observe, float* __restrict__ cur_minmax) {
+                                                           int observe, float* cur_minmax) {
   pdl_enter();
   float mn = INFINITY, mx = -INFINITY;
   for (int i = threadIdx.x; i < nparts; i += blockDim.x) {

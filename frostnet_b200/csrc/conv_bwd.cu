@@ -14,9 +14,9 @@ constexpr int GB_LD = GB_T + 4;
 
 // ---------------------------------------------------------------- pointwise dgrad
 // dx[m][k] (+)= s_w * sum_co dz[m][co] * (wq[co][k] - zp_w)
-__global__ void __launch_bounds__(256) pw_dgrad_kernel(const float* __restrict__ dz, const int8_t* __restrict__ wq,
-                                                      const float* __restrict__ w_scale_p, const int32_t* __restrict__ w_zp_p,
-                                                      int64_t M, int K, int cout, float* __restrict__ dx, int accumulate) {
+__global__ void __launch_bounds__(256) pw_dgrad_kernel(const float* dz, const int8_t* wq,
+                                                      const float* w_scale_p, const int32_t* w_zp_p,
+                                                      int64_t M, int K, int cout, float* dx, int accumulate) {
   __shared__ __align__(16) float a_s[GB_RC][GB_LD];  // dz^T : [co][m]
   __shared__ __align__(16) float b_s[GB_RC][GB_LD];  // w    : [co][k]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) pw_dgrad_kernel(const float* __restrict__
       const int64_t m = m0 + r;
       const int co = c0 + c4 * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < M && co < cout) v = __ldg(reinterpret_cast<const float4*>(dz + m * cout + co));  // cout % 4 == 0
+      if (m < M && co < cout) v = ld_cg(reinterpret_cast<const float4*>(dz + m * cout + co));  // cout % 4 == 0
       a_s[c4 * 4 + 0][r] = v.x;
       a_s[c4 * 4 + 1][r] = v.y;
       a_s[c4 * 4 + 2][r] = v.z;
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) pw_dgrad_kernel(const float* __restrict__
       const int co = c0 + r, k = k0 + k4 * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (co < cout && k < K) {
-        const unsigned pk = __ldg(reinterpret_cast<const unsigned*>(wq + (int64_t)co * K + k));
+        const unsigned pk = ld_cg(reinterpret_cast<const unsigned*>(wq + (int64_t)co * K + k));
         v.x = (float)(int8_t)(pk & 0xff) - zp_w;
         v.y = (float)(int8_t)((pk >> 8) & 0xff) - zp_w;
         v.z = (float)(int8_t)((pk >> 16) & 0xff) - zp_w;
@@ -89,10 +89,10 @@ __global__ void __launch_bounds__(256) pw_dgrad_kernel(const float* __restrict__
 // ---------------------------------------------------------------- pointwise wgrad (split over M)
 // dwq[co][k] += s_a * sum_m dz[m][co] * (x[m][k] - zp_a);  X = uint8 indices or fp32 (classifier)
 template <typename XT>
-__global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__ dz, const XT* __restrict__ x,
-                                                      const float* __restrict__ x_scale_p, const int32_t* __restrict__ x_zp_p,
+__global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* dz, const XT* x,
+                                                      const float* x_scale_p, const int32_t* x_zp_p,
                                                       int64_t M, int K, int cout, int64_t rows_per_split,
-                                                      float* __restrict__ dwq) {
+                                                      float* dwq) {
   __shared__ __align__(16) float a_s[GB_RC][GB_LD];  // dz : [m][co]
   __shared__ __align__(16) float b_s[GB_RC][GB_LD];  // x  : [m][k]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__
     {
       const int co = co0 + c4 * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < m_end && co < cout) v = __ldg(reinterpret_cast<const float4*>(dz + m * cout + co));
+      if (m < m_end && co < cout) v = ld_cg(reinterpret_cast<const float4*>(dz + m * cout + co));
       *reinterpret_cast<float4*>(&a_s[r][c4 * 4]) = v;
     }
     {
@@ -120,13 +120,13 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (m < m_end && k < K) {
         if constexpr (sizeof(XT) == 1) {
-          const unsigned pk = __ldg(reinterpret_cast<const unsigned*>(x + m * K + k));
+          const unsigned pk = ld_cg(reinterpret_cast<const unsigned*>(x + m * K + k));
           v.x = (float)(pk & 0xff) - zp_a;
           v.y = (float)((pk >> 8) & 0xff) - zp_a;
           v.z = (float)((pk >> 16) & 0xff) - zp_a;
           v.w = (float)((pk >> 24) & 0xff) - zp_a;
         } else {
-          v = __ldg(reinterpret_cast<const float4*>(x + m * K + k));
+          v = ld_cg(reinterpret_cast<const float4*>(x + m * K + k));
         }
       }
       *reinterpret_cast<float4*>(&b_s[r][c4 * 4]) = v;
@@ -165,10 +165,10 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__
 // The four pixel subsets are summed through shared memory, then one scalar atomic per (co, tap) per CTA;
 // the grid is one resident wave (frost::tunable).
 constexpr int STEMW_PIX = 64;
-__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ dz, const uint8_t* __restrict__ xq,
-                                                        const float* __restrict__ x_scale_p, const int32_t* __restrict__ x_zp_p,
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* dz, const uint8_t* xq,
+                                                        const float* x_scale_p, const int32_t* x_zp_p,
                                                         int N, int H, int W, int cin, int cout, int k, int stride, int pad,
-                                                        int Ho, int Wo, int64_t pix_per_block, float* __restrict__ dwq) {
+                                                        int Ho, int Wo, int64_t pix_per_block, float* dwq) {
   constexpr int PP = 36;                       // patch pitch: 16-byte aligned rows, fill stores spread over banks
   __shared__ __align__(16) float s_buf[STEMW_PIX * PP + STEMW_PIX * 32];
   pdl_enter();
@@ -208,12 +208,12 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
         const int ih = ih0 + r, iw = iw0 + sx;
         const bool ok = pv && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W;
         const uint8_t* px = img + ((int64_t)ih * W + iw) * cin;
-        for (int ci = 0; ci < cin; ++ci) s_patch[fp * PP + rs * cin + ci] = ok ? (float)__ldg(px + ci) - zp_a : 0.0f;
+        for (int ci = 0; ci < cin; ++ci) s_patch[fp * PP + rs * cin + ci] = ok ? (float)ld_cg(px + ci) - zp_a : 0.0f;
       }
     }
     for (int i = threadIdx.x; i < STEMW_PIX * 32; i += blockDim.x) {
       const int pl = i >> 5, c = i & 31;
-      s_dz[i] = (pl < np && c < cout) ? __ldg(dz + (pb + pl) * cout + c) : 0.0f;
+      s_dz[i] = (pl < np && c < cout) ? ld_cg(dz + (pb + pl) * cout + c) : 0.0f;
     }
     __syncthreads();
 #pragma unroll 4
@@ -246,10 +246,10 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
 
 // ---------------------------------------------------------------- classifier forward
 // out[n][co] = sum_k x[n][k] * (wq[co][k]-zp_w)*s_w + bias[co]
-__global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict__ x, const int8_t* __restrict__ wq,
-                                                        const float* __restrict__ w_scale_p, const int32_t* __restrict__ w_zp_p,
-                                                        const float* __restrict__ bias, int N, int K, int cout,
-                                                        float* __restrict__ out) {
+__global__ void __launch_bounds__(256) linear_fwd_kernel(const float* x, const int8_t* wq,
+                                                        const float* w_scale_p, const int32_t* w_zp_p,
+                                                        const float* bias, int N, int K, int cout,
+                                                        float* out) {
   __shared__ __align__(16) float a_s[GB_RC][GB_LD];  // x^T : [k][n]
   __shared__ __align__(16) float b_s[GB_RC][GB_LD];  // w^T : [k][co]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -265,13 +265,13 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict
     const int k = k0 + k4 * 4;
     {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n0 + r < N && k < K) v = __ldg(reinterpret_cast<const float4*>(x + (int64_t)(n0 + r) * K + k));
+      if (n0 + r < N && k < K) v = ld_cg(reinterpret_cast<const float4*>(x + (int64_t)(n0 + r) * K + k));
       a_s[k4 * 4 + 0][r] = v.x; a_s[k4 * 4 + 1][r] = v.y; a_s[k4 * 4 + 2][r] = v.z; a_s[k4 * 4 + 3][r] = v.w;
     }
     {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (co0 + r < cout && k < K) {
-        const unsigned pk = __ldg(reinterpret_cast<const unsigned*>(wq + (int64_t)(co0 + r) * K + k));
+        const unsigned pk = ld_cg(reinterpret_cast<const unsigned*>(wq + (int64_t)(co0 + r) * K + k));
         v.x = ((float)(int8_t)(pk & 0xff) - zp_w) * s_w;
         v.y = ((float)(int8_t)((pk >> 8) & 0xff) - zp_w) * s_w;
         v.z = ((float)(int8_t)((pk >> 16) & 0xff) - zp_w) * s_w;
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict
   }
 }
 
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d, int N, int C, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) colsum_kernel(const float* d, int N, int C, float* out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float s = 0.0f;

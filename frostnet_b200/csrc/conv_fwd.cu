@@ -52,10 +52,10 @@ constexpr int PW_KC = 64;
 constexpr int PW_LD = 80;
 
 template <int BN>
-__global__ void __launch_bounds__(256) pw_conv_fwd_kernel(const uint8_t* __restrict__ xq, const int32_t* __restrict__ x_zp_p,
-                                                         const int8_t* __restrict__ wq, const int32_t* __restrict__ w_zp_p,
-                                                         const int32_t* __restrict__ wsum, int64_t M, int K, int cout,
-                                                         int32_t* __restrict__ acc_out, FrostChanStats* __restrict__ stats) {
+__global__ void __launch_bounds__(256) pw_conv_fwd_kernel(const uint8_t* xq, const int32_t* x_zp_p,
+                                                         const int8_t* wq, const int32_t* w_zp_p,
+                                                         const int32_t* wsum, int64_t M, int K, int cout,
+                                                         int32_t* acc_out, FrostChanStats* stats) {
   constexpr int TN = BN / 16;
   constexpr int A_LOADS = PW_BM * PW_KC / 8 / 256;  // uint2 per thread = 4
   constexpr int B_LOADS = (BN * PW_KC / 8 + 255) / 256;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) pw_conv_fwd_kernel(const uint8_t* __restr
       const int64_t m = m0 + r;
       const int k = k0 + c8 * 8;
       pa[l] = make_uint2(0u, 0u);
-      if (m < M && k < K) pa[l] = __ldg(reinterpret_cast<const uint2*>(xq + m * K + k));
+      if (m < M && k < K) pa[l] = ld_cg(reinterpret_cast<const uint2*>(xq + m * K + k));
     }
 #pragma unroll
     for (int l = 0; l < B_LOADS; ++l) {
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) pw_conv_fwd_kernel(const uint8_t* __restr
       const int r = idx >> 3, c8 = idx & 7;
       const int k = k0 + c8 * 8;
       pb[l] = make_uint2(0u, 0u);
-      if (r < BN && n0 + r < cout && k < K) pb[l] = __ldg(reinterpret_cast<const uint2*>(wq + (int64_t)(n0 + r) * K + k));
+      if (r < BN && n0 + r < cout && k < K) pb[l] = ld_cg(reinterpret_cast<const uint2*>(wq + (int64_t)(n0 + r) * K + k));
     }
   };
   auto store_chunk = [&]() {
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) pw_conv_fwd_kernel(const uint8_t* __restr
   for (int j = 0; j < TN; ++j) {
     const int co = n0 + tx + 16 * j;
     const bool cvalid = co < cout;
-    const int corr_c = cvalid ? zp_a * __ldg(wsum + co) : 0;
+    const int corr_c = cvalid ? zp_a * ld_cg(wsum + co) : 0;
     long long s = 0;
     unsigned long long sq = 0;
     int mn = INT_MAX, mx = INT_MIN;
@@ -188,9 +188,9 @@ constexpr int STEM_MAXC = 32;
 constexpr int STEM_THREADS = 256;
 
 __global__ void __launch_bounds__(STEM_THREADS) stem_conv_fwd_kernel(
-    const uint8_t* __restrict__ xq, const int32_t* __restrict__ x_zp_p, const int8_t* __restrict__ wq,
-    const int32_t* __restrict__ w_zp_p, int N, int H, int W, int cin, int cout, int k, int stride, int pad, int Ho,
-    int Wo, int32_t* __restrict__ acc_out, FrostChanStats* __restrict__ stats) {
+    const uint8_t* xq, const int32_t* x_zp_p, const int8_t* wq,
+    const int32_t* w_zp_p, int N, int H, int W, int cin, int cout, int k, int stride, int pad, int Ho,
+    int Wo, int32_t* acc_out, FrostChanStats* stats) {
   extern __shared__ int s_mem[];
   pdl_enter();
   const int KK = k * k * cin;
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(STEM_THREADS) stem_conv_fwd_kernel(
           if (iw < 0 || iw >= W) continue;
           const uint8_t* px = xq + (((int64_t)n * H + ih) * W + iw) * cin;
           for (int ci = 0; ci < cin; ++ci) {
-            const int xa = (int)__ldg(px + ci) - zp_a;
+            const int xa = (int)ld_cg(px + ci) - zp_a;
             const int* wrow = s_w + ((r * k + s) * cin + ci) * STEM_MAXC;
 #pragma unroll
             for (int c = 0; c < STEM_MAXC; ++c) acc[c] += xa * wrow[c];

@@ -99,10 +99,10 @@ __device__ __forceinline__ void transpose4x4(unsigned a, unsigned b, unsigned c,
 }
 
 template <int KS, int S>
-__global__ void __launch_bounds__(256, 2) dw_conv_fwd_kernel(const uint8_t* __restrict__ xq, const int32_t* __restrict__ x_zp_p,
-                                                            const int8_t* __restrict__ wq, const int32_t* __restrict__ w_zp_p,
+__global__ void __launch_bounds__(256, 2) dw_conv_fwd_kernel(const uint8_t* xq, const int32_t* x_zp_p,
+                                                            const int8_t* wq, const int32_t* w_zp_p,
                                                             int N, int H, int W, int C, int Ho, int Wo, int cgb,
-                                                            int32_t* __restrict__ acc_out, FrostChanStats* __restrict__ stats) {
+                                                            int32_t* acc_out, FrostChanStats* stats) {
   extern __shared__ __align__(16) unsigned char dw_smem[];
   pdl_enter();
   constexpr int PAD = (KS - 1) / 2;
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_kernel(const uint8_t* __re
       for (int j = 0; j < NB * 4; ++j) {
         const int iw = ow0 * S - PAD + j;
         const bool ok = (j < IW) && rok && ((unsigned)iw < (unsigned)W);
-        xw_all[r][j] = ok ? __ldg(reinterpret_cast<const unsigned*>(row + (int64_t)iw * C)) : zp4;
+        xw_all[r][j] = ok ? ld_cg(reinterpret_cast<const unsigned*>(row + (int64_t)iw * C)) : zp4;
       }
     }
 #pragma unroll
@@ -241,10 +241,10 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_kernel(const uint8_t* __re
 // ================================================================= forward, generic zero-points (byte unpacking)
 // Only runs when the weight zero-point is not 0 (one-signed weight tensor: SURVEY K5); exits otherwise.
 template <int KS, int S>
-__global__ void __launch_bounds__(256, 2) dw_conv_fwd_generic_kernel(const uint8_t* __restrict__ xq, const int32_t* __restrict__ x_zp_p,
-                                                            const int8_t* __restrict__ wq, const int32_t* __restrict__ w_zp_p,
+__global__ void __launch_bounds__(256, 2) dw_conv_fwd_generic_kernel(const uint8_t* xq, const int32_t* x_zp_p,
+                                                            const int8_t* wq, const int32_t* w_zp_p,
                                                             int N, int H, int W, int C, int Ho, int Wo, int cgb,
-                                                            int32_t* __restrict__ acc_out, FrostChanStats* __restrict__ stats) {
+                                                            int32_t* acc_out, FrostChanStats* stats) {
   extern __shared__ __align__(16) unsigned char dw_smem[];
   pdl_enter();
   unsigned* s_w = reinterpret_cast<unsigned*>(dw_smem);                               // [KS*KS][cgb] packed int8x4
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_generic_kernel(const uint8
 
   for (int i = threadIdx.x; i < KS * KS * cgb; i += blockDim.x) {
     const int t = i / cgb, g = i % cgb;
-    s_w[t * cgb + g] = __ldg(reinterpret_cast<const unsigned*>(wq + (int64_t)t * C + (blockIdx.y * cgb + g) * 4));
+    s_w[t * cgb + g] = ld_cg(reinterpret_cast<const unsigned*>(wq + (int64_t)t * C + (blockIdx.y * cgb + g) * 4));
   }
   for (int i = threadIdx.x; i < cgb * 4; i += blockDim.x) {
     s_stat[i].sum = 0; s_stat[i].sq = 0; s_stat[i].mn = INT_MAX; s_stat[i].mx = INT_MIN;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_generic_kernel(const uint8
       for (int j = 0; j < IW; ++j) {
         const int iw = ow0 * S - PAD + j;
         const bool ok = rok && ((unsigned)iw < (unsigned)W);
-        xw[j] = ok ? __ldg(reinterpret_cast<const unsigned*>(row + (int64_t)iw * C)) : zp4;
+        xw[j] = ok ? ld_cg(reinterpret_cast<const unsigned*>(row + (int64_t)iw * C)) : zp4;
       }
       int wr[KS][4];
 #pragma unroll
@@ -357,10 +357,10 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_generic_kernel(const uint8
 // Strips start at multiples of 4 along W, so for stride 2 the set of (pixel, tap) pairs that hit an
 // output column is known at compile time; valid kernel rows are a run-time (per-thread) stride-S loop.
 template <int KS, int S>
-__global__ void __launch_bounds__(256, 3) dw_dgrad_kernel(const float* __restrict__ dz, const int8_t* __restrict__ wq,
-                                                         const float* __restrict__ w_scale_p, const int32_t* __restrict__ w_zp_p,
+__global__ void __launch_bounds__(256, 3) dw_dgrad_kernel(const float* dz, const int8_t* wq,
+                                                         const float* w_scale_p, const int32_t* w_zp_p,
                                                          int N, int H, int W, int C, int Ho, int Wo, int cgb,
-                                                         float* __restrict__ dx, int accumulate) {
+                                                         float* dx, int accumulate) {
   extern __shared__ __align__(16) unsigned char dw_smem[];
   pdl_enter();
   float4* s_w = reinterpret_cast<float4*>(dw_smem);  // [KS*KS][cgb] dequantised weights
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256, 3) dw_dgrad_kernel(const float* __restric
     const float zp_w = (float)*w_zp_p, s_wt = *w_scale_p;
     for (int i = threadIdx.x; i < KS * KS * cgb; i += blockDim.x) {
       const int t = i / cgb, g = i % cgb;
-      const unsigned pk = __ldg(reinterpret_cast<const unsigned*>(wq + (int64_t)t * C + (blockIdx.y * cgb + g) * 4));
+      const unsigned pk = ld_cg(reinterpret_cast<const unsigned*>(wq + (int64_t)t * C + (blockIdx.y * cgb + g) * 4));
       s_w[t * cgb + g] = make_float4(((float)sext_byte(pk, 0) - zp_w) * s_wt, ((float)sext_byte(pk, 1) - zp_w) * s_wt,
                                      ((float)sext_byte(pk, 2) - zp_w) * s_wt, ((float)sext_byte(pk, 3) - zp_w) * s_wt);
     }
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(256, 3) dw_dgrad_kernel(const float* __restric
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int ow = ow_base + JLO + j;
-        d[j] = ((unsigned)ow < (unsigned)Wo) ? __ldg(reinterpret_cast<const float4*>(row + (int64_t)ow * C))
+        d[j] = ((unsigned)ow < (unsigned)Wo) ? ld_cg(reinterpret_cast<const float4*>(row + (int64_t)ow * C))
                                              : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(256, 3) dw_dgrad_kernel(const float* __restric
         float4* o = reinterpret_cast<float4*>(dx + (((int64_t)n * H + ih) * W + iw) * C) + cg;
         float4 v = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
         if (accumulate) {
-          const float4 old = *o;
+          const float4 old = ld_cg(o);
           v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
         }
         *o = v;
@@ -447,10 +447,10 @@ __global__ void __launch_bounds__(256, 3) dw_dgrad_kernel(const float* __restric
 // CTAs fit per SM), strips of 4 output pixels.  The KS threads that share a strip read the same dz words
 // (L1 hits); each reads its own input row.
 template <int KS, int S>
-__global__ void __launch_bounds__(256, 3) dw_wgrad_kernel(const float* __restrict__ dz, const uint8_t* __restrict__ xq,
-                                                         const float* __restrict__ x_scale_p, const int32_t* __restrict__ x_zp_p,
+__global__ void __launch_bounds__(256, 3) dw_wgrad_kernel(const float* dz, const uint8_t* xq,
+                                                         const float* x_scale_p, const int32_t* x_zp_p,
                                                          int N, int H, int W, int C, int Ho, int Wo, int cgb,
-                                                         float* __restrict__ dwq) {
+                                                         float* dwq) {
   extern __shared__ __align__(16) unsigned char dw_smem[];
   pdl_enter();
   float* s_acc = reinterpret_cast<float*>(dw_smem);  // [KS*KS][cgb*4]
@@ -485,11 +485,11 @@ __global__ void __launch_bounds__(256, 3) dw_wgrad_kernel(const float* __restric
     unsigned xw[IW];
 #pragma unroll
     for (int t = 0; t < DW_TW; ++t)
-      d[t] = (ow0 + t < Wo) ? __ldg(reinterpret_cast<const float4*>(drow + (int64_t)(ow0 + t) * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      d[t] = (ow0 + t < Wo) ? ld_cg(reinterpret_cast<const float4*>(drow + (int64_t)(ow0 + t) * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < IW; ++j) {
       const int iw = ow0 * S - PAD + j;
-      xw[j] = ((unsigned)iw < (unsigned)W) ? __ldg(reinterpret_cast<const unsigned*>(row + (int64_t)iw * C)) : zp4;
+      xw[j] = ((unsigned)iw < (unsigned)W) ? ld_cg(reinterpret_cast<const unsigned*>(row + (int64_t)iw * C)) : zp4;
     }
 #pragma unroll
     for (int j = 0; j < IW; ++j) {

@@ -32,7 +32,7 @@ __global__ void cat_finalize_kernel(FrostQTensor a, FrostQTensor b, FrostFQ fq, 
 
 // one thread-iteration = 8 output bytes (C1, C2 multiples of 8)
 __global__ void __launch_bounds__(256) cat_requant_kernel(FrostQTensor a, FrostQTensor b, int64_t M, const float* out_scale,
-                                                         const int32_t* out_zp, uint8_t* __restrict__ q_out) {
+                                                         const int32_t* out_zp, uint8_t* q_out) {
   pdl_enter();
   const QSrc sa = load_src(a), sb = load_src(b);
   const float so = *out_scale, zo = (float)*out_zp;
@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(256) cat_requant_kernel(FrostQTensor a, FrostQ
     const int g = (int)(i - m * G);
     uint2 in;
     QSrc s;
-    if (g < G1) { in = __ldg(reinterpret_cast<const uint2*>(a.q + m * C1) + g); s = sa; }
-    else { in = __ldg(reinterpret_cast<const uint2*>(b.q + m * C2) + (g - G1)); s = sb; }
+    if (g < G1) { in = ld_cg(reinterpret_cast<const uint2*>(a.q + m * C1) + g); s = sa; }
+    else { in = ld_cg(reinterpret_cast<const uint2*>(b.q + m * C2) + (g - G1)); s = sb; }
     const unsigned w[2] = {in.x, in.y};
     unsigned o[2] = {0u, 0u};
 #pragma unroll
@@ -61,9 +61,9 @@ __global__ void __launch_bounds__(256) cat_requant_kernel(FrostQTensor a, FrostQ
 }
 
 // one thread-iteration = 4 fp32 gradient elements
-__global__ void __launch_bounds__(256) cat_backward_kernel(const float* __restrict__ dcat, FrostQTensor a, FrostQTensor b,
+__global__ void __launch_bounds__(256) cat_backward_kernel(const float* dcat, FrostQTensor a, FrostQTensor b,
                                                           int64_t M, const float* out_scale, const int32_t* out_zp,
-                                                          float* __restrict__ da, float* __restrict__ db, int accumulate_b) {
+                                                          float* da, float* db, int accumulate_b) {
   pdl_enter();
   const QSrc sa = load_src(a), sb = load_src(b);
   const float so = *out_scale, zo = (float)*out_zp;
@@ -75,10 +75,10 @@ __global__ void __launch_bounds__(256) cat_backward_kernel(const float* __restri
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int64_t m = i / G;
     const int g = (int)(i - m * G);
-    const float4 d = __ldg(reinterpret_cast<const float4*>(dcat + m * C) + g);
+    const float4 d = ld_cg(reinterpret_cast<const float4*>(dcat + m * C) + g);
     const bool from_a = g < G1;
-    const unsigned in = from_a ? __ldg(reinterpret_cast<const unsigned*>(a.q + m * C1) + g)
-                               : __ldg(reinterpret_cast<const unsigned*>(b.q + m * C2) + (g - G1));
+    const unsigned in = from_a ? ld_cg(reinterpret_cast<const unsigned*>(a.q + m * C1) + g)
+                               : ld_cg(reinterpret_cast<const unsigned*>(b.q + m * C2) + (g - G1));
     const QSrc s = from_a ? sa : sb;
     const float dv[4] = {d.x, d.y, d.z, d.w};
     float o[4];
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) cat_backward_kernel(const float* __restri
     } else {
       float4* p = reinterpret_cast<float4*>(db + m * C2) + (g - G1);
       if (accumulate_b) {
-        const float4 old = *p;
+        const float4 old = ld_cg(p);
         *p = make_float4(old.x + o[0], old.y + o[1], old.z + o[2], old.w + o[3]);
       } else {
         *p = make_float4(o[0], o[1], o[2], o[3]);
@@ -102,14 +102,14 @@ __global__ void __launch_bounds__(256) cat_backward_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------- add
-__global__ void __launch_bounds__(256) add_minmax_kernel(FrostQTensor a, FrostQTensor b, int64_t n4, float* __restrict__ partial) {
+__global__ void __launch_bounds__(256) add_minmax_kernel(FrostQTensor a, FrostQTensor b, int64_t n4, float* partial) {
   pdl_enter();
   const QSrc sa = load_src(a), sb = load_src(b);
   float mn = INFINITY, mx = -INFINITY;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const unsigned wa = __ldg(reinterpret_cast<const unsigned*>(a.q) + i);
-    const unsigned wb = __ldg(reinterpret_cast<const unsigned*>(b.q) + i);
+    const unsigned wa = ld_cg(reinterpret_cast<const unsigned*>(a.q) + i);
+    const unsigned wb = ld_cg(reinterpret_cast<const unsigned*>(b.q) + i);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float v = __fadd_rn(deq((wa >> (8 * e)) & 0xff, sa), deq((wb >> (8 * e)) & 0xff, sb));
@@ -125,15 +125,15 @@ __global__ void __launch_bounds__(256) add_minmax_kernel(FrostQTensor a, FrostQT
 }
 
 __global__ void __launch_bounds__(256) add_requant_kernel(FrostQTensor a, FrostQTensor b, int64_t n4, const float* out_scale,
-                                                         const int32_t* out_zp, uint8_t* __restrict__ q_out) {
+                                                         const int32_t* out_zp, uint8_t* q_out) {
   pdl_enter();
   const QSrc sa = load_src(a), sb = load_src(b);
   const float so = *out_scale, zo = (float)*out_zp;
   const float inv = __fdiv_rn(1.0f, so);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const unsigned wa = __ldg(reinterpret_cast<const unsigned*>(a.q) + i);
-    const unsigned wb = __ldg(reinterpret_cast<const unsigned*>(b.q) + i);
+    const unsigned wa = ld_cg(reinterpret_cast<const unsigned*>(a.q) + i);
+    const unsigned wb = ld_cg(reinterpret_cast<const unsigned*>(b.q) + i);
     unsigned o = 0u;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -145,18 +145,18 @@ __global__ void __launch_bounds__(256) add_requant_kernel(FrostQTensor a, FrostQ
   }
 }
 
-__global__ void __launch_bounds__(256) add_backward_kernel(const float* __restrict__ dout, FrostQTensor a, FrostQTensor b,
+__global__ void __launch_bounds__(256) add_backward_kernel(const float* dout, FrostQTensor a, FrostQTensor b,
                                                           int64_t n4, const float* out_scale, const int32_t* out_zp,
-                                                          float* __restrict__ dsum, float* __restrict__ da, int accumulate_a) {
+                                                          float* dsum, float* da, int accumulate_a) {
   pdl_enter();
   const QSrc sa = load_src(a), sb = load_src(b);
   const float so = *out_scale, zo = (float)*out_zp;
   const float inv = __fdiv_rn(1.0f, so);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const unsigned wa = __ldg(reinterpret_cast<const unsigned*>(a.q) + i);
-    const unsigned wb = __ldg(reinterpret_cast<const unsigned*>(b.q) + i);
-    const float4 d = __ldg(reinterpret_cast<const float4*>(dout) + i);
+    const unsigned wa = ld_cg(reinterpret_cast<const unsigned*>(a.q) + i);
+    const unsigned wb = ld_cg(reinterpret_cast<const unsigned*>(b.q) + i);
+    const float4 d = ld_cg(reinterpret_cast<const float4*>(dout) + i);
     const float dv[4] = {d.x, d.y, d.z, d.w};
     float o[4];
 #pragma unroll
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) add_backward_kernel(const float* __restri
     reinterpret_cast<float4*>(dsum)[i] = r;
     float4* p = reinterpret_cast<float4*>(da) + i;
     if (accumulate_a) {
-      const float4 old = *p;
+      const float4 old = ld_cg(p);
       *p = make_float4(old.x + r.x, old.y + r.y, old.z + r.z, old.w + r.w);
     } else {
       *p = r;
@@ -177,17 +177,17 @@ __global__ void __launch_bounds__(256) add_backward_kernel(const float* __restri
   }
 }
 
-__global__ void __launch_bounds__(256) axpy_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+__global__ void __launch_bounds__(256) axpy_kernel(const float* x, float* y, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] += x[i];
 }
 
 // ---------------------------------------------------------------- head: avg-pool + dropout
 // thread -> (n, 4 channels); integer sum over HW is exact.
-__global__ void __launch_bounds__(256) pool_dropout_fwd_kernel(const uint8_t* __restrict__ q, const float* scale_p,
+__global__ void __launch_bounds__(256) pool_dropout_fwd_kernel(const uint8_t* q, const float* scale_p,
                                                               const int32_t* zp_p, int N, int HW, int C,
-                                                              const float* __restrict__ keep, float keep_scale,
-                                                              float* __restrict__ pooled) {
+                                                              const float* keep, float keep_scale,
+                                                              float* pooled) {
   const float s = *scale_p;
   const int zp = *zp_p;
   const int CG = C >> 2;
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256) pool_dropout_fwd_kernel(const uint8_t* __
     int sum[4] = {0, 0, 0, 0};
     const uint8_t* base = q + ((int64_t)n * HW) * C + cg * 4;
     for (int p = 0; p < HW; ++p) {
-      const unsigned w = __ldg(reinterpret_cast<const unsigned*>(base + (int64_t)p * C));
+      const unsigned w = ld_cg(reinterpret_cast<const unsigned*>(base + (int64_t)p * C));
 #pragma unroll
       for (int e = 0; e < 4; ++e) sum[e] += (int)((w >> (8 * e)) & 0xff);
     }
@@ -211,18 +211,18 @@ __global__ void __launch_bounds__(256) pool_dropout_fwd_kernel(const uint8_t* __
   }
 }
 
-__global__ void __launch_bounds__(256) pool_dropout_bwd_kernel(const float* __restrict__ dpooled, int N, int HW, int C,
-                                                              const float* __restrict__ keep, float keep_scale,
-                                                              float* __restrict__ dy) {
+__global__ void __launch_bounds__(256) pool_dropout_bwd_kernel(const float* dpooled, int N, int HW, int C,
+                                                              const float* keep, float keep_scale,
+                                                              float* dy) {
   const int CG = C >> 2;
   const int64_t total = (int64_t)N * HW * CG;
   const float inv_hw = 1.0f / (float)HW;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int cg = (int)(i % CG);
     const int64_t n = i / ((int64_t)HW * CG);
-    float4 d = __ldg(reinterpret_cast<const float4*>(dpooled + n * C) + cg);
+    float4 d = ld_cg(reinterpret_cast<const float4*>(dpooled + n * C) + cg);
     if (keep) {
-      const float4 k = __ldg(reinterpret_cast<const float4*>(keep + n * C) + cg);
+      const float4 k = ld_cg(reinterpret_cast<const float4*>(keep + n * C) + cg);
       d.x *= k.x * keep_scale; d.y *= k.y * keep_scale; d.z *= k.z * keep_scale; d.w *= k.w * keep_scale;
     }
     reinterpret_cast<float4*>(dy)[i] = make_float4(d.x * inv_hw, d.y * inv_hw, d.z * inv_hw, d.w * inv_hw);

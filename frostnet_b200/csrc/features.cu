@@ -21,10 +21,10 @@ __global__ void stats_reset_f32_kernel(FrostChanStats* s, int64_t n) {
 }
 
 // z[m][co] = sum_{r,s,ci} x[n][ci][ih][iw] * (q_w[co][r][s][ci] - zp_w);  one thread per output pixel.
-__global__ void __launch_bounds__(FS_THREADS) stem_conv_fwd_f32_kernel(const float* __restrict__ x, const int8_t* __restrict__ wq,
-                                                                      const int32_t* __restrict__ w_zp_p, int N, int H, int W,
+__global__ void __launch_bounds__(FS_THREADS) stem_conv_fwd_f32_kernel(const float* x, const int8_t* wq,
+                                                                      const int32_t* w_zp_p, int N, int H, int W,
                                                                       int cin, int cout, int k, int stride, int pad, int Ho,
-                                                                      int Wo, float* __restrict__ z, FrostChanStats* __restrict__ stats) {
+                                                                      int Wo, float* z, FrostChanStats* stats) {
   extern __shared__ float fs_mem[];
   const int KK = k * k * cin;
   float* s_w = fs_mem;                          // [KK][FS_MAXC]
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(FS_THREADS) stem_conv_fwd_f32_kernel(const flo
         const int iw = ow * stride - pad + s;
         if (iw < 0 || iw >= W) continue;
         for (int ci = 0; ci < cin; ++ci) {
-          const float xa = __ldg(x + (((int64_t)n * cin + ci) * H + ih) * W + iw);
+          const float xa = ld_cg(x + (((int64_t)n * cin + ci) * H + ih) * W + iw);
           const float* wrow = s_w + ((r * k + s) * cin + ci) * FS_MAXC;
 #pragma unroll
           for (int c = 0; c < FS_MAXC; ++c) acc[c] = fmaf(xa, wrow[c], acc[c]);
@@ -90,9 +90,9 @@ __global__ void __launch_bounds__(FS_THREADS) stem_conv_fwd_f32_kernel(const flo
 
 // dwq[co][r][s][ci] += sum_pix dz[pix][co] * x[n][ci][ih][iw]
 constexpr int FSW_PIX = 64;
-__global__ void __launch_bounds__(256) stem_wgrad_f32_kernel(const float* __restrict__ dz, const float* __restrict__ x, int N, int H,
+__global__ void __launch_bounds__(256) stem_wgrad_f32_kernel(const float* dz, const float* x, int N, int H,
                                                             int W, int cin, int cout, int k, int stride, int pad, int Ho, int Wo,
-                                                            int64_t pix_per_block, float* __restrict__ dwq) {
+                                                            int64_t pix_per_block, float* dwq) {
   extern __shared__ float fs_mem[];
   const int KK = k * k * cin;
   const int KP = KK | 1;
@@ -122,13 +122,13 @@ __global__ void __launch_bounds__(256) stem_wgrad_f32_kernel(const float* __rest
         const int ih = ih0 + r, iw = iw0 + sx;
         float v = 0.0f;
         if (pv && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
-          v = __ldg(x + (((int64_t)n * cin + ci) * H + ih) * W + iw);
+          v = ld_cg(x + (((int64_t)n * cin + ci) * H + ih) * W + iw);
         s_patch[fp * KP + t] = v;
       }
     }
     for (int i = threadIdx.x; i < FSW_PIX * 32; i += blockDim.x) {
       const int pl = i >> 5, c = i & 31;
-      s_dz[i] = (pl < np && c < cout) ? __ldg(dz + (pb + pl) * cout + c) : 0.0f;
+      s_dz[i] = (pl < np && c < cout) ? ld_cg(dz + (pb + pl) * cout + c) : 0.0f;
     }
     __syncthreads();
 #pragma unroll 4
@@ -152,8 +152,8 @@ __global__ void __launch_bounds__(256) stem_wgrad_f32_kernel(const float* __rest
 }
 
 // NHWC uint8 indices -> NCHW fp32 values, 32x32 (pixel x channel) tiles through shared memory
-__global__ void __launch_bounds__(256) dequant_to_nchw_kernel(const uint8_t* __restrict__ q, const float* scale_p,
-                                                             const int32_t* zp_p, int HW, int C, float* __restrict__ y) {
+__global__ void __launch_bounds__(256) dequant_to_nchw_kernel(const uint8_t* q, const float* scale_p,
+                                                             const int32_t* zp_p, int HW, int C, float* y) {
   __shared__ float tile[32][33];
   const float s = *scale_p, zp = (float)*zp_p;
   const int n = blockIdx.z;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) dequant_to_nchw_kernel(const uint8_t* __r
   }
 }
 
-__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ g, int HW, int C, float* __restrict__ out,
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* g, int HW, int C, float* out,
                                                           int accumulate) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;

@@ -27,8 +27,8 @@ struct HyperDev {
   FrostOptHyper h;
 };
 
-__global__ void __launch_bounds__(256) gradboost_kernel(const FrostOptTensor* __restrict__ tensors,
-                                                       const FrostOptChunk* __restrict__ chunks, HyperDev hd) {
+__global__ void __launch_bounds__(256) gradboost_kernel(const FrostOptTensor* tensors,
+                                                       const FrostOptChunk* chunks, HyperDev hd) {
   const FrostOptHyper& h = hd.h;
   const FrostOptChunk ck = chunks[blockIdx.x];
   const FrostOptTensor t = tensors[ck.tensor];

@@ -35,11 +35,11 @@ constexpr size_t dg_smem_bytes() {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(DG_THREADS, 1) pw_dgrad_tc_kernel(const uint16_t* __restrict__ dz_hi,
-                                                                   const uint16_t* __restrict__ dz_lo,
-                                                                   const uint16_t* __restrict__ wt,
-                                                                   const float* __restrict__ w_scale_p, int64_t M, int K,
-                                                                   int cout, float* __restrict__ dx, int accumulate) {
+__global__ void __launch_bounds__(DG_THREADS, 1) pw_dgrad_tc_kernel(const uint16_t* dz_hi,
+                                                                   const uint16_t* dz_lo,
+                                                                   const uint16_t* wt,
+                                                                   const float* w_scale_p, int64_t M, int K,
+                                                                   int cout, float* dx, int accumulate) {
   constexpr int STAGES = dg_stages<BN>();
   constexpr int BW_LAG = STAGES > 2 ? 2 : 1;   // cp.async groups in flight per producer thread (< STAGES)
   constexpr int A_BYTES = DG_BM * 128, B_BYTES = BN * 128, STAGE = 2 * A_BYTES + B_BYTES;
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) pw_dgrad_tc_kernel(const uint16
               float4 val = *reinterpret_cast<const float4*>(my + row * 36 + col4);
               float4* dst = reinterpret_cast<float4*>(dx + m * K + n);
               if (accumulate) {
-                const float4 o = *dst;
+                const float4 o = ld_cg(dst);
                 val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
               }
               *dst = val;
@@ -243,12 +243,12 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16_t* __restrict__ dz_hi,
-                                                                   const uint16_t* __restrict__ dz_lo,
-                                                                   const uint8_t* __restrict__ xq,
-                                                                   const float* __restrict__ x_scale_p,
-                                                                   const int32_t* __restrict__ x_zp_p, int64_t M, int K,
-                                                                   int cout, int64_t rows_per_split, float* __restrict__ dwq) {
+__global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16_t* dz_hi,
+                                                                   const uint16_t* dz_lo,
+                                                                   const uint8_t* xq,
+                                                                   const float* x_scale_p,
+                                                                   const int32_t* x_zp_p, int64_t M, int K,
+                                                                   int cout, int64_t rows_per_split, float* dwq) {
   constexpr int STAGES = wg_stages<BN>();
   constexpr int BW_LAG = 2;
   constexpr int A_BYTES = 2 * WG_BLK;                       // 128 co x 64 rows, one of (hi, lo)
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
           const int r = idx / cpr, kc = idx - r * cpr;
           xpk[q] = make_uint2(0u, 0u);
           if (idx < WG_ROWS * cpr && mb + r < m_end && k0 + kc * 8 < K)
-            xpk[q] = __ldg(reinterpret_cast<const uint2*>(xq + (mb + r) * K + k0 + kc * 8));
+            xpk[q] = ld_cg(reinterpret_cast<const uint2*>(xq + (mb + r) * K + k0 + kc * 8));
         }
         mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
         // dz hi/lo: cp.async straight into the MN-major tiles

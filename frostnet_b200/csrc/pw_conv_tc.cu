@@ -43,9 +43,9 @@ constexpr size_t tc_smem_bytes() {
 
 template <int BN, bool VEC16>
 __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
-    const uint8_t* __restrict__ xq, const int32_t* __restrict__ x_zp_p, const int8_t* __restrict__ wq,
-    const int32_t* __restrict__ w_zp_p, const int32_t* __restrict__ wsum, int64_t M, int K, int cout,
-    int32_t* __restrict__ acc_out, FrostChanStats* __restrict__ stats) {
+    const uint8_t* xq, const int32_t* x_zp_p, const int8_t* wq,
+    const int32_t* w_zp_p, const int32_t* wsum, int64_t M, int K, int cout,
+    int32_t* acc_out, FrostChanStats* stats) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int TC_STAGES = tc_stages<BN>();
@@ -148,8 +148,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
             const bool rv = r < n_valid;
             const int8_t* src = wq + (int64_t)(n0 + (rv ? r : 0)) * K + kk;
             uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
-            if (rv && kk < K) { lo = __ldg(reinterpret_cast<const uint2*>(src)); lo.x ^= wxor; lo.y ^= wxor; }
-            if (rv && kk + 8 < K) { hi = __ldg(reinterpret_cast<const uint2*>(src + 8)); hi.x ^= wxor; hi.y ^= wxor; }
+            if (rv && kk < K) { lo = ld_cg(reinterpret_cast<const uint2*>(src)); lo.x ^= wxor; lo.y ^= wxor; }
+            if (rv && kk + 8 < K) { hi = ld_cg(reinterpret_cast<const uint2*>(src + 8)); hi.x ^= wxor; hi.y ^= wxor; }
             *reinterpret_cast<uint4*>(smem + s * STAGE + A_BYTES + sw128_offset(r, c)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
           }
         }
@@ -294,7 +294,8 @@ static int launch_tc(const uint8_t* xq, const int32_t* x_zp, const int8_t* wq, c
   const int n_tiles = (cout + BN - 1) / BN;
   const int64_t m_tiles = ceil_div(M, TC_BM);
   const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(m_tiles, kNumSMs / n_tiles));
-  launch_pdl(pw_conv_fwd_tc_kernel<BN, VEC16>, dim3(gx, n_tiles), dim3(TC_THREADS), smem, st, xq, x_zp, wq, w_zp, wsum, M, K, cout, acc, stats);
+  // the 8-byte cp.async of the K % 16 != 0 variant allocates in L1 (cp.async.ca): ordinary launch (common.cuh)
+  launch_pdl_if(VEC16, pw_conv_fwd_tc_kernel<BN, VEC16>, dim3(gx, n_tiles), dim3(TC_THREADS), smem, st, xq, x_zp, wq, w_zp, wsum, M, K, cout, acc, stats);
   return FROST_OK;
 }
 

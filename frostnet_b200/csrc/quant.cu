@@ -11,8 +11,8 @@ namespace frost {
 constexpr int kMinMaxThreads = 256;
 constexpr int kMinMaxMaxBlocks = FROST_FQ_SCRATCH_FLOATS / 2;  // 1024
 
-__global__ void __launch_bounds__(kMinMaxThreads) minmax_partial_kernel(const float* __restrict__ x, int64_t n,
-                                                                        float* __restrict__ partial) {
+__global__ void __launch_bounds__(kMinMaxThreads) minmax_partial_kernel(const float* x, int64_t n,
+                                                                        float* partial) {
   float mn = INFINITY, mx = -INFINITY;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -20,12 +20,12 @@ __global__ void __launch_bounds__(kMinMaxThreads) minmax_partial_kernel(const fl
   const int64_t n4 = vec_ok ? (n >> 2) : 0;
   const float4* x4 = reinterpret_cast<const float4*>(x);
   for (int64_t i = tid; i < n4; i += stride) {
-    const float4 v = __ldg(x4 + i);
+    const float4 v = ld_cg(x4 + i);
     mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
     mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
   }
   for (int64_t i = (n4 << 2) + tid; i < n; i += stride) {
-    const float v = __ldg(x + i);
+    const float v = ld_cg(x + i);
     mn = fminf(mn, v);
     mx = fmaxf(mx, v);
   }
@@ -36,15 +36,15 @@ __global__ void __launch_bounds__(kMinMaxThreads) minmax_partial_kernel(const fl
   }
 }
 
-__global__ void __launch_bounds__(256) fq_apply_kernel(const float* __restrict__ x, int64_t n, const float* scale_p,
-                                                       const int32_t* zp_p, int qmin, int qmax, float* __restrict__ y,
-                                                       uint8_t* __restrict__ mask, int32_t* __restrict__ q) {
+__global__ void __launch_bounds__(256) fq_apply_kernel(const float* x, int64_t n, const float* scale_p,
+                                                       const int32_t* zp_p, int qmin, int qmax, float* y,
+                                                       uint8_t* mask, int32_t* q) {
   const float s = *scale_p, zp = (float)*zp_p;
   const float inv = __fdiv_rn(1.0f, s);
   const float lo = (float)qmin, hi = (float)qmax;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float idx = fq_index(__ldg(x + i), inv, zp);
+    const float idx = fq_index(ld_cg(x + i), inv, zp);
     const float qc = fminf(fmaxf(idx, lo), hi);
     if (y) y[i] = fq_dequant(qc, zp, s);
     if (mask) mask[i] = (idx >= lo && idx <= hi) ? 1 : 0;
@@ -52,17 +52,17 @@ __global__ void __launch_bounds__(256) fq_apply_kernel(const float* __restrict__
   }
 }
 
-__global__ void __launch_bounds__(256) fq_backward_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ mask,
-                                                          int64_t n, float* __restrict__ dx) {
+__global__ void __launch_bounds__(256) fq_backward_kernel(const float* dy, const uint8_t* mask,
+                                                          int64_t n, float* dx) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     dx[i] = mask[i] ? dy[i] : 0.0f;
 }
 
 // QuantStub apply: NCHW fp32 -> NHWC uint8.  One thread per (n,h,w) pixel.
-__global__ void __launch_bounds__(256) input_quant_apply_kernel(const float* __restrict__ x, int N, int C, int HW,
+__global__ void __launch_bounds__(256) input_quant_apply_kernel(const float* x, int N, int C, int HW,
                                                                 const float* scale_p, const int32_t* zp_p,
-                                                                uint8_t* __restrict__ q) {
+                                                                uint8_t* q) {
   const float s = *scale_p, zp = (float)*zp_p;
   const float inv = __fdiv_rn(1.0f, s);
   const int64_t total = (int64_t)N * HW;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) input_quant_apply_kernel(const float* __r
     const float* src = x + (n * C) * HW + p;
     uint8_t* dst = q + i * C;
     for (int c = 0; c < C; ++c) {
-      const float idx = fq_index(__ldg(src + (int64_t)c * HW), inv, zp);
+      const float idx = fq_index(ld_cg(src + (int64_t)c * HW), inv, zp);
       dst[c] = (uint8_t)fminf(fmaxf(idx, 0.0f), 255.0f);
     }
   }
@@ -102,9 +102,9 @@ __device__ __forceinline__ float weight_sf(const FrostWeightDesc& d, int c, floa
 }
 
 // pass 1 (one CTA per FROST_WEIGHT_CHUNK elements): min/max of Ws = W * scale_factor
-__global__ void __launch_bounds__(kWeightThreads) weight_minmax_kernel(const FrostWeightDesc* __restrict__ descs,
-                                                                      const FrostOptChunk* __restrict__ chunks,
-                                                                      float* __restrict__ scratch) {
+__global__ void __launch_bounds__(kWeightThreads) weight_minmax_kernel(const FrostWeightDesc* descs,
+                                                                      const FrostOptChunk* chunks,
+                                                                      float* scratch) {
   const FrostOptChunk ck = chunks[blockIdx.x];
   const FrostWeightDesc& d = descs[ck.tensor];
   if (!d.observe) return;
@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(kWeightThreads) weight_minmax_kernel(const Fro
 }
 
 // pass 2 (one CTA per layer): scale_factor arrays, observer EMA + qparams, reset of the scratch slot
-__global__ void __launch_bounds__(kWeightThreads) weight_finalize_kernel(const FrostWeightDesc* __restrict__ descs,
-                                                                        float* __restrict__ scratch) {
+__global__ void __launch_bounds__(kWeightThreads) weight_finalize_kernel(const FrostWeightDesc* descs,
+                                                                        float* scratch) {
   const FrostWeightDesc& d = descs[blockIdx.x];
   for (int c = threadIdx.x; c < d.cout; c += blockDim.x) {
     float rstd;
@@ -144,8 +144,8 @@ __global__ void __launch_bounds__(kWeightThreads) weight_finalize_kernel(const F
 }
 
 // pass 3 (one CTA per chunk): int8 indices in the kernel layout, STE mask, per-cout index sums
-__global__ void __launch_bounds__(kWeightThreads) weight_quant_kernel(const FrostWeightDesc* __restrict__ descs,
-                                                                     const FrostOptChunk* __restrict__ chunks) {
+__global__ void __launch_bounds__(kWeightThreads) weight_quant_kernel(const FrostWeightDesc* descs,
+                                                                     const FrostOptChunk* chunks) {
   const FrostOptChunk ck = chunks[blockIdx.x];
   const FrostWeightDesc& d = descs[ck.tensor];
   const int K = d.cin_g * d.kh * d.kw;
@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(kWeightThreads) weight_quant_kernel(const Fros
 
 // dW = dWq*mask*sf ; dgamma = dgamma_bn + (dsf_bn + sum_k dWq*mask*W) * rstd_run   (SURVEY 8a' 5-6)
 // one CTA (8 warps) per 8 output channels of one layer: chunks[i] = {layer, first channel / 8}
-__global__ void __launch_bounds__(kWeightThreads) weight_backward_kernel(const FrostWeightDesc* __restrict__ descs,
-                                                                        const FrostOptChunk* __restrict__ chunks) {
+__global__ void __launch_bounds__(kWeightThreads) weight_backward_kernel(const FrostWeightDesc* descs,
+                                                                        const FrostOptChunk* chunks) {
   const FrostOptChunk ck = chunks[blockIdx.x];
   const FrostWeightDesc& d = descs[ck.tensor];
   const int K = d.cin_g * d.kh * d.kw;
