@@ -252,7 +252,9 @@ def run_b200(args):
         step(x, y)
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = L.launch_count()
+    torch.cuda.nvtx.range_push("frost_timed")         # ncu --nvtx --nvtx-include "frost_timed/" profiles exactly these steps
     ms = timed(lambda: step(x, y), K)
+    torch.cuda.nvtx.range_pop()
     launches = L.launch_count() - l0
     value = world * bs * K / (ms * 1e-3)
 

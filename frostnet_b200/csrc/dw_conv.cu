@@ -238,6 +238,205 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_kernel(const uint8_t* xq, 
   }
 }
 
+// ================================================================= forward, shared-memory tiles (dp4a)
+// The register-gather kernel above keeps one strip's window in flight per thread and is latency-bound (13 warps
+// per SM, one L2 round trip per strip: 5-8x off the HBM time on the 14x14 / 7x7 layers).  Here a CTA owns CGB
+// channel groups and walks tiles of (one image, TH output rows, full width): all 256 threads first copy the
+// input window of the tile - zero-point bytes where it leaves the image - into shared memory, many independent
+// loads in flight per thread, then every thread computes strips of 4 output pixels from shared memory with the
+// same transposed-dp4a arithmetic.
+// Tile layout: 32-bit words (4 channels of one pixel) as [row][channel group][col], col = iw + PAD, pitch = 4 mod 32
+// words: a strip's window is NB aligned 16-byte reads, conflict-free across the channel groups of a quarter warp,
+// and the fill (lanes = CGB groups x 32/CGB pixels) hits 32 distinct banks.
+template <int KS, int S, int CGB>
+__global__ void __launch_bounds__(256, 2) dw_conv_fwd_tiled_kernel(const uint8_t* xq, const int32_t* x_zp_p, const int8_t* wq,
+                                                                  const int32_t* w_zp_p, int N, int H, int W, int C, int Ho, int Wo,
+                                                                  int TH, int PITCH, int32_t* acc_out, FrostChanStats* stats) {
+  extern __shared__ __align__(16) unsigned char dw_smem[];
+  pdl_enter();
+  constexpr int PAD = (KS - 1) / 2;
+  constexpr int IW = (DW_TW - 1) * S + KS;
+  constexpr int NB = (IW + 3) / 4;
+  constexpr int SLOTS = 256 / CGB;
+  unsigned* s_wA = reinterpret_cast<unsigned*>(dw_smem);            // [KS][4][CGB]
+  unsigned* s_wB = s_wA + KS * 4 * CGB;                             // [KS][4][CGB]
+  int* s_wsum = reinterpret_cast<int*>(s_wB + KS * 4 * CGB);        // [CGB*4]
+  SmemStat* s_stat = reinterpret_cast<SmemStat*>(s_wsum + CGB * 4); // [CGB*4]
+  unsigned* s_tile = reinterpret_cast<unsigned*>(s_stat + CGB * 4); // [IH][CGB][PITCH]
+  const int zp_a = *x_zp_p, zp_w = *w_zp_p;
+  if (zp_w != 0) return;                     // one-signed weights: dw_conv_fwd_generic_kernel takes over
+  const unsigned zp4 = (unsigned)zp_a * 0x01010101u;
+  const int CG = C >> 2;
+  const int cg0 = blockIdx.y * CGB;
+  const int ncg = min(CGB, CG - cg0);
+  const int cg_l = threadIdx.x % CGB;
+  const int slot = threadIdx.x / CGB;
+  const bool cg_ok = cg_l < ncg;
+  const int c_first = (cg0 + cg_l) * 4;
+
+  for (int i = threadIdx.x; i < KS * 4 * CGB; i += blockDim.x) {
+    const int g = i % CGB, ch = (i / CGB) & 3, r = i / (CGB * 4);
+    const int c = (cg0 + g) * 4 + ch;
+    unsigned wa = 0u, wb = 0u;
+    if (g < ncg) {
+#pragma unroll
+      for (int dx = 0; dx < KS; ++dx) {
+        const unsigned byte = (unsigned)(uint8_t)wq[(int64_t)(r * KS + dx) * C + c];
+        if (dx < 4) wa |= byte << (8 * dx);
+        else wb |= byte;
+      }
+    }
+    s_wA[(r * 4 + ch) * CGB + g] = wa;
+    s_wB[(r * 4 + ch) * CGB + g] = wb;
+  }
+  for (int i = threadIdx.x; i < CGB * 4; i += blockDim.x) {
+    int sum = 0;
+    if ((i >> 2) < ncg)
+      for (int t = 0; t < KS * KS; ++t) sum += (int)wq[(int64_t)t * C + cg0 * 4 + i];
+    s_wsum[i] = sum;
+    s_stat[i].sum = 0; s_stat[i].sq = 0; s_stat[i].mn = INT_MAX; s_stat[i].mx = INT_MIN;
+  }
+  __syncthreads();
+  int corr[4];
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) corr[ch] = -zp_a * s_wsum[cg_l * 4 + ch];
+
+  long long st_sum[4] = {0, 0, 0, 0};
+  unsigned long long st_sq[4] = {0, 0, 0, 0};
+  int st_mn[4] = {INT_MAX, INT_MAX, INT_MAX, INT_MAX};
+  int st_mx[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};
+
+  const int strips_w = (Wo + DW_TW - 1) / DW_TW;
+  const int fill_w = (strips_w - 1) * DW_TW * S + NB * 4;     // tile columns any strip may read (<= PITCH)
+  const int tiles_h = (Ho + TH - 1) / TH;
+  const int d_row = SLOTS / strips_w, d_sw = SLOTS % strips_w;
+  for (int tile = blockIdx.x; tile < N * tiles_h; tile += gridDim.x) {
+    const int n = tile / tiles_h;
+    const int oh0 = (tile - n * tiles_h) * TH;
+    const int th = min(TH, Ho - oh0);
+    const int ih_rows = (th - 1) * S + KS;
+    const int ih0 = oh0 * S - PAD;
+    __syncthreads();                                          // the previous tile has been consumed
+    // ---- fill: thread = (channel group, column slot); 2 rows x 4 columns of loads in flight
+    for (int row = 0; row < ih_rows; row += 2) {
+      unsigned v[2][4];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int ih = ih0 + row + rr;
+        const bool rok = cg_ok && (row + rr < ih_rows) && ((unsigned)ih < (unsigned)H);
+        const uint8_t* src = xq + (((int64_t)n * H + (rok ? ih : 0)) * W) * C + c_first;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int col = slot + q * SLOTS;
+          const int iw = col - PAD;
+          v[rr][q] = (rok && col < fill_w && (unsigned)iw < (unsigned)W) ? ld_cg(reinterpret_cast<const unsigned*>(src + (int64_t)iw * C)) : zp4;
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        if (row + rr < ih_rows) {
+          unsigned* dst = s_tile + ((size_t)(row + rr) * CGB + cg_l) * PITCH;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int col = slot + q * SLOTS;
+            if (col < fill_w) dst[col] = v[rr][q];
+          }
+        }
+      }
+      for (int col = slot + 4 * SLOTS; col < fill_w; col += SLOTS) {   // wider than 4*SLOTS columns (never for W <= 112)
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int ih = ih0 + row + rr;
+          if (row + rr >= ih_rows) continue;
+          const int iw = col - PAD;
+          const bool ok = cg_ok && ((unsigned)ih < (unsigned)H) && ((unsigned)iw < (unsigned)W);
+          s_tile[((size_t)(row + rr) * CGB + cg_l) * PITCH + col] =
+              ok ? ld_cg(reinterpret_cast<const unsigned*>(xq + (((int64_t)n * H + ih) * W + iw) * C + c_first)) : zp4;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- compute: strips of 4 output pixels, window rows read from shared memory
+    if (cg_ok) {
+      int orow = slot / strips_w, sw = slot - orow * strips_w;
+      for (; orow < th; ) {
+        int acc[DW_TW][4];
+#pragma unroll
+        for (int t = 0; t < DW_TW; ++t)
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) acc[t][ch] = 0;
+#pragma unroll
+        for (int r = 0; r < KS; ++r) {
+          const uint4* src = reinterpret_cast<const uint4*>(s_tile + ((size_t)(orow * S + r) * CGB + cg_l) * PITCH + sw * DW_TW * S);
+          unsigned T[NB + 1][4];
+#pragma unroll
+          for (int b4 = 0; b4 < NB; ++b4) {
+            const uint4 w4 = src[b4];
+            transpose4x4(w4.x, w4.y, w4.z, w4.w, T[b4]);
+          }
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) T[NB][ch] = 0u;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const unsigned wa = s_wA[(r * 4 + ch) * CGB + cg_l];
+            const unsigned wb = (KS == 5) ? s_wB[(r * 4 + ch) * CGB + cg_l] : 0u;
+#pragma unroll
+            for (int t = 0; t < DW_TW; ++t) {
+              const int start = t * S;
+              const int b0 = start >> 2, o0 = start & 3;
+              const unsigned win = (o0 == 0) ? T[b0][ch] : __byte_perm(T[b0][ch], T[b0 + 1][ch], 0x3210u + 0x1111u * o0);
+              acc[t][ch] = dp4a_us(win, wa, acc[t][ch]);
+              if (KS == 5) {
+                const int s4 = start + 4, b1 = s4 >> 2, o1 = s4 & 3;
+                const unsigned x4 = (o1 == 0) ? T[b1][ch] : __byte_perm(T[b1][ch], 0u, (unsigned)o1);
+                acc[t][ch] = dp4a_us(x4, wb, acc[t][ch]);
+              }
+            }
+          }
+        }
+        const int oh = oh0 + orow, ow0 = sw * DW_TW;
+#pragma unroll
+        for (int t = 0; t < DW_TW; ++t) {
+          const int ow = ow0 + t;
+          if (ow < Wo) {
+            int I[4];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) I[ch] = acc[t][ch] + corr[ch];
+            *reinterpret_cast<int4*>(acc_out + (((int64_t)n * Ho + oh) * Wo + ow) * C + c_first) = make_int4(I[0], I[1], I[2], I[3]);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              st_sum[ch] += I[ch];
+              st_sq[ch] += (unsigned long long)((long long)I[ch] * (long long)I[ch]);
+              st_mn[ch] = min(st_mn[ch], I[ch]);
+              st_mx[ch] = max(st_mx[ch], I[ch]);
+            }
+          }
+        }
+        sw += d_sw;
+        orow += d_row;
+        if (sw >= strips_w) { sw -= strips_w; ++orow; }
+      }
+    }
+  }
+  if (cg_ok) {
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      if (st_mn[ch] <= st_mx[ch]) {
+        SmemStat* sst = &s_stat[cg_l * 4 + ch];
+        atomicAdd(reinterpret_cast<unsigned long long*>(&sst->sum), (unsigned long long)st_sum[ch]);
+        atomicAdd(&sst->sq, st_sq[ch]);
+        atomicMin(&sst->mn, st_mn[ch]);
+        atomicMax(&sst->mx, st_mx[ch]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ncg * 4; i += blockDim.x) {
+    const SmemStat t = s_stat[i];
+    chan_stats_flush(stats + cg0 * 4 + i, t.sum, t.sq, t.mn, t.mx);
+  }
+}
+
 // ================================================================= forward, generic zero-points (byte unpacking)
 // Only runs when the weight zero-point is not 0 (one-signed weight tensor: SURVEY K5); exits otherwise.
 template <int KS, int S>
@@ -542,17 +741,54 @@ extern "C" int frost_dw_conv_forward(const uint8_t* xq, const int32_t* x_zp, con
   int cgb, chunks, threads;
   dw_launch_shape(C, DW_MAX_CGB, &cgb, &chunks, &threads);
   const int spb = threads / cgb;
-  const int64_t total_strips = (int64_t)N * Ho * ((Wo + DW_TW - 1) / DW_TW);
+  const int strips_w = (Wo + DW_TW - 1) / DW_TW;
+  const int64_t total_strips = (int64_t)N * Ho * strips_w;
+  const size_t smem_g = sizeof(unsigned) * k * k * DW_MAX_CGB + sizeof(SmemStat) * cgb * 4;
+  // ---- shared-memory tiled kernel (symmetric weights, the normal case)
+  const int IW = (DW_TW - 1) * stride + k, NB = (IW + 3) / 4;
+  const int fill_w = (strips_w - 1) * DW_TW * stride + NB * 4;
+  int pitch = (fill_w + 31) / 32 * 32 + 4;
+  if (pitch - 32 >= fill_w) pitch -= 32;
+  const int tcgb = (C >= 256 && Ho * strips_w <= 64) ? 16 : 8;      // small planes: 16 groups x 16 strip slots
+  const int max_ih = (int)(44 * 1024 / ((size_t)tcgb * pitch * 4));
+  // measured on B200 (tools/microbench_ops.py dw): the tiles win only on the widest stride-1 planes (112x112: 161 vs
+  // 189 us); elsewhere the gather kernel is ALU-bound, not latency-bound, and the fill/compute barrier costs more
+  // than it hides.  FROST_TUNE_DW_FWD_TILED: 1 = this rule, 2 = never, 3 = wherever a tile fits.
+  const int tmode = tunable(FROST_TUNE_DW_FWD_TILED);
+  bool tiled = max_ih >= k && (tmode == 3 || (tmode == 1 && stride == 1 && Wo >= 100));
+  if (tiled) {
+    int th = std::min(Ho, (max_ih - k) / stride + 1);
+    const int tiles_h = (Ho + th - 1) / th;
+    th = (Ho + tiles_h - 1) / tiles_h;
+    const int ih = (th - 1) * stride + k;
+    const size_t smem_t = sizeof(unsigned) * (2 * k * 4 * tcgb + 4 * tcgb) + sizeof(SmemStat) * 4 * tcgb + sizeof(unsigned) * (size_t)ih * tcgb * pitch;
+    const int tchunks = (C / 4 + tcgb - 1) / tcgb;
+    const int64_t wave = std::max<int64_t>(1, (int64_t)kNumSMs * tunable(FROST_TUNE_DW_FWD_CTAS_PER_SM) / tchunks);
+    const dim3 tgrid((unsigned)std::min<int64_t>((int64_t)N * tiles_h, wave), tchunks);
+#define LT(KS, S, G)                                                                                                     \
+  launch_pdl(dw_conv_fwd_tiled_kernel<KS, S, G>, tgrid, dim3(256), smem_t, st, xq, x_zp, wq, w_zp, N, H, W, C, Ho, Wo, th, \
+             pitch, acc, stats)
+#define LTG(KS, S)                 \
+  do {                             \
+    if (tcgb == 16) LT(KS, S, 16); \
+    else LT(KS, S, 8);             \
+  } while (0)
+    if (k == 3 && stride == 1) LTG(3, 1);
+    else if (k == 3 && stride == 2) LTG(3, 2);
+    else if (k == 5 && stride == 1) LTG(5, 1);
+    else LTG(5, 2);
+#undef LTG
+#undef LT
+  }
   // one resident wave: every CTA ends with one set of atomics per channel on the same 32-byte records, and
   // same-sector atomics serialise in L2 - 16 waves of CTAs cost more in that tail than the convolution itself
   const int64_t wave = std::max<int64_t>(1, (int64_t)kNumSMs * tunable(FROST_TUNE_DW_FWD_CTAS_PER_SM) / chunks);
   const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total_strips, (int64_t)spb * 2), wave));
   dim3 grid(gx, chunks);
   const size_t smem = sizeof(unsigned) * (2 * k * 4 * DW_MAX_CGB + DW_MAX_CGB * 4) + sizeof(SmemStat) * cgb * 4;
-  const size_t smem_g = sizeof(unsigned) * k * k * DW_MAX_CGB + sizeof(SmemStat) * cgb * 4;
 #define L(KS, S)                                                                                                        \
   do {                                                                                                                  \
-    launch_pdl(dw_conv_fwd_kernel<KS, S>, grid, dim3(threads), smem, st, xq, x_zp, wq, w_zp, N, H, W, C, Ho, Wo, cgb, acc, stats);     \
+    if (!tiled) launch_pdl(dw_conv_fwd_kernel<KS, S>, grid, dim3(threads), smem, st, xq, x_zp, wq, w_zp, N, H, W, C, Ho, Wo, cgb, acc, stats);     \
     launch_pdl(dw_conv_fwd_generic_kernel<KS, S>, grid, dim3(threads), smem_g, st, xq, x_zp, wq, w_zp, N, H, W, C, Ho, Wo, cgb, acc, stats); \
   } while (0)
   if (k == 3 && stride == 1) L(3, 1);

@@ -649,7 +649,7 @@ def test_bad_arguments_are_reported_not_crashed():
 
 
 # ------------------------------------------------------------------------------------------ launch-shape knobs
-@pytest.mark.parametrize("knob,values", [(0, [1, 16]), (4, [1, 8])])
+@pytest.mark.parametrize("knob,values", [(0, [1, 16]), (4, [1, 8]), (11, [2, 3])])
 def test_results_do_not_depend_on_launch_knobs(knob, values):
     """FROST_TUNE_* only reshape grids: integer outputs and statistics must be identical for every value."""
     lib = L().load()
@@ -657,9 +657,11 @@ def test_results_do_not_depend_on_launch_knobs(knob, values):
     try:
         for v in values:
             assert lib.frost_set_tunable(knob, v) == 0 and lib.frost_get_tunable(knob) == v
-            if knob == 0:
+            if knob in (0, 11):
                 test_dw_conv_forward_exact(3, 7, 7, 1728, 5, 1, 0)
                 test_dw_conv_forward_exact(2, 9, 11, 32, 3, 1, 0)
+                test_dw_conv_forward_exact(6, 56, 56, 144, 5, 2, 0)
+                test_dw_conv_forward_exact(2, 112, 112, 32, 3, 1, 0)
             else:
                 test_stem_conv_forward_exact(2, 224, 224, 32)
             outs.append(v)

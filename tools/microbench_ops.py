@@ -15,7 +15,7 @@ from frostnet_b200 import _lib as L  # noqa: E402
 dev = "cuda:0"
 N = 256
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-T_DW_FWD, T_DW_WGRAD, T_BN_RED, T_BN_CGB, T_STEM_FWD, T_STEM_WGRAD, T_DW_DGRAD, T_PDL, T_BN_RED_UNROLL, T_BN_APPLY_UNROLL, T_BNQ_UNROLL = range(11)
+T_DW_FWD, T_DW_WGRAD, T_BN_RED, T_BN_CGB, T_STEM_FWD, T_STEM_WGRAD, T_DW_DGRAD, T_PDL, T_BN_RED_UNROLL, T_BN_APPLY_UNROLL, T_BNQ_UNROLL, T_DW_FWD_TILED = range(12)
 QUICK = "--quick" in sys.argv
 
 
@@ -74,7 +74,7 @@ def bench_dw(H, W, Cc, k, s):
     nin, nout = N * H * W * Cc, N * Ho * Wo * Cc
     sweep("dw_fwd", shape, lambda: L.call("frost_dw_conv_forward", xq.data_ptr(), za.data_ptr(), wq.data_ptr(), zw.data_ptr(),
                                           N, H, W, Cc, k, s, acc.data_ptr(), stats.data_ptr(), st()),
-          nin + 4 * nout, T_DW_FWD, [2, 4])
+          nin + 4 * nout, T_DW_FWD_TILED, [1, 2])
     dz = torch.randn(N, Ho, Wo, Cc, device=dev)
     dwq = torch.empty(k * k, Cc, device=dev)
     sa = f32(0.02)
@@ -169,20 +169,25 @@ def bench_pw(M, K, cout):
 
 
 if __name__ == "__main__":
+    only = [a for a in sys.argv[1:] if not a.startswith("--")]
+    want = lambda k: not only or k in only  # noqa: E731
     ca = torch.empty(1 << 28, dtype=torch.float32, device=dev)
     cb = torch.empty(1 << 28, dtype=torch.float32, device=dev)
     print("torch copy 1 GiB: %.0f GB/s" % (2 * (1 << 30) / timeit(lambda: cb.copy_(ca)) / 1e3))
     del ca, cb
-    bench_stem()
-    for shp in ([(112, 112, 32, 3, 1), (112, 112, 96, 3, 2), (56, 56, 144, 5, 2), (14, 14, 360, 5, 1), (7, 7, 1440, 5, 1)]
-                if not QUICK else [(112, 112, 32, 3, 1), (14, 14, 360, 5, 1)]):
-        bench_dw(*shp)
-        torch.cuda.empty_cache()
-    for shp in ([(3211264, 96), (3211264, 16), (802816, 72), (200704, 168), (50176, 360), (12544, 1440), (12544, 192)]
-                if not QUICK else [(3211264, 96), (50176, 360), (12544, 1440)]):
-        bench_bn(*shp)
-        torch.cuda.empty_cache()
-    for shp in [(3211264, 16, 96), (3211264, 32, 16), (802816, 96, 24), (802816, 24, 144), (200704, 56, 168), (50176, 360, 96),
-                (50176, 120, 360), (12544, 240, 1440), (12544, 1440, 192), (12544, 320, 1280)]:
-        bench_pw(*shp)
-        torch.cuda.empty_cache()
+    if want("stem"):
+        bench_stem()
+    if want("dw"):
+        for shp in [(112, 112, 32, 3, 1), (112, 112, 96, 3, 2), (56, 56, 72, 3, 1), (56, 56, 144, 5, 2), (28, 28, 168, 3, 1),
+                    (28, 28, 336, 5, 2), (14, 14, 624, 5, 1), (14, 14, 360, 3, 1), (14, 14, 864, 5, 2), (7, 7, 1440, 5, 1)]:
+            bench_dw(*shp)
+            torch.cuda.empty_cache()
+    if want("bn"):
+        for shp in [(3211264, 96), (3211264, 16), (802816, 72), (200704, 168), (50176, 360), (12544, 1440), (12544, 192)]:
+            bench_bn(*shp)
+            torch.cuda.empty_cache()
+    if want("pw"):
+        for shp in [(3211264, 16, 96), (3211264, 32, 16), (802816, 96, 24), (802816, 24, 144), (200704, 56, 168), (50176, 360, 96),
+                    (50176, 120, 360), (12544, 240, 1440), (12544, 1440, 192), (12544, 320, 1280)]:
+            bench_pw(*shp)
+            torch.cuda.empty_cache()
