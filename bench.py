@@ -252,9 +252,11 @@ def run_b200(args):
         step(x, y)
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = L.launch_count()
-    torch.cuda.nvtx.range_push("frost_timed")         # ncu --nvtx --nvtx-include "frost_timed/" profiles exactly these steps
+    # ncu --nvtx --nvtx-include "frost_step" profiles exactly these steps (a start/end range: backward runs on the
+    # autograd thread, which a push/pop range of this thread would not cover)
+    nvtx_id = torch.cuda.nvtx.range_start("frost_step")
     ms = timed(lambda: step(x, y), K)
-    torch.cuda.nvtx.range_pop()
+    torch.cuda.nvtx.range_end(nvtx_id)
     launches = L.launch_count() - l0
     value = world * bs * K / (ms * 1e-3)
 

@@ -1,6 +1,6 @@
 """Summarise an ncu CSV of one profiled step taken with
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-        --nvtx --nvtx-include "frost_timed/" --csv --log-file gpurun_out/step.csv python bench.py --quick --steps 1
+        --nvtx --nvtx-include "frost_step" --csv --log-file gpurun_out/step.csv python bench.py --quick --steps 1
 Per kernel: launches, summed device time (cold-cache, serialised: compare SHARES), share, DRAM bytes per launch.
 usage: python profiles/summarize_step.py gpurun_out/step.csv [traffic.json to write] > profiles/rNN_step_summary.txt"""
 import collections
