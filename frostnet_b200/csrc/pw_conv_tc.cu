@@ -5,13 +5,16 @@
 //
 // tcgen05.mma kind::i8 (u8 x s8 -> s32), accumulators in TMEM (double buffered), operands staged in
 // shared memory in the canonical K-major SWIZZLE_128B layout.  Warp-specialised persistent CTA:
-//   warps 0-3  epilogue : tcgen05.ld -> zero-point correction -> smem transpose -> coalesced int32 stores
+//   warps 0-15 epilogue : tcgen05.ld -> zero-point correction -> smem transpose -> coalesced int32 stores
 //                         + per-channel integer statistics (sum, sum^2, min, max) kept in smem for the
-//                         CTA's lifetime, flushed once with integer atomics
-//   warps 4-7  producer : cp.async (LDGSTS, zero-filled) global -> swizzled smem, 4-stage mbarrier ring.
+//                         CTA's lifetime, flushed once with integer atomics.  Four groups of 4 warps: group g
+//                         drains accumulator buffer g&1 and the 32-column chunks of parity g>>1.  The epilogue
+//                         (~26 instructions per output with the statistics) is latency-bound, so it gets 16 of
+//                         the CTA's 21 warps (8 warps: 475 us on the 16->96 112x112 layer)
+//   warps 16-19 producer: cp.async (LDGSTS, zero-filled) global -> swizzled smem, 3-4-stage mbarrier ring.
 //                         (NHWC rows are K bytes apart and K % 16 != 0 for half the layers (24, 40, 56, 72,
 //                         104, ...), which a TMA tensor map cannot describe; 8/16-byte cp.async can.)
-//   warp 8     MMA      : one elected lane issues tcgen05.mma, tcgen05.commit releases stages / signals TMEM
+//   warp 20    MMA      : one elected lane issues tcgen05.mma, tcgen05.commit releases stages / signals TMEM
 // Weight zero-points: per_tensor_symmetric gives zp_w = 0 (s8 operand).  One-signed weight tensors make the
 // reference fall back to affine with zp_w = -128 or 127; then q_w - zp_w (or its negation) fits
 // u8: the producer rewrites the bytes (xor 0x80 / 0x7f) and the MMA runs u8 x u8 with a sign in the epilogue.
@@ -32,12 +35,13 @@ constexpr int TC_BK = 128;  // bytes of K per stage (= one swizzle span)
 template <int BN>
 __host__ __device__ constexpr int tc_stages() { return BN >= 256 ? 3 : 4; }
 constexpr int TC_LAG = 2;   // cp.async groups in flight per producer thread
-constexpr int TC_THREADS = 416;   // warps 0-7 epilogue (2 groups), 8-11 producer, 12 MMA
+constexpr int TC_EPI_WARPS = 16;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 5) * 32;   // warps 0-15 epilogue (4 groups), 16-19 producer, 20 MMA
 constexpr int TC_SCR = 32 * 36;  // ints of transpose scratch per epilogue warp
 
 template <int BN>
 constexpr size_t tc_smem_bytes() {
-  return 1024 + (size_t)tc_stages<BN>() * (TC_BM * TC_BK + BN * TC_BK) + 8 * TC_SCR * 4 + BN * 4 + BN * sizeof(TcStat) +
+  return 1024 + (size_t)tc_stages<BN>() * (TC_BM * TC_BK + BN * TC_BK) + TC_EPI_WARPS * TC_SCR * 4 + BN * 4 + BN * sizeof(TcStat) +
          (2 * tc_stages<BN>() + 4) * 8 + 16;
 }
 
@@ -51,7 +55,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
   constexpr int TC_STAGES = tc_stages<BN>();
   constexpr int A_BYTES = TC_BM * TC_BK, B_BYTES = BN * TC_BK, STAGE = A_BYTES + B_BYTES;
   int* scratch = reinterpret_cast<int*>(smem + TC_STAGES * STAGE);
-  int* s_corr = scratch + 8 * TC_SCR;
+  int* s_corr = scratch + TC_EPI_WARPS * TC_SCR;
   TcStat* s_stat = reinterpret_cast<TcStat*>(s_corr + BN);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stat + BN);
   uint64_t* empty_bar = full_bar + TC_STAGES;
@@ -66,10 +70,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
   // allocated first would block our tcgen05.alloc while waiting for our grid - a deadlock.
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], TC_EPI_WARPS / 2); }
     mbar_fence_init();
   }
-  if (warp == 12) tmem_alloc<2 * BN>(tmem_slot);
+  if (warp == TC_EPI_WARPS + 4) tmem_alloc<2 * BN>(tmem_slot);
   pdl_wait();
   const int zp_a = *x_zp_p, zp_w = *w_zp_p;
   if (zp_w != 0 && zp_w != -128 && zp_w != 127) __trap();  // not reachable with ChooseQuantizationParams
@@ -96,9 +100,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
   pdl_trigger();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 8 && warp < 12) {
+  if (warp >= TC_EPI_WARPS && warp < TC_EPI_WARPS + 4) {
     // ================================================================= producer
-    const int tp = threadIdx.x - 256;
+    const int tp = threadIdx.x - TC_EPI_WARPS * 32;
     const int c16 = tp & 7, r0 = tp >> 3;  // 16 rows per pass
     uint32_t it = 0;
     for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
@@ -165,7 +169,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
     cp_async_wait<0>();
     fence_proxy_async();
     for (uint32_t j = (it > (uint32_t)TC_LAG ? it - TC_LAG : 0u); j < it; ++j) mbar_arrive(&full_bar[j % TC_STAGES]);
-  } else if (warp == 12) {
+  } else if (warp == TC_EPI_WARPS + 4) {
     // ================================================================= MMA issuer
     const uint32_t idesc = umma_idesc(2 /*S32*/, 0 /*A: u8*/, zp_w == 0 ? 1 : 0 /*B: s8 | u8*/, TC_BM, n_eff);
     uint32_t it = 0, tile_i = 0;
@@ -192,9 +196,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
     }
   } else {
     // ================================================================= epilogue
-    // two groups of 4 warps; group g drains accumulator buffer g (tiles g, g+2, ...); warp w of a group owns
-    // TMEM lanes 32*(w%4).. (the hardware restricts a warp to the lane quarter warp_id % 4)
-    const int grp = warp >> 2, wq4 = warp & 3;
+    // four groups of 4 warps; group g drains accumulator buffer g&1 (tiles g&1, (g&1)+2, ...) and the chunks of
+    // parity g>>1; warp w of a group owns TMEM lanes 32*(w%4).. (the hardware restricts a warp to the lane quarter
+    // warp_id % 4)
+    const int grp = (warp >> 2) & 1, cpar = warp >> 3, wq4 = warp & 3;
     int* my = scratch + warp * TC_SCR;
     uint32_t tile_i = 0;
     for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++tile_i) {
@@ -203,7 +208,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
       const int64_t m0 = mt * TC_BM + wq4 * 32;
       mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1);
       tc_fence_after();
-      for (int chunk = 0; chunk * 32 < n_valid; ++chunk) {
+      for (int chunk = cpar; chunk * 32 < n_valid; chunk += 2) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + acc * BN + chunk * 32 + ((uint32_t)(wq4 * 32) << 16), v);
 #pragma unroll
@@ -272,7 +277,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
     const TcStat s = s_stat[j];
     chan_stats_flush(stats + n0 + j, s.sum, s.sq, s.mn, s.mx);
   }
-  if (warp == 12) {
+  if (warp == TC_EPI_WARPS + 4) {
     tc_fence_after();
     tmem_dealloc<2 * BN>(tmem_base);
   }
