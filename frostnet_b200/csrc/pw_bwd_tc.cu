@@ -223,7 +223,8 @@ static int launch_dgrad_tc(const uint16_t* dz_hi, const uint16_t* dz_lo, const u
 // 64 columns one block further (LBO).
 constexpr int WG_ROWS = 64;       // reduction rows (m) per stage
 constexpr int WG_BLK = 64 * 128;  // one 64-column block of a stage: 64 rows x 128 B
-constexpr int WG_THREADS = 288;   // warps 0-3 epilogue, 4-7 producer, 8 MMA
+constexpr int WG_PROD_WARPS = 8;   // the producers convert x (u8 -> bf16) in registers: 4 warps were the per-stage critical path
+constexpr int WG_THREADS = (4 + WG_PROD_WARPS + 1) * 32;   // warps 0-3 epilogue, 4-11 producer, 12 MMA
 
 template <int BN>
 __host__ __device__ constexpr int wg_stages() { return BN >= 256 ? 3 : 4; }
@@ -271,11 +272,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
   const int num_kb = (int)((m_end - m_begin + WG_ROWS - 1) / WG_ROWS);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], WG_PROD_WARPS * 32); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tfull_bar[0], 1);
     mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc<BN>(tmem_slot);
+  if (warp == 4 + WG_PROD_WARPS) tmem_alloc<BN>(tmem_slot);
   pdl_wait();
   tc_fence_before();
   __syncthreads();
@@ -284,13 +285,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
   const uint32_t tmem_base = *tmem_slot;
 
   if (num_kb > 0) {
-    if (warp >= 4 && warp < 8) {
+    if (warp >= 4 && warp < 4 + WG_PROD_WARPS) {
       // ================================================================= producer
+      constexpr int PT = WG_PROD_WARPS * 32;           // producer threads
+      constexpr int RPP = PT / 16;                     // dz rows per pass (16 chunks of 8 co per row)
       const int tp = threadIdx.x - 128;
-      const int cidx = tp & 15, r0 = tp >> 4;          // 16 chunks of 8 co per row, 8 rows per pass
-      const float zp_a = (float)*x_zp_p;
+      const int cidx = tp & 15, r0 = tp >> 4;
+      // byte -> float without I2F: 0x4B0000bb is the float 2^23 + bb; subtracting 2^23 + zp_a is exact
+      const float zp_magic = 8388608.0f + (float)*x_zp_p;
       const int cpr = n_eff >> 3;                      // 8-channel chunks per row of x
-      constexpr int XL = WG_ROWS * (BN / 8) / 128;     // x chunks per thread (<= 16)
+      constexpr int XL = (WG_ROWS * (BN / 8) + PT - 1) / PT;   // x chunks per thread (<= 8)
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         uint8_t* stage = smem + s * STAGE;
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
         uint2 xpk[XL];
 #pragma unroll
         for (int q = 0; q < XL; ++q) {
-          const int idx = tp + 128 * q;
+          const int idx = tp + PT * q;
           const int r = idx / cpr, kc = idx - r * cpr;
           xpk[q] = make_uint2(0u, 0u);
           if (idx < WG_ROWS * cpr && mb + r < m_end && k0 + kc * 8 < K)
@@ -311,8 +315,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
         // dz hi/lo: cp.async straight into the MN-major tiles
         const int co = co0 + cidx * 8;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r0 + 8 * i;
+        for (int i = 0; i < WG_ROWS / RPP; ++i) {
+          const int r = r0 + RPP * i;
           const int64_t m = mb + r;
           const bool v = (m < m_end) && (co < cout);
           const int64_t off = v ? m * cout + co : 0;
@@ -323,7 +327,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
         cp_async_commit();
 #pragma unroll
         for (int q = 0; q < XL; ++q) {
-          const int idx = tp + 128 * q;
+          const int idx = tp + PT * q;
           if (idx < WG_ROWS * cpr) {
             const int r = idx / cpr, kc = idx - r * cpr;
             const bool v = (mb + r < m_end) && (k0 + kc * 8 < K);
@@ -331,7 +335,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const unsigned word = e < 4 ? xpk[q].x : xpk[q].y;
-              w[e] = v ? (float)((word >> (8 * (e & 3))) & 0xff) - zp_a : 0.0f;
+              w[e] = v ? __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650u + (e & 3))) - zp_magic : 0.0f;
             }
             *reinterpret_cast<uint4*>(b_s + (uint32_t)(kc >> 3) * WG_BLK + sw128_offset(r, kc & 7)) =
                 make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
@@ -346,7 +350,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
       cp_async_wait<0>();
       fence_proxy_async();
       for (int j = (num_kb > BW_LAG ? num_kb - BW_LAG : 0); j < num_kb; ++j) mbar_arrive(&full_bar[j % STAGES]);
-    } else if (warp == 8) {
+    } else if (warp == 4 + WG_PROD_WARPS) {
       // ================================================================= MMA issuer (A and B MN-major)
       const uint32_t idesc = umma_idesc(1, 1, 1, 128, n_eff) | (1u << 15) | (1u << 16);
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -402,7 +406,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 4 + WG_PROD_WARPS) {
     tc_fence_after();
     tmem_dealloc<BN>(tmem_base);
   }
