@@ -155,18 +155,35 @@ __global__ void __launch_bounds__(kWeightThreads) weight_quant_kernel(const Fros
   const float s = *d.wfq.scale, zp = (float)*d.wfq.zero_point;
   const float inv = __fdiv_rn(1.0f, s);
   const int khw = d.kh * d.kw;
-  for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-    const int c = (int)(e / K);
-    const int r = (int)(e - (int64_t)c * K);
-    const int ci = r / khw, yx = r - ci * khw;
-    const int y = yx / d.kw, x = yx - y * d.kw;
-    const float ws = __fmul_rn(d.weight[e], d.sf[c]);
-    const float idx = fq_index(ws, inv, zp);
-    const float qc = fminf(fmaxf(idx, -128.0f), 127.0f);
-    d.wq[wq_index(d, c, ci, y, x)] = (int8_t)qc;
-    if (d.wt_bf16) d.wt_bf16[(int64_t)r * d.cout + c] = __bfloat16_as_ushort(__float2bfloat16_rn(qc - zp));  // 1x1: r == ci; exact
-    d.wmask[e] = (idx >= -128.0f && idx <= 127.0f) ? 1 : 0;
-    atomicAdd(d.wsum + c, (int)qc);
+  const int lane = threadIdx.x & 31;
+  // warp-uniform trip count; 32-bit index arithmetic (a weight tensor has < 2^31 elements: checked on the host side of
+  // the descriptor table by construction, cout*K <= 1728*1728).  The per-cout index sum is reduced in the warp first:
+  // consecutive elements share their output channel, one atomic per warp instead of one per element.
+  for (int64_t base = e0 + (threadIdx.x - lane); base < e1; base += blockDim.x) {
+    const int64_t e = base + lane;
+    const bool live = e < e1;
+    int c = -1, qi = 0;
+    if (live) {
+      const int e32 = (int)e;
+      c = e32 / K;
+      const int r = e32 - c * K;
+      const int ci = r / khw, yx = r - ci * khw;
+      const int y = yx / d.kw, x = yx - y * d.kw;
+      const float ws = __fmul_rn(d.weight[e], d.sf[c]);
+      const float idx = fq_index(ws, inv, zp);
+      const float qc = fminf(fmaxf(idx, -128.0f), 127.0f);
+      d.wq[wq_index(d, c, ci, y, x)] = (int8_t)qc;
+      if (d.wt_bf16) d.wt_bf16[(int64_t)r * d.cout + c] = __bfloat16_as_ushort(__float2bfloat16_rn(qc - zp));  // 1x1: r == ci; exact
+      d.wmask[e] = (idx >= -128.0f && idx <= 127.0f) ? 1 : 0;
+      qi = (int)qc;
+    }
+    const int c0 = __shfl_sync(0xffffffffu, c, 0);
+    if (__all_sync(0xffffffffu, c == c0 || !live)) {
+      const int tot = __reduce_add_sync(0xffffffffu, qi);
+      if (lane == 0 && c0 >= 0) atomicAdd(d.wsum + c0, tot);
+    } else if (live) {
+      atomicAdd(d.wsum + c, qi);
+    }
   }
 }
 
