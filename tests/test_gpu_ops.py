@@ -103,9 +103,10 @@ def test_fq_ties_and_mask_known_answers():
     assert mask.tolist() == [1, 1, 1, 1, 1, 1, 0, 1, 0]
 
 
-def test_input_quant_matches_oracle():
+@pytest.mark.parametrize("H,W", [(17, 13), (16, 12), (224, 224)])      # odd plane: per-pixel kernel; HW % 4 == 0: rgb4 kernel
+def test_input_quant_matches_oracle(H, W):
     torch.manual_seed(0)
-    N, Cc, H, W = 3, 3, 17, 13
+    N, Cc = 3, 3
     fq = DevFQ(0, 255, False)
     sc = scratch()
     for it in range(2):
