@@ -171,3 +171,24 @@ def test_observer_toggle_protocol():
     assert all(f._observe and int(f.observer_enabled) == 1 for f in fqs)
     with pytest.raises(RuntimeError):
         model.apply(taq.disable_fake_quant)              # the engine computes on indices: cannot be disabled
+
+
+def test_launch_knobs_roundtrip_without_a_gpu():
+    """frost_set_tunable / frost_get_tunable are host-only: defaults, overrides, reset with 0, error reporting."""
+    from frostnet_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "frost_b200.h")).read()
+    count = int(re.search(r"FROST_TUNE_COUNT\s*=\s*(\d+)", header).group(1))
+    defaults = [lib.frost_get_tunable(k) for k in range(count)]
+    assert all(v > 0 for v in defaults)
+    try:
+        for k in range(count):
+            assert lib.frost_set_tunable(k, 7) == 0 and lib.frost_get_tunable(k) == 7
+            assert lib.frost_set_tunable(k, 0) == 0 and lib.frost_get_tunable(k) == defaults[k]
+        assert lib.frost_set_tunable(count, 1) != 0
+        assert b"unknown knob" in lib.frost_last_error()
+        assert lib.frost_set_tunable(0, -3) != 0
+        assert lib.frost_get_tunable(-1) < 0
+    finally:
+        for k in range(count):
+            lib.frost_set_tunable(k, 0)
