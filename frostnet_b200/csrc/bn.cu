@@ -136,9 +136,9 @@ __device__ __forceinline__ float bn_dv(float dy, float I, float A, float B, int 
 // that few CTAs contribute to any one channel: the partials are combined through shared memory (no atomics)
 // and each CTA issues ONE fp64 atomic per (channel, sum) - same-sector L2 atomics serialise (~12 ns each), and
 // with all-channel CTAs that tail was longer than the streaming pass for most layers.
-template <int U>   // rows in flight per thread: 2*U independent 16-byte loads
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(FrostBnBackwardArgs a, int cg_per_block) {
-  extern __shared__ double s_part[];  // [rows_per_block][cg_per_block][4 channels][2 sums]
+template <int U, int MINB>   // U rows in flight per thread (2*U independent 16-byte loads), MINB resident CTAs per SM
+__global__ void __launch_bounds__(256, MINB) bn_bwd_reduce_kernel(FrostBnBackwardArgs a, int cg_per_block) {
+  extern __shared__ double s_part[];  // [rows_per_block][cg_per_block][4 channels][2 sums], then [cg_per_block][3] float4 (A, B, mean)
   pdl_enter();
   const int C = a.C;
   const int cg_local = threadIdx.x % cg_per_block;
@@ -152,9 +152,14 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(FrostBnBackwardArgs 
   for (int j = 0; j < 8; ++j) mine[j] = 0.0;
   {
     const float inv = __fdiv_rn(1.0f, *a.out_scale), zp = (float)*a.out_zp;
-    const float4 A = ld_cg(reinterpret_cast<const float4*>(a.A) + cg);
-    const float4 B = ld_cg(reinterpret_cast<const float4*>(a.B) + cg);
-    const float4 mu = ld_cg(reinterpret_cast<const float4*>(a.mean_I) + cg);
+    // per-channel-group coefficients live in shared memory (12 registers less: 4 CTAs per SM instead of 3)
+    float4* s_coef = reinterpret_cast<float4*>(s_part + (size_t)blockDim.x * 8) + cg_local * 3;
+    if (row_local == 0) {
+      s_coef[0] = ld_cg(reinterpret_cast<const float4*>(a.A) + cg);
+      s_coef[1] = ld_cg(reinterpret_cast<const float4*>(a.B) + cg);
+      s_coef[2] = ld_cg(reinterpret_cast<const float4*>(a.mean_I) + cg);
+    }
+    __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * rows_per_block;
     int batches = 0;
     float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -171,6 +176,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(FrostBnBackwardArgs 
           I[u] = ld_cg(reinterpret_cast<const int4*>(a.acc + mm * C) + cg);
         }
       }
+      const float4 A = s_coef[0], B = s_coef[1], mu = s_coef[2];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const float i0 = acc_val(I[u].x, a.acc_format), i1 = acc_val(I[u].y, a.acc_format);
@@ -359,10 +365,13 @@ extern "C" int frost_bn_backward_reduce(const FrostBnBackwardArgs* a, void* stre
   const int rows_per_block = threads / cgb;
   const int64_t wave = std::max<int64_t>(1, (int64_t)kNumSMs * tunable(FROST_TUNE_BN_RED_CTAS_PER_SM) / chunks);
   int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(a->M, (int64_t)rows_per_block * 8), wave));
+  const size_t smem = sizeof(double) * threads * 8 + sizeof(float4) * 3 * cgb;
   if (tunable(FROST_TUNE_BN_RED_UNROLL) >= 8)
-    launch_pdl(bn_bwd_reduce_kernel<8>, dim3(gx, chunks), dim3(threads), sizeof(double) * threads * 8, st, *a, cgb);
+    launch_pdl(bn_bwd_reduce_kernel<8, 2>, dim3(gx, chunks), dim3(threads), smem, st, *a, cgb);
+  else if (tunable(FROST_TUNE_BN_RED_CTAS_PER_SM) >= 4)
+    launch_pdl(bn_bwd_reduce_kernel<4, 4>, dim3(gx, chunks), dim3(threads), smem, st, *a, cgb);
   else
-    launch_pdl(bn_bwd_reduce_kernel<4>, dim3(gx, chunks), dim3(threads), sizeof(double) * threads * 8, st, *a, cgb);
+    launch_pdl(bn_bwd_reduce_kernel<4, 3>, dim3(gx, chunks), dim3(threads), smem, st, *a, cgb);
   FROST_LAUNCH_CHECK("bn_bwd_reduce");
   return FROST_OK;
 }
