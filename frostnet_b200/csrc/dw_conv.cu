@@ -161,18 +161,21 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_kernel(const uint8_t* xq, 
     for (int t = 0; t < DW_TW; ++t)
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) acc[t][ch] = 0;
-    // all KS rows of the window are requested before any arithmetic: one memory latency per strip, not KS
+    // all KS rows of the window are requested before any arithmetic: one memory latency per strip, not KS.
+    // One 64-bit base per strip; every load adds a 32-bit (row, column) offset to it (a 64-bit multiply per load
+    // was ~7 address instructions for each of the 24-60 loads of a strip - these kernels are issue-bound).
     unsigned xw_all[KS][NB * 4];
+    const int ih0 = oh * S - PAD, iw0 = ow0 * S - PAD;
+    const uint8_t* pbase = xq + (((int64_t)n * H + ih0) * W + iw0) * C + cg * 4;     // only dereferenced inside the image
+    const int rowstep = W * C;
 #pragma unroll
     for (int r = 0; r < KS; ++r) {
-      const int ih = oh * S - PAD + r;
-      const bool rok = (unsigned)ih < (unsigned)H;
-      const uint8_t* row = xq + (((int64_t)n * H + (rok ? ih : 0)) * W) * C + cg * 4;
+      const bool rok = (unsigned)(ih0 + r) < (unsigned)H;
+      const uint8_t* row = pbase + r * rowstep;
 #pragma unroll
       for (int j = 0; j < NB * 4; ++j) {
-        const int iw = ow0 * S - PAD + j;
-        const bool ok = (j < IW) && rok && ((unsigned)iw < (unsigned)W);
-        xw_all[r][j] = ok ? ld_cg(reinterpret_cast<const unsigned*>(row + (int64_t)iw * C)) : zp4;
+        const bool ok = (j < IW) && rok && ((unsigned)(iw0 + j) < (unsigned)W);
+        xw_all[r][j] = ok ? ld_cg(reinterpret_cast<const unsigned*>(row + j * C)) : zp4;
       }
     }
 #pragma unroll
@@ -203,6 +206,7 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_kernel(const uint8_t* xq, 
         }
       }
     }
+    int32_t* obase = acc_out + (((int64_t)n * Ho + oh) * Wo + ow0) * C + cg * 4;
 #pragma unroll
     for (int t = 0; t < DW_TW; ++t) {
       const int ow = ow0 + t;
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_kernel(const uint8_t* xq, 
         int I[4];
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) I[ch] = acc[t][ch] + corr[ch];
-        *reinterpret_cast<int4*>(acc_out + (((int64_t)n * Ho + oh) * Wo + ow) * C + cg * 4) = make_int4(I[0], I[1], I[2], I[3]);
+        *reinterpret_cast<int4*>(obase + t * C) = make_int4(I[0], I[1], I[2], I[3]);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           st_sum[ch] += I[ch];
@@ -485,15 +489,14 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_generic_kernel(const uint8
       for (int ch = 0; ch < 4; ++ch) acc[t][ch] = 0;
 #pragma unroll
     for (int r = 0; r < KS; ++r) {
-      const int ih = oh * S - PAD + r;
+      const int ih = oh * S - PAD + r, iw0 = ow0 * S - PAD;
       const bool rok = (unsigned)ih < (unsigned)H;
-      const uint8_t* row = xq + (((int64_t)n * H + (rok ? ih : 0)) * W) * C + cg * 4;
+      const uint8_t* row = xq + (((int64_t)n * H + ih) * W + iw0) * C + cg * 4;      // only dereferenced inside the image
       unsigned xw[IW];
 #pragma unroll
       for (int j = 0; j < IW; ++j) {
-        const int iw = ow0 * S - PAD + j;
-        const bool ok = rok && ((unsigned)iw < (unsigned)W);
-        xw[j] = ok ? ld_cg(reinterpret_cast<const unsigned*>(row + (int64_t)iw * C)) : zp4;
+        const bool ok = rok && ((unsigned)(iw0 + j) < (unsigned)W);
+        xw[j] = ok ? ld_cg(reinterpret_cast<const unsigned*>(row + j * C)) : zp4;
       }
       int wr[KS][4];
 #pragma unroll
@@ -601,12 +604,12 @@ __global__ void __launch_bounds__(256, 3) dw_dgrad_kernel(const float* dz, const
       if (th < 0) break;
       const int oh = th / S;
       if (oh >= Ho) continue;
-      const float* row = dz + (((int64_t)n * Ho + oh) * Wo) * C + cg * 4;
+      const float* row = dz + (((int64_t)n * Ho + oh) * Wo + (ow_base + JLO)) * C + cg * 4;   // only dereferenced in range
       float4 d[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int ow = ow_base + JLO + j;
-        d[j] = ((unsigned)ow < (unsigned)Wo) ? ld_cg(reinterpret_cast<const float4*>(row + (int64_t)ow * C))
+        d[j] = ((unsigned)ow < (unsigned)Wo) ? ld_cg(reinterpret_cast<const float4*>(row + j * C))
                                              : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
@@ -624,11 +627,12 @@ __global__ void __launch_bounds__(256, 3) dw_dgrad_kernel(const float* dz, const
         }
       }
     }
+    float* obase = dx + (((int64_t)n * H + ih) * W + iw0) * C + cg * 4;
 #pragma unroll
     for (int t = 0; t < DW_TW; ++t) {
       const int iw = iw0 + t;
       if (iw < W) {
-        float4* o = reinterpret_cast<float4*>(dx + (((int64_t)n * H + ih) * W + iw) * C) + cg;
+        float4* o = reinterpret_cast<float4*>(obase + t * C);
         float4 v = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
         if (accumulate) {
           const float4 old = ld_cg(o);
@@ -678,17 +682,17 @@ __global__ void __launch_bounds__(256, 3) dw_wgrad_kernel(const float* dz, const
     const int ow0 = wk.sw * DW_TW;
     const int ih = oh * S - PAD + r;
     if ((unsigned)ih >= (unsigned)H) continue;       // this kernel row falls outside the image for this strip
-    const float* drow = dz + (((int64_t)n * Ho + oh) * Wo) * C + cg * 4;
-    const uint8_t* row = xq + (((int64_t)n * H + ih) * W) * C + cg * 4;
+    const int iw0 = ow0 * S - PAD;
+    const float* drow = dz + (((int64_t)n * Ho + oh) * Wo + ow0) * C + cg * 4;
+    const uint8_t* row = xq + (((int64_t)n * H + ih) * W + iw0) * C + cg * 4;        // only dereferenced inside the image
     float4 d[DW_TW];
     unsigned xw[IW];
 #pragma unroll
     for (int t = 0; t < DW_TW; ++t)
-      d[t] = (ow0 + t < Wo) ? ld_cg(reinterpret_cast<const float4*>(drow + (int64_t)(ow0 + t) * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      d[t] = (ow0 + t < Wo) ? ld_cg(reinterpret_cast<const float4*>(drow + t * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < IW; ++j) {
-      const int iw = ow0 * S - PAD + j;
-      xw[j] = ((unsigned)iw < (unsigned)W) ? ld_cg(reinterpret_cast<const unsigned*>(row + (int64_t)iw * C)) : zp4;
+      xw[j] = ((unsigned)(iw0 + j) < (unsigned)W) ? ld_cg(reinterpret_cast<const unsigned*>(row + j * C)) : zp4;
     }
 #pragma unroll
     for (int j = 0; j < IW; ++j) {
