@@ -87,12 +87,15 @@ __global__ void __launch_bounds__(DG_THREADS, 1) pw_dgrad_tc_kernel(const uint16
         const uint32_t a_hi = smem_u32(smem + s * STAGE);
         const uint32_t a_lo = a_hi + A_BYTES, b_s = a_lo + A_BYTES;
         const int co = kb * DG_KE + c16 * 8;           // 8 bf16 = 16 bytes; cout % 8 == 0
+        // one 64-bit base per stage, 32-bit row steps (the producers' instruction count is the stage latency)
+        const int64_t abase = (m0 + r0) * cout + co;
+        const int rows_left = (int)min((int64_t)DG_BM, M - m0);
+        const bool co_ok = co < cout;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = r0 + 16 * i;
-          const int64_t m = m0 + r;
-          const bool v = (m < M) && (co < cout);
-          const int64_t off = v ? m * cout + co : 0;
+          const bool v = (r < rows_left) && co_ok;
+          const int64_t off = v ? abase + i * (16 * cout) : 0;
           const uint32_t d = sw128_offset(r, c16);
           cp_async_zfill<16>(a_hi + d, dz_hi + off, v);
           cp_async_zfill<16>(a_lo + d, dz_lo + off, v);
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) pw_dgrad_tc_kernel(const uint16
           const int r = idx >> 3, c = idx & 7;
           const int cc = kb * DG_KE + c * 8;
           const bool v = (r < n_valid) && (cc < cout);
-          cp_async_zfill<16>(b_s + sw128_offset(r, c), wt + (v ? (int64_t)(n0 + r) * cout + cc : 0), v);
+          cp_async_zfill<16>(b_s + sw128_offset(r, c), wt + (v ? (n0 + r) * cout + cc : 0), v);   // K*cout < 2^31
         }
         cp_async_commit();
         if (it >= (uint32_t)BW_LAG) {
@@ -295,6 +298,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
       const float zp_magic = 8388608.0f + (float)*x_zp_p;
       const int cpr = n_eff >> 3;                      // 8-channel chunks per row of x
       constexpr int XL = (WG_ROWS * (BN / 8) + PT - 1) / PT;   // x chunks per thread (<= 8)
+      // stage-invariant coordinates of this thread's x chunks (an integer division per chunk and stage otherwise)
+      int xoff[XL];          // element offset of the chunk inside a 64-row stage of x, -1: none
+      uint32_t xdst[XL];     // its byte offset inside the B tile
+      short xrow[XL];
+#pragma unroll
+      for (int q = 0; q < XL; ++q) {
+        const int idx = tp + PT * q;
+        const int r = idx / cpr, kc = idx - r * cpr;
+        const bool has = idx < WG_ROWS * cpr && k0 + kc * 8 < K;
+        xoff[q] = has ? r * K + k0 + kc * 8 : -1;
+        xrow[q] = (short)r;
+        xdst[q] = (uint32_t)(kc >> 3) * WG_BLK + sw128_offset(r, kc & 7);
+        if (idx >= WG_ROWS * cpr) xrow[q] = -1;
+      }
+      const int co = co0 + cidx * 8;
+      const bool co_ok = co < cout;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         uint8_t* stage = smem + s * STAGE;
@@ -303,23 +322,21 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
         const int64_t mb = m_begin + (int64_t)kb * WG_ROWS;
         // x: all loads first (registers), so their latency overlaps the wait for the stage
         uint2 xpk[XL];
+        const uint8_t* xstage = xq + mb * K;
+        const int rows_left = (int)min((int64_t)WG_ROWS, m_end - mb);
 #pragma unroll
         for (int q = 0; q < XL; ++q) {
-          const int idx = tp + PT * q;
-          const int r = idx / cpr, kc = idx - r * cpr;
           xpk[q] = make_uint2(0u, 0u);
-          if (idx < WG_ROWS * cpr && mb + r < m_end && k0 + kc * 8 < K)
-            xpk[q] = ld_cg(reinterpret_cast<const uint2*>(xq + (mb + r) * K + k0 + kc * 8));
+          if (xoff[q] >= 0 && xrow[q] < rows_left) xpk[q] = ld_cg(reinterpret_cast<const uint2*>(xstage + xoff[q]));
         }
         mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
         // dz hi/lo: cp.async straight into the MN-major tiles
-        const int co = co0 + cidx * 8;
+        const int64_t dzbase = (mb + r0) * cout + co;
 #pragma unroll
         for (int i = 0; i < WG_ROWS / RPP; ++i) {
           const int r = r0 + RPP * i;
-          const int64_t m = mb + r;
-          const bool v = (m < m_end) && (co < cout);
-          const int64_t off = v ? m * cout + co : 0;
+          const bool v = (r < rows_left) && co_ok;
+          const int64_t off = v ? dzbase + i * (RPP * cout) : 0;
           const uint32_t d = (uint32_t)(cidx >> 3) * WG_BLK + sw128_offset(r, cidx & 7);
           cp_async_zfill<16>(a_hi + d, dz_hi + off, v);
           cp_async_zfill<16>(a_lo + d, dz_lo + off, v);
@@ -327,17 +344,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
         cp_async_commit();
 #pragma unroll
         for (int q = 0; q < XL; ++q) {
-          const int idx = tp + PT * q;
-          if (idx < WG_ROWS * cpr) {
-            const int r = idx / cpr, kc = idx - r * cpr;
-            const bool v = (mb + r < m_end) && (k0 + kc * 8 < K);
+          if (xrow[q] >= 0) {
+            const bool v = xoff[q] >= 0 && xrow[q] < rows_left;
             float w[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const unsigned word = e < 4 ? xpk[q].x : xpk[q].y;
               w[e] = v ? __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650u + (e & 3))) - zp_magic : 0.0f;
             }
-            *reinterpret_cast<uint4*>(b_s + (uint32_t)(kc >> 3) * WG_BLK + sw128_offset(r, kc & 7)) =
+            *reinterpret_cast<uint4*>(b_s + xdst[q]) =
                 make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
           }
         }
@@ -442,6 +457,7 @@ extern "C" int frost_pw_dgrad_tc(const void* dz_hi, const void* dz_lo, const voi
   FROST_REQUIRE(dz_hi && dz_lo && wt_bf16 && w_scale && dx, "frost_pw_dgrad_tc: null pointer");
   FROST_REQUIRE(M > 0 && K > 0 && cout > 0 && K % 4 == 0 && cout % 8 == 0,
                 "frost_pw_dgrad_tc: K=%d must be a multiple of 4 and cout=%d of 8", K, cout);
+  FROST_REQUIRE((int64_t)K * cout < ((int64_t)1 << 31), "frost_pw_dgrad_tc: weight tensor K*cout must be < 2^31 elements");
   FROST_REQUIRE((reinterpret_cast<uintptr_t>(dz_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(dz_lo) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(dx) & 15) == 0 && (reinterpret_cast<uintptr_t>(wt_bf16) & 15) == 0,
                 "frost_pw_dgrad_tc: operands must be 16-byte aligned");

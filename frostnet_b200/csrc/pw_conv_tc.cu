@@ -113,12 +113,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
         const uint32_t a_s = smem_u32(smem + s * STAGE);
         const uint32_t b_s = a_s + A_BYTES;
         const int kbyte = kb * TC_BK + c16 * 16;
+        const uint8_t* abase = xq + (m0 + r0) * K + kbyte;      // one 64-bit base per stage, 32-bit row steps
+        const int rows_left = (int)min((int64_t)TC_BM, M - m0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = r0 + 16 * i;
-          const int64_t m = m0 + r;
-          const bool rv = m < M;
-          const uint8_t* src = xq + (rv ? m : 0) * K + kbyte;
+          const bool rv = r < rows_left;
+          const uint8_t* src = abase + i * (16 * K);             // only dereferenced when rv
           const uint32_t dst = a_s + sw128_offset(r, c16);
           if constexpr (VEC16) {
             const bool v = rv && kbyte < K;
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
             const int r = idx >> 3, c = idx & 7;
             const int kk = kb * TC_BK + c * 16;
             const bool rv = r < n_valid;
-            const int8_t* src = wq + (int64_t)(n0 + (rv ? r : 0)) * K + kk;
+            const int8_t* src = wq + (n0 + (rv ? r : 0)) * K + kk;                   // cout*K < 2^31
             const uint32_t dst = b_s + sw128_offset(r, c);
             if constexpr (VEC16) {
               const bool v = rv && kk < K;
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
             const int r = idx >> 3, c = idx & 7;
             const int kk = kb * TC_BK + c * 16;
             const bool rv = r < n_valid;
-            const int8_t* src = wq + (int64_t)(n0 + (rv ? r : 0)) * K + kk;
+            const int8_t* src = wq + (n0 + (rv ? r : 0)) * K + kk;                   // cout*K < 2^31
             uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
             if (rv && kk < K) { lo = ld_cg(reinterpret_cast<const uint2*>(src)); lo.x ^= wxor; lo.y ^= wxor; }
             if (rv && kk + 8 < K) { hi = ld_cg(reinterpret_cast<const uint2*>(src + 8)); hi.x ^= wxor; hi.y ^= wxor; }
@@ -313,6 +314,7 @@ extern "C" int frost_pw_conv_forward(const uint8_t* xq, const int32_t* x_zp, con
                                      FrostChanStats* stats, void* stream) {
   FROST_REQUIRE(xq && x_zp && wq && w_zp && wsum && acc && stats, "frost_pw_conv_forward: null pointer");
   FROST_REQUIRE(M > 0 && K > 0 && cout > 0, "frost_pw_conv_forward: empty problem M=%lld K=%d cout=%d", (long long)M, K, cout);
+  FROST_REQUIRE((int64_t)K * cout < ((int64_t)1 << 31), "frost_pw_conv_forward: weight tensor K*cout must be < 2^31 elements");
   FROST_REQUIRE(K % 8 == 0 && cout % 4 == 0, "frost_pw_conv_forward: K=%d must be a multiple of 8 and cout=%d of 4", K, cout);
   FROST_REQUIRE((reinterpret_cast<uintptr_t>(xq) & 15) == 0 && (reinterpret_cast<uintptr_t>(wq) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(acc) & 15) == 0,
