@@ -168,13 +168,14 @@ __global__ void __launch_bounds__(DG_THREADS, 1) pw_dgrad_tc_kernel(const uint16
         const int col4 = (lane & 7) * 4;
         const int n = n0 + chunk * 32 + col4;
         if (n < K) {
+          float* obase = dx + (m0 + (lane >> 3)) * K + n;                 // one 64-bit base per chunk, 32-bit row steps
+          const int rows_left = (int)min((int64_t)32, M - m0);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int row = (lane >> 3) + 4 * i;
-            const int64_t m = m0 + row;
-            if (m < M) {
+            if (row < rows_left) {
               float4 val = *reinterpret_cast<const float4*>(my + row * 36 + col4);
-              float4* dst = reinterpret_cast<float4*>(dx + m * K + n);
+              float4* dst = reinterpret_cast<float4*>(obase + i * (4 * K));
               if (accumulate) {
                 const float4 o = ld_cg(dst);
                 val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;

@@ -228,13 +228,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_conv_fwd_tc_kernel(
         unsigned long long q4[4] = {0, 0, 0, 0};
         int mn4[4] = {INT_MAX, INT_MAX, INT_MAX, INT_MAX}, mx4[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};
         if (n < cout) {
+          int32_t* obase = acc_out + (m0 + (lane >> 3)) * cout + n;      // one 64-bit base per chunk, 32-bit row steps
+          const int rows_left = (int)min((int64_t)32, M - m0);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int row = (lane >> 3) + 4 * i;
-            const int64_t m = m0 + row;
-            if (m < M) {
+            if (row < rows_left) {
               const int4 val = *reinterpret_cast<const int4*>(my + row * 36 + col4);
-              *reinterpret_cast<int4*>(acc_out + m * cout + n) = val;
+              *reinterpret_cast<int4*>(obase + i * (4 * cout)) = val;
               const int e[4] = {val.x, val.y, val.z, val.w};
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
