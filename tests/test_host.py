@@ -192,3 +192,22 @@ def test_launch_knobs_roundtrip_without_a_gpu():
     finally:
         for k in range(count):
             lib.frost_set_tunable(k, 0)
+
+
+def test_sass_obeys_the_pdl_load_rule_and_uses_the_tensor_cores():
+    """Static guard for the rule of csrc/common.cuh: kernels launched with programmatic dependent launch must not
+    read through the non-coherent path (LDG.E...CONSTANT = ld.global.nc), and the griddepcontrol pair is present.
+    Also the evidence that the 1x1 convs run on tcgen05 (UTCIMMA = kind::i8, UTCHMMA = kind::f16)."""
+    import shutil
+    import subprocess
+    from frostnet_b200 import build
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        import pytest
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", build.build_library()], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert not re.search(r"LDG\.E[.\w]*\.CONSTANT", sass), "ld.global.nc in a PDL library (see common.cuh)"
+    assert sass.count("ACQBULK") >= 20 and sass.count("PREEXIT") >= 20      # griddepcontrol.wait / launch_dependents
+    assert "UTCIMMA" in sass and "UTCHMMA" in sass
+    assert "LDGSTS.E.BYPASS.128" in sass                                    # 16-byte cp.async.cg (L2 only)
