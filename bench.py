@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 METRIC = "images/sec FrostNet-L QAT fwd+bwd+GradBoost step, bs=256/GPU, 224x224"
 UNIT = "images/s"
 FLOP_PER_IMG = 2.563e9           # fwd+bwd conv FLOPs per image (FrostNet-L 1.0 @224)
+ALG_BYTES_PER_IMG = 26.6e6       # ideal bottleneck-fused HBM traffic per image, fwd+bwd (6.81 GB at bs=256)
 
 
 class Args:                       # Classification/setting/train.json
@@ -125,25 +126,77 @@ def cpu_qat_images_per_s(batch, steps, warmup, threads=None):
     return batch * len(times) / sum(times), threads, sum(times) / len(times)
 
 
+CPU_BYTES_PER_IMAGE = 0.23e9      # measured peak RSS of the reference's QAT step: 3.3 GB at bs=16 (fp32 autograd graph)
+
+
+def reference_batch_that_fits(batch):
+    """The reference's CPU step keeps ~0.2 GB of fp32 autograd state per image: bs=256 needs ~60 GB of host RAM."""
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        return batch
+    bs = batch
+    while bs > 16 and bs * CPU_BYTES_PER_IMAGE * 1.3 > avail:
+        bs //= 2
+    return bs
+
+
 def run_reference(args):
+    """The reference arm: the UNMODIFIED reference files (baseline/_ref, see oracle/ref_harness.py) running their own
+    QAT training step on the host cores, same workload (FrostNet-L, bs=256, 224x224); the oracle port only if the
+    reference copy did not travel.  Each step is one full bs=256 batch: 1 warm-up + up to 3 timed steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_bs = 16
-    steps = max(1, min(args.steps, 6))
-    warm = max(1, min(args.warmup, 1))
-    ips, threads, spstep = cpu_qat_images_per_s(sample_bs, steps, warm)
-    sample = "%d timed + %d warm-up QAT steps (fwd+bwd+QSGD GradBoost) of FrostNet-L at bs=%d on %d host threads" % (
-        steps, warm, sample_bs, threads)
+    import warnings
+    warnings.filterwarnings("ignore")
+    from oracle import ref_harness as R
+    bs = reference_batch_that_fits(args.batch)
+    steps = max(1, min(args.steps, 3))
+    warm = 1
+    if R.available():
+        kind = "reference"
+        ips, threads, spstep = R.qat_images_per_s(bs, steps, warm)
+        c1_ms, _ = R.c1_small_fp32_ms_per_image()
+    else:
+        kind = "port"
+        ips, threads, spstep = cpu_qat_images_per_s(bs, steps, warm)
+        c1_ms = None
+    sample = "%d timed + %d warm-up QAT steps (fwd+bwd+QSGD GradBoost) of FrostNet-L at bs=%d on %d host threads, %.1f s/step" % (
+        steps, warm, bs, threads, spstep)
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "FrostNet-Large 1.0 QAT (StatAssist+GradBoost QSGD) bs=256/GPU 224x224 synthetic ImageNet",
-                       "global_batch": 256 * max(1, args.gpus), "parallelism": "dp%d" % max(1, args.gpus),
-                       "reference_sample": "CPU path, bs=%d per step (bounded sample of the same workload)" % sample_bs},
-            "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": "FrostNet-Large 1.0 QAT (StatAssist+GradBoost QSGD) bs=%d/GPU 224x224 synthetic ImageNet" % bs,
+                       "global_batch": bs * max(1, args.gpus), "parallelism": "dp%d" % max(1, args.gpus),
+                       "l2": "CPU arm"},
+            "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+            "c1_cpu_reference": None if c1_ms is None else {
+                "workload": "BASELINE configs[0]: FrostNet-Small 1.0 fp32 forward, bs=1, 224x224, eval, CPU",
+                "ms_per_image": c1_ms, "images_per_s": 1e3 / c1_ms, "cores": threads, "kind": kind},
             "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if bs != args.batch:
+        line["config"]["note"] = "host RAM too small for bs=%d on the CPU (needs ~%d GB); ran bs=%d" % (
+            args.batch, int(args.batch * CPU_BYTES_PER_IMAGE * 1.3 / 1e9), bs)
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(batch, steps):
+    """cpu_baseline leg of the B200 line: the reference arm on a bounded sample (bs=`batch`), in a process of its own
+    (the reference needs torch-global shims, oracle/ref_harness.py).  Returns (cpu_baseline dict, c1 dict)."""
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--batch", str(batch),
+                        "--steps", str(steps), "--warmup", "1"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                       text=True, env=env, timeout=1500)
+    for ln in reversed(r.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            d = json.loads(ln)
+            return d["cpu_baseline"], d.get("c1_cpu_reference")
+    raise RuntimeError("the reference arm printed no JSON line (exit code %d)" % r.returncode)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -395,11 +448,36 @@ def run_b200(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    cpu = None
+    cpu, c1 = None, None
     if world == 1 and not args.no_cpu_baseline:
-        ips, threads, spstep = cpu_qat_images_per_s(16, 3, 1)
-        cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "3 timed + 1 warm-up QAT steps (fwd+bwd+QSGD GradBoost) of FrostNet-L at bs=16, %.1f s/step" % spstep}
+        cpu, c1 = cpu_baseline_subprocess(32, 2)
+    # step-level roofline: the whole step against the ideal bottleneck-fused traffic and the conv FLOPs
+    step_roofline = None
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        peaks = {}
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    alg_bytes = ALG_BYTES_PER_IMG * bs
+    alg_flops = FLOP_PER_IMG * bs
+    t_step = ms / K * 1e-3
+    step_roofline = {
+        "algorithmic_bytes_per_step": alg_bytes, "algorithmic_flops_per_step": alg_flops,
+        "hbm_frac": alg_bytes / t_step / 1e9 / hbm_peak, "tensor_frac": alg_flops / t_step / 1e12 / tf_peak,
+        "hbm_peak_GBps": hbm_peak, "tensor_peak_TFLOPps": tf_peak,
+        "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
+        "definition": "SURVEY 8d: 26.6 MB/img = block-boundary tensors only, fp32, fwd+bwd (ideal bottleneck fusion); "
+                      "2.563 GFLOP/img conv fwd+bwd",
+        "measured_dram_bytes_per_step": None}
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if "step_total" in tr:
+            step_roofline["measured_dram_bytes_per_step"] = tr["step_total"]["dram_bytes"]
+            step_roofline["measured_dram_source"] = tr["step_total"]["source"]
+            step_roofline["dram_over_algorithmic"] = tr["step_total"]["dram_bytes"] / alg_bytes
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -417,8 +495,10 @@ def run_b200(args):
         "roofline": roofline,
         "conv_roofline": {"algorithmic_tflops": FLOP_PER_IMG * bs * K / (ms * 1e-3) / 1e12,
                           "note": "2.563 GFLOP/img conv fwd+bwd (SURVEY 8d) / step time; tensor peak %s" % "1407 TF/s sustained bf16"},
+        "step_roofline": step_roofline,
         "breakdown": breakdown,
         "cpu_baseline": cpu,
+        "c1_cpu_reference": c1,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -183,8 +183,8 @@ def ptr(t):
     return t.data_ptr()
 
 
-def stream():
-    return torch.cuda.current_stream().cuda_stream
+def stream(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def require_cuda(t, what="tensor"):

@@ -3,6 +3,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
+#include <unordered_map>
 
 namespace frost {
 static thread_local char g_err[512] = "";
@@ -15,6 +17,19 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool first_use_on_device(const void* key) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, uint64_t> seen;   // kernel -> bit mask of devices
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) dev = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  uint64_t& mask = seen[key];
+  const uint64_t bit = 1ull << dev;
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
 
 // launch-shape knobs (FROST_TUNE_*): defaults are the values measured best on B200 (tools/microbench_ops.py)
 static std::atomic<int> g_tune[FROST_TUNE_COUNT] = {};

@@ -21,6 +21,10 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(FrostBnFinalizeArgs a
   pdl_enter();
   const double M = (double)a.count;
   const double sa_sw = (double)(*a.x_scale) * (double)(*a.w_scale);
+  // momentum < 0 <-> nn.BatchNorm2d(momentum=None): cumulative moving average, factor 1/num_batches_tracked
+  // (the counter is incremented by thread 0 after the barrier below, so every thread reads the old value here)
+  const double mom = a.momentum >= 0.0f ? (double)a.momentum
+                                        : 1.0 / (double)((a.num_batches_tracked ? *a.num_batches_tracked : 0) + 1);
   float gmn = INFINITY, gmx = -INFINITY;
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
     const FrostChanStats st = a.stats[c];
@@ -37,8 +41,8 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(FrostBnFinalizeArgs a
       const double var_u = m_c * m_c * var_I;
       invstd = 1.0 / sqrt(var_u + (double)a.eps);
       const double unbiased = (a.count > 1) ? var_u * (M / (M - 1.0)) : var_u;
-      a.running_mean[c] = (float)((1.0 - (double)a.momentum) * (double)a.running_mean[c] + (double)a.momentum * mean_u);
-      a.running_var[c] = (float)((1.0 - (double)a.momentum) * (double)a.running_var[c] + (double)a.momentum * unbiased);
+      a.running_mean[c] = (float)((1.0 - mom) * (double)a.running_mean[c] + mom * mean_u);
+      a.running_var[c] = (float)((1.0 - mom) * (double)a.running_var[c] + mom * unbiased);
     } else {
       mean_u = (double)a.running_mean[c];
       invstd = 1.0 / sqrt((double)a.running_var[c] + (double)a.eps);
@@ -385,8 +389,9 @@ extern "C" int frost_bn_backward_apply(const FrostBnBackwardArgs* a, void* strea
 #define LAUNCH_APPLY(U)                                                                                                    \
   do {                                                                                                                     \
     static int per_sm = 0;                                                                                                 \
-    if (!per_sm) {                                                                                                         \
+    if (first_use_on_device(reinterpret_cast<const void*>(&bn_bwd_apply_kernel<U>)))                                       \
       cudaFuncSetAttribute(bn_bwd_apply_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                \
+    if (!per_sm) {                                                                                                         \
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_apply_kernel<U>, 256, 24 * 1024) != cudaSuccess)   \
         per_sm = 3;                                                                                                        \
     }                                                                                                                      \

@@ -15,6 +15,9 @@ namespace frost {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int tunable(int which);  // FROST_TUNE_* launch-shape knob (api.cu)
+// true the first time `key` (a kernel's address) is seen on the CURRENT device: per-kernel function attributes
+// (cudaFuncSetAttribute) are per device, and one process may drive several GPUs (nn.DataParallel threads).
+bool first_use_on_device(const void* key);
 
 #define FROST_REQUIRE(cond, ...)            \
   do {                                      \

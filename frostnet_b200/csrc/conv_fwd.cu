@@ -304,11 +304,8 @@ extern "C" int frost_stem_conv_forward(const uint8_t* xq, const int32_t* x_zp, c
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   const int64_t total = (int64_t)N * Ho * Wo;
   const size_t smem = sizeof(int) * ((size_t)k * k * cin * STEM_MAXC + (size_t)STEM_THREADS * (STEM_MAXC + 1));
-  static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
+  if (smem > 48 * 1024 && first_use_on_device(reinterpret_cast<const void*>(&stem_conv_fwd_kernel)))
     cudaFuncSetAttribute(stem_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr_set = true;
-  }
   const int64_t wave = (int64_t)kNumSMs * tunable(FROST_TUNE_STEM_FWD_CTAS_PER_SM);
   launch_pdl(stem_conv_fwd_kernel, dim3((unsigned)std::min<int64_t>(ceil_div(total, STEM_THREADS), wave)), dim3(STEM_THREADS), smem, st,
              xq, x_zp, wq, w_zp, N, H, W, cin, cout, k, stride, pad, Ho, Wo, acc, stats);

@@ -211,11 +211,8 @@ extern "C" int frost_stem_conv_forward_f32(const float* x_nchw, const int8_t* wq
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   const int64_t total = (int64_t)N * Ho * Wo;
   const size_t smem = sizeof(float) * ((size_t)k * k * cin * FS_MAXC + (size_t)FS_THREADS * (FS_MAXC + 1));
-  static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
+  if (smem > 48 * 1024 && first_use_on_device(reinterpret_cast<const void*>(&stem_conv_fwd_f32_kernel)))
     cudaFuncSetAttribute(stem_conv_fwd_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr_set = true;
-  }
   stem_conv_fwd_f32_kernel<<<(unsigned)ceil_div(total, FS_THREADS), FS_THREADS, smem, (cudaStream_t)stream>>>(
       x_nchw, wq, w_zp, N, H, W, cin, cout, k, stride, pad, Ho, Wo, z, stats);
   FROST_LAUNCH_CHECK("stem_conv_fwd_f32");

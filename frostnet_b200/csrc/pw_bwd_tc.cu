@@ -203,15 +203,13 @@ template <int BN>
 static int launch_dgrad_tc(const uint16_t* dz_hi, const uint16_t* dz_lo, const uint16_t* wt, const float* w_scale, int64_t M,
                            int K, int cout, float* dx, int accumulate, cudaStream_t st) {
   constexpr size_t smem = dg_smem_bytes<BN>();
-  static bool attr_done = false;
-  if (!attr_done) {
+  if (first_use_on_device(reinterpret_cast<const void*>(&pw_dgrad_tc_kernel<BN>))) {
     cudaError_t e = cudaFuncSetAttribute(pw_dgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("pw_dgrad_tc: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
       (void)cudaGetLastError();
       return FROST_ECUDA;
     }
-    attr_done = true;
   }
   const int n_tiles = (K + BN - 1) / BN;
   const int64_t m_tiles = ceil_div(M, DG_BM);
@@ -432,14 +430,12 @@ template <int BN>
 static int launch_wgrad_tc(const uint16_t* dz_hi, const uint16_t* dz_lo, const uint8_t* xq, const float* x_scale,
                            const int32_t* x_zp, int64_t M, int K, int cout, float* dwq, cudaStream_t st) {
   constexpr size_t smem = wg_smem_bytes<BN>();
-  static bool attr_done = false;
-  if (!attr_done) {
+  if (first_use_on_device(reinterpret_cast<const void*>(&pw_wgrad_tc_kernel<BN>))) {
     cudaError_t e = cudaFuncSetAttribute(pw_wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("pw_wgrad_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return FROST_ECUDA;
     }
-    attr_done = true;
   }
   const int ct = (int)ceil_div(cout, 128), kt = (int)ceil_div(K, BN);
   int64_t splits = std::max<int64_t>(1, std::min<int64_t>(ceil_div(M, WG_ROWS * 4), (int64_t)kNumSMs / ((int64_t)ct * kt)));

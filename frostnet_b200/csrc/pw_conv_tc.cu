@@ -289,14 +289,12 @@ template <int BN, bool VEC16>
 static int launch_tc(const uint8_t* xq, const int32_t* x_zp, const int8_t* wq, const int32_t* w_zp, const int32_t* wsum,
                      int64_t M, int K, int cout, int32_t* acc, FrostChanStats* stats, cudaStream_t st) {
   constexpr size_t smem = tc_smem_bytes<BN>();
-  static bool attr_done = false;
-  if (!attr_done) {
+  if (first_use_on_device(reinterpret_cast<const void*>(&pw_conv_fwd_tc_kernel<BN, VEC16>))) {
     cudaError_t e = cudaFuncSetAttribute(pw_conv_fwd_tc_kernel<BN, VEC16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("pw_conv_fwd_tc: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
       return FROST_ECUDA;
     }
-    attr_done = true;
   }
   const int n_tiles = (cout + BN - 1) / BN;
   const int64_t m_tiles = ceil_div(M, TC_BM);

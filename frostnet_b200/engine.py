@@ -17,8 +17,6 @@ import torch
 from . import _lib as L
 from . import qat as Q
 
-BN_MOMENTUM_DEFAULT = 0.1
-
 
 class _QT:
     """A quantised activation tensor: uint8 NHWC indices + pointers to its (scale, zero_point)
@@ -69,6 +67,11 @@ class _Layer:
     def alloc(self, dev):
         f32 = dict(dtype=torch.float32, device=dev)
         n = self.cout * self.cin_g * self.kh * self.kw
+        if self.kind == "cls":
+            # the classifier GEMMs read 4 output channels at a time: nclass that is not a multiple of 4 (CIFAR-10)
+            # runs on a zero-padded copy of the weight-index / gradient rows
+            self.cout_p = (self.cout + 3) // 4 * 4
+            n = self.cout_p * self.cin_g * self.kh * self.kw
         self.wq = torch.zeros(n, dtype=torch.int8, device=dev)
         self.wt_bf16 = torch.zeros(n, dtype=torch.bfloat16, device=dev) if self.kind == "pw" else None
         self.wmask = torch.zeros(n, dtype=torch.uint8, device=dev)
@@ -102,9 +105,32 @@ class QATEngine:
         self.force = None
         self.force_report = {}
         self.grad_sync = None         # callable(flat_grad) -> None, set by frostnet_b200.parallel
+        # every forward overwrites the per-layer persistent device state the backward reads (quantised weights,
+        # BN affine / saved statistics, live scale / zero_point buffers): a graph is only valid for backward while
+        # no later forward has run.  `generation` stamps the graphs (see backward()).
+        self.generation = 0
+        self._fingerprint = None
 
     def invalidate(self):
         self._built = False
+
+    # A copy (copy.deepcopy(model) for an EMA model, torch.save(model)) must not inherit raw device pointers into
+    # the ORIGINAL model's tensors: it gets a fresh, unbuilt engine bound to the copied module tree.
+    def __deepcopy__(self, memo):
+        import copy
+        new = QATEngine(copy.deepcopy(self.model, memo))
+        new.grad_sync = self.grad_sync
+        return new
+
+    def __getstate__(self):
+        return {"model": self.model}
+
+    def __setstate__(self, state):
+        self.__init__(state["model"])
+
+    def _tensor_fingerprint(self):
+        m = self.model
+        return tuple(t.data_ptr() for t in m.parameters()) + tuple(t.data_ptr() for t in m.buffers())
 
     def _maybe_force(self, name, q):
         if self.force is None or name not in self.force:
@@ -117,7 +143,11 @@ class QATEngine:
     # ------------------------------------------------------------------ build
     def _ensure_built(self):
         if self._built:
-            return
+            # p.data = ..., load_state_dict(assign=True), vector_to_parameters ... move tensors without going
+            # through Module._apply: the cached pointer tables would silently address freed memory
+            if self._tensor_fingerprint() == self._fingerprint:
+                return
+            self._built = False
         m = self.model
         L.load()
         named = dict(m.named_modules())
@@ -179,6 +209,7 @@ class QATEngine:
         self._wchunks, self._n_wchunks = L.chunk_table([ly.wq.numel() for ly in self.layers], L.WEIGHT_CHUNK, dev)
         self._wbchunks, self._n_wbchunks = L.chunk_table([ly.cout for ly in self.layers], L.WEIGHT_BWD_CHANNELS, dev)
         self._wscratch = torch.tensor([float("inf"), float("-inf")] * len(self.layers), dtype=torch.float32, device=dev)
+        self._fingerprint = self._tensor_fingerprint()
         self._built = True
 
     def _build_wdesc(self, which):
@@ -254,7 +285,7 @@ class QATEngine:
         a.gamma, a.beta = bn.weight.data_ptr(), bn.bias.data_ptr()
         a.running_mean, a.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
         a.num_batches_tracked = bn.num_batches_tracked.data_ptr()
-        a.momentum = BN_MOMENTUM_DEFAULT if bn.momentum is None else bn.momentum
+        a.momentum = -1.0 if bn.momentum is None else bn.momentum     # None: cumulative average 1/num_batches_tracked
         a.eps = bn.eps
         a.training = 1 if (training and bn.training) else 0
         a.relu = 1 if ly.relu else 0
@@ -278,8 +309,17 @@ class QATEngine:
 
     def forward(self, x, save):
         self._ensure_built()
+        with torch.cuda.device(self.dev):       # kernels launch on the CURRENT device: make it the model's
+            return self._forward(x, save)
+
+    def backward(self, saved, dlogits):
+        with torch.cuda.device(self.dev):
+            return self._backward(saved, dlogits)
+
+    def _forward(self, x, save):
         self._refresh_flags()
-        m, dev, st = self.model, self.dev, L.stream()
+        m, dev, st = self.model, self.dev, L.stream(self.dev)
+        self.generation += 1
         training = m.training
         if x.device != dev:
             raise RuntimeError("frostnet_b200: input on %s, model on %s" % (x.device, dev))
@@ -287,7 +327,7 @@ class QATEngine:
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
         N, Cin, H, W = x.shape
-        saved = {} if save else None
+        saved = {"gen": self.generation} if save else None
         if self.record_taps:
             self.last_taps = {}
         # all weights: scale_factor, observer, int8 indices - one launch
@@ -456,9 +496,14 @@ class QATEngine:
             L.call("frost_stem_wgrad", dz.data_ptr(), xin.q.data_ptr(), xin.scale.data_ptr(), xin.zp.data_ptr(), xin.N,
                    xin.H, xin.W, xin.C, ly.cout, ly.kh, ly.stride, ly.pad, ly.dwq.data_ptr(), st)
 
-    def backward(self, saved, dlogits):
+    def _backward(self, saved, dlogits):
         """dlogits: grad of the logits (classifier) or the list of 4 NCHW feature-map grads (feature backbone)."""
-        dev, st = self.dev, L.stream()
+        if saved.get("gen") != self.generation:
+            raise RuntimeError(
+                "frostnet_b200: backward through a forward pass that is no longer the latest one - every forward "
+                "(also an eval / no_grad one) overwrites the per-layer quantised weights, BN coefficients and "
+                "scale/zero_point buffers this graph's backward reads.  Run backward before the next forward.")
+        dev, st = self.dev, L.stream(self.dev)
         which = self._pick_gflat()
         gflat = self.gflat[which]
         gbase = gflat.data_ptr()
@@ -477,9 +522,16 @@ class QATEngine:
             dpre = torch.empty_like(dlogits)
             L.call("frost_fq_backward", dlogits.data_ptr(), lmask.data_ptr(), dlogits.numel(), dpre.data_ptr(), st)
             dpooled = torch.empty((N, cls.cin), **f32)
+            dbias_ptr = gbase + 4 * self.param_off[id(cmod.bias)] if cmod.bias is not None else None
+            if cls.cout_p != cls.cout:
+                dpre = torch.nn.functional.pad(dpre, (0, cls.cout_p - cls.cout)).contiguous()
+                dbias_p = torch.empty(cls.cout_p, **f32)
+                dbias_ptr = dbias_p.data_ptr()
             L.call("frost_linear_backward", dpre.data_ptr(), pooled.data_ptr(), cls.wq.data_ptr(),
                    cmod.weight_fake_quant.scale.data_ptr(), cmod.weight_fake_quant.zero_point.data_ptr(), N, cls.cin,
-                   cls.cout, dpooled.data_ptr(), cls.dwq.data_ptr(), gbase + 4 * self.param_off[id(cmod.bias)], st)
+                   cls.cout_p, dpooled.data_ptr(), cls.dwq.data_ptr(), dbias_ptr, st)
+            if cls.cout_p != cls.cout and cmod.bias is not None:
+                gflat.narrow(0, self.param_off[id(cmod.bias)], cls.cout).copy_(dbias_p[:cls.cout])
             dy = torch.empty((N * HW, t_last.C), **f32)
             L.call("frost_pool_dropout_backward", dpooled.data_ptr(), N, HW, t_last.C, L.ptr(keep), keep_scale,
                    dy.data_ptr(), st)
@@ -555,6 +607,9 @@ class QATEngine:
         self._ensure_built()
         if not x.is_cuda:
             raise RuntimeError("frostnet_b200: the QAT path runs on a CUDA device (B200) only; got a CPU tensor")
+        if x.requires_grad and torch.is_grad_enabled():
+            raise RuntimeError("frostnet_b200: the input requires grad, but the QAT engine does not propagate a gradient to "
+                               "the image (the stem has no dgrad); detach the input")
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.params)
         if need_grad:
             out = _QATFunction.apply(self, x, *self.params)

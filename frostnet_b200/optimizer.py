@@ -103,8 +103,7 @@ class _GradBoostBase(Optimizer):
         for key, (group0, items) in batches.items():
             dev = items[0][1].device
             L.require_cuda(items[0][1], "parameter")
-            if st is None:
-                st = L.stream()
+            st = L.stream(dev)
             arr = (L.OptTensor * len(items))()
             chunks = []
             keep = []
@@ -152,7 +151,8 @@ class _GradBoostBase(Optimizer):
             tab = host.to(dev, non_blocking=False)
             ck = torch.tensor(chunks, dtype=torch.int32).to(dev)
             h = self._hyper(group0)
-            L.call("frost_gradboost_multi", tab.data_ptr(), len(items), ck.data_ptr(), len(chunks), C.byref(h), st)
+            with torch.cuda.device(dev):      # the kernel launches on the current device: make it the parameters'
+                L.call("frost_gradboost_multi", tab.data_ptr(), len(items), ck.data_ptr(), len(chunks), C.byref(h), st)
             keep += [tab, ck]
             self._keepalive = keep
         if self._inject is not None and not self.is_warmup:

@@ -253,10 +253,52 @@ def main():
         print(f"G3 ok: {kind} oracle == reference bit-exact over {nsteps} steps")
     out["gradboost"] = gb
 
+    # ------------------------------------------------------------------ G4: the headline topology (Large 1.0)
+    # FrostNet-Large-1.0 is 5.8 M parameters: the fixture keeps the SEED of the state (oracle.fresh_state_dict is a
+    # deterministic function of it) instead of 23 MB of weights, the input, and digests of what the reference produced.
+    lspec = O.net_spec("large", 1.0, 1000)
+    lseed = 1882
+    lmodel = ref_frostnet.FrostNet(nclass=1000, mode="large", width_mult=1.0, quantized=True, drop_rate=0.0)
+    prepare(lmodel)
+    missing, unexpected = lmodel.load_state_dict(O.fresh_state_dict(lspec, seed=lseed), strict=False)
+    assert not unexpected and all("fake_quant" in k or "activation_post_process" in k for k in missing), missing
+    lsd0 = {k: v.clone() for k, v in lmodel.state_dict().items()}
+    lnet = O.OracleNet(lspec, lsd0)
+    lnet.record = True
+    assert list(dict(lmodel.named_parameters()).keys()) == list(lnet.P.keys())
+    assert len(lnet.P) == 209 and sum(p.numel() for p in lnet.parameters()) == 5807056
+    lx = torch.randn(2, 3, 64, 64, generator=g)
+    ly = torch.randint(0, 1000, (2,), generator=g)
+    llogits = lmodel(lx)
+    lloss = crit(llogits, ly)
+    lloss.backward()
+    ologits = lnet.forward(lx, training=True, drop_rate=0.0)
+    oloss = crit(ologits, ly)
+    oloss.backward()
+    assert torch.equal(llogits, ologits), "Large: oracle logits differ from the reference"
+    lgrads = {k: p.grad for k, p in lmodel.named_parameters()}
+    for k, p in lnet.named_parameters():
+        assert torch.equal(lgrads[k], p.grad), "Large: oracle grad %s differs" % k
+    lsd_ref, lsd_or = lmodel.state_dict(), lnet.state_dict()
+    for k in lsd_ref:
+        assert torch.equal(lsd_ref[k], lsd_or[k]), "Large: oracle state %s differs" % k
+    out["large"] = dict(
+        mode="large", width_mult=1.0, nclass=1000, seed=lseed, x=lx, y=ly, logits=llogits.detach().clone(),
+        loss=lloss.detach().clone(),
+        grad_norm={k: float(v.double().norm()) for k, v in lgrads.items()},
+        grad_head={k: v.flatten()[:8].clone() for k, v in lgrads.items()},
+        state={k: v.clone() for k, v in lsd_ref.items()
+               if v.numel() == 1 and ("activation_post_process" in k or "fake_quant" in k)},
+        bn_digest={k: float(v.double().sum()) for k, v in lsd_ref.items() if "running_" in k},
+        w_idx_digest={k: int(v.clamp(-128, 127).long().abs().sum()) for k, v in lnet.taps.items() if k.endswith("w_idx")},
+        stem_out_idx=lnet.taps["conv1.conv.0.out_idx"].clamp(0, 255).to(torch.uint8))
+    print("G4 ok: Large-1.0 oracle == reference bit-exact (logits, 209 grads, all buffers), N=2 64x64")
+
+    torch.save(out["large"], os.path.join(HERE, "net_large10_digest.pt"))
     torch.save(out["net"], os.path.join(HERE, "net_small035.pt"))
     torch.save(out["features"], os.path.join(HERE, "features_small035.pt"))
     torch.save(out["gradboost"], os.path.join(HERE, "gradboost.pt"))
-    for f in ("net_small035.pt", "features_small035.pt", "gradboost.pt"):
+    for f in ("net_small035.pt", "features_small035.pt", "gradboost.pt", "net_large10_digest.pt"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 
