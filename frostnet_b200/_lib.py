@@ -26,7 +26,7 @@ class WeightDesc(C.Structure):
     _fields_ = [("weight", c_p), ("bn_weight", c_p), ("bn_var", c_p), ("bn_eps", C.c_float),
                 ("cout", C.c_int32), ("cin_g", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
                 ("layout", C.c_int32), ("observe", C.c_int32), ("averaging_const", C.c_float),
-                ("wfq", FQ), ("wq", c_p), ("wt_bf16", c_p), ("wmask", c_p), ("sf", c_p), ("rstd_run", c_p), ("wsum", c_p),
+                ("wfq", FQ), ("wq", c_p), ("wq_mma", c_p), ("ldw", C.c_int32), ("wt_bf16", c_p), ("wmask", c_p), ("sf", c_p), ("rstd_run", c_p), ("wsum", c_p),
                 ("dwq", c_p), ("dgamma_bn", c_p), ("dsf_bn", c_p), ("dweight", c_p), ("dgamma", c_p)]
 
 
@@ -43,7 +43,21 @@ class BnBackwardArgs(C.Structure):
     _fields_ = [("dy", c_p), ("acc", c_p), ("acc_format", C.c_int32), ("M", C.c_int64), ("C", C.c_int32), ("relu", C.c_int32),
                 ("A", c_p), ("B", c_p), ("mean_I", c_p), ("kfac", c_p), ("gamma", c_p), ("sf", c_p),
                 ("x_scale", c_p), ("w_scale", c_p), ("out_scale", c_p), ("out_zp", c_p), ("eps", C.c_float),
-                ("sums", c_p), ("coef", c_p), ("dz", c_p), ("dz_lo", c_p), ("dz_format", C.c_int32), ("dgamma_bn", c_p), ("dbeta", c_p), ("dsf_bn", c_p)]
+                ("sums", c_p), ("coef", c_p), ("dz", c_p), ("dz_lo", c_p), ("dz_format", C.c_int32), ("dgamma_bn", c_p), ("dbeta", c_p), ("dsf_bn", c_p),
+                ("frozen", C.c_int32)]
+
+
+class PwOperands(C.Structure):
+    _fields_ = [("x", c_p), ("M", C.c_int64), ("K", C.c_int32), ("ldx", C.c_int32), ("w_mma", c_p), ("ldw", C.c_int32),
+                ("cout", C.c_int32), ("x_zp", c_p), ("w_zp", c_p), ("wsum", c_p)]
+
+
+class PwFusedFwdArgs(C.Structure):
+    _fields_ = [("op", PwOperands), ("bn", BnFinalizeArgs), ("grid_barrier", c_p), ("q", c_p), ("ldq", C.c_int32)]
+
+
+class PwFusedBwdArgs(C.Structure):
+    _fields_ = [("op", PwOperands), ("bn", BnBackwardArgs)]
 
 
 class QTensor(C.Structure):
@@ -99,6 +113,9 @@ _SIGNATURES = {
     "frost_bn_backward": [C.POINTER(BnBackwardArgs), c_p],
     "frost_bn_backward_reduce": [C.POINTER(BnBackwardArgs), c_p],
     "frost_bn_backward_apply": [C.POINTER(BnBackwardArgs), c_p],
+    "frost_pw_fused_forward": [C.POINTER(PwFusedFwdArgs), c_p],
+    "frost_pw_fused_bwd_reduce": [C.POINTER(PwFusedBwdArgs), c_p],
+    "frost_pw_fused_bwd_apply": [C.POINTER(PwFusedBwdArgs), c_p],
     "frost_cat_forward": [QTensor, QTensor, i64, FQ, i32, f32, c_p, c_p, c_p],
     "frost_cat_backward": [c_p, QTensor, QTensor, i64, c_p, c_p, c_p, c_p, i32, c_p],
     "frost_add_forward": [QTensor, QTensor, i64, FQ, i32, f32, c_p, c_p, c_p, c_p],
@@ -144,7 +161,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int
-    if lib.frost_abi_version() != 1:
+    if lib.frost_abi_version() != 2:
         raise RuntimeError("libfrost_b200.so ABI mismatch; rebuild with python -m frostnet_b200.build --force")
     # measurement aid: FROST_TUNE="knob=value,knob=value" presets the launch-shape knobs (include/frost_b200.h)
     for item in filter(None, os.environ.get("FROST_TUNE", "").split(",")):

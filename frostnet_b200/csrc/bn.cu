@@ -5,15 +5,11 @@
 //   v = bn(conv_orig) = A_c*I + B_c          (training: batch statistics from exact integer sums)
 //   y = FQ_a(relu(v))
 #include <cuda_bf16.h>
-#include "common.cuh"
+#include "bn_math.cuh"
 
 namespace frost {
 
 void dw_launch_shape(int C, int max_cgb, int* cg_per_block, int* nchunks, int* threads);
-
-// raw conv output of one element as a float: int32 accumulator (format 0) or fp32 bits (format 1)
-__device__ __forceinline__ float acc_val(int raw, int fmt) { return fmt ? __int_as_float(raw) : (float)raw; }
-__device__ __forceinline__ float bn_affine(float I, float A, float B) { return fmaf(I, A, B); }
 
 // ---------------------------------------------------------------- finalize (1 CTA)
 __global__ void __launch_bounds__(1024) bn_finalize_kernel(FrostBnFinalizeArgs a) {
@@ -27,38 +23,18 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(FrostBnFinalizeArgs a
                                         : 1.0 / (double)((a.num_batches_tracked ? *a.num_batches_tracked : 0) + 1);
   float gmn = INFINITY, gmx = -INFINITY;
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-    const FrostChanStats st = a.stats[c];
-    const double sum = a.stats_format ? __longlong_as_double(st.sum) : (double)st.sum;
-    const double sq = a.stats_format ? __longlong_as_double((long long)st.sq_lo)
-                                     : (double)st.sq_hi * 4294967296.0 + (double)st.sq_lo;
-    const double mean_I = sum / M;
-    double var_I = sq / M - mean_I * mean_I;
-    if (var_I < 0.0) var_I = 0.0;
-    const double m_c = sa_sw / (double)a.sf[c];
-    double mean_u, invstd;
+    const BnChannel r = bn_channel_finalize(a.stats[c], a.stats_format, M, a.count > 1, sa_sw, a.sf[c], a.gamma[c], a.beta[c],
+                                            a.running_mean[c], a.running_var[c], a.eps, mom, a.training, a.relu);
     if (a.training) {
-      mean_u = m_c * mean_I;
-      const double var_u = m_c * m_c * var_I;
-      invstd = 1.0 / sqrt(var_u + (double)a.eps);
-      const double unbiased = (a.count > 1) ? var_u * (M / (M - 1.0)) : var_u;
-      a.running_mean[c] = (float)((1.0 - mom) * (double)a.running_mean[c] + mom * mean_u);
-      a.running_var[c] = (float)((1.0 - mom) * (double)a.running_var[c] + mom * unbiased);
-    } else {
-      mean_u = (double)a.running_mean[c];
-      invstd = 1.0 / sqrt((double)a.running_var[c] + (double)a.eps);
+      a.running_mean[c] = r.new_running_mean;
+      a.running_var[c] = r.new_running_var;
     }
-    const double g = (double)a.gamma[c];
-    const float A = (float)(m_c * invstd * g);
-    const float B = (float)((double)a.beta[c] - mean_u * invstd * g);
-    a.A[c] = A;
-    a.B[c] = B;
-    a.mean_I[c] = (float)mean_I;
-    a.kfac[c] = (float)(m_c * invstd);
-    // v is monotone in I for fixed (A,B): the channel extrema of v sit at the integer extrema.
-    float v0 = bn_affine(acc_val(st.min, a.stats_format), A, B), v1 = bn_affine(acc_val(st.max, a.stats_format), A, B);
-    if (a.relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
-    gmn = fminf(gmn, fminf(v0, v1));
-    gmx = fmaxf(gmx, fmaxf(v0, v1));
+    a.A[c] = r.A;
+    a.B[c] = r.B;
+    a.mean_I[c] = r.mean_I;
+    a.kfac[c] = r.kfac;
+    gmn = fminf(gmn, r.v_lo);
+    gmx = fmaxf(gmx, r.v_hi);
   }
   gmn = warp_min(gmn);
   gmx = warp_max(gmx);
@@ -126,15 +102,6 @@ __global__ void __launch_bounds__(256) bnq_apply_kernel(const int32_t* acc, int 
 }
 
 // ---------------------------------------------------------------- backward
-// dv = dy * [0 <= idx <= 255] * [v > 0 if relu]
-__device__ __forceinline__ float bn_dv(float dy, float I, float A, float B, int relu, float inv, float zp) {
-  const float v = bn_affine(I, A, B);
-  const float r = relu ? fmaxf(v, 0.0f) : v;
-  const float idx = fq_index(r, inv, zp);
-  const bool pass = (idx >= 0.0f) && (idx <= 255.0f) && (!relu || v > 0.0f);
-  return pass ? dy : 0.0f;
-}
-
 // Per-channel S1 = sum dv, S2 = sum dv*(I - mean_I).  Thread -> fixed 4-channel group, strided rows.
 // A CTA owns a narrow slice of channels (cg_per_block <= 16 groups: 256-byte row segments) and many rows, so
 // that few CTAs contribute to any one channel: the partials are combined through shared memory (no atomics)
@@ -226,23 +193,19 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(FrostBnBackwardArgs a
     const double M = (double)a.M;
     const double sa_sw = (double)(*a.x_scale) * (double)(*a.w_scale);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const double S1 = a.sums[2 * c], S2 = a.sums[2 * c + 1];
-      const double k = (double)a.kfac[c];
-      const float mean_I = a.mean_I[c];
-      const double T = k * S2;                              // sum dv*xhat (S2 is already centred)
-      const float A = a.A[c];
+      const float A = a.A[c], mean_I = a.mean_I[c];
+      const BnBwdChannel r = bn_bwd_channel(a.sums[2 * c], a.sums[2 * c + 1], M, sa_sw, A, a.kfac[c], mean_I, a.gamma[c], a.sf[c],
+                                            a.eps, a.frozen ? 0 : 1);
       s_c[c] = A;
       s_c[C + c] = a.B[c];
       s_c[2 * C + c] = mean_I;
-      s_c[3 * C + c] = (float)((double)A / sa_sw);          // c1 = gamma*invstd/sf
-      s_c[4 * C + c] = (float)(S1 / M);                     // a0
-      s_c[5 * C + c] = (float)(k * T / M);                  // a1
+      s_c[3 * C + c] = r.c1;
+      s_c[4 * C + c] = r.a0;
+      s_c[5 * C + c] = r.a1;
       if (blockIdx.x == 0) {
-        const double g = (double)a.gamma[c], sf = (double)a.sf[c];
-        const double invstd = k * sf / sa_sw;               // k = m_c*invstd, m_c = sa_sw/sf
-        a.dgamma_bn[c] = (float)T;
-        a.dbeta[c] = (float)S1;
-        a.dsf_bn[c] = (float)(-g * T * (double)a.eps * invstd * invstd / sf);
+        a.dgamma_bn[c] = r.dgamma_bn;
+        a.dbeta[c] = r.dbeta;
+        a.dsf_bn[c] = r.dsf_bn;
       }
     }
   }

@@ -201,6 +201,11 @@ __global__ void __launch_bounds__(kWeightThreads) weight_quant_kernel(const Fros
       const float idx = fq_index(ws, inv, zp);
       const float qc = fminf(fmaxf(idx, -128.0f), 127.0f);
       d.wq[wq_index(d, c, ci, y, x)] = (int8_t)qc;
+      if (d.wq_mma) {   // 1x1 only (r == ci): the tensor-core operand bytes, zero point folded for one-signed weights
+        const int zpi = (int)zp;
+        const unsigned flip = zpi == 0 ? 0u : (zpi == -128 ? 0x80u : 0x7fu);
+        d.wq_mma[(int64_t)c * d.ldw + r] = (int8_t)(((unsigned)(int)qc ^ flip) & 0xffu);
+      }
       if (d.wt_bf16) d.wt_bf16[(int64_t)r * d.cout + c] = __bfloat16_as_ushort(__float2bfloat16_rn(qc - zp));  // 1x1: r == ci; exact
       d.wmask[e] = (idx >= -128.0f && idx <= 127.0f) ? 1 : 0;
       qi = (int)qc;

@@ -21,10 +21,11 @@ from . import qat as Q
 class _QT:
     """A quantised activation tensor: uint8 NHWC indices + pointers to its (scale, zero_point)
     buffers and to the dequantised [min, max] of its current contents."""
-    __slots__ = ("q", "N", "H", "W", "C", "scale", "zp", "mm")
+    __slots__ = ("q", "N", "H", "W", "C", "scale", "zp", "mm", "ld")
 
-    def __init__(self, q, N, H, W, Cc, scale, zp, mm):
+    def __init__(self, q, N, H, W, Cc, scale, zp, mm, ld=None):
         self.q, self.N, self.H, self.W, self.C, self.scale, self.zp, self.mm = q, N, H, W, Cc, scale, zp, mm
+        self.ld = Cc if ld is None else ld          # row pitch in bytes (== C: dense NHWC)
 
     @property
     def M(self):
@@ -74,6 +75,9 @@ class _Layer:
             n = self.cout_p * self.cin_g * self.kh * self.kw
         self.wq = torch.zeros(n, dtype=torch.int8, device=dev)
         self.wt_bf16 = torch.zeros(n, dtype=torch.bfloat16, device=dev) if self.kind == "pw" else None
+        # tensor-core operand bytes of the fused 1x1 kernels: rows padded to a multiple of 16 bytes (TMA's stride rule)
+        self.ldw = (self.cin_g + 15) // 16 * 16 if self.kind == "pw" else 0
+        self.wq_mma = torch.zeros(self.cout * self.ldw, dtype=torch.int8, device=dev) if self.kind == "pw" else None
         self.wmask = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.sf = torch.ones(self.cout, **f32)
         self.rstd = torch.ones(self.cout, **f32)
@@ -93,7 +97,6 @@ class _Layer:
 class QATEngine:
     def __init__(self, model):
         self.model = model
-        self.features = not hasattr(model, "classifier")
         self._built = False
         self.last_taps = None
         self.record_taps = False
@@ -110,6 +113,9 @@ class QATEngine:
         # no later forward has run.  `generation` stamps the graphs (see backward()).
         self.generation = 0
         self._fingerprint = None
+        # 1x1 ConvBn(ReLU): one fused tensor-core launch per pass, int32 accumulators never stored (csrc/pw_fused.cu).
+        # False selects the first-generation chain conv -> bn_finalize -> bnq_apply / bn_backward_* (kept as the cross-check).
+        self.fused_pw = True
 
     def invalidate(self):
         self._built = False
@@ -150,6 +156,7 @@ class QATEngine:
             self._built = False
         m = self.model
         L.load()
+        self.features = not hasattr(m, "classifier")     # feature backbone (frostnet_features.py): no head, 4 taps out
         named = dict(m.named_modules())
         self.layers, self.blocks = [], []
 
@@ -202,6 +209,10 @@ class QATEngine:
                 ly.stats_ptr = self.stats.data_ptr() + o * C.sizeof(L.ChanStats)
                 o += ly.cout
         self.n_stat_chan = tot_c
+        # one grid-barrier word per layer, zeroed with the statistics at the start of every forward
+        self.barriers = torch.zeros(len(self.layers), dtype=torch.int32, device=dev)
+        for i, ly in enumerate(self.layers):
+            ly.barrier_ptr = self.barriers.data_ptr() + 4 * i
         self.scratch = torch.zeros(L.FQ_SCRATCH_FLOATS, dtype=torch.float32, device=dev)
         self.one = torch.ones(1, dtype=torch.float32, device=dev)
         self._wdesc_dev = [self._build_wdesc(i) for i in range(2)]
@@ -231,6 +242,8 @@ class QATEngine:
             d.wq, d.wmask, d.sf, d.rstd_run, d.wsum = (ly.wq.data_ptr(), ly.wmask.data_ptr(), ly.sf.data_ptr(),
                                                        ly.rstd.data_ptr(), ly.wsum.data_ptr())
             d.wt_bf16 = ly.wt_bf16.data_ptr() if ly.wt_bf16 is not None else None
+            d.wq_mma = ly.wq_mma.data_ptr() if ly.wq_mma is not None else None
+            d.ldw = ly.ldw
             d.dwq = ly.dwq.data_ptr()
             d.dweight = g.data_ptr() + 4 * self.param_off[id(mod.weight)]
             if ly.has_bn:
@@ -249,35 +262,9 @@ class QATEngine:
             self._flag_epoch = Q.FrostFakeQuantize.flag_epoch
 
     # ------------------------------------------------------------------ forward pieces
-    def _conv_bn(self, ly, xin, training, st, saved):
-        mod, dev = ly.mod, self.dev
-        N = xin.N
-        if ly.kind == "pw":
-            Ho, Wo = xin.H, xin.W
-        else:
-            Ho = (xin.H + 2 * ly.pad - ly.kh) // ly.stride + 1
-            Wo = (xin.W + 2 * ly.pad - ly.kw) // ly.stride + 1
-        M = N * Ho * Wo
-        acc = torch.empty((M, ly.cout), dtype=torch.int32, device=dev)
-        wzp = mod.weight_fake_quant.zero_point
-        raw = isinstance(xin, _RawInput)          # feature backbone stem: fp32 image, fp32 raw conv output
-        if raw:
-            L.call("frost_stats_reset_f32", ly.stats_ptr, ly.cout, st)
-            L.call("frost_stem_conv_forward_f32", xin.x.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(), N, xin.H, xin.W, xin.C,
-                   ly.cout, ly.kh, ly.stride, ly.pad, acc.data_ptr(), ly.stats_ptr, st)
-        elif ly.kind == "pw":
-            if xin.C != ly.cin:
-                raise RuntimeError("%s: input has %d channels, expected %d" % (ly.name, xin.C, ly.cin))
-            L.call("frost_pw_conv_forward", xin.q.data_ptr(), xin.zp.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(),
-                   ly.wsum.data_ptr(), M, ly.cin, ly.cout, acc.data_ptr(), ly.stats_ptr, st)
-        elif ly.kind == "dw":
-            L.call("frost_dw_conv_forward", xin.q.data_ptr(), xin.zp.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(),
-                   N, xin.H, xin.W, xin.C, ly.kh, ly.stride, acc.data_ptr(), ly.stats_ptr, st)
-        else:
-            L.call("frost_stem_conv_forward", xin.q.data_ptr(), xin.zp.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(),
-                   N, xin.H, xin.W, xin.C, ly.cout, ly.kh, ly.stride, ly.pad, acc.data_ptr(), ly.stats_ptr, st)
-        afq = mod.activation_post_process
-        bn = mod.bn
+    def _finalize_args(self, ly, xin, M, training, raw):
+        mod = ly.mod
+        afq, bn = mod.activation_post_process, mod.bn
         a = L.BnFinalizeArgs()
         a.stats, a.C, a.count = ly.stats_ptr, ly.cout, M
         a.stats_format = 1 if raw else 0
@@ -294,17 +281,65 @@ class QATEngine:
         a.afq = _fq_struct(afq)
         a.A, a.B, a.mean_I, a.kfac = ly.A.data_ptr(), ly.B.data_ptr(), ly.mean_I.data_ptr(), ly.kfac.data_ptr()
         a.cur_minmax = ly.mm.data_ptr()
-        L.call("frost_bn_finalize", C.byref(a), st)
+        return a
+
+    def _pw_operands(self, ly, xin, M):
+        wfq = ly.mod.weight_fake_quant
+        op = L.PwOperands()
+        op.x, op.M, op.K, op.ldx = xin.q.data_ptr(), M, ly.cin, xin.ld
+        op.w_mma, op.ldw, op.cout = ly.wq_mma.data_ptr(), ly.ldw, ly.cout
+        op.x_zp, op.w_zp, op.wsum = xin.zp.data_ptr(), wfq.zero_point.data_ptr(), ly.wsum.data_ptr()
+        return op
+
+    def _conv_bn(self, ly, xin, training, st, saved):
+        mod, dev = ly.mod, self.dev
+        N = xin.N
+        if ly.kind == "pw":
+            Ho, Wo = xin.H, xin.W
+        else:
+            Ho = (xin.H + 2 * ly.pad - ly.kh) // ly.stride + 1
+            Wo = (xin.W + 2 * ly.pad - ly.kw) // ly.stride + 1
+        M = N * Ho * Wo
+        wzp = mod.weight_fake_quant.zero_point
+        afq = mod.activation_post_process
+        raw = isinstance(xin, _RawInput)          # feature backbone stem: fp32 image, fp32 raw conv output
+        a = self._finalize_args(ly, xin, M, training, raw)
         q = torch.empty((M, ly.cout), dtype=torch.uint8, device=dev)
-        L.call("frost_bnq_apply", acc.data_ptr(), 1 if raw else 0, M, ly.cout, ly.A.data_ptr(), ly.B.data_ptr(), a.relu,
-               afq.scale.data_ptr(), afq.zero_point.data_ptr(), q.data_ptr(), st)
+        acc = None
+        if ly.kind == "pw" and xin.C != ly.cin:
+            raise RuntimeError("%s: input has %d channels, expected %d" % (ly.name, xin.C, ly.cin))
+        if ly.kind == "pw" and self.fused_pw:
+            # conv + BN statistics + finalize + observer + quantise: one launch, no int32 accumulator in HBM
+            f = L.PwFusedFwdArgs()
+            f.op, f.bn = self._pw_operands(ly, xin, M), a
+            f.grid_barrier, f.q, f.ldq = ly.barrier_ptr, q.data_ptr(), ly.cout
+            L.call("frost_pw_fused_forward", C.byref(f), st)
+        else:
+            acc = torch.empty((M, ly.cout), dtype=torch.int32, device=dev)
+            if raw:
+                L.call("frost_stats_reset_f32", ly.stats_ptr, ly.cout, st)
+                L.call("frost_stem_conv_forward_f32", xin.x.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(), N, xin.H, xin.W, xin.C,
+                       ly.cout, ly.kh, ly.stride, ly.pad, acc.data_ptr(), ly.stats_ptr, st)
+            elif ly.kind == "pw":
+                L.call("frost_pw_conv_forward", xin.q.data_ptr(), xin.zp.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(),
+                       ly.wsum.data_ptr(), M, ly.cin, ly.cout, acc.data_ptr(), ly.stats_ptr, st)
+            elif ly.kind == "dw":
+                L.call("frost_dw_conv_forward", xin.q.data_ptr(), xin.zp.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(),
+                       N, xin.H, xin.W, xin.C, ly.kh, ly.stride, acc.data_ptr(), ly.stats_ptr, st)
+            else:
+                L.call("frost_stem_conv_forward", xin.q.data_ptr(), xin.zp.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(),
+                       N, xin.H, xin.W, xin.C, ly.cout, ly.kh, ly.stride, ly.pad, acc.data_ptr(), ly.stats_ptr, st)
+            L.call("frost_bn_finalize", C.byref(a), st)
+            L.call("frost_bnq_apply", acc.data_ptr(), 1 if raw else 0, M, ly.cout, ly.A.data_ptr(), ly.B.data_ptr(), a.relu,
+                   afq.scale.data_ptr(), afq.zero_point.data_ptr(), q.data_ptr(), st)
         self._maybe_force(ly.name, q)
         out = _QT(q, N, Ho, Wo, ly.cout, afq.scale, afq.zero_point, ly.mm)
         if saved is not None:
-            saved[ly.name] = (xin, acc, out, a.training)
+            saved[ly.name] = (xin, acc, out, a.training, M)
         if self.record_taps:
             self.last_taps[ly.name + ".out_q"] = q
-            self.last_taps[ly.name + ".acc"] = acc
+            if acc is not None:
+                self.last_taps[ly.name + ".acc"] = acc
         return out
 
     def forward(self, x, save):
@@ -334,6 +369,7 @@ class QATEngine:
         L.call("frost_weight_prep_multi", self._wdesc_dev[0].data_ptr(), len(self.layers), self._wchunks.data_ptr(),
                self._n_wchunks, self._wscratch.data_ptr(), st)
         L.call("frost_stats_reset", self.stats.data_ptr(), self.n_stat_chan, st)
+        self.barriers.zero_()
         if self.features:
             t = _RawInput(x, self.one)           # frostnet_features.py:342-343: conv1 sees the raw image
         else:
@@ -447,11 +483,8 @@ class QATEngine:
     def _conv_bn_bwd(self, ly, dy, saved, gbase, dx, accumulate, st):
         """dy: fp32 [M, cout] grad wrt the layer's fake-quantised output.  Writes the BN/weight grads and,
         if dx is not None, (accumulates) the grad wrt the layer input into dx [M_in, cin]."""
-        xin, acc, out, was_training = saved[ly.name]
-        if not was_training:
-            raise RuntimeError("frostnet_b200: backward through eval-mode BatchNorm is not supported")
+        xin, acc, out, was_training, M = saved[ly.name]
         mod, dev = ly.mod, self.dev
-        M = acc.shape[0]
         # pointwise layers get dz as two bf16 planes (the operand format of the tensor-core dgrad/wgrad);
         # depthwise / stem consumers read fp32
         tc_fmt = ly.kind == "pw"
@@ -463,7 +496,7 @@ class QATEngine:
             dz_lo = None
         a = L.BnBackwardArgs()
         raw = isinstance(xin, _RawInput)
-        a.dy, a.acc, a.M, a.C, a.relu = dy.data_ptr(), acc.data_ptr(), M, ly.cout, 1 if ly.relu else 0
+        a.dy, a.acc, a.M, a.C, a.relu = dy.data_ptr(), L.ptr(acc), M, ly.cout, 1 if ly.relu else 0
         a.acc_format = 1 if raw else 0
         a.A, a.B, a.mean_I, a.kfac = ly.A.data_ptr(), ly.B.data_ptr(), ly.mean_I.data_ptr(), ly.kfac.data_ptr()
         a.gamma, a.sf = mod.bn.weight.data_ptr(), ly.sf.data_ptr()
@@ -474,8 +507,16 @@ class QATEngine:
         a.dz_lo, a.dz_format = L.ptr(dz_lo), 1 if tc_fmt else 0
         a.dgamma_bn, a.dsf_bn = ly.dgamma_bn.data_ptr(), ly.dsf_bn.data_ptr()
         a.dbeta = gbase + 4 * self.param_off[id(mod.bn.bias)]
-        L.call("frost_bn_backward_reduce", C.byref(a), st)
-        L.call("frost_bn_backward_apply", C.byref(a), st)
+        a.frozen = 0 if was_training else 1        # eval-mode BatchNorm (frozen statistics): still differentiable
+        if acc is None:
+            # fused 1x1 path: both passes recompute the accumulator tile on the tensor cores from the uint8 rows
+            f = L.PwFusedBwdArgs()
+            f.op, f.bn = self._pw_operands(ly, xin, M), a
+            L.call("frost_pw_fused_bwd_reduce", C.byref(f), st)
+            L.call("frost_pw_fused_bwd_apply", C.byref(f), st)
+        else:
+            L.call("frost_bn_backward_reduce", C.byref(a), st)
+            L.call("frost_bn_backward_apply", C.byref(a), st)
         wfq = mod.weight_fake_quant
         if ly.kind == "pw":
             L.call("frost_pw_wgrad_tc", dz.data_ptr(), dz_lo.data_ptr(), xin.q.data_ptr(), xin.scale.data_ptr(),

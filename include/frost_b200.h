@@ -29,7 +29,7 @@ extern "C" {
 #define FROST_ECUDA (-2)  /* a CUDA runtime call or launch failed           */
 #define FROST_ENOSUP (-3) /* configuration not supported by this build      */
 
-/* ABI version; bumped on any signature change. */
+/* ABI version; bumped on any signature change (2: pw_fused entry points, FrostWeightDesc.wq_mma, FrostBnBackwardArgs.frozen). */
 int frost_abi_version(void);
 /* Text of the last error on the calling thread ("" if none). */
 const char* frost_last_error(void);
@@ -51,7 +51,8 @@ enum {
   FROST_TUNE_BN_APPLY_UNROLL = 9,      /* bn_backward_apply: elements in flight per thread (1, 2 or 4)          */
   FROST_TUNE_BNQ_UNROLL = 10,          /* bnq_apply: 16-byte loads in flight per thread (2, 4 or 8)             */
   FROST_TUNE_DW_FWD_TILED = 11,        /* depthwise forward smem tiles: 1 wide stride-1 planes only, 2 never, 3 always */
-  FROST_TUNE_COUNT = 12
+  FROST_TUNE_PW_TMA = 12,              /* fused 1x1 kernels: 1 TMA operand loads / output stores where the pitches allow, 2 cp.async only */
+  FROST_TUNE_COUNT = 13
 };
 int frost_set_tunable(int which, int value);
 int frost_get_tunable(int which);
@@ -125,6 +126,11 @@ typedef struct {
   float averaging_const;
   FrostFQ wfq;
   int8_t* wq;               /* out: int8 indices in `layout`                                   */
+  int8_t* wq_mma;           /* out (layout 0, 1x1 only; may be NULL): the same indices as the tensor-core A operand of the
+                               fused kernels, rows `ldw` bytes apart (ldw % 16 == 0, padding stays zero).  zp_w == 0: the
+                               s8 indices; zp_w == -128 / 127 (one-signed weights): q_w - zp_w resp. zp_w - q_w
+                               as u8 (byte ^ 0x80 / ^ 0x7f)                                    */
+  int32_t ldw;
   uint16_t* wt_bf16;        /* out (layout 0, 1x1 only; may be NULL): (q_w - zp_w) as bf16, transposed [cin][cout],
                                the B operand of the tensor-core dgrad                          */
   uint8_t* wmask;           /* out: STE mask, PyTorch layout                                   */
@@ -238,10 +244,47 @@ typedef struct {
   float* dgamma_bn;            /* out [C]                                                     */
   float* dbeta;                /* out [C]                                                     */
   float* dsf_bn;               /* out [C]                                                     */
+  int32_t frozen;              /* 1: the forward ran this BatchNorm in eval mode (running statistics are constants:
+                                  nn.BatchNorm2d.eval() / frostnet_features.py:354-359 _freeze_stages): dz = c1*dv */
 } FrostBnBackwardArgs;
 int frost_bn_backward(const FrostBnBackwardArgs* a, void* stream);          /* reduce, then apply */
 int frost_bn_backward_reduce(const FrostBnBackwardArgs* a, void* stream);   /* pass 1: the two per-channel sums */
 int frost_bn_backward_apply(const FrostBnBackwardArgs* a, void* stream);    /* pass 2: dz + BN parameter grads  */
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused 1x1 ConvBn(ReLU)2d (pw_fused.cu): the conv_fused.py:131-167,708-710 chain + activation fake-quant of one
+ * squeeze / expand / reduce / last_layer conv (frostnet.py:98-119,293) as ONE launch, and the first two stages of its
+ * autograd.  The int32 accumulator is never stored: every pass recomputes it on the tensor cores from the uint8 rows
+ * (tcgen05.mma kind::i8; operands by TMA when ldx/ldq are multiples of 16, cp.async otherwise).
+ *   forward     : stats (sum I, sum I^2, min, max per channel) -> grid barrier -> BN finalize + observer + qparams
+ *                 (same arithmetic and side effects as frost_bn_finalize) -> q = clamp(rint(relu(A*I+B)/s)+zp)
+ *   bwd_reduce  : S1 = sum dv, S2 = sum dv*(I-mean_I)            (== frost_bn_backward_reduce)
+ *   bwd_apply   : dz as bf16 hi/lo planes + BN parameter grads    (== frost_bn_backward_apply, dz_format 1)
+ * All CTAs of the forward launch must be co-resident (the callee sizes the grid to <= #SMs). */
+typedef struct {
+  const uint8_t* x;            /* [M][ldx] uint8 indices of the conv input (K valid bytes per row)          */
+  int64_t M;
+  int32_t K, ldx;              /* K % 8 == 0, ldx % 8 == 0 (TMA path: ldx % 16 == 0)                        */
+  const int8_t* w_mma;         /* FrostWeightDesc.wq_mma [cout][ldw]                                        */
+  int32_t ldw, cout;           /* cout % 4 == 0                                                             */
+  const int32_t* x_zp;         /* zero point of x                                                           */
+  const int32_t* w_zp;         /* zero point of the weight fake-quant (0, -128 or 127)                      */
+  const int32_t* wsum;         /* FrostWeightDesc.wsum [cout]: sum_k q_w                                    */
+} FrostPwOperands;
+typedef struct {
+  FrostPwOperands op;
+  FrostBnFinalizeArgs bn;      /* stats: this layer's records, reset; C == cout, count == M                 */
+  uint32_t* grid_barrier;      /* one zeroed uint32 in device memory per launch                             */
+  uint8_t* q;                  /* out [M][ldq]                                                              */
+  int32_t ldq;
+} FrostPwFusedFwdArgs;
+typedef struct {
+  FrostPwOperands op;
+  FrostBnBackwardArgs bn;      /* acc is ignored (recomputed); apply: dz / dz_lo planes with dz_format 1    */
+} FrostPwFusedBwdArgs;
+int frost_pw_fused_forward(const FrostPwFusedFwdArgs* a, void* stream);
+int frost_pw_fused_bwd_reduce(const FrostPwFusedBwdArgs* a, void* stream);
+int frost_pw_fused_bwd_apply(const FrostPwFusedBwdArgs* a, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * FloatFunctional.cat / .add (frostnet.py:129,142;

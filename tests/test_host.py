@@ -23,7 +23,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, name), "libfrost_b200.so does not export %s" % name
     assert sorted(declared) == _lib.EXPORTED_SYMBOLS, "ctypes binding and header disagree"
     lib.frost_abi_version.restype = ctypes.c_int
-    assert lib.frost_abi_version() == 1
+    assert lib.frost_abi_version() == 2
     _lib.load()
     assert _lib.launch_count() == 0            # nothing launched on a CPU-only box
 
