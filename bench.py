@@ -207,22 +207,34 @@ def algorithmic_cost(name, a):
     if name in ("frost_pw_conv_forward", "frost_pw_conv_forward_simt"):
         M, K, co = a[5], a[6], a[7]
         return M * K + co * K + 4 * M * co, 2 * M * K * co
+    if name in ("frost_pw_fused_forward", "frost_pw_fused_bwd_reduce", "frost_pw_fused_bwd_apply"):
+        args = getattr(a[0], "_obj", None)          # ctypes.byref(struct) keeps the struct in _obj
+        if args is not None:
+            M, K, co = args.op.M, args.op.K, args.op.cout
+            if name == "frost_pw_fused_forward":    # x twice (statistics pass + quantise pass), q once
+                return 2 * M * K + co * K + M * co, 4 * M * K * co
+            if name == "frost_pw_fused_bwd_reduce":  # x + dy
+                return M * K + co * K + 4 * M * co, 2 * M * K * co
+            return M * K + co * K + 8 * M * co, 2 * M * K * co      # x + dy + dz planes
     if name == "frost_bnq_apply":
         M, Cc = a[2], a[3]
         return 5 * M * Cc, 0
     if name in ("frost_pw_dgrad", "frost_pw_dgrad_tc"):
         M, K, co = a[4], a[5], a[6]
         return 4 * M * co + co * K + 4 * M * K, 2 * M * K * co
-    if name in ("frost_pw_wgrad", "frost_pw_wgrad_tc"):
-        M, K, co = (a[5], a[6], a[7]) if name.endswith("_tc") else (a[4], a[5], a[6])
+    if name == "frost_pw_wgrad":
+        M, K, co = a[4], a[5], a[6]
+        return 4 * M * co + M * K + 4 * co * K, 2 * M * K * co
+    if name == "frost_pw_wgrad_tc":
+        M, K, co = a[6], a[7], a[8]
         return 4 * M * co + M * K + 4 * co * K, 2 * M * K * co
     if name in ("frost_bn_backward", "frost_bn_backward_reduce", "frost_bn_backward_apply"):
-        args = getattr(a[0], "_obj", None)          # ctypes.byref(struct) keeps the struct in _obj
+        args = getattr(a[0], "_obj", None)
         if args is not None:                        # reduce: dy+I (8 B); apply: dy+I+dz (12 B)
             per = {"frost_bn_backward": 20, "frost_bn_backward_reduce": 8, "frost_bn_backward_apply": 12}[name]
             return per * args.M * args.C, 0
     if name == "frost_dw_conv_forward":
-        N, H, W, Cc, k, s = a[4], a[5], a[6], a[7], a[8], a[9]
+        N, H, W, Cc, k, s = a[5], a[6], a[7], a[8], a[9], a[10]
         Ho, Wo = (H + s - 1) // s, (W + s - 1) // s
         return N * H * W * Cc + 4 * N * Ho * Wo * Cc, 2 * N * Ho * Wo * Cc * k * k
     if name == "frost_dw_dgrad":
@@ -230,7 +242,7 @@ def algorithmic_cost(name, a):
         Ho, Wo = (H + s - 1) // s, (W + s - 1) // s
         return 4 * N * H * W * Cc + 4 * N * Ho * Wo * Cc, 2 * N * Ho * Wo * Cc * k * k
     if name == "frost_dw_wgrad":
-        N, H, W, Cc, k, s = a[4], a[5], a[6], a[7], a[8], a[9]
+        N, H, W, Cc, k, s = a[5], a[6], a[7], a[8], a[9], a[10]
         Ho, Wo = (H + s - 1) // s, (W + s - 1) // s
         return N * H * W * Cc + 4 * N * Ho * Wo * Cc, 2 * N * Ho * Wo * Cc * k * k
     return 0, 0
@@ -373,6 +385,8 @@ def run_b200(args):
         if args.dump_calls:
             if name.startswith("frost_bn_backward"):
                 sig = [a[0]._obj.M, a[0]._obj.C]
+            elif name.startswith("frost_pw_fused"):
+                sig = [a[0]._obj.op.M, a[0]._obj.op.K, a[0]._obj.op.cout]
             else:
                 sig = [v for v in a[:-1] if isinstance(v, int) and 0 <= v < (1 << 40)]
             call_log.append((name, sig, e0, e1, algorithmic_cost(name, a)[0]))
@@ -424,6 +438,8 @@ def run_b200(args):
                             "frac": ach / hbm_peak, "traffic": None}
             kernel_of = {"frost_bn_backward_apply": "bn_bwd_apply_kernel", "frost_bn_backward_reduce": "bn_bwd_reduce_kernel",
                          "frost_pw_conv_forward": "pw_conv_fwd_tc_kernel", "frost_pw_wgrad_tc": "pw_wgrad_tc_kernel",
+                         "frost_pw_fused_forward": "pw_fused_kernel<0>", "frost_pw_fused_bwd_reduce": "pw_fused_kernel<1>",
+                         "frost_pw_fused_bwd_apply": "pw_fused_kernel<2>",
                          "frost_pw_dgrad_tc": "pw_dgrad_tc_kernel", "frost_bnq_apply": "bnq_apply_kernel",
                          "frost_dw_conv_forward": "dw_conv_fwd_kernel", "frost_dw_wgrad": "dw_wgrad_kernel",
                          "frost_dw_dgrad": "dw_dgrad_kernel"}

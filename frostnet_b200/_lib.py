@@ -61,7 +61,7 @@ class PwFusedBwdArgs(C.Structure):
 
 
 class QTensor(C.Structure):
-    _fields_ = [("q", c_p), ("scale", c_p), ("zp", c_p), ("cur_minmax", c_p), ("C", C.c_int32)]
+    _fields_ = [("q", c_p), ("scale", c_p), ("zp", c_p), ("cur_minmax", c_p), ("C", C.c_int32), ("ld", C.c_int32)]
 
 
 class OptTensor(C.Structure):
@@ -97,7 +97,7 @@ _SIGNATURES = {
     "frost_stats_reset_f32": [c_p, i64, c_p],
     "frost_stem_conv_forward_f32": [c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, i32, c_p, c_p, c_p],
     "frost_stem_wgrad_f32": [c_p, c_p, i32, i32, i32, i32, i32, i32, i32, i32, c_p, c_p],
-    "frost_dequant_to_nchw": [c_p, c_p, c_p, i32, i32, i32, i32, c_p, c_p],
+    "frost_dequant_to_nchw": [c_p, i32, c_p, c_p, i32, i32, i32, i32, c_p, c_p],
     "frost_nchw_to_nhwc": [c_p, i32, i32, i32, i32, c_p, i32, c_p],
     "frost_fq_forward": [c_p, i64, FQ, i32, i32, i32, i32, f32, c_p, c_p, c_p, c_p, c_p],
     "frost_fq_backward": [c_p, c_p, i64, c_p, c_p],
@@ -106,19 +106,19 @@ _SIGNATURES = {
     "frost_weight_backward_multi": [c_p, i32, c_p, i32, c_p],
     "frost_pw_conv_forward": [c_p, c_p, c_p, c_p, c_p, i64, i32, i32, c_p, c_p, c_p],
     "frost_pw_conv_forward_simt": [c_p, c_p, c_p, c_p, c_p, i64, i32, i32, c_p, c_p, c_p],
-    "frost_dw_conv_forward": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, c_p, c_p, c_p],
+    "frost_dw_conv_forward": [c_p, i32, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, c_p, c_p, c_p],
     "frost_stem_conv_forward": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, i32, c_p, c_p, c_p],
     "frost_bn_finalize": [C.POINTER(BnFinalizeArgs), c_p],
-    "frost_bnq_apply": [c_p, i32, i64, i32, c_p, c_p, i32, c_p, c_p, c_p, c_p],
+    "frost_bnq_apply": [c_p, i32, i64, i32, c_p, c_p, i32, c_p, c_p, c_p, i32, c_p],
     "frost_bn_backward": [C.POINTER(BnBackwardArgs), c_p],
     "frost_bn_backward_reduce": [C.POINTER(BnBackwardArgs), c_p],
     "frost_bn_backward_apply": [C.POINTER(BnBackwardArgs), c_p],
     "frost_pw_fused_forward": [C.POINTER(PwFusedFwdArgs), c_p],
     "frost_pw_fused_bwd_reduce": [C.POINTER(PwFusedBwdArgs), c_p],
     "frost_pw_fused_bwd_apply": [C.POINTER(PwFusedBwdArgs), c_p],
-    "frost_cat_forward": [QTensor, QTensor, i64, FQ, i32, f32, c_p, c_p, c_p],
+    "frost_cat_forward": [QTensor, QTensor, i64, FQ, i32, f32, c_p, i32, c_p, c_p],
     "frost_cat_backward": [c_p, QTensor, QTensor, i64, c_p, c_p, c_p, c_p, i32, c_p],
-    "frost_add_forward": [QTensor, QTensor, i64, FQ, i32, f32, c_p, c_p, c_p, c_p],
+    "frost_add_forward": [QTensor, QTensor, i64, FQ, i32, f32, c_p, i32, c_p, c_p, c_p],
     "frost_add_backward": [c_p, QTensor, QTensor, i64, c_p, c_p, c_p, c_p, i32, c_p],
     "frost_axpy": [c_p, c_p, i64, c_p],
     "frost_pool_dropout_forward": [c_p, c_p, c_p, i32, i32, i32, c_p, f32, c_p, c_p],
@@ -128,9 +128,9 @@ _SIGNATURES = {
     "frost_pw_dgrad": [c_p, c_p, c_p, c_p, i64, i32, i32, c_p, i32, c_p],
     "frost_pw_dgrad_tc": [c_p, c_p, c_p, c_p, i64, i32, i32, c_p, i32, c_p],
     "frost_pw_wgrad": [c_p, c_p, c_p, c_p, i64, i32, i32, c_p, c_p],
-    "frost_pw_wgrad_tc": [c_p, c_p, c_p, c_p, c_p, i64, i32, i32, c_p, c_p],
+    "frost_pw_wgrad_tc": [c_p, c_p, c_p, i32, c_p, c_p, i64, i32, i32, c_p, c_p],
     "frost_dw_dgrad": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, c_p, i32, c_p],
-    "frost_dw_wgrad": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, c_p, c_p],
+    "frost_dw_wgrad": [c_p, c_p, i32, c_p, c_p, i32, i32, i32, i32, i32, i32, c_p, c_p],
     "frost_stem_wgrad": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, i32, c_p, c_p],
     "frost_gradboost_multi": [c_p, i32, c_p, i32, C.POINTER(OptHyper), c_p],
     "frost_set_tunable": [i32, i32],

@@ -71,7 +71,7 @@ template <int U>   // 16-byte loads in flight per thread
 __global__ void __launch_bounds__(256) bnq_apply_kernel(const int32_t* acc, int fmt, int64_t n4, int C,
                                                        const float* A, const float* B,
                                                        int relu, const float* scale_p,
-                                                       const int32_t* zp_p, uint8_t* q) {
+                                                       const int32_t* zp_p, uint8_t* q, int ldq) {
   extern __shared__ __align__(16) float s_ab[];  // A[C], B[C]
   pdl_enter();
   for (int c = threadIdx.x; c < C; c += blockDim.x) { s_ab[c] = A[c]; s_ab[C + c] = B[c]; }
@@ -81,8 +81,13 @@ __global__ void __launch_bounds__(256) bnq_apply_kernel(const int32_t* acc, int 
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int C4 = C >> 2;
-  int cg = (int)(i0 % C4);                       // 4-channel group of this thread's element, no division in the loop
+  // (row, 4-channel group) of this thread's element, advanced without divisions in the loop; the output rows are
+  // ldq bytes apart (ldq == C: dense)
+  int cg = (int)(i0 % C4);
+  int64_t row = i0 / C4;
   const int cstep = (int)(stride % C4);
+  const int64_t rstep = stride / C4;
+  const int ld4 = ldq >> 2;
   const int4* in = reinterpret_cast<const int4*>(acc);
   unsigned* out = reinterpret_cast<unsigned*>(q);
   const float4* sA = reinterpret_cast<const float4*>(s_ab);
@@ -94,9 +99,10 @@ __global__ void __launch_bounds__(256) bnq_apply_kernel(const int32_t* acc, int 
       if (i + u * stride < n4) v[u] = ld_cg(in + i + u * stride);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (i + u * stride < n4) out[i + u * stride] = bnq4(v[u], fmt, sA[cg], sB[cg], relu, inv, zp);
+      if (i + u * stride < n4) out[row * ld4 + cg] = bnq4(v[u], fmt, sA[cg], sB[cg], relu, inv, zp);
       cg += cstep;
-      if (cg >= C4) cg -= C4;
+      row += rstep;
+      if (cg >= C4) { cg -= C4; ++row; }
     }
   }
 }
@@ -285,9 +291,10 @@ extern "C" int frost_bn_finalize(const FrostBnFinalizeArgs* a, void* stream) {
 }
 
 extern "C" int frost_bnq_apply(const int32_t* acc, int acc_format, int64_t M, int C, const float* A, const float* B, int relu,
-                               const float* out_scale, const int32_t* out_zp, uint8_t* q, void* stream) {
+                               const float* out_scale, const int32_t* out_zp, uint8_t* q, int ldq, void* stream) {
   FROST_REQUIRE(acc && A && B && out_scale && out_zp && q, "frost_bnq_apply: null pointer");
   FROST_REQUIRE(M > 0 && C > 0 && C % 4 == 0, "frost_bnq_apply: C=%d must be a positive multiple of 4", C);
+  FROST_REQUIRE(ldq >= C && ldq % 4 == 0, "frost_bnq_apply: ldq=%d must be >= C and a multiple of 4", ldq);
   const int64_t n4 = M * C / 4;
   const size_t smem = 2 * C * sizeof(float);
   // one resident wave, U loads in flight per thread: bytes in flight per SM is what the HBM pipe needs
@@ -298,7 +305,7 @@ extern "C" int frost_bnq_apply(const int32_t* acc, int acc_format, int64_t M, in
     if (!per_sm && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bnq_apply_kernel<U>, 256, 16 * 1024) != cudaSuccess) \
       per_sm = 4;                                                                                                          \
     launch_pdl(bnq_apply_kernel<U>, dim3(grid_for(n4, 256 * U, kNumSMs * std::max(per_sm, 1))), dim3(256), smem,         \
-               (cudaStream_t)stream, acc, acc_format, n4, C, A, B, relu, out_scale, out_zp, q);                            \
+               (cudaStream_t)stream, acc, acc_format, n4, C, A, B, relu, out_scale, out_zp, q, ldq);                            \
   } while (0)
   if (u >= 8) LAUNCH_BNQ(8);
   else if (u >= 4) LAUNCH_BNQ(4);

@@ -101,7 +101,7 @@ __device__ __forceinline__ void transpose4x4(unsigned a, unsigned b, unsigned c,
 template <int KS, int S>
 __global__ void __launch_bounds__(256, 2) dw_conv_fwd_kernel(const uint8_t* xq, const int32_t* x_zp_p,
                                                             const int8_t* wq, const int32_t* w_zp_p,
-                                                            int N, int H, int W, int C, int Ho, int Wo, int cgb,
+                                                            int N, int H, int W, int C, int ldx, int Ho, int Wo, int cgb,
                                                             int32_t* acc_out, FrostChanStats* stats) {
   extern __shared__ __align__(16) unsigned char dw_smem[];
   pdl_enter();
@@ -166,8 +166,8 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_kernel(const uint8_t* xq, 
     // was ~7 address instructions for each of the 24-60 loads of a strip - these kernels are issue-bound).
     unsigned xw_all[KS][NB * 4];
     const int ih0 = oh * S - PAD, iw0 = ow0 * S - PAD;
-    const uint8_t* pbase = xq + (((int64_t)n * H + ih0) * W + iw0) * C + cg * 4;     // only dereferenced inside the image
-    const int rowstep = W * C;
+    const uint8_t* pbase = xq + (((int64_t)n * H + ih0) * W + iw0) * ldx + cg * 4;   // only dereferenced inside the image
+    const int rowstep = W * ldx;                 // input pixels are ldx bytes apart (ldx == C: dense NHWC)
 #pragma unroll
     for (int r = 0; r < KS; ++r) {
       const bool rok = (unsigned)(ih0 + r) < (unsigned)H;
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_kernel(const uint8_t* xq, 
 #pragma unroll
       for (int j = 0; j < NB * 4; ++j) {
         const bool ok = (j < IW) && rok && ((unsigned)(iw0 + j) < (unsigned)W);
-        xw_all[r][j] = ok ? ld_cg(reinterpret_cast<const unsigned*>(row + j * C)) : zp4;
+        xw_all[r][j] = ok ? ld_cg(reinterpret_cast<const unsigned*>(row + j * ldx)) : zp4;
       }
     }
 #pragma unroll
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_kernel(const uint8_t* xq, 
 // and the fill (lanes = CGB groups x 32/CGB pixels) hits 32 distinct banks.
 template <int KS, int S, int CGB>
 __global__ void __launch_bounds__(256, 2) dw_conv_fwd_tiled_kernel(const uint8_t* xq, const int32_t* x_zp_p, const int8_t* wq,
-                                                                  const int32_t* w_zp_p, int N, int H, int W, int C, int Ho, int Wo,
+                                                                  const int32_t* w_zp_p, int N, int H, int W, int C, int ldx, int Ho, int Wo,
                                                                   int TH, int PITCH, int32_t* acc_out, FrostChanStats* stats) {
   extern __shared__ __align__(16) unsigned char dw_smem[];
   pdl_enter();
@@ -328,12 +328,12 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_tiled_kernel(const uint8_t
       for (int rr = 0; rr < 2; ++rr) {
         const int ih = ih0 + row + rr;
         const bool rok = cg_ok && (row + rr < ih_rows) && ((unsigned)ih < (unsigned)H);
-        const uint8_t* src = xq + (((int64_t)n * H + (rok ? ih : 0)) * W) * C + c_first;
+        const uint8_t* src = xq + (((int64_t)n * H + (rok ? ih : 0)) * W) * ldx + c_first;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int col = slot + q * SLOTS;
           const int iw = col - PAD;
-          v[rr][q] = (rok && col < fill_w && (unsigned)iw < (unsigned)W) ? ld_cg(reinterpret_cast<const unsigned*>(src + (int64_t)iw * C)) : zp4;
+          v[rr][q] = (rok && col < fill_w && (unsigned)iw < (unsigned)W) ? ld_cg(reinterpret_cast<const unsigned*>(src + (int64_t)iw * ldx)) : zp4;
         }
       }
 #pragma unroll
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_tiled_kernel(const uint8_t
           const int iw = col - PAD;
           const bool ok = cg_ok && ((unsigned)ih < (unsigned)H) && ((unsigned)iw < (unsigned)W);
           s_tile[((size_t)(row + rr) * CGB + cg_l) * PITCH + col] =
-              ok ? ld_cg(reinterpret_cast<const unsigned*>(xq + (((int64_t)n * H + ih) * W + iw) * C + c_first)) : zp4;
+              ok ? ld_cg(reinterpret_cast<const unsigned*>(xq + (((int64_t)n * H + ih) * W + iw) * ldx + c_first)) : zp4;
         }
       }
     }
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_tiled_kernel(const uint8_t
 template <int KS, int S>
 __global__ void __launch_bounds__(256, 2) dw_conv_fwd_generic_kernel(const uint8_t* xq, const int32_t* x_zp_p,
                                                             const int8_t* wq, const int32_t* w_zp_p,
-                                                            int N, int H, int W, int C, int Ho, int Wo, int cgb,
+                                                            int N, int H, int W, int C, int ldx, int Ho, int Wo, int cgb,
                                                             int32_t* acc_out, FrostChanStats* stats) {
   extern __shared__ __align__(16) unsigned char dw_smem[];
   pdl_enter();
@@ -491,12 +491,12 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_generic_kernel(const uint8
     for (int r = 0; r < KS; ++r) {
       const int ih = oh * S - PAD + r, iw0 = ow0 * S - PAD;
       const bool rok = (unsigned)ih < (unsigned)H;
-      const uint8_t* row = xq + (((int64_t)n * H + ih) * W + iw0) * C + cg * 4;      // only dereferenced inside the image
+      const uint8_t* row = xq + (((int64_t)n * H + ih) * W + iw0) * ldx + cg * 4;    // only dereferenced inside the image
       unsigned xw[IW];
 #pragma unroll
       for (int j = 0; j < IW; ++j) {
         const bool ok = rok && ((unsigned)(iw0 + j) < (unsigned)W);
-        xw[j] = ok ? ld_cg(reinterpret_cast<const unsigned*>(row + j * C)) : zp4;
+        xw[j] = ok ? ld_cg(reinterpret_cast<const unsigned*>(row + j * ldx)) : zp4;
       }
       int wr[KS][4];
 #pragma unroll
@@ -652,7 +652,7 @@ __global__ void __launch_bounds__(256, 3) dw_dgrad_kernel(const float* dz, const
 template <int KS, int S>
 __global__ void __launch_bounds__(256, 3) dw_wgrad_kernel(const float* dz, const uint8_t* xq,
                                                          const float* x_scale_p, const int32_t* x_zp_p,
-                                                         int N, int H, int W, int C, int Ho, int Wo, int cgb,
+                                                         int N, int H, int W, int C, int ldx, int Ho, int Wo, int cgb,
                                                          float* dwq) {
   extern __shared__ __align__(16) unsigned char dw_smem[];
   pdl_enter();
@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(256, 3) dw_wgrad_kernel(const float* dz, const
     if ((unsigned)ih >= (unsigned)H) continue;       // this kernel row falls outside the image for this strip
     const int iw0 = ow0 * S - PAD;
     const float* drow = dz + (((int64_t)n * Ho + oh) * Wo + ow0) * C + cg * 4;
-    const uint8_t* row = xq + (((int64_t)n * H + ih) * W + iw0) * C + cg * 4;        // only dereferenced inside the image
+    const uint8_t* row = xq + (((int64_t)n * H + ih) * W + iw0) * ldx + cg * 4;      // only dereferenced inside the image
     float4 d[DW_TW];
     unsigned xw[IW];
 #pragma unroll
@@ -692,7 +692,7 @@ __global__ void __launch_bounds__(256, 3) dw_wgrad_kernel(const float* dz, const
       d[t] = (ow0 + t < Wo) ? ld_cg(reinterpret_cast<const float4*>(drow + t * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < IW; ++j) {
-      xw[j] = ((unsigned)(iw0 + j) < (unsigned)W) ? ld_cg(reinterpret_cast<const unsigned*>(row + j * C)) : zp4;
+      xw[j] = ((unsigned)(iw0 + j) < (unsigned)W) ? ld_cg(reinterpret_cast<const unsigned*>(row + j * ldx)) : zp4;
     }
 #pragma unroll
     for (int j = 0; j < IW; ++j) {
@@ -733,10 +733,11 @@ using namespace frost;
 
 static bool dw_shape_ok(int C, int k, int stride) { return C > 0 && C % 4 == 0 && (k == 3 || k == 5) && (stride == 1 || stride == 2); }
 
-extern "C" int frost_dw_conv_forward(const uint8_t* xq, const int32_t* x_zp, const int8_t* wq, const int32_t* w_zp,
+extern "C" int frost_dw_conv_forward(const uint8_t* xq, int ldx, const int32_t* x_zp, const int8_t* wq, const int32_t* w_zp,
                                      int N, int H, int W, int C, int k, int stride, int32_t* acc,
                                      FrostChanStats* stats, void* stream) {
   FROST_REQUIRE(xq && x_zp && wq && w_zp && acc && stats, "frost_dw_conv_forward: null pointer");
+  FROST_REQUIRE(ldx >= C && ldx % 4 == 0, "frost_dw_conv_forward: ldx=%d must be >= C and a multiple of 4", ldx);
   FROST_REQUIRE(N > 0 && H > 0 && W > 0 && dw_shape_ok(C, k, stride),
                 "frost_dw_conv_forward: bad shape (C%%4==0, k in {3,5}, stride in {1,2})");
   cudaStream_t st = (cudaStream_t)stream;
@@ -770,7 +771,7 @@ extern "C" int frost_dw_conv_forward(const uint8_t* xq, const int32_t* x_zp, con
     const int64_t wave = std::max<int64_t>(1, (int64_t)kNumSMs * tunable(FROST_TUNE_DW_FWD_CTAS_PER_SM) / tchunks);
     const dim3 tgrid((unsigned)std::min<int64_t>((int64_t)N * tiles_h, wave), tchunks);
 #define LT(KS, S, G)                                                                                                     \
-  launch_pdl(dw_conv_fwd_tiled_kernel<KS, S, G>, tgrid, dim3(256), smem_t, st, xq, x_zp, wq, w_zp, N, H, W, C, Ho, Wo, th, \
+  launch_pdl(dw_conv_fwd_tiled_kernel<KS, S, G>, tgrid, dim3(256), smem_t, st, xq, x_zp, wq, w_zp, N, H, W, C, ldx, Ho, Wo, th, \
              pitch, acc, stats)
 #define LTG(KS, S)                 \
   do {                             \
@@ -792,8 +793,8 @@ extern "C" int frost_dw_conv_forward(const uint8_t* xq, const int32_t* x_zp, con
   const size_t smem = sizeof(unsigned) * (2 * k * 4 * DW_MAX_CGB + DW_MAX_CGB * 4) + sizeof(SmemStat) * cgb * 4;
 #define L(KS, S)                                                                                                        \
   do {                                                                                                                  \
-    if (!tiled) launch_pdl(dw_conv_fwd_kernel<KS, S>, grid, dim3(threads), smem, st, xq, x_zp, wq, w_zp, N, H, W, C, Ho, Wo, cgb, acc, stats);     \
-    launch_pdl(dw_conv_fwd_generic_kernel<KS, S>, grid, dim3(threads), smem_g, st, xq, x_zp, wq, w_zp, N, H, W, C, Ho, Wo, cgb, acc, stats); \
+    if (!tiled) launch_pdl(dw_conv_fwd_kernel<KS, S>, grid, dim3(threads), smem, st, xq, x_zp, wq, w_zp, N, H, W, C, ldx, Ho, Wo, cgb, acc, stats);     \
+    launch_pdl(dw_conv_fwd_generic_kernel<KS, S>, grid, dim3(threads), smem_g, st, xq, x_zp, wq, w_zp, N, H, W, C, ldx, Ho, Wo, cgb, acc, stats); \
   } while (0)
   if (k == 3 && stride == 1) L(3, 1);
   else if (k == 3 && stride == 2) L(3, 2);
@@ -829,9 +830,10 @@ extern "C" int frost_dw_dgrad(const float* dz, const int8_t* wq, const float* w_
   return FROST_OK;
 }
 
-extern "C" int frost_dw_wgrad(const float* dz, const uint8_t* xq, const float* x_scale, const int32_t* x_zp, int N, int H,
+extern "C" int frost_dw_wgrad(const float* dz, const uint8_t* xq, int ldx, const float* x_scale, const int32_t* x_zp, int N, int H,
                               int W, int C, int k, int stride, float* dwq, void* stream) {
   FROST_REQUIRE(dz && xq && x_scale && x_zp && dwq, "frost_dw_wgrad: null pointer");
+  FROST_REQUIRE(ldx >= C && ldx % 4 == 0, "frost_dw_wgrad: ldx=%d must be >= C and a multiple of 4", ldx);
   FROST_REQUIRE(N > 0 && H > 0 && W > 0 && dw_shape_ok(C, k, stride), "frost_dw_wgrad: bad shape");
   FROST_REQUIRE((reinterpret_cast<uintptr_t>(dwq) & 15) == 0, "frost_dw_wgrad: dwq must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
@@ -851,7 +853,7 @@ extern "C" int frost_dw_wgrad(const float* dz, const uint8_t* xq, const float* x
   const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total_strips, (int64_t)spb * 8), wave));
   dim3 grid(gx, chunks);
   const size_t smem = sizeof(float) * k * k * cgb * 4;
-#define L(KS, S) launch_pdl(dw_wgrad_kernel<KS, S>, grid, dim3(threads), smem, st, dz, xq, x_scale, x_zp, N, H, W, C, Ho, Wo, cgb, dwq)
+#define L(KS, S) launch_pdl(dw_wgrad_kernel<KS, S>, grid, dim3(threads), smem, st, dz, xq, x_scale, x_zp, N, H, W, C, ldx, Ho, Wo, cgb, dwq)
   if (k == 3 && stride == 1) L(3, 1);
   else if (k == 3 && stride == 2) L(3, 2);
   else if (k == 5 && stride == 1) L(5, 1);

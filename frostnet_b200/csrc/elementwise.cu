@@ -32,7 +32,7 @@ __global__ void cat_finalize_kernel(FrostQTensor a, FrostQTensor b, FrostFQ fq, 
 
 // one thread-iteration = 8 output bytes (C1, C2 multiples of 8)
 __global__ void __launch_bounds__(256) cat_requant_kernel(FrostQTensor a, FrostQTensor b, int64_t M, const float* out_scale,
-                                                         const int32_t* out_zp, uint8_t* q_out) {
+                                                         const int32_t* out_zp, uint8_t* q_out, int ld_out) {
   pdl_enter();
   const QSrc sa = load_src(a), sb = load_src(b);
   const float so = *out_scale, zo = (float)*out_zp;
@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(256) cat_requant_kernel(FrostQTensor a, FrostQ
     const int g = (int)(i - m * G);
     uint2 in;
     QSrc s;
-    if (g < G1) { in = ld_cg(reinterpret_cast<const uint2*>(a.q + m * C1) + g); s = sa; }
-    else { in = ld_cg(reinterpret_cast<const uint2*>(b.q + m * C2) + (g - G1)); s = sb; }
+    if (g < G1) { in = ld_cg(reinterpret_cast<const uint2*>(a.q + m * a.ld) + g); s = sa; }
+    else { in = ld_cg(reinterpret_cast<const uint2*>(b.q + m * b.ld) + (g - G1)); s = sb; }
     const unsigned w[2] = {in.x, in.y};
     unsigned o[2] = {0u, 0u};
 #pragma unroll
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) cat_requant_kernel(FrostQTensor a, FrostQ
       const float qc = fminf(fmaxf(fq_index(x, inv, zo), 0.0f), 255.0f);
       o[e >> 2] |= ((unsigned)qc) << (8 * (e & 3));
     }
-    *reinterpret_cast<uint2*>(q_out + m * C + (int64_t)g * 8) = make_uint2(o[0], o[1]);
+    *reinterpret_cast<uint2*>(q_out + m * ld_out + (int64_t)g * 8) = make_uint2(o[0], o[1]);
   }
 }
 
@@ -77,8 +77,8 @@ __global__ void __launch_bounds__(256) cat_backward_kernel(const float* dcat, Fr
     const int g = (int)(i - m * G);
     const float4 d = ld_cg(reinterpret_cast<const float4*>(dcat + m * C) + g);
     const bool from_a = g < G1;
-    const unsigned in = from_a ? ld_cg(reinterpret_cast<const unsigned*>(a.q + m * C1) + g)
-                               : ld_cg(reinterpret_cast<const unsigned*>(b.q + m * C2) + (g - G1));
+    const unsigned in = from_a ? ld_cg(reinterpret_cast<const unsigned*>(a.q + m * a.ld) + g)
+                               : ld_cg(reinterpret_cast<const unsigned*>(b.q + m * b.ld) + (g - G1));
     const QSrc s = from_a ? sa : sb;
     const float dv[4] = {d.x, d.y, d.z, d.w};
     float o[4];
@@ -102,14 +102,22 @@ __global__ void __launch_bounds__(256) cat_backward_kernel(const float* dcat, Fr
 }
 
 // ---------------------------------------------------------------- add
+// word i of the logical [M][C] tensor -> byte offset in a tensor whose rows are ld bytes apart
+__device__ __forceinline__ int64_t pitched(int64_t i, int C4, int ld) {
+  if (ld == C4 * 4) return i * 4;
+  const int64_t row = i / C4;
+  return row * ld + (i - row * C4) * 4;
+}
+
 __global__ void __launch_bounds__(256) add_minmax_kernel(FrostQTensor a, FrostQTensor b, int64_t n4, float* partial) {
   pdl_enter();
   const QSrc sa = load_src(a), sb = load_src(b);
   float mn = INFINITY, mx = -INFINITY;
+  const int C4 = a.C >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const unsigned wa = ld_cg(reinterpret_cast<const unsigned*>(a.q) + i);
-    const unsigned wb = ld_cg(reinterpret_cast<const unsigned*>(b.q) + i);
+    const unsigned wa = ld_cg(reinterpret_cast<const unsigned*>(a.q + pitched(i, C4, a.ld)));
+    const unsigned wb = ld_cg(reinterpret_cast<const unsigned*>(b.q + pitched(i, C4, b.ld)));
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float v = __fadd_rn(deq((wa >> (8 * e)) & 0xff, sa), deq((wb >> (8 * e)) & 0xff, sb));
@@ -125,15 +133,16 @@ __global__ void __launch_bounds__(256) add_minmax_kernel(FrostQTensor a, FrostQT
 }
 
 __global__ void __launch_bounds__(256) add_requant_kernel(FrostQTensor a, FrostQTensor b, int64_t n4, const float* out_scale,
-                                                         const int32_t* out_zp, uint8_t* q_out) {
+                                                         const int32_t* out_zp, uint8_t* q_out, int ld_out) {
   pdl_enter();
   const QSrc sa = load_src(a), sb = load_src(b);
   const float so = *out_scale, zo = (float)*out_zp;
   const float inv = __fdiv_rn(1.0f, so);
+  const int C4 = a.C >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const unsigned wa = ld_cg(reinterpret_cast<const unsigned*>(a.q) + i);
-    const unsigned wb = ld_cg(reinterpret_cast<const unsigned*>(b.q) + i);
+    const unsigned wa = ld_cg(reinterpret_cast<const unsigned*>(a.q + pitched(i, C4, a.ld)));
+    const unsigned wb = ld_cg(reinterpret_cast<const unsigned*>(b.q + pitched(i, C4, b.ld)));
     unsigned o = 0u;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -141,7 +150,7 @@ __global__ void __launch_bounds__(256) add_requant_kernel(FrostQTensor a, FrostQ
       const float qc = fminf(fmaxf(fq_index(v, inv, zo), 0.0f), 255.0f);
       o |= ((unsigned)qc) << (8 * e);
     }
-    reinterpret_cast<unsigned*>(q_out)[i] = o;
+    *reinterpret_cast<unsigned*>(q_out + pitched(i, C4, ld_out)) = o;
   }
 }
 
@@ -152,10 +161,11 @@ __global__ void __launch_bounds__(256) add_backward_kernel(const float* dout, Fr
   const QSrc sa = load_src(a), sb = load_src(b);
   const float so = *out_scale, zo = (float)*out_zp;
   const float inv = __fdiv_rn(1.0f, so);
+  const int C4 = a.C >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const unsigned wa = ld_cg(reinterpret_cast<const unsigned*>(a.q) + i);
-    const unsigned wb = ld_cg(reinterpret_cast<const unsigned*>(b.q) + i);
+    const unsigned wa = ld_cg(reinterpret_cast<const unsigned*>(a.q + pitched(i, C4, a.ld)));
+    const unsigned wb = ld_cg(reinterpret_cast<const unsigned*>(b.q + pitched(i, C4, b.ld)));
     const float4 d = ld_cg(reinterpret_cast<const float4*>(dout) + i);
     const float dv[4] = {d.x, d.y, d.z, d.w};
     float o[4];
@@ -233,19 +243,20 @@ __global__ void __launch_bounds__(256) pool_dropout_bwd_kernel(const float* dpoo
 
 using namespace frost;
 
-static int check_qt(const FrostQTensor& t) { return t.q && t.scale && t.zp && t.C > 0; }
+static int check_qt(const FrostQTensor& t) { return t.q && t.scale && t.zp && t.C > 0 && t.ld >= t.C && t.ld % 4 == 0; }
 
 extern "C" int frost_cat_forward(FrostQTensor a, FrostQTensor b, int64_t M, FrostFQ fq, int observe,
-                                 float averaging_const, uint8_t* q_out, float* cur_minmax_out, void* stream) {
+                                 float averaging_const, uint8_t* q_out, int ld_out, float* cur_minmax_out, void* stream) {
   FROST_REQUIRE(check_qt(a) && check_qt(b) && a.cur_minmax && b.cur_minmax && q_out && cur_minmax_out && fq.scale &&
                     fq.zero_point && fq.min_val && fq.max_val,
                 "frost_cat_forward: null pointer");
   FROST_REQUIRE(M > 0 && a.C % 8 == 0 && b.C % 8 == 0, "frost_cat_forward: channel counts must be multiples of 8");
+  FROST_REQUIRE(ld_out >= a.C + b.C && ld_out % 8 == 0 && a.ld % 8 == 0 && b.ld % 8 == 0, "frost_cat_forward: row pitches must be multiples of 8");
   cudaStream_t st = (cudaStream_t)stream;
   launch_pdl(cat_finalize_kernel, dim3(1), dim3(32), 0, st, a, b, fq, observe, averaging_const, cur_minmax_out);
   FROST_LAUNCH_CHECK("cat_finalize");
   const int64_t total = M * ((a.C + b.C) / 8);
-  launch_pdl(cat_requant_kernel, dim3(grid_for(total, 256 * 2)), dim3(256), 0, st, a, b, M, fq.scale, fq.zero_point, q_out);
+  launch_pdl(cat_requant_kernel, dim3(grid_for(total, 256 * 2)), dim3(256), 0, st, a, b, M, fq.scale, fq.zero_point, q_out, ld_out);
   FROST_LAUNCH_CHECK("cat_requant");
   return FROST_OK;
 }
@@ -262,12 +273,14 @@ extern "C" int frost_cat_backward(const float* dcat, FrostQTensor a, FrostQTenso
 }
 
 extern "C" int frost_add_forward(FrostQTensor a, FrostQTensor b, int64_t n, FrostFQ fq, int observe,
-                                 float averaging_const, uint8_t* q_out, float* cur_minmax_out, float* scratch,
+                                 float averaging_const, uint8_t* q_out, int ld_out, float* cur_minmax_out, float* scratch,
                                  void* stream) {
   FROST_REQUIRE(check_qt(a) && check_qt(b) && q_out && cur_minmax_out && scratch && fq.scale && fq.zero_point &&
                     fq.min_val && fq.max_val,
                 "frost_add_forward: null pointer");
   FROST_REQUIRE(n > 0 && n % 4 == 0, "frost_add_forward: n must be a positive multiple of 4");
+  FROST_REQUIRE(a.C == b.C && a.C % 4 == 0 && n % a.C == 0 && ld_out >= a.C && ld_out % 4 == 0,
+                "frost_add_forward: both operands are [n/C][C] with C %% 4 == 0; ld_out >= C");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n4 = n / 4;
   const int nblk = grid_for(n4, 256 * 4, FROST_FQ_SCRATCH_FLOATS / 2);
@@ -275,7 +288,7 @@ extern "C" int frost_add_forward(FrostQTensor a, FrostQTensor b, int64_t n, Fros
   FROST_LAUNCH_CHECK("add_minmax");
   launch_pdl(fq_finalize_kernel, dim3(1), dim3(1024), 0, st, scratch, nblk, fq, 0, 255, 0, averaging_const, observe ? 1 : 0, cur_minmax_out);
   FROST_LAUNCH_CHECK("add_finalize");
-  launch_pdl(add_requant_kernel, dim3(grid_for(n4, 256 * 4)), dim3(256), 0, st, a, b, n4, fq.scale, fq.zero_point, q_out);
+  launch_pdl(add_requant_kernel, dim3(grid_for(n4, 256 * 4)), dim3(256), 0, st, a, b, n4, fq.scale, fq.zero_point, q_out, ld_out);
   FROST_LAUNCH_CHECK("add_requant");
   return FROST_OK;
 }
@@ -283,7 +296,7 @@ extern "C" int frost_add_forward(FrostQTensor a, FrostQTensor b, int64_t n, Fros
 extern "C" int frost_add_backward(const float* dout, FrostQTensor a, FrostQTensor b, int64_t n, const float* out_scale,
                                   const int32_t* out_zp, float* dsum, float* da, int accumulate_a, void* stream) {
   FROST_REQUIRE(dout && check_qt(a) && check_qt(b) && out_scale && out_zp && dsum && da, "frost_add_backward: null pointer");
-  FROST_REQUIRE(n > 0 && n % 4 == 0, "frost_add_backward: n must be a positive multiple of 4");
+  FROST_REQUIRE(n > 0 && n % 4 == 0 && a.C == b.C && a.C % 4 == 0 && n % a.C == 0, "frost_add_backward: n must be a positive multiple of C, C %% 4 == 0");
   launch_pdl(add_backward_kernel, dim3(grid_for(n / 4, 256 * 4)), dim3(256), 0, (cudaStream_t)stream, dout, a, b, n / 4, out_scale, out_zp,
              dsum, da, accumulate_a);
   FROST_LAUNCH_CHECK("add_backward");

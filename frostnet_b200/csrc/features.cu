@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_f32_kernel(const float* dz, co
 }
 
 // NHWC uint8 indices -> NCHW fp32 values, 32x32 (pixel x channel) tiles through shared memory
-__global__ void __launch_bounds__(256) dequant_to_nchw_kernel(const uint8_t* q, const float* scale_p,
+__global__ void __launch_bounds__(256) dequant_to_nchw_kernel(const uint8_t* q, int ldq, const float* scale_p,
                                                              const int32_t* zp_p, int HW, int C, float* y) {
   __shared__ float tile[32][33];
   const float s = *scale_p, zp = (float)*zp_p;
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) dequant_to_nchw_kernel(const uint8_t* q, 
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows per pass
   for (int r = ty; r < 32; r += 8) {
     const int p = p0 + r, c = c0 + tx;
-    tile[r][tx] = (p < HW && c < C) ? fq_dequant((float)q[((int64_t)n * HW + p) * C + c], zp, s) : 0.0f;
+    tile[r][tx] = (p < HW && c < C) ? fq_dequant((float)q[((int64_t)n * HW + p) * ldq + c], zp, s) : 0.0f;
   }
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
@@ -240,11 +240,11 @@ extern "C" int frost_stem_wgrad_f32(const float* dz, const float* x_nchw, int N,
   return FROST_OK;
 }
 
-extern "C" int frost_dequant_to_nchw(const uint8_t* q, const float* scale, const int32_t* zp, int N, int H, int W, int C,
+extern "C" int frost_dequant_to_nchw(const uint8_t* q, int ldq, const float* scale, const int32_t* zp, int N, int H, int W, int C,
                                      float* y_nchw, void* stream) {
-  FROST_REQUIRE(q && scale && zp && y_nchw && N > 0 && H > 0 && W > 0 && C > 0, "frost_dequant_to_nchw: bad args");
+  FROST_REQUIRE(q && scale && zp && y_nchw && N > 0 && H > 0 && W > 0 && C > 0 && ldq >= C, "frost_dequant_to_nchw: bad args");
   dim3 grid((unsigned)ceil_div(H * W, 32), (unsigned)ceil_div(C, 32), (unsigned)N);
-  dequant_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(q, scale, zp, H * W, C, y_nchw);
+  dequant_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(q, ldq, scale, zp, H * W, C, y_nchw);
   FROST_LAUNCH_CHECK("dequant_to_nchw");
   return FROST_OK;
 }

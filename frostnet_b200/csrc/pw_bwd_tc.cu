@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
                                                                    const uint16_t* dz_lo,
                                                                    const uint8_t* xq,
                                                                    const float* x_scale_p,
-                                                                   const int32_t* x_zp_p, int64_t M, int K,
+                                                                   const int32_t* x_zp_p, int64_t M, int K, int ldx,
                                                                    int cout, int64_t rows_per_split, float* dwq) {
   constexpr int STAGES = wg_stages<BN>();
   constexpr int BW_LAG = 2;
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
         const int idx = tp + PT * q;
         const int r = idx / cpr, kc = idx - r * cpr;
         const bool has = idx < WG_ROWS * cpr && k0 + kc * 8 < K;
-        xoff[q] = has ? r * K + k0 + kc * 8 : -1;
+        xoff[q] = has ? r * ldx + k0 + kc * 8 : -1;      // x rows are ldx bytes apart (ldx == K: dense)
         xrow[q] = (short)r;
         xdst[q] = (uint32_t)(kc >> 3) * WG_BLK + sw128_offset(r, kc & 7);
         if (idx >= WG_ROWS * cpr) xrow[q] = -1;
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
         const int64_t mb = m_begin + (int64_t)kb * WG_ROWS;
         // x: all loads first (registers), so their latency overlaps the wait for the stage
         uint2 xpk[XL];
-        const uint8_t* xstage = xq + mb * K;
+        const uint8_t* xstage = xq + mb * ldx;
         const int rows_left = (int)min((int64_t)WG_ROWS, m_end - mb);
 #pragma unroll
         for (int q = 0; q < XL; ++q) {
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
 }
 
 template <int BN>
-static int launch_wgrad_tc(const uint16_t* dz_hi, const uint16_t* dz_lo, const uint8_t* xq, const float* x_scale,
+static int launch_wgrad_tc(const uint16_t* dz_hi, const uint16_t* dz_lo, const uint8_t* xq, int ldx, const float* x_scale,
                            const int32_t* x_zp, int64_t M, int K, int cout, float* dwq, cudaStream_t st) {
   constexpr size_t smem = wg_smem_bytes<BN>();
   if (first_use_on_device(reinterpret_cast<const void*>(&pw_wgrad_tc_kernel<BN>))) {
@@ -441,7 +441,7 @@ static int launch_wgrad_tc(const uint16_t* dz_hi, const uint16_t* dz_lo, const u
   int64_t splits = std::max<int64_t>(1, std::min<int64_t>(ceil_div(M, WG_ROWS * 4), (int64_t)kNumSMs / ((int64_t)ct * kt)));
   int64_t rows = ceil_div(ceil_div(M, splits), WG_ROWS) * WG_ROWS;
   splits = ceil_div(M, rows);
-  launch_pdl(pw_wgrad_tc_kernel<BN>, dim3(ct, kt, (unsigned)splits), dim3(WG_THREADS), smem, st, dz_hi, dz_lo, xq, x_scale, x_zp, M, K, cout, rows, dwq);
+  launch_pdl(pw_wgrad_tc_kernel<BN>, dim3(ct, kt, (unsigned)splits), dim3(WG_THREADS), smem, st, dz_hi, dz_lo, xq, x_scale, x_zp, M, K, ldx, cout, rows, dwq);
   return FROST_OK;
 }
 
@@ -471,9 +471,10 @@ extern "C" int frost_pw_dgrad_tc(const void* dz_hi, const void* dz_lo, const voi
   return FROST_OK;
 }
 
-extern "C" int frost_pw_wgrad_tc(const void* dz_hi, const void* dz_lo, const uint8_t* xq, const float* x_scale,
+extern "C" int frost_pw_wgrad_tc(const void* dz_hi, const void* dz_lo, const uint8_t* xq, int ldx, const float* x_scale,
                                  const int32_t* x_zp, int64_t M, int K, int cout, float* dwq, void* stream) {
   FROST_REQUIRE(dz_hi && dz_lo && xq && x_scale && x_zp && dwq, "frost_pw_wgrad_tc: null pointer");
+  FROST_REQUIRE(ldx >= K && ldx % 8 == 0, "frost_pw_wgrad_tc: ldx=%d must be >= K and a multiple of 8", ldx);
   FROST_REQUIRE(M > 0 && K > 0 && cout > 0 && K % 8 == 0 && cout % 8 == 0, "frost_pw_wgrad_tc: K and cout must be multiples of 8");
   FROST_REQUIRE((reinterpret_cast<uintptr_t>(dz_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(dz_lo) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(dwq) & 15) == 0 && (reinterpret_cast<uintptr_t>(xq) & 7) == 0,
@@ -486,9 +487,9 @@ extern "C" int frost_pw_wgrad_tc(const void* dz_hi, const void* dz_lo, const uin
   const uint16_t* hi = static_cast<const uint16_t*>(dz_hi);
   const uint16_t* lo = static_cast<const uint16_t*>(dz_lo);
   int rc;
-  if (K <= 64) rc = launch_wgrad_tc<64>(hi, lo, xq, x_scale, x_zp, M, K, cout, dwq, st);
-  else if (K <= 128) rc = launch_wgrad_tc<128>(hi, lo, xq, x_scale, x_zp, M, K, cout, dwq, st);
-  else rc = launch_wgrad_tc<256>(hi, lo, xq, x_scale, x_zp, M, K, cout, dwq, st);
+  if (K <= 64) rc = launch_wgrad_tc<64>(hi, lo, xq, ldx, x_scale, x_zp, M, K, cout, dwq, st);
+  else if (K <= 128) rc = launch_wgrad_tc<128>(hi, lo, xq, ldx, x_scale, x_zp, M, K, cout, dwq, st);
+  else rc = launch_wgrad_tc<256>(hi, lo, xq, ldx, x_scale, x_zp, M, K, cout, dwq, st);
   if (rc) return rc;
   FROST_LAUNCH_CHECK("pw_wgrad_tc");
   return FROST_OK;

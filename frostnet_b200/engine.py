@@ -32,7 +32,7 @@ class _QT:
         return self.N * self.H * self.W
 
     def c(self):
-        return L.QTensor(self.q.data_ptr(), self.scale.data_ptr(), self.zp.data_ptr(), self.mm.data_ptr(), self.C)
+        return L.QTensor(self.q.data_ptr(), self.scale.data_ptr(), self.zp.data_ptr(), self.mm.data_ptr(), self.C, self.ld)
 
 
 class _RawInput:
@@ -138,9 +138,17 @@ class QATEngine:
         m = self.model
         return tuple(t.data_ptr() for t in m.parameters()) + tuple(t.data_ptr() for t in m.buffers())
 
-    def _maybe_force(self, name, q):
+    def _alloc_q(self, M, Cc):
+        """uint8 index tensor [M][ld]: rows padded to a multiple of 16 bytes (TMA's stride rule; the padding is
+        don't-care) on the fused path, dense for the first-generation kernels."""
+        ld = (Cc + 15) // 16 * 16 if self.fused_pw else Cc
+        return torch.empty((M, ld), dtype=torch.uint8, device=self.dev), ld
+
+    def _maybe_force(self, name, q, Cc=None):
         if self.force is None or name not in self.force:
             return
+        if Cc is not None:
+            q = q[:, :Cc]                              # the logical [M][C] part of a row-padded tensor
         ref = self.force[name].to(q.device).reshape(q.shape)
         d = (q.int() - ref.int()).abs()
         self.force_report[name] = (float((d > 0).float().mean()), int(d.max()))
@@ -304,7 +312,7 @@ class QATEngine:
         afq = mod.activation_post_process
         raw = isinstance(xin, _RawInput)          # feature backbone stem: fp32 image, fp32 raw conv output
         a = self._finalize_args(ly, xin, M, training, raw)
-        q = torch.empty((M, ly.cout), dtype=torch.uint8, device=dev)
+        q, ldq = self._alloc_q(M, ly.cout)
         acc = None
         if ly.kind == "pw" and xin.C != ly.cin:
             raise RuntimeError("%s: input has %d channels, expected %d" % (ly.name, xin.C, ly.cin))
@@ -312,7 +320,7 @@ class QATEngine:
             # conv + BN statistics + finalize + observer + quantise: one launch, no int32 accumulator in HBM
             f = L.PwFusedFwdArgs()
             f.op, f.bn = self._pw_operands(ly, xin, M), a
-            f.grid_barrier, f.q, f.ldq = ly.barrier_ptr, q.data_ptr(), ly.cout
+            f.grid_barrier, f.q, f.ldq = ly.barrier_ptr, q.data_ptr(), ldq
             L.call("frost_pw_fused_forward", C.byref(f), st)
         else:
             acc = torch.empty((M, ly.cout), dtype=torch.int32, device=dev)
@@ -324,20 +332,20 @@ class QATEngine:
                 L.call("frost_pw_conv_forward", xin.q.data_ptr(), xin.zp.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(),
                        ly.wsum.data_ptr(), M, ly.cin, ly.cout, acc.data_ptr(), ly.stats_ptr, st)
             elif ly.kind == "dw":
-                L.call("frost_dw_conv_forward", xin.q.data_ptr(), xin.zp.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(),
+                L.call("frost_dw_conv_forward", xin.q.data_ptr(), xin.ld, xin.zp.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(),
                        N, xin.H, xin.W, xin.C, ly.kh, ly.stride, acc.data_ptr(), ly.stats_ptr, st)
             else:
                 L.call("frost_stem_conv_forward", xin.q.data_ptr(), xin.zp.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(),
                        N, xin.H, xin.W, xin.C, ly.cout, ly.kh, ly.stride, ly.pad, acc.data_ptr(), ly.stats_ptr, st)
             L.call("frost_bn_finalize", C.byref(a), st)
             L.call("frost_bnq_apply", acc.data_ptr(), 1 if raw else 0, M, ly.cout, ly.A.data_ptr(), ly.B.data_ptr(), a.relu,
-                   afq.scale.data_ptr(), afq.zero_point.data_ptr(), q.data_ptr(), st)
-        self._maybe_force(ly.name, q)
-        out = _QT(q, N, Ho, Wo, ly.cout, afq.scale, afq.zero_point, ly.mm)
+                   afq.scale.data_ptr(), afq.zero_point.data_ptr(), q.data_ptr(), ldq, st)
+        self._maybe_force(ly.name, q, ly.cout)
+        out = _QT(q, N, Ho, Wo, ly.cout, afq.scale, afq.zero_point, ly.mm, ldq)
         if saved is not None:
             saved[ly.name] = (xin, acc, out, a.training, M)
         if self.record_taps:
-            self.last_taps[ly.name + ".out_q"] = q
+            self.last_taps[ly.name + ".out_q"] = q[:, :ly.cout].contiguous()
             if acc is not None:
                 self.last_taps[ly.name + ".acc"] = acc
         return out
@@ -394,16 +402,16 @@ class QATEngine:
                 if b["squeeze"] is not None:
                     sq = self._conv_bn(b["squeeze"], xin, training, st, saved)
                     cfq = blk.quant_cat.activation_post_process
-                    qc = torch.empty((xin.M, sq.C + xin.C), dtype=torch.uint8, device=dev)
+                    qc, ldc = self._alloc_q(xin.M, sq.C + xin.C)
                     mmc = torch.empty(2, dtype=torch.float32, device=dev)
                     L.call("frost_cat_forward", sq.c(), xin.c(), xin.M, _fq_struct(cfq), 1 if cfq._observe else 0,
-                           Q.AVERAGING_CONSTANT, qc.data_ptr(), mmc.data_ptr(), st)
-                    self._maybe_force(b["name"] + ".cat", qc)
-                    cat = _QT(qc, xin.N, xin.H, xin.W, sq.C + xin.C, cfq.scale, cfq.zero_point, mmc)
+                           Q.AVERAGING_CONSTANT, qc.data_ptr(), ldc, mmc.data_ptr(), st)
+                    self._maybe_force(b["name"] + ".cat", qc, sq.C + xin.C)
+                    cat = _QT(qc, xin.N, xin.H, xin.W, sq.C + xin.C, cfq.scale, cfq.zero_point, mmc, ldc)
                     if saved is not None:
                         saved[b["name"] + ".cat"] = (sq, xin, cat)
                     if self.record_taps:
-                        self.last_taps[b["name"] + ".cat_q"] = qc
+                        self.last_taps[b["name"] + ".cat_q"] = qc[:, :cat.C].contiguous()
                     o = cat
                 else:
                     o = xin
@@ -414,21 +422,21 @@ class QATEngine:
             o = self._conv_bn(b["reduce"], o, training, st, saved)
             if b["skip"]:
                 afq = blk.skip_add.activation_post_process
-                qa = torch.empty((o.M, o.C), dtype=torch.uint8, device=dev)
+                qa, lda = self._alloc_q(o.M, o.C)
                 mma = torch.empty(2, dtype=torch.float32, device=dev)
                 L.call("frost_add_forward", xin.c(), o.c(), o.M * o.C, _fq_struct(afq), 1 if afq._observe else 0,
-                       Q.AVERAGING_CONSTANT, qa.data_ptr(), mma.data_ptr(), self.scratch.data_ptr(), st)
-                self._maybe_force(b["name"] + ".add", qa)
-                s = _QT(qa, o.N, o.H, o.W, o.C, afq.scale, afq.zero_point, mma)
+                       Q.AVERAGING_CONSTANT, qa.data_ptr(), lda, mma.data_ptr(), self.scratch.data_ptr(), st)
+                self._maybe_force(b["name"] + ".add", qa, o.C)
+                s = _QT(qa, o.N, o.H, o.W, o.C, afq.scale, afq.zero_point, mma, lda)
                 if saved is not None:
                     saved[b["name"] + ".add"] = (xin, o, s)
                 if self.record_taps:
-                    self.last_taps[b["name"] + ".add_q"] = qa
+                    self.last_taps[b["name"] + ".add_q"] = qa[:, :o.C].contiguous()
                 o = s
             t = o
             if self.features and b["stage_end"] and b["stage"] != 3:     # [x1, x2, x3, x5]
                 y = torch.empty((t.N, t.C, t.H, t.W), dtype=torch.float32, device=dev)
-                L.call("frost_dequant_to_nchw", t.q.data_ptr(), t.scale.data_ptr(), t.zp.data_ptr(), t.N, t.H, t.W, t.C,
+                L.call("frost_dequant_to_nchw", t.q.data_ptr(), t.ld, t.scale.data_ptr(), t.zp.data_ptr(), t.N, t.H, t.W, t.C,
                        y.data_ptr(), st)
                 feats.append(y)
                 if saved is not None:
@@ -519,13 +527,13 @@ class QATEngine:
             L.call("frost_bn_backward_apply", C.byref(a), st)
         wfq = mod.weight_fake_quant
         if ly.kind == "pw":
-            L.call("frost_pw_wgrad_tc", dz.data_ptr(), dz_lo.data_ptr(), xin.q.data_ptr(), xin.scale.data_ptr(),
+            L.call("frost_pw_wgrad_tc", dz.data_ptr(), dz_lo.data_ptr(), xin.q.data_ptr(), xin.ld, xin.scale.data_ptr(),
                    xin.zp.data_ptr(), M, ly.cin, ly.cout, ly.dwq.data_ptr(), st)
             if dx is not None:
                 L.call("frost_pw_dgrad_tc", dz.data_ptr(), dz_lo.data_ptr(), ly.wt_bf16.data_ptr(), wfq.scale.data_ptr(),
                        M, ly.cin, ly.cout, dx.data_ptr(), 1 if accumulate else 0, st)
         elif ly.kind == "dw":
-            L.call("frost_dw_wgrad", dz.data_ptr(), xin.q.data_ptr(), xin.scale.data_ptr(), xin.zp.data_ptr(), xin.N,
+            L.call("frost_dw_wgrad", dz.data_ptr(), xin.q.data_ptr(), xin.ld, xin.scale.data_ptr(), xin.zp.data_ptr(), xin.N,
                    xin.H, xin.W, xin.C, ly.kh, ly.stride, ly.dwq.data_ptr(), st)
             if dx is not None:
                 L.call("frost_dw_dgrad", dz.data_ptr(), ly.wq.data_ptr(), wfq.scale.data_ptr(), wfq.zero_point.data_ptr(),

@@ -168,8 +168,9 @@ int frost_pw_conv_forward(const uint8_t* xq, const int32_t* x_zp, const int8_t* 
 int frost_pw_conv_forward_simt(const uint8_t* xq, const int32_t* x_zp, const int8_t* wq,
                                const int32_t* w_zp, const int32_t* wsum, int64_t M, int K, int cout,
                                int32_t* acc, FrostChanStats* stats, void* stream);
-/* depthwise kxk (k in {3,5}), stride in {1,2}, pad=(k-1)/2: xq[N][H][W][C] -> acc[N][Ho][Wo][C]. C%4==0 */
-int frost_dw_conv_forward(const uint8_t* xq, const int32_t* x_zp, const int8_t* wq,
+/* depthwise kxk (k in {3,5}), stride in {1,2}, pad=(k-1)/2: xq[N][H][W][C] -> acc[N][Ho][Wo][C]. C%4==0.
+ * ldx: bytes between consecutive input pixels (>= C; == C: dense) */
+int frost_dw_conv_forward(const uint8_t* xq, int ldx, const int32_t* x_zp, const int8_t* wq,
                           const int32_t* w_zp, int N, int H, int W, int C, int k, int stride,
                           int32_t* acc, FrostChanStats* stats, void* stream);
 /* dense kxk stem (frostnet.py:277: 3->32, 3x3, s2, p1): xq[N][H][W][cin] u8, wq[cout][k][k][cin]. */
@@ -212,7 +213,7 @@ typedef struct {
 int frost_bn_finalize(const FrostBnFinalizeArgs* a, void* stream);
 /* acc_format: 0 = int32 accumulators, 1 = fp32 raw conv output (bit pattern in the same buffer). */
 int frost_bnq_apply(const int32_t* acc, int acc_format, int64_t M, int C, const float* A, const float* B, int relu,
-                    const float* out_scale, const int32_t* out_zp, uint8_t* q, void* stream);
+                    const float* out_scale, const int32_t* out_zp, uint8_t* q, int ldq, void* stream);
 
 /* Backward of the same chain (SURVEY.md 8a'): dy = grad wrt the fake-quantised output.
  * reduce: S1_c = sum dv, S2_c = sum dv*(I-mean_I)  with dv = dy*[0<=idx<=255]*[v>0]   (double[2*C], zeroed by callee)
@@ -295,17 +296,19 @@ typedef struct {
   const int32_t* zp;
   const float* cur_minmax;     /* dequantised min/max of this tensor */
   int32_t C;
+  int32_t ld;                  /* row pitch in bytes (>= C; == C: dense NHWC).  The engine pads rows to multiples of 16
+                                  bytes so that TMA can address them; padding bytes are don't-care */
 } FrostQTensor;
 /* out[M][C1+C2] = FQ(cat([a, b], channel)) */
 int frost_cat_forward(FrostQTensor a, FrostQTensor b, int64_t M, FrostFQ fq, int observe,
-                      float averaging_const, uint8_t* q_out, float* cur_minmax_out, void* stream);
+                      float averaging_const, uint8_t* q_out, int ld_out, float* cur_minmax_out, void* stream);
 /* da[M][C1] = dcat[:, :C1]*mask ; db[M][C2] (+)= dcat[:, C1:]*mask */
 int frost_cat_backward(const float* dcat, FrostQTensor a, FrostQTensor b, int64_t M,
                        const float* out_scale, const int32_t* out_zp, float* da, float* db,
                        int accumulate_b, void* stream);
 /* out[n] = FQ(a + b)  (two passes: min/max, then quantise). scratch: FROST_FQ_SCRATCH_FLOATS. */
 int frost_add_forward(FrostQTensor a, FrostQTensor b, int64_t n, FrostFQ fq, int observe,
-                      float averaging_const, uint8_t* q_out, float* cur_minmax_out, float* scratch,
+                      float averaging_const, uint8_t* q_out, int ld_out, float* cur_minmax_out, float* scratch,
                       void* stream);
 /* dsum = dout*mask ; da (+)= dsum */
 int frost_add_backward(const float* dout, FrostQTensor a, FrostQTensor b, int64_t n,
@@ -343,7 +346,7 @@ int frost_pw_dgrad(const float* dz, const int8_t* wq, const float* w_scale, cons
 int frost_pw_dgrad_tc(const void* dz_hi, const void* dz_lo, const void* wt_bf16, const float* w_scale,
                       int64_t M, int K, int cout, float* dx, int accumulate, void* stream);
 /* Tensor-core wgrad: reduction over the rows m with MN-major bf16 operands (dz hi/lo planes), fp32 atomics. */
-int frost_pw_wgrad_tc(const void* dz_hi, const void* dz_lo, const uint8_t* xq, const float* x_scale,
+int frost_pw_wgrad_tc(const void* dz_hi, const void* dz_lo, const uint8_t* xq, int ldx, const float* x_scale,
                       const int32_t* x_zp, int64_t M, int K, int cout, float* dwq, void* stream);
 /* dwq[cout][K] = s_a * sum_m dz[m][co]*(xq[m][K]-zp_a)     (dwq zeroed by callee; CUDA-core fp32 version) */
 int frost_pw_wgrad(const float* dz, const uint8_t* xq, const float* x_scale, const int32_t* x_zp,
@@ -352,7 +355,7 @@ int frost_dw_dgrad(const float* dz, const int8_t* wq, const float* w_scale, cons
                    int N, int H, int W, int C, int k, int stride, float* dx, int accumulate,
                    void* stream);
 /* dwq[k*k][C] */
-int frost_dw_wgrad(const float* dz, const uint8_t* xq, const float* x_scale, const int32_t* x_zp,
+int frost_dw_wgrad(const float* dz, const uint8_t* xq, int ldx, const float* x_scale, const int32_t* x_zp,
                    int N, int H, int W, int C, int k, int stride, float* dwq, void* stream);
 /* Feature backbone (frostnet_features.py:342-352): the stem convolves the raw fp32 NCHW image with the
  * fake-quantised weights: z[m][co] = sum x * (q_w - zp_w)   (conv == s_w * z), fp32 statistics. */
@@ -362,7 +365,7 @@ int frost_stem_conv_forward_f32(const float* x_nchw, const int8_t* wq, const int
 int frost_stem_wgrad_f32(const float* dz, const float* x_nchw, int N, int H, int W, int cin, int cout, int k,
                          int stride, int pad, float* dwq, void* stream);
 /* feature taps: y_nchw = (q - zp) * s ; and the way back: g_nhwc (+)= transpose(g_nchw) */
-int frost_dequant_to_nchw(const uint8_t* q, const float* scale, const int32_t* zp, int N, int H, int W, int C,
+int frost_dequant_to_nchw(const uint8_t* q, int ldq, const float* scale, const int32_t* zp, int N, int H, int W, int C,
                           float* y_nchw, void* stream);
 int frost_nchw_to_nhwc(const float* g_nchw, int N, int C, int H, int W, float* g_nhwc, int accumulate, void* stream);
 /* dwq[cout][k][k][cin] (the stem has no dgrad: its input is the image) */

@@ -122,7 +122,7 @@ def _run_case(M, K, cout, zpw, relu, training, observe, padded, tma, steps=2, ch
             L().call("frost_bn_finalize", C.byref(a), stream())
             q_ref = torch.empty(M, cout, dtype=torch.uint8, device=DEV)
             L().call("frost_bnq_apply", acc.data_ptr(), 0, M, cout, ref.A.data_ptr(), ref.B.data_ptr(), int(relu), ref.scale.data_ptr(),
-                     ref.zp.data_ptr(), q_ref.data_ptr(), stream())
+                     ref.zp.data_ptr(), q_ref.data_ptr(), cout, stream())
             # ---- fused
             f = L().PwFusedFwdArgs()
             f.op, f.bn = fus.operands(xp, M, ldx, x_zp), fus.fin_args(M, training, observe)

@@ -160,7 +160,7 @@ def test_bn_passes_at_headline_size(M):
     L().call("frost_bn_finalize", C.byref(a), stream())
     q = torch.empty(M, Cc, dtype=torch.uint8, device=DEV)
     L().call("frost_bnq_apply", I.data_ptr(), 0, M, Cc, A.data_ptr(), B.data_ptr(), relu, scale.data_ptr(), zp.data_ptr(),
-             q.data_ptr(), stream())
+             q.data_ptr(), Cc, stream())
     # float64 restatement of conv_fused.py:156-167 on conv = s_a*s_w*I
     sasw = float(xs.double() * ws.double())
     u = I.double() * sasw / sf.double()
@@ -225,7 +225,7 @@ def test_depthwise_family_at_headline_size(N):
     za, zw = torch.tensor([zpa], dtype=torch.int32, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV)
     acc = torch.empty(N, H, W, Cc, dtype=torch.int32, device=DEV)
     st = _stats_buf(Cc)
-    L().call("frost_dw_conv_forward", xq.data_ptr(), za.data_ptr(), wd.data_ptr(), zw.data_ptr(), N, H, W, Cc, k, s,
+    L().call("frost_dw_conv_forward", xq.data_ptr(), Cc, za.data_ptr(), wd.data_ptr(), zw.data_ptr(), N, H, W, Cc, k, s,
              acc.data_ptr(), st.data_ptr(), stream())
     with torch.backends.cudnn.flags(enabled=False):
         # |sum| <= 9 * 255 * 128 < 2^24: exact in fp32
@@ -245,7 +245,7 @@ def test_depthwise_family_at_headline_size(N):
         assert float((dx - dx_ref).abs().max()) <= 1e-5 * float(dx_ref.abs().max())
         del dx, dx_ref
         dwq = torch.empty(k * k, Cc, device=DEV)
-        L().call("frost_dw_wgrad", dz.data_ptr(), xq.data_ptr(), sa.data_ptr(), za.data_ptr(), N, H, W, Cc, k, s, dwq.data_ptr(),
+        L().call("frost_dw_wgrad", dz.data_ptr(), xq.data_ptr(), Cc, sa.data_ptr(), za.data_ptr(), N, H, W, Cc, k, s, dwq.data_ptr(),
                  stream())
         # float64 reference of the weight gradient, image chunks at a time
         ref = torch.zeros(Cc, 1, k, k, dtype=torch.float64, device=DEV)
@@ -277,7 +277,7 @@ def test_pw_backward_tc_at_headline_size(M):
     dx_ref = (dz.double() @ wq.double()) * float(sw)
     assert float((dx.double() - dx_ref).abs().max()) <= 1e-4 * float(dx_ref.abs().max())
     dwq = torch.empty(cout, K, device=DEV)
-    L().call("frost_pw_wgrad_tc", hi.data_ptr(), lo.data_ptr(), xq.data_ptr(), sa.data_ptr(), za.data_ptr(), M, K, cout,
+    L().call("frost_pw_wgrad_tc", hi.data_ptr(), lo.data_ptr(), xq.data_ptr(), K, sa.data_ptr(), za.data_ptr(), M, K, cout,
              dwq.data_ptr(), stream())
     ref = (dz.double().t() @ (xq.double() - 5.0)) * float(sa)
     assert float((dwq.double() - ref).abs().max()) <= 2e-4 * float(ref.abs().max())

@@ -219,6 +219,18 @@ def test_weight_prep_and_backward_vs_oracle(shape, layout):
                 torch.testing.assert_close(bufs["dgamma"].cpu(), exp, rtol=2e-5, atol=1e-5)
 
 
+def _pitched(t2d, ld):
+    """[M, C] uint8 -> a [M, ld] buffer (ld >= C) whose padding bytes are garbage; returns the buffer."""
+    M, Cc = t2d.shape
+    buf = torch.randint(0, 256, (M, ld), dtype=torch.uint8, device=t2d.device)
+    buf[:, :Cc] = t2d
+    return buf
+
+
+def _r16(v):
+    return (v + 15) // 16 * 16
+
+
 # ------------------------------------------------------------------------------------------ convs
 STAT_DT = np.dtype([("sum", "<i8"), ("lo", "<u8"), ("hi", "<u8"), ("mn", "<i4"), ("mx", "<i4")])
 
@@ -272,18 +284,22 @@ def _conv_int_ref(xq, zpa, w, zpw, stride, pad, groups):
 @pytest.mark.parametrize("N,H,W,Cc,k,s,zpw", [(2, 9, 11, 32, 3, 1, 0), (1, 14, 14, 96, 5, 2, 0), (3, 7, 7, 1728, 5, 1, 0),
                                               (2, 16, 15, 72, 3, 2, -128), (1, 5, 6, 1440, 5, 1, 0), (2, 3, 3, 16, 5, 1, 0),
                                               (6, 56, 56, 144, 5, 2, 0), (40, 28, 30, 32, 3, 1, 0), (5, 33, 57, 96, 3, 2, 127)])
-def test_dw_conv_forward_exact(N, H, W, Cc, k, s, zpw):
+@pytest.mark.parametrize("padded", [False, True])
+def test_dw_conv_forward_exact(N, H, W, Cc, k, s, zpw, padded):
     g = torch.Generator().manual_seed(H * W + Cc)
     xq = torch.randint(0, 256, (N, H, W, Cc), generator=g, dtype=torch.int64)
     w = torch.randint(-128, 128, (Cc, 1, k, k), generator=g, dtype=torch.int64)
     zpa = int(torch.randint(0, 256, (1,), generator=g))
     I = _conv_int_ref(xq, zpa, w, zpw, s, (k - 1) // 2, Cc)
     xd = xq.to(torch.uint8).to(DEV)
+    ldx = _r16(Cc) + 16 if padded else Cc                 # bytes between consecutive pixels
+    if padded:
+        xd = _pitched(xd.reshape(-1, Cc), ldx)
     wd = w.reshape(Cc, k * k).t().contiguous().to(torch.int8).to(DEV)
     za, zw = torch.tensor([zpa], dtype=torch.int32, device=DEV), torch.tensor([zpw], dtype=torch.int32, device=DEV)
     acc = torch.empty(I.shape, dtype=torch.int32, device=DEV)
     st = _stats_buf(Cc)
-    L().call("frost_dw_conv_forward", xd.data_ptr(), za.data_ptr(), wd.data_ptr(), zw.data_ptr(), N, H, W, Cc, k, s,
+    L().call("frost_dw_conv_forward", xd.data_ptr(), ldx, za.data_ptr(), wd.data_ptr(), zw.data_ptr(), N, H, W, Cc, k, s,
              acc.data_ptr(), st.data_ptr(), stream())
     assert torch.equal(acc.cpu().long(), I)
     _check_stats(st, I.reshape(-1, Cc))
@@ -360,9 +376,12 @@ def test_bn_finalize_apply_and_backward(M, Cc, relu, training):
     a.afq = fq.c()
     a.A, a.B, a.mean_I, a.kfac, a.cur_minmax = A.data_ptr(), B.data_ptr(), meanI.data_ptr(), kfac.data_ptr(), mm.data_ptr()
     L().call("frost_bn_finalize", C.byref(a), stream())
-    q = torch.empty(M, Cc, dtype=torch.uint8, device=DEV)
+    ldq = _r16(Cc) + (16 if M % 2 else 0)                 # row-padded output (dense when C % 16 == 0 and M is even)
+    qbuf = torch.full((M, ldq), 0xAB, dtype=torch.uint8, device=DEV)
     L().call("frost_bnq_apply", Id.data_ptr(), 0, M, Cc, A.data_ptr(), B.data_ptr(), int(relu), fq.scale.data_ptr(),
-             fq.zp.data_ptr(), q.data_ptr(), stream())
+             fq.zp.data_ptr(), qbuf.data_ptr(), ldq, stream())
+    q = qbuf[:, :Cc].contiguous()
+    assert bool((qbuf[:, Cc:] == 0xAB).all())             # the row padding is not touched
     conv, g64, b64, v, r, y, rm64, rv64 = _bn_reference(I, gamma, beta, rm, rv, sf, s_a, s_w, relu, training, fq.oracle)
     # observer state: min/max of the pre-quant tensor agree to fp32 rounding; qparams follow
     assert abs(float(fq.min_val) - float(fq.oracle.min_val)) <= 2e-6 * max(1.0, abs(float(fq.oracle.min_val)))
@@ -418,30 +437,35 @@ def test_bn_finalize_apply_and_backward(M, Cc, relu, training):
 
 
 # ------------------------------------------------------------------------------------------ cat / add
-def _rand_qt(M, Cc, seed):
+def _rand_qt(M, Cc, seed, ld=None):
     g = torch.Generator().manual_seed(seed)
     q = torch.randint(0, 256, (M, Cc), generator=g, dtype=torch.int64)
     scale = float(np.float32(0.01 + 0.05 * float(torch.rand(1, generator=g))))
     zp = int(torch.randint(0, 200, (1,), generator=g))
     val = ((q - zp).float() * scale)
-    d = dict(q=q.to(torch.uint8).to(DEV), scale=torch.tensor([scale], device=DEV),
+    qd = q.to(torch.uint8).to(DEV)
+    d = dict(q=qd if ld is None else _pitched(qd, ld), ld=Cc if ld is None else ld, scale=torch.tensor([scale], device=DEV),
              zp=torch.tensor([zp], dtype=torch.int32, device=DEV), mm=torch.tensor([float(val.min()), float(val.max())], device=DEV))
     return d, val
 
 
 def _qt(d, Cc):
-    return L().QTensor(d["q"].data_ptr(), d["scale"].data_ptr(), d["zp"].data_ptr(), d["mm"].data_ptr(), Cc)
+    return L().QTensor(d["q"].data_ptr(), d["scale"].data_ptr(), d["zp"].data_ptr(), d["mm"].data_ptr(), Cc, d["ld"])
 
 
-def test_cat_forward_backward_bit_exact():
+@pytest.mark.parametrize("padded", [False, True])
+def test_cat_forward_backward_bit_exact(padded):
     M, C1, C2 = 333, 16, 40
     fq = DevFQ(0, 255, False)
     for it in range(2):
-        a, va = _rand_qt(M, C1, 10 + it)
-        b, vb = _rand_qt(M, C2, 20 + it)
-        out = torch.empty(M, C1 + C2, dtype=torch.uint8, device=DEV)
+        a, va = _rand_qt(M, C1, 10 + it, 32 if padded else None)
+        b, vb = _rand_qt(M, C2, 20 + it, 48 if padded else None)
+        ld_out = 64 if padded else C1 + C2
+        obuf = torch.full((M, ld_out), 0xAB, dtype=torch.uint8, device=DEV)
         mm = torch.empty(2, device=DEV)
-        L().call("frost_cat_forward", _qt(a, C1), _qt(b, C2), M, fq.c(), 1, 0.01, out.data_ptr(), mm.data_ptr(), stream())
+        L().call("frost_cat_forward", _qt(a, C1), _qt(b, C2), M, fq.c(), 1, 0.01, obuf.data_ptr(), ld_out, mm.data_ptr(), stream())
+        out = obuf[:, :C1 + C2]
+        assert bool((obuf[:, C1 + C2:] == 0xAB).all())
         x = torch.cat([va, vb], 1).requires_grad_(True)
         y = fq.oracle(x)
         fq.assert_state_equal()
@@ -457,17 +481,21 @@ def test_cat_forward_backward_bit_exact():
         assert torch.equal(db.cpu(), x.grad[:, C1:] + 1.0)
 
 
-def test_add_forward_backward_bit_exact():
+@pytest.mark.parametrize("padded", [False, True])
+def test_add_forward_backward_bit_exact(padded):
     M, Cc = 257, 24
     fq = DevFQ(0, 255, False)
     sc = scratch()
     for it in range(2):
-        a, va = _rand_qt(M, Cc, 30 + it)
-        b, vb = _rand_qt(M, Cc, 40 + it)
-        out = torch.empty(M, Cc, dtype=torch.uint8, device=DEV)
+        a, va = _rand_qt(M, Cc, 30 + it, 32 if padded else None)
+        b, vb = _rand_qt(M, Cc, 40 + it, 48 if padded else None)
+        ld_out = 32 if padded else Cc
+        obuf = torch.full((M, ld_out), 0xAB, dtype=torch.uint8, device=DEV)
         mm = torch.empty(2, device=DEV)
-        L().call("frost_add_forward", _qt(a, Cc), _qt(b, Cc), M * Cc, fq.c(), 1, 0.01, out.data_ptr(), mm.data_ptr(),
+        L().call("frost_add_forward", _qt(a, Cc), _qt(b, Cc), M * Cc, fq.c(), 1, 0.01, obuf.data_ptr(), ld_out, mm.data_ptr(),
                  sc.data_ptr(), stream())
+        out = obuf[:, :Cc]
+        assert bool((obuf[:, Cc:] == 0xAB).all())
         x = (va + vb).requires_grad_(True)
         y = fq.oracle(x)
         fq.assert_state_equal()
@@ -533,8 +561,15 @@ def test_pw_dgrad_wgrad(M, K, cout):
              dwq.data_ptr(), stream())
     torch.testing.assert_close(dwq.cpu().double(), dw_ref, rtol=1e-4, atol=1e-4 * float(dw_ref.abs().max()))
     dwq2 = torch.empty(cout, K, device=DEV)
-    L().call("frost_pw_wgrad_tc", dz_hi.data_ptr(), dz_lo.data_ptr(), xd.data_ptr(), sa_t.data_ptr(), za_t.data_ptr(), M, K,
+    L().call("frost_pw_wgrad_tc", dz_hi.data_ptr(), dz_lo.data_ptr(), xd.data_ptr(), K, sa_t.data_ptr(), za_t.data_ptr(), M, K,
              cout, dwq2.data_ptr(), stream())
+    torch.cuda.synchronize()
+    ldx = _r16(K) + 16                                   # the same through row-padded x
+    xp = _pitched(xd, ldx)
+    dwq3 = torch.empty(cout, K, device=DEV)
+    L().call("frost_pw_wgrad_tc", dz_hi.data_ptr(), dz_lo.data_ptr(), xp.data_ptr(), ldx, sa_t.data_ptr(), za_t.data_ptr(), M, K,
+             cout, dwq3.data_ptr(), stream())
+    assert float((dwq3 - dwq2).abs().max()) <= 1e-4 * float(dwq2.abs().max())
     torch.cuda.synchronize()
     errw = float((dwq2.cpu().double() - dw_ref).abs().max()) / float(dw_ref.abs().max())
     assert errw < 5e-5, errw
@@ -542,7 +577,7 @@ def test_pw_dgrad_wgrad(M, K, cout):
         dzs = torch.randint(-8, 9, (M, cout), generator=g).float()
         one_w = torch.ones(1, device=DEV)
         s_hi, s_lo = _split_bf16(dzs.to(DEV))
-        L().call("frost_pw_wgrad_tc", s_hi.data_ptr(), s_lo.data_ptr(), xd.data_ptr(), one_w.data_ptr(), za_t.data_ptr(), M, K,
+        L().call("frost_pw_wgrad_tc", s_hi.data_ptr(), s_lo.data_ptr(), xd.data_ptr(), K, one_w.data_ptr(), za_t.data_ptr(), M, K,
                  cout, dwq2.data_ptr(), stream())
         torch.cuda.synchronize()
         assert torch.equal(dwq2.cpu().double(), dzs.double().t() @ (xq - zp_a).double())
@@ -572,10 +607,16 @@ def test_dw_dgrad_wgrad(N, H, W, Cc, k, s):
     ref = xf.grad.permute(0, 2, 3, 1)
     torch.testing.assert_close(dx.cpu().double(), ref, rtol=1e-4, atol=1e-5 * float(ref.abs().max()))
     dwq = torch.empty(k * k, Cc, device=DEV)
-    L().call("frost_dw_wgrad", dz_nhwc.data_ptr(), xd.data_ptr(), sa_t.data_ptr(), za_t.data_ptr(), N, H, W, Cc, k,
+    L().call("frost_dw_wgrad", dz_nhwc.data_ptr(), xd.data_ptr(), Cc, sa_t.data_ptr(), za_t.data_ptr(), N, H, W, Cc, k,
              s, dwq.data_ptr(), stream())
     refw = wf.grad.reshape(Cc, k * k).t()
     torch.testing.assert_close(dwq.cpu().double(), refw, rtol=1e-4, atol=1e-4 * float(refw.abs().max()))
+    ldx = _r16(Cc) + 16                                   # the same through row-padded x
+    xp = _pitched(xd.reshape(-1, Cc), ldx)
+    dwq_p = torch.empty(k * k, Cc, device=DEV)
+    L().call("frost_dw_wgrad", dz_nhwc.data_ptr(), xp.data_ptr(), ldx, sa_t.data_ptr(), za_t.data_ptr(), N, H, W, Cc, k,
+             s, dwq_p.data_ptr(), stream())
+    torch.testing.assert_close(dwq_p.cpu().double(), refw, rtol=1e-4, atol=1e-4 * float(refw.abs().max()))
 
 
 @pytest.mark.parametrize("N,H,W,cout", [(2, 33, 31, 16), (5, 224, 224, 32), (1, 8, 8, 24)])
@@ -646,7 +687,7 @@ def test_bad_arguments_are_reported_not_crashed():
     with pytest.raises(RuntimeError, match="multiple of 8"):
         L().call("frost_pw_conv_forward", 8, 8, 8, 8, 8, 4, 12, 16, 8, 8, None)
     with pytest.raises(RuntimeError):
-        L().call("frost_dw_conv_forward", 8, 8, 8, 8, 1, 4, 4, 16, 7, 1, 8, 8, None)
+        L().call("frost_dw_conv_forward", 8, 16, 8, 8, 8, 1, 4, 4, 16, 7, 1, 8, 8, None)
 
 
 # ------------------------------------------------------------------------------------------ launch-shape knobs

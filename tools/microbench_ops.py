@@ -72,13 +72,13 @@ def bench_dw(H, W, Cc, k, s):
     L.call("frost_stats_reset", stats.data_ptr(), Cc, st())
     shape = "dw %dx%d C=%d k%d s%d" % (H, W, Cc, k, s)
     nin, nout = N * H * W * Cc, N * Ho * Wo * Cc
-    sweep("dw_fwd", shape, lambda: L.call("frost_dw_conv_forward", xq.data_ptr(), za.data_ptr(), wq.data_ptr(), zw.data_ptr(),
+    sweep("dw_fwd", shape, lambda: L.call("frost_dw_conv_forward", xq.data_ptr(), Cc, za.data_ptr(), wq.data_ptr(), zw.data_ptr(),
                                           N, H, W, Cc, k, s, acc.data_ptr(), stats.data_ptr(), st()),
           nin + 4 * nout, T_DW_FWD_TILED, [1, 2])
     dz = torch.randn(N, Ho, Wo, Cc, device=dev)
     dwq = torch.empty(k * k, Cc, device=dev)
     sa = f32(0.02)
-    sweep("dw_wgrad", shape, lambda: L.call("frost_dw_wgrad", dz.data_ptr(), xq.data_ptr(), sa.data_ptr(), za.data_ptr(),
+    sweep("dw_wgrad", shape, lambda: L.call("frost_dw_wgrad", dz.data_ptr(), xq.data_ptr(), Cc, sa.data_ptr(), za.data_ptr(),
                                             N, H, W, Cc, k, s, dwq.data_ptr(), st()),
           nin + 4 * nout, T_DW_WGRAD, [3, 6])
     dx = torch.empty(N, H, W, Cc, device=dev)
@@ -116,7 +116,7 @@ def bench_bn(M, Cc):
     sweep("bn_apply", shape, lambda: L.call("frost_bn_backward_apply", C.byref(b), st()), 12 * n, T_BN_APPLY_UNROLL, [1, 2, 4])
     q = torch.empty(M, Cc, dtype=torch.uint8, device=dev)
     sweep("bnq_apply", shape, lambda: L.call("frost_bnq_apply", acc.data_ptr(), 0, M, Cc, A.data_ptr(), B.data_ptr(), 1, sc.data_ptr(),
-                                             zp.data_ptr(), q.data_ptr(), st()), 5 * n, T_BNQ_UNROLL, [2, 4, 8])
+                                             zp.data_ptr(), q.data_ptr(), Cc, st()), 5 * n, T_BNQ_UNROLL, [2, 4, 8])
 
 
 def bench_stem():
@@ -162,7 +162,7 @@ def bench_pw(M, K, cout):
     print("%-16s %-28s %.1f us (%.0f GB/s)" % ("pw_dgrad", "M=%d K=%d cout=%d" % (M, K, cout), t, nb / t / 1e3), flush=True)
     dwq = torch.empty(cout, K, device=dev)
     sa = f32(0.02)
-    t = timeit(lambda: L.call("frost_pw_wgrad_tc", hi.data_ptr(), lo.data_ptr(), xq.data_ptr(), sa.data_ptr(), za.data_ptr(), M, K,
+    t = timeit(lambda: L.call("frost_pw_wgrad_tc", hi.data_ptr(), lo.data_ptr(), xq.data_ptr(), K, sa.data_ptr(), za.data_ptr(), M, K,
                               cout, dwq.data_ptr(), st()))
     nb = 4 * M * cout + M * K
     print("%-16s %-28s %.1f us (%.0f GB/s)" % ("pw_wgrad", "M=%d K=%d cout=%d" % (M, K, cout), t, nb / t / 1e3), flush=True)
