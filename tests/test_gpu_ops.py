@@ -700,10 +700,10 @@ def test_results_do_not_depend_on_launch_knobs(knob, values):
         for v in values:
             assert lib.frost_set_tunable(knob, v) == 0 and lib.frost_get_tunable(knob) == v
             if knob in (0, 11):
-                test_dw_conv_forward_exact(3, 7, 7, 1728, 5, 1, 0)
-                test_dw_conv_forward_exact(2, 9, 11, 32, 3, 1, 0)
-                test_dw_conv_forward_exact(6, 56, 56, 144, 5, 2, 0)
-                test_dw_conv_forward_exact(2, 112, 112, 32, 3, 1, 0)
+                test_dw_conv_forward_exact(3, 7, 7, 1728, 5, 1, 0, True)
+                test_dw_conv_forward_exact(2, 9, 11, 32, 3, 1, 0, False)
+                test_dw_conv_forward_exact(6, 56, 56, 144, 5, 2, 0, True)
+                test_dw_conv_forward_exact(2, 112, 112, 32, 3, 1, 0, False)
             else:
                 test_stem_conv_forward_exact(2, 224, 224, 32)
             outs.append(v)
