@@ -5,23 +5,30 @@
 //   aten::convolution -> div -> native_batch_norm -> relu -> fused_moving_avg_obs_fake_quant   (conv_fused.py:131-167,708-710)
 // and the first two stages of its autograd (SURVEY.md 8a' steps 1-3).
 //
-// Orientation: D[channel][pixel] = W[channel][k] * X[pixel][k]^T.  The weight tile is the UMMA A operand (M = 128 output
-// channels -> the 128 TMEM lanes), the activation tile the B operand (N = 256 pixels -> TMEM columns).  A thread of the
-// epilogue therefore owns ONE OUTPUT CHANNEL for the CTA's lifetime: the BatchNorm statistics, the per-channel affine and
-// the backward coefficients live in its registers, the per-channel reductions (sum I, sum I^2, min, max; sum dv, sum dv*xhat)
-// need no shuffles and no shared memory, and global accesses to [pixel][channel] gradients are coalesced across the warp.
+// One pair of shared-memory tiles (activations: 256 pixels x 128 bytes of K, weights: 128 rows x 128 bytes of K, both
+// staged by TMA in the K-major SWIZZLE_128B layout) feeds the tensor cores in TWO orientations, chosen per pass:
 //
-//   forward   phase A: GEMM -> per-channel integer statistics (registers) -> integer atomics
+//   channel-per-thread ("cpt", the reduction passes):  D[channel][pixel] = W * X^T.  Weight tile = UMMA A (128 TMEM lanes =
+//     output channels), activation tile = UMMA B (N = 256 pixels = TMEM columns).  An epilogue thread owns ONE output channel:
+//     sum I, sum I^2, min, max (forward statistics) and sum dv, sum dv*(I-mean) (BatchNorm backward) accumulate in registers,
+//     no shuffles, no shared memory; dy[pixel][channel] loads are coalesced across the warp.  When a tile has <= 64 (<= 32)
+//     channels the weight rows are REPLICATED 2x (4x) down the 128 rows, so every lane quarter holds a copy of the result and
+//     all warps work on different pixel columns.
+//   pixel-per-thread ("ppt", the elementwise passes):  D[pixel][channel] = X * W^T (two M = 128 MMAs per 256-pixel tile).
+//     A thread owns one pixel and 16 consecutive channels per step: the quantised bytes / bf16 gradient planes leave as 16-byte
+//     vector stores, dy arrives as 16-byte vector loads, the per-channel coefficients are shared-memory broadcasts.
+//
+//   forward   phase A (cpt): GEMM -> per-channel integer statistics -> integer atomics
 //             grid barrier (all CTAs resident: grid <= 148, 1 CTA/SM) -> every CTA finalises BN / observer / qparams
-//             phase B: the same GEMM again (the operands are 1/6..1x the output bytes; the tensor pipe is idle anyway)
-//                      -> A_c*I+B_c -> ReLU -> quantise -> uint8 tile in shared memory -> TMA store
+//             phase B (ppt): the same GEMM again (the operands are 1/6..1x the output bytes; the tensor pipe is idle anyway)
+//                      -> A_c*I+B_c -> ReLU -> quantise -> uint8 rows
 //             With frozen BatchNorm and the observer off (eval / late QAT) phase A and the barrier are skipped.
-//   backward  reduce: GEMM -> dv = dy*mask -> S1, S2 per channel (registers) -> fp64 atomics
-//             apply : GEMM -> dz = c1*(dv - a0 - a1*(I - mean)) -> bf16 hi/lo planes (operands of the tensor-core dgrad/wgrad)
+//   backward  reduce (cpt): GEMM -> dv = dy*mask -> S1, S2 per channel -> fp64 atomics
+//             apply  (ppt): GEMM -> dz = c1*(dv - a0 - a1*(I - mean)) -> bf16 hi/lo planes (operands of the tensor-core dgrad/wgrad)
 //
-// Operand staging: TMA (cp.async.bulk.tensor, SWIZZLE_128B, zero fill out of bounds) when the row pitches are multiples
-// of 16 bytes - one elected thread, the mbarrier counts bytes; otherwise (dense NHWC rows with C % 16 != 0) the
-// cp.async path of the first-generation kernel (pw_conv_tc.cu).  Weights stay resident in shared memory when K <= 384.
+// Warp roles: 16 epilogue warps (4 per TMEM lane quarter), 1 TMA producer (one elected thread; the mbarriers count bytes),
+// 1 MMA issuer.  TMEM: 2 x 256 columns, double buffered (MMAs of tile i+1 overlap the epilogue of tile i).  Weights stay
+// resident in shared memory when K <= 384.  Row pitches must be multiples of 16 bytes (TMA's stride rule; the engine pads).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <algorithm>
@@ -33,18 +40,16 @@ namespace frost {
 
 using namespace tc;
 
-constexpr int PF_NPX = 256;          // pixels per tile (UMMA N)
-constexpr int PF_CH = 128;           // channel rows per tile (UMMA M)
+constexpr int PF_NPX = 256;          // pixels per tile
+constexpr int PF_CH = 128;           // weight rows per tile
 constexpr int PF_BK = 128;           // bytes of K per k-block (one swizzle span)
 constexpr int PF_RES_KB = 3;         // weight k-blocks that stay resident
-constexpr int PF_EPI_WARPS = 8;      // two per TMEM lane quarter: columns [0,128) and [128,256)
+constexpr int PF_EPI_WARPS = 16;
 constexpr int PF_EPI_THREADS = PF_EPI_WARPS * 32;
-constexpr int PF_PROD_WARPS = 4;
-constexpr int PF_THREADS = (PF_EPI_WARPS + PF_PROD_WARPS + 1) * 32;   // warps 0-7 epilogue, 8-11 producer, 12 MMA
+constexpr int PF_THREADS = (PF_EPI_WARPS + 2) * 32;   // warps 0-15 epilogue, 16 TMA producer, 17 MMA
 constexpr int PF_W_BYTES = PF_CH * PF_BK;       // 16 KB
 constexpr int PF_X_BYTES = PF_NPX * PF_BK;      // 32 KB
-constexpr int PF_STAGING = PF_NPX * PF_CH;      // 32 KB uint8 output tile
-constexpr int PF_TAIL = 8192;                   // barriers + per-channel combine buffers
+constexpr int PF_TAIL = 12288;                  // barriers + per-channel buffers
 
 enum { PF_FWD = 0, PF_BWD_REDUCE = 1, PF_BWD_APPLY = 2 };
 
@@ -53,11 +58,10 @@ struct PwFusedParams {
   int64_t M;
   int K, ldx;
   const int8_t* w;        // MMA-ready weight bytes [cout][ldw]
-  int ldw, cout, bn, n_kb;
+  int ldw, cout, bn, bnr, n_kb;
   const int32_t* x_zp;
   const int32_t* w_zp;
   const int32_t* wsum;
-  int tma_in, tma_out, vec16;
   // forward
   FrostBnFinalizeArgs fin;
   unsigned* grid_bar;
@@ -67,7 +71,7 @@ struct PwFusedParams {
   FrostBnBackwardArgs bwd;
 };
 
-struct PfCombine {       // per channel of the tile: the two column halves meet here
+struct PfCombine {       // per channel of the tile: the partial results of the threads that share a channel meet here
   unsigned long long sum, sq;
   int mn, mx;
   double s1, s2;
@@ -83,14 +87,6 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1)
-               : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -102,11 +98,22 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   return v;
 }
 
+// 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // ================================================================= the kernel
 template <int MODE>
 __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                                 const __grid_constant__ CUtensorMap tm_w,
-                                                                const __grid_constant__ CUtensorMap tm_q,
                                                                 const __grid_constant__ PwFusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -115,8 +122,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
   const int stage_bytes = resident ? PF_X_BYTES : PF_X_BYTES + PF_W_BYTES;
   uint8_t* wres = smem;                                              // [n_kb][128 rows][128 B] when resident
   uint8_t* stages = smem + (resident ? PF_RES_KB * PF_W_BYTES : 0);  // [S][x 32 KB (+ w 16 KB)]
-  uint8_t* staging = stages + S * stage_bytes;                       // forward: [256 px][bn] uint8
-  uint8_t* tail = staging + (MODE == PF_FWD ? PF_STAGING : 0);
+  uint8_t* tail = stages + S * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);            // [4]
   uint64_t* empty_bar = full_bar + 4;                                // [4]
   uint64_t* tfull_bar = empty_bar + 4;                               // [2]
@@ -125,23 +131,26 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
   float* s_red = reinterpret_cast<float*>(tmem_slot + 2);            // [2 * PF_EPI_WARPS] block min / max
   float* s_qp = s_red + 2 * PF_EPI_WARPS;                            // scale, zero point (as float), 1/scale, spare
-  PfCombine* s_comb = reinterpret_cast<PfCombine*>(tail + 256);      // [128]
+  float4* s_cf = reinterpret_cast<float4*>(tail + 512);              // [128] per channel: A, B, corr (int bits), P
+  float2* s_cg = reinterpret_cast<float2*>(tail + 512 + 2048);       // [128] per channel: R, Q (backward apply)
+  PfCombine* s_comb = reinterpret_cast<PfCombine*>(tail + 512 + 2048 + 1024);   // [128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ct = blockIdx.y;
   const int c_tile0 = ct * p.bn;
   const int n_valid = min(p.bn, p.cout - c_tile0);
   const int64_t n_ptiles = (p.M + PF_NPX - 1) / PF_NPX;
-  const int prod_arrivals = p.tma_in ? 1 : PF_PROD_WARPS * 32;
+  const int bnr = p.bnr;                       // replica stride of the weight rows: 32, 64 or 128
+  const int R = PF_CH / bnr;
 
   // ---- one-time setup (overlaps the tail of the previous kernel: programmatic dependent launch, common.cuh)
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], prod_arrivals); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], PF_EPI_WARPS); }
-    mbar_init(wfull_bar, prod_arrivals);
+    mbar_init(wfull_bar, 1);
     mbar_fence_init();
   }
-  if (warp == PF_EPI_WARPS + PF_PROD_WARPS) tmem_alloc<512>(tmem_slot);
+  if (warp == PF_EPI_WARPS + 1) tmem_alloc<512>(tmem_slot);
   if (threadIdx.x < PF_CH) {
     PfCombine& c = s_comb[threadIdx.x];
     c.sum = 0; c.sq = 0; c.mn = INT_MAX; c.mx = INT_MIN; c.s1 = 0.0; c.s2 = 0.0;
@@ -158,120 +167,75 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
   // forward: does this launch need batch statistics / the observer's min-max (phase A + grid barrier)?
   const bool need_stats = (MODE == PF_FWD) && (p.fin.training || p.fin.observe);
   const int n_phases = (MODE == PF_FWD && need_stats) ? 2 : 1;
+  // orientation of phase `ph`: forward = [cpt,] ppt ; reduce = cpt ; apply = ppt
+  auto phase_is_cpt = [&](int ph) { return MODE == PF_BWD_REDUCE || (MODE == PF_FWD && need_stats && ph == 0); };
 
-  if (warp >= PF_EPI_WARPS && warp < PF_EPI_WARPS + PF_PROD_WARPS) {
-    // ================================================================= producer
-    const int tp = threadIdx.x - PF_EPI_WARPS * 32;
-    if (p.tma_in) {
-      if (tp == 0) {
-        tma_prefetch_desc(&tm_x);
-        tma_prefetch_desc(&tm_w);
-        if (resident) {
-          mbar_expect_tx(wfull_bar, (uint32_t)(p.n_kb * PF_W_BYTES));
-          for (int kb = 0; kb < p.n_kb; ++kb) tma_load_2d(&tm_w, wfull_bar, smem_u32(wres + kb * PF_W_BYTES), kb * PF_BK, c_tile0);
-        }
-        uint32_t it = 0;
-        for (int ph = 0; ph < n_phases; ++ph) {
-          for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x) {
-            for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
-              const int s = it % S;
-              mbar_wait(&empty_bar[s], ((it / S) & 1) ^ 1);
-              uint8_t* st = stages + s * stage_bytes;
-              mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-              tma_load_2d(&tm_x, &full_bar[s], smem_u32(st), kb * PF_BK, (int)(pt * PF_NPX));
-              if (!resident) tma_load_2d(&tm_w, &full_bar[s], smem_u32(st + PF_X_BYTES), kb * PF_BK, c_tile0);
-            }
-          }
-        }
-      }
-    } else {
-      // cp.async (LDGSTS) with zero fill into the same SWIZZLE_128B tiles
-      const int c16 = tp & 7, r0 = tp >> 3;            // 16 rows per pass
-      auto load_w = [&](uint8_t* dst_tile, int kb) {
-        const uint32_t dst0 = smem_u32(dst_tile);
-        const int kk = kb * PF_BK + c16 * 16;
-#pragma unroll
-        for (int i = 0; i < PF_CH / 16; ++i) {
-          const int r = r0 + 16 * i;
-          const bool v = (r < n_valid) && (kk < p.K);     // ldw is a multiple of 16 and its padding bytes are zero
-          cp_async_zfill<16>(dst0 + sw128_offset(r, c16), v ? (const void*)(p.w + (int64_t)(c_tile0 + r) * p.ldw + kk) : (const void*)p.w, v);
-        }
-      };
+  if (warp == PF_EPI_WARPS) {
+    // ================================================================= TMA producer (one elected thread)
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_x);
+      tma_prefetch_desc(&tm_w);
       if (resident) {
-        for (int kb = 0; kb < p.n_kb; ++kb) load_w(wres + kb * PF_W_BYTES, kb);
-        cp_async_commit();
-        cp_async_wait<0>();
-        fence_proxy_async();
-        mbar_arrive(wfull_bar);
+        mbar_expect_tx(wfull_bar, (uint32_t)(p.n_kb * PF_W_BYTES));
+        for (int kb = 0; kb < p.n_kb; ++kb)
+          for (int j = 0; j < R; ++j)          // the same bnr weight rows, replicated down the 128-row tile
+            tma_load_2d(&tm_w, wfull_bar, smem_u32(wres + kb * PF_W_BYTES + j * bnr * PF_BK), kb * PF_BK, c_tile0);
       }
-      constexpr int LAG = 2;
       uint32_t it = 0;
       for (int ph = 0; ph < n_phases; ++ph) {
         for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x) {
-          const int64_t m0 = pt * PF_NPX;
-          const int rows_left = (int)min((int64_t)PF_NPX, p.M - m0);
           for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
             const int s = it % S;
             mbar_wait(&empty_bar[s], ((it / S) & 1) ^ 1);
             uint8_t* st = stages + s * stage_bytes;
-            const uint32_t a_s = smem_u32(st);
-            const int kbyte = kb * PF_BK + c16 * 16;
-            const uint8_t* abase = p.x + (m0 + r0) * p.ldx + kbyte;
-#pragma unroll
-            for (int i = 0; i < PF_NPX / 16; ++i) {
-              const int r = r0 + 16 * i;
-              const bool rv = r < rows_left;
-              const uint8_t* src = abase + (int64_t)i * 16 * p.ldx;
-              const uint32_t dst = a_s + sw128_offset(r, c16);
-              if (p.vec16) {
-                const bool v = rv && kbyte < p.K;
-                cp_async_zfill<16>(dst, v ? src : p.x, v);
-              } else {
-                const bool v0 = rv && kbyte < p.K, v1 = rv && kbyte + 8 < p.K;
-                cp_async_zfill<8>(dst, v0 ? src : p.x, v0);
-                cp_async_zfill<8>(dst + 8, v1 ? src + 8 : p.x, v1);
-              }
-            }
-            if (!resident) load_w(st + PF_X_BYTES, kb);
-            cp_async_commit();
-            if (it >= (uint32_t)LAG) {
-              cp_async_wait<LAG>();
-              fence_proxy_async();
-              mbar_arrive(&full_bar[(it - LAG) % S]);
-            }
+            mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+            tma_load_2d(&tm_x, &full_bar[s], smem_u32(st), kb * PF_BK, (int)(pt * PF_NPX));
+            if (!resident)
+              for (int j = 0; j < R; ++j)
+                tma_load_2d(&tm_w, &full_bar[s], smem_u32(st + PF_X_BYTES + j * bnr * PF_BK), kb * PF_BK, c_tile0);
           }
         }
       }
-      cp_async_wait<0>();
-      fence_proxy_async();
-      for (uint32_t j = (it > (uint32_t)LAG ? it - LAG : 0u); j < it; ++j) mbar_arrive(&full_bar[j % S]);
     }
-  } else if (warp == PF_EPI_WARPS + PF_PROD_WARPS) {
+  } else if (warp == PF_EPI_WARPS + 1) {
     // ================================================================= MMA issuer
-    // A = weights (s8, or u8 after the producer-side zero-point rewrite done by weight prep), B = activations (u8)
-    const uint32_t idesc = umma_idesc(2 /*S32*/, zp_w == 0 ? 1 : 0, 0, PF_CH, PF_NPX);
+    // weights: s8, or u8 after the zero-point rewrite done by weight prep (one-signed weights); activations: u8
+    const int w_fmt = zp_w == 0 ? 1 : 0;
+    const int n_mma = (n_valid + 15) & ~15;
+    const uint32_t idesc_cpt = umma_idesc(2 /*S32*/, w_fmt, 0, PF_CH, PF_NPX);   // A = W (128 rows), B = X (256 pixels)
+    const uint32_t idesc_ppt = umma_idesc(2 /*S32*/, 0, w_fmt, 128, n_mma);      // A = X (128 pixels), B = W (n_mma rows)
     if (resident) {
       mbar_wait(wfull_bar, 0);
       tc_fence_after();
     }
     uint32_t it = 0, tile_i = 0;
     for (int ph = 0; ph < n_phases; ++ph) {
+      const bool cpt = phase_is_cpt(ph);
       for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x, ++tile_i) {
         const uint32_t acc = tile_i & 1;
         mbar_wait(&tempty_bar[acc], ((tile_i >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * PF_NPX;
+        const bool second_half = p.M - pt * PF_NPX > 128;
         for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
           const int s = it % S;
           mbar_wait(&full_bar[s], (it / S) & 1);
           tc_fence_after();
           if (lane == 0) {
             uint8_t* st = stages + s * stage_bytes;
-            const uint64_t bdesc = umma_desc_sw128(smem_u32(st));
-            const uint64_t adesc = umma_desc_sw128(smem_u32(resident ? wres + kb * PF_W_BYTES : st + PF_X_BYTES));
+            const uint64_t xdesc = umma_desc_sw128(smem_u32(st));
+            const uint64_t wdesc = umma_desc_sw128(smem_u32(resident ? wres + kb * PF_W_BYTES : st + PF_X_BYTES));
             const int nk = min(PF_BK / 32, (p.K - kb * PF_BK + 31) / 32);
-            for (int k4 = 0; k4 < nk; ++k4)
-              umma_i8(d_tmem, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), idesc, (kb | k4) != 0 ? 1u : 0u);
+            if (cpt) {
+              for (int k4 = 0; k4 < nk; ++k4)
+                umma_i8(d_tmem, wdesc + (uint64_t)(2 * k4), xdesc + (uint64_t)(2 * k4), idesc_cpt, (kb | k4) != 0 ? 1u : 0u);
+            } else {
+              for (int h = 0; h < (second_half ? 2 : 1); ++h) {
+                const uint64_t xh = xdesc + (uint64_t)((h * 128 * PF_BK) >> 4);       // pixels 128h .. 128h+127 of the tile
+                for (int k4 = 0; k4 < nk; ++k4)
+                  umma_i8(d_tmem + h * 128, xh + (uint64_t)(2 * k4), wdesc + (uint64_t)(2 * k4), idesc_ppt, (kb | k4) != 0 ? 1u : 0u);
+              }
+            }
             umma_commit(&empty_bar[s]);
             if (kb == p.n_kb - 1) umma_commit(&tfull_bar[acc]);
           }
@@ -280,30 +244,35 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
       }
     }
   } else {
-    // ================================================================= epilogue: thread <-> output channel
-    const int quarter = warp & 3, half = warp >> 2;
-    const int c_local = quarter * 32 + lane;
-    const bool active = c_local < n_valid;
-    const bool warp_active = quarter * 32 < n_valid;
-    const int c = c_tile0 + (active ? c_local : 0);
-    const int tid = threadIdx.x;                         // 0..255 within the epilogue
-    // I = wsign * (raw - corr): activation zero point folded through the (rewritten) weight row sum
-    const int wsign = (zp_w == 127) ? -1 : 1;
-    int corr_s;                                          // wsign * corr
-    {
+    // ================================================================= epilogue (16 warps)
+    const int quarter = warp & 3, grp = warp >> 2;        // TMEM lane quarter (hardware: warp_id % 4), group 0..3
+    const int tid = threadIdx.x;                          // 0..511 within the epilogue
+    const int wsign = (zp_w == 127) ? -1 : 1;             // I = wsign * raw - corr_s
+    auto corr_of = [&](int c) {
       const int ws = p.wsum[c];
       const int ws_eff = zp_w == 0 ? ws : (zp_w == -128 ? ws + 128 * p.K : 127 * p.K - ws);
-      corr_s = wsign * zp_a * ws_eff;
-    }
-    uint32_t tile_i = 0;
+      return wsign * zp_a * ws_eff;
+    };
+    // ---- channel-per-thread mapping
+    const int lane_g = quarter * 32 + lane;
+    const int rep = lane_g / bnr;                         // which replica of the weight rows this lane holds
+    const int c_local = lane_g - rep * bnr;
+    const bool active = c_local < n_valid;
+    const bool warp_active = (quarter * 32) % bnr < n_valid;
+    const int c = c_tile0 + (active ? c_local : 0);
+    const int cols_per = 64 / R;                          // pixel columns per (replica, group): 64, 32 or 16
+    const int col_begin = (rep * 4 + grp) * cols_per;
+    // ---- pixel-per-thread mapping
+    const int ppt_h = grp & 1, ppt_par = grp >> 1;        // 128-pixel block, chunk parity
+    const int ppt_pix = ppt_h * 128 + quarter * 32 + lane;
 
-    // per-thread channel state
-    float cA = 0.f, cB = 0.f, cMean = 0.f;
+    uint32_t tile_i = 0;
     float inv = 1.f, zpf = 0.f;
     int relu = 0;
 
     if constexpr (MODE == PF_FWD) {
       relu = p.fin.relu;
+      const int corr_s = corr_of(c);
       const double Mcount = (double)p.fin.count;
       const double sa_sw = (double)(*p.fin.x_scale) * (double)(*p.fin.w_scale);
       const double mom = p.fin.momentum >= 0.0f ? (double)p.fin.momentum
@@ -311,7 +280,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
       // the observer state as it was BEFORE this layer ran: every CTA derives the same new state from it after the barrier
       float rmin = *p.fin.afq.min_val, rmax = *p.fin.afq.max_val;
       if (need_stats) {
-        // ---------------- phase A: statistics
+        // ---------------- phase A (cpt): statistics
         long long sum = 0;
         unsigned long long sq = 0;
         int mn = INT_MAX, mx = INT_MIN;
@@ -322,16 +291,15 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
           tc_fence_after();
           if (warp_active) {
 #pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
-              const int col0 = half * 128 + ch * 32;
+            for (int col0 = col_begin; col0 < col_begin + cols_per; col0 += 16) {
               if (col0 >= px_valid) break;
-              uint32_t v[32];
-              tmem_ld_32x32(tmem_base + acc * PF_NPX + col0 + ((uint32_t)(quarter * 32) << 16), v);
-              const int nv = min(32, px_valid - col0);
+              uint32_t v[16];
+              tmem_ld_32x16(tmem_base + acc * PF_NPX + col0 + ((uint32_t)(quarter * 32) << 16), v);
+              const int nv = min(16, px_valid - col0);
               int s32 = 0;
-              if (nv == 32) {
+              if (nv == 16) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+                for (int j = 0; j < 16; ++j) {
                   const int I = wsign * (int)v[j] - corr_s;
                   s32 += I;
                   sq += (unsigned long long)((long long)I * (long long)I);
@@ -340,7 +308,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
                 }
               } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+                for (int j = 0; j < 16; ++j) {
                   if (j < nv) {
                     const int I = wsign * (int)v[j] - corr_s;
                     s32 += I;
@@ -357,7 +325,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
-        // the two column halves of a channel meet in shared memory, one set of integer atomics per channel and CTA
+        // the threads that share a channel meet in shared memory; one set of integer atomics per channel and CTA
         if (active && mn <= mx) {
           PfCombine& cb = s_comb[c_local];
           atomicAdd(&cb.sum, (unsigned long long)sum);
@@ -366,9 +334,9 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
           atomicMax(&cb.mx, mx);
         }
         epi_bar_sync();
-        if (active && half == 0) {
-          const PfCombine cb = s_comb[c_local];
-          chan_stats_flush(const_cast<FrostChanStats*>(p.fin.stats) + c, (long long)cb.sum, cb.sq, cb.mn, cb.mx);
+        if (tid < n_valid) {
+          const PfCombine cb = s_comb[tid];
+          chan_stats_flush(const_cast<FrostChanStats*>(p.fin.stats) + c_tile0 + tid, (long long)cb.sum, cb.sq, cb.mn, cb.mx);
         }
         // ---------------- grid barrier: every CTA of this launch is resident (host: grid <= #SMs, 1 CTA per SM)
         __threadfence();
@@ -386,9 +354,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         }
         epi_bar_sync();
       }
-      // ---------------- finalize: BN affine of my channel, observer over all channels, qparams (same result in every CTA)
-      BnChannel mine;
-      mine.A = mine.B = mine.mean_I = mine.kfac = 0.f;
+      // ---------------- finalize: BN affine of the tile's channels, observer over all channels, qparams (same in every CTA)
       float gmn = INFINITY, gmx = -INFINITY;
       for (int cc = tid; cc < p.cout; cc += PF_EPI_THREADS) {
         FrostChanStats st;
@@ -401,14 +367,19 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         gmn = fminf(gmn, r.v_lo);
         gmx = fmaxf(gmx, r.v_hi);
       }
-      if (active) {
+      BnChannel mine;
+      mine.A = mine.B = mine.mean_I = mine.kfac = 0.f;
+      mine.new_running_mean = mine.new_running_var = 0.f;
+      if (tid < n_valid) {                                   // thread tid <-> channel c_tile0 + tid
+        const int cc = c_tile0 + tid;
         FrostChanStats st;
-        const FrostChanStats* g = p.fin.stats + c;
+        const FrostChanStats* g = p.fin.stats + cc;
         st.sum = __ldcg(&g->sum); st.sq_lo = __ldcg(&g->sq_lo); st.sq_hi = __ldcg(&g->sq_hi);
         st.min = __ldcg(&g->min); st.max = __ldcg(&g->max);
         if (!need_stats) { st.min = 0; st.max = 0; }
-        mine = bn_channel_finalize(st, 0, Mcount, p.fin.count > 1, sa_sw, p.fin.sf[c], p.fin.gamma[c], p.fin.beta[c],
-                                   p.fin.running_mean[c], p.fin.running_var[c], p.fin.eps, mom, p.fin.training, relu);
+        mine = bn_channel_finalize(st, 0, Mcount, p.fin.count > 1, sa_sw, p.fin.sf[cc], p.fin.gamma[cc], p.fin.beta[cc],
+                                   p.fin.running_mean[cc], p.fin.running_var[cc], p.fin.eps, mom, p.fin.training, relu);
+        s_cf[tid] = make_float4(mine.A, mine.B, __int_as_float(corr_of(cc)), 0.f);
       }
       gmn = warp_min(gmn);
       gmx = warp_max(gmx);
@@ -448,40 +419,52 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
       epi_bar_sync();
       inv = s_qp[2];
       zpf = s_qp[1];
-      cA = mine.A;
-      cB = mine.B;
-      if (blockIdx.x == 0 && active && half == 0) {       // one writer per channel
-        p.fin.A[c] = mine.A;
-        p.fin.B[c] = mine.B;
-        p.fin.mean_I[c] = mine.mean_I;
-        p.fin.kfac[c] = mine.kfac;
+      if (blockIdx.x == 0 && tid < n_valid) {                // one writer per channel
+        const int cc = c_tile0 + tid;
+        p.fin.A[cc] = mine.A;
+        p.fin.B[cc] = mine.B;
+        p.fin.mean_I[cc] = mine.mean_I;
+        p.fin.kfac[cc] = mine.kfac;
         if (p.fin.training) {
-          p.fin.running_mean[c] = mine.new_running_mean;
-          p.fin.running_var[c] = mine.new_running_var;
+          p.fin.running_mean[cc] = mine.new_running_mean;
+          p.fin.running_var[cc] = mine.new_running_var;
         }
       }
-      // ---------------- phase B: quantise
-      const int bn = p.bn;
+      // ---------------- phase B (ppt): quantise
       for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x, ++tile_i) {
         const uint32_t acc = tile_i & 1;
-        const int px_valid = (int)min((int64_t)PF_NPX, p.M - pt * PF_NPX);
-        if (p.tma_out && tid == 0) tma_store_wait_read();      // the previous tile's store has finished reading `staging`
-        epi_bar_sync();
+        const int64_t pix = pt * PF_NPX + ppt_pix;
+        const bool pvalid = pix < p.M;
+        const bool wvalid = pt * PF_NPX + ppt_h * 128 + quarter * 32 < p.M;      // warp-uniform
         mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1);
         tc_fence_after();
-        if (warp_active) {
+        if (wvalid) {
+          uint8_t* qrow = p.q + pix * (int64_t)p.ldq + c_tile0;
 #pragma unroll 1
-          for (int ch = 0; ch < 4; ++ch) {
-            const int col0 = half * 128 + ch * 32;
-            if (col0 >= px_valid) break;
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_base + acc * PF_NPX + col0 + ((uint32_t)(quarter * 32) << 16), v);
-            if (active) {
-              uint8_t* dst = staging + col0 * bn + c_local;
+          for (int ci = ppt_par; ci * 16 < n_valid; ci += 2) {
+            uint32_t v[16];
+            tmem_ld_32x16(tmem_base + acc * PF_NPX + ppt_h * 128 + ci * 16 + ((uint32_t)(quarter * 32) << 16), v);
+            unsigned w4[4];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float I = (float)(wsign * (int)v[j] - corr_s);
-                dst[j * bn] = (uint8_t)bnq1(I, cA, cB, relu, inv, zpf);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              unsigned word = 0u;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float4 cf = s_cf[ci * 16 + j4 * 4 + e];
+                const float I = (float)(wsign * (int)v[j4 * 4 + e] - __float_as_int(cf.z));
+                word |= bnq1(I, cf.x, cf.y, relu, inv, zpf) << (8 * e);
+              }
+              w4[j4] = word;
+            }
+            if (pvalid) {
+              const int nvc = min(16, n_valid - ci * 16);         // 4, 8, 12 or 16 valid channels in this chunk
+              uint8_t* dst = qrow + ci * 16;
+              if (nvc == 16) {
+                *reinterpret_cast<uint4*>(dst) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+              } else {
+#pragma unroll
+                for (int j4 = 0; j4 < 3; ++j4)
+                  if (j4 * 4 < nvc) *reinterpret_cast<unsigned*>(dst + 4 * j4) = w4[j4];
               }
             }
           }
@@ -489,93 +472,165 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        if (p.tma_out) {
-          fence_proxy_async();
-          epi_bar_sync();
-          if (tid == 0) tma_store_2d(&tm_q, smem_u32(staging), c_tile0, (int)(pt * PF_NPX));
-        } else {
-          epi_bar_sync();
-          // cooperative copy: 4-byte words, consecutive threads -> consecutive words of a row (coalesced)
-          const int wpr = n_valid >> 2;                        // words per row (cout % 4 == 0)
-          uint8_t* qbase = p.q + pt * PF_NPX * (int64_t)p.ldq + c_tile0;
-          for (int i = tid; i < px_valid * wpr; i += PF_EPI_THREADS) {
-            const int r = i / wpr, wd = i - r * wpr;
-            *reinterpret_cast<uint32_t*>(qbase + (int64_t)r * p.ldq + 4 * wd) = *reinterpret_cast<const uint32_t*>(staging + r * bn + 4 * wd);
-          }
-        }
       }
-      if (p.tma_out && tid == 0) tma_store_wait_all();
-    } else {
-      // ================================================================= backward passes
+    } else if constexpr (MODE == PF_BWD_REDUCE) {
+      // ================================================================= backward reduce (cpt)
       const FrostBnBackwardArgs& b = p.bwd;
       relu = b.relu;
       inv = __fdiv_rn(1.0f, *b.out_scale);
       zpf = (float)*b.out_zp;
-      cA = b.A[c];
-      cB = b.B[c];
-      cMean = b.mean_I[c];
+      const int corr_s = corr_of(c);
+      const float cA = b.A[c], cB = b.B[c], cMean = b.mean_I[c];
       const int cout = p.cout;
-      float c1 = 0.f, a0 = 0.f, a1 = 0.f;
-      if constexpr (MODE == PF_BWD_APPLY) {
-        const double sa_sw = (double)(*b.x_scale) * (double)(*b.w_scale);
-        const BnBwdChannel r = bn_bwd_channel(__ldcg(b.sums + 2 * c), __ldcg(b.sums + 2 * c + 1), (double)b.M, sa_sw, cA, b.kfac[c], cMean,
-                                              b.gamma[c], b.sf[c], b.eps, b.frozen ? 0 : 1);
-        c1 = r.c1; a0 = r.a0; a1 = r.a1;
-        if (blockIdx.x == 0 && active && half == 0) {
-          b.dgamma_bn[c] = r.dgamma_bn;
-          b.dbeta[c] = r.dbeta;
-          b.dsf_bn[c] = r.dsf_bn;
-        }
-      }
       double S1 = 0.0, S2 = 0.0;
-      uint16_t* dz_hi = reinterpret_cast<uint16_t*>(b.dz);
-      uint16_t* dz_lo = reinterpret_cast<uint16_t*>(b.dz_lo);
       for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x, ++tile_i) {
         const uint32_t acc = tile_i & 1;
         const int px_valid = (int)min((int64_t)PF_NPX, p.M - pt * PF_NPX);
         // dy of the first chunk is requested before the accumulator is waited for
+        float dy[16];
+        const float* src = b.dy + (pt * PF_NPX + col_begin) * (int64_t)cout + c;
+        if (active) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dy[j] = (col_begin + j < px_valid) ? ld_cg(src + j * cout) : 0.0f;
+        }
         mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1);
         tc_fence_after();
         if (warp_active) {
+          float p1 = 0.f, p2 = 0.f;
 #pragma unroll 1
-          for (int ch = 0; ch < 4; ++ch) {
-            const int col0 = half * 128 + ch * 32;
+          for (int col0 = col_begin; col0 < col_begin + cols_per; col0 += 16) {
             if (col0 >= px_valid) break;
-            const int nv = min(32, px_valid - col0);
-            const int64_t e0 = (pt * PF_NPX + col0) * (int64_t)cout + c;      // element (pixel, channel) of column 0
-            float dy[32];
-            if (active) {
-              const float* src = b.dy + e0;
+            uint32_t v[16];
+            tmem_ld_32x16(tmem_base + acc * PF_NPX + col0 + ((uint32_t)(quarter * 32) << 16), v);
+            float dyn[16];                       // the next chunk's dy, in flight while this chunk is reduced
+            const bool more = col0 + 16 < col_begin + cols_per && col0 + 16 < px_valid;
+            if (active && more) {
+              const float* nsrc = src + (int64_t)(col0 + 16 - col_begin) * cout;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) dy[j] = (j < nv) ? ld_cg(src + j * cout) : 0.0f;
+              for (int j = 0; j < 16; ++j) dyn[j] = (col0 + 16 + j < px_valid) ? ld_cg(nsrc + j * cout) : 0.0f;
             }
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_base + acc * PF_NPX + col0 + ((uint32_t)(quarter * 32) << 16), v);
             if (active) {
-              if constexpr (MODE == PF_BWD_REDUCE) {
-                float p1 = 0.f, p2 = 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const float I = (float)(wsign * (int)v[j] - corr_s);
-                  const float dv = bn_dv(dy[j], I, cA, cB, relu, inv, zpf);
-                  p1 += dv;
-                  p2 = fmaf(dv, I - cMean, p2);
-                }
-                S1 += (double)p1;
-                S2 += (double)p2;
-              } else {
+              for (int j = 0; j < 16; ++j) {
+                const float I = (float)(wsign * (int)v[j] - corr_s);
+                const float dv = bn_dv(dy[j], I, cA, cB, relu, inv, zpf);
+                p1 += dv;
+                p2 = fmaf(dv, I - cMean, p2);
+              }
+              if (more) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  if (j < nv) {
-                    const float I = (float)(wsign * (int)v[j] - corr_s);
-                    const float dv = bn_dv(dy[j], I, cA, cB, relu, inv, zpf);
-                    const float o = c1 * (dv - a0 - a1 * (I - cMean));
-                    const __nv_bfloat16 h = __float2bfloat16_rn(o);
-                    const __nv_bfloat16 l = __float2bfloat16_rn(o - __bfloat162float(h));
-                    dz_hi[e0 + (int64_t)j * cout] = __bfloat16_as_ushort(h);
-                    dz_lo[e0 + (int64_t)j * cout] = __bfloat16_as_ushort(l);
-                  }
+                for (int j = 0; j < 16; ++j) dy[j] = dyn[j];
+              }
+            }
+          }
+          S1 += (double)p1;                      // <= 64 terms per fp32 partial
+          S2 += (double)p2;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
+      if (active) {
+        atomicAdd(&s_comb[c_local].s1, S1);
+        atomicAdd(&s_comb[c_local].s2, S2);
+      }
+      epi_bar_sync();
+      if (tid < n_valid) {
+        atomicAdd(b.sums + 2 * (c_tile0 + tid), s_comb[tid].s1);
+        atomicAdd(b.sums + 2 * (c_tile0 + tid) + 1, s_comb[tid].s2);
+      }
+    } else {
+      // ================================================================= backward apply (ppt)
+      const FrostBnBackwardArgs& b = p.bwd;
+      relu = b.relu;
+      inv = __fdiv_rn(1.0f, *b.out_scale);
+      zpf = (float)*b.out_zp;
+      const int cout = p.cout;
+      if (tid < n_valid) {
+        const int cc = c_tile0 + tid;
+        const double sa_sw = (double)(*b.x_scale) * (double)(*b.w_scale);
+        const float A = b.A[cc], mean = b.mean_I[cc];
+        const BnBwdChannel r = bn_bwd_channel(__ldcg(b.sums + 2 * cc), __ldcg(b.sums + 2 * cc + 1), (double)b.M, sa_sw, A, b.kfac[cc], mean,
+                                              b.gamma[cc], b.sf[cc], b.eps, b.frozen ? 0 : 1);
+        // dz = c1*(dv - a0 - a1*(I - mean)) = P*dv + R*I + Q
+        s_cf[tid] = make_float4(A, b.B[cc], __int_as_float(corr_of(cc)), r.c1);
+        s_cg[tid] = make_float2(-r.c1 * r.a1, r.c1 * (r.a1 * mean - r.a0));
+        if (blockIdx.x == 0) {
+          b.dgamma_bn[cc] = r.dgamma_bn;
+          b.dbeta[cc] = r.dbeta;
+          b.dsf_bn[cc] = r.dsf_bn;
+        }
+      }
+      epi_bar_sync();
+      uint16_t* dz_hi = reinterpret_cast<uint16_t*>(b.dz);
+      uint16_t* dz_lo = reinterpret_cast<uint16_t*>(b.dz_lo);
+      for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x, ++tile_i) {
+        const uint32_t acc = tile_i & 1;
+        const int64_t pix = pt * PF_NPX + ppt_pix;
+        const bool pvalid = pix < p.M;
+        const bool wvalid = pt * PF_NPX + ppt_h * 128 + quarter * 32 < p.M;      // warp-uniform
+        const int64_t e_row = pix * (int64_t)cout + c_tile0;
+        // the first chunk's dy is requested before the accumulator is waited for
+        float4 dy4[4];
+        const int ci0 = ppt_par;
+        if (pvalid && ci0 * 16 < n_valid) {
+          const int nvc = min(16, n_valid - ci0 * 16);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4)
+            dy4[j4] = (j4 * 4 < nvc) ? ld_cg(reinterpret_cast<const float4*>(b.dy + e_row + ci0 * 16) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1);
+        tc_fence_after();
+        if (wvalid) {
+#pragma unroll 1
+          for (int ci = ppt_par; ci * 16 < n_valid; ci += 2) {
+            uint32_t v[16];
+            tmem_ld_32x16(tmem_base + acc * PF_NPX + ppt_h * 128 + ci * 16 + ((uint32_t)(quarter * 32) << 16), v);
+            const int nvc = min(16, n_valid - ci * 16);
+            float4 dyn[4];
+            const bool more = (ci + 2) * 16 < n_valid;
+            if (pvalid && more) {
+              const int nvn = min(16, n_valid - (ci + 2) * 16);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4)
+                dyn[j4] = (j4 * 4 < nvn) ? ld_cg(reinterpret_cast<const float4*>(b.dy + e_row + (ci + 2) * 16) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (pvalid) {
+              uint32_t hi[8], lo[8];
+#pragma unroll
+              for (int j2 = 0; j2 < 8; ++j2) {
+                float o[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int j = j2 * 2 + e;
+                  const float4 cf = s_cf[ci * 16 + j];
+                  const float2 cg = s_cg[ci * 16 + j];
+                  const float4 d4 = dy4[j >> 2];
+                  const float dyv = (j & 3) == 0 ? d4.x : ((j & 3) == 1 ? d4.y : ((j & 3) == 2 ? d4.z : d4.w));
+                  const float I = (float)(wsign * (int)v[j] - __float_as_int(cf.z));
+                  const float dv = bn_dv(dyv, I, cf.x, cf.y, relu, inv, zpf);
+                  o[e] = fmaf(cf.w, dv, fmaf(cg.x, I, cg.y));
                 }
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[0], o[1]);
+                const float2 hf = __bfloat1622float2(h2);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(o[0] - hf.x, o[1] - hf.y);
+                hi[j2] = *reinterpret_cast<const uint32_t*>(&h2);
+                lo[j2] = *reinterpret_cast<const uint32_t*>(&l2);
+              }
+              uint16_t* ph = dz_hi + e_row + ci * 16;
+              uint16_t* pl = dz_lo + e_row + ci * 16;
+              if (nvc == 16) {
+                reinterpret_cast<uint4*>(ph)[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                reinterpret_cast<uint4*>(ph)[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                reinterpret_cast<uint4*>(pl)[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                reinterpret_cast<uint4*>(pl)[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+              } else {                                      // cout % 8 == 0: nvc == 8
+                reinterpret_cast<uint4*>(ph)[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                reinterpret_cast<uint4*>(pl)[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              }
+              if (more) {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) dy4[j4] = dyn[j4];
               }
             }
           }
@@ -583,17 +638,6 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      }
-      if constexpr (MODE == PF_BWD_REDUCE) {
-        if (active) {
-          atomicAdd(&s_comb[c_local].s1, S1);
-          atomicAdd(&s_comb[c_local].s2, S2);
-        }
-        epi_bar_sync();
-        if (active && half == 0) {
-          atomicAdd(b.sums + 2 * c, s_comb[c_local].s1);
-          atomicAdd(b.sums + 2 * c + 1, s_comb[c_local].s2);
-        }
       }
     }
   }
@@ -601,7 +645,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
   // ---- teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == PF_EPI_WARPS + PF_PROD_WARPS) {
+  if (warp == PF_EPI_WARPS + 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
@@ -627,9 +671,9 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D uint8 tensor [rows][pitch] with `cols` valid bytes per row; box = box_cols x box_rows
+// 2-D uint8 tensor [rows][pitch] with `cols` valid bytes per row; box = box_cols x box_rows, SWIZZLE_128B
 static bool make_map_u8(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch, uint32_t box_cols,
-                        uint32_t box_rows, bool swizzle128) {
+                        uint32_t box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   const cuuint64_t dims[2] = {cols, rows};
@@ -637,8 +681,7 @@ static bool make_map_u8(CUtensorMap* m, const void* base, uint64_t cols, uint64_
   const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 struct PwOperands {
@@ -651,7 +694,7 @@ static int check_operands(const char* who, const PwOperands& o) {
   FROST_REQUIRE(o.x && o.w && o.x_zp && o.w_zp && o.wsum, "%s: null pointer", who);
   FROST_REQUIRE(o.M > 0 && o.M < ((int64_t)1 << 31) && o.K > 0 && o.cout > 0, "%s: empty problem or more than 2^31 pixels", who);
   FROST_REQUIRE(o.K % 8 == 0 && o.cout % 4 == 0, "%s: K=%d must be a multiple of 8 and cout=%d of 4", who, o.K, o.cout);
-  FROST_REQUIRE(o.ldx >= o.K && o.ldx % 8 == 0, "%s: ldx=%d must be >= K and a multiple of 8", who, o.ldx);
+  FROST_REQUIRE(o.ldx >= o.K && o.ldx % 16 == 0, "%s: ldx=%d must be >= K and a multiple of 16 (TMA stride rule)", who, o.ldx);
   FROST_REQUIRE(o.ldw >= o.K && o.ldw % 16 == 0, "%s: ldw=%d must be >= K and a multiple of 16", who, o.ldw);
   FROST_REQUIRE((reinterpret_cast<uintptr_t>(o.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(o.w) & 15) == 0,
                 "%s: operands must be 16-byte aligned", who);
@@ -660,42 +703,26 @@ static int check_operands(const char* who, const PwOperands& o) {
 
 template <int MODE>
 static int launch_fused(const char* who, const PwOperands& o, PwFusedParams& p, cudaStream_t st) {
+  if (!encode_fn()) {
+    set_error("%s: cuTensorMapEncodeTiled is not available from this driver (the fused kernels stage operands by TMA)", who);
+    return FROST_ENOSUP;
+  }
   p.x = o.x; p.M = o.M; p.K = o.K; p.ldx = o.ldx;
   p.w = o.w; p.ldw = o.ldw; p.cout = o.cout;
   p.x_zp = o.x_zp; p.w_zp = o.w_zp; p.wsum = o.wsum;
   p.n_kb = (o.K + PF_BK - 1) / PF_BK;
   const int n_ct = (o.cout + PF_CH - 1) / PF_CH;
   p.bn = (((o.cout + n_ct - 1) / n_ct) + 15) & ~15;          // balanced channel tiles, multiple of 16 (<= 128)
+  p.bnr = p.bn <= 32 ? 32 : (p.bn <= 64 ? 64 : 128);          // replica stride of the weight rows in the 128-row tile
   const int n_ct_eff = (o.cout + p.bn - 1) / p.bn;
-  const bool tma_allowed = tunable(FROST_TUNE_PW_TMA) == 1 && encode_fn() != nullptr;
-  p.tma_in = (tma_allowed && o.ldx % 16 == 0) ? 1 : 0;
-  p.vec16 = (o.ldx % 16 == 0 && o.K % 16 == 0) ? 1 : 0;
-  p.tma_out = 0;
-  CUtensorMap tm_x, tm_w, tm_q;
-  memset(&tm_x, 0, sizeof(tm_x));
-  memset(&tm_w, 0, sizeof(tm_w));
-  memset(&tm_q, 0, sizeof(tm_q));
-  if (p.tma_in) {
-    if (!make_map_u8(&tm_x, o.x, (uint64_t)o.K, (uint64_t)o.M, (uint64_t)o.ldx, PF_BK, PF_NPX, true) ||
-        !make_map_u8(&tm_w, o.w, (uint64_t)o.K, (uint64_t)o.cout, (uint64_t)o.ldw, PF_BK, PF_CH, true)) {
-      set_error("%s: cuTensorMapEncodeTiled failed for the operands", who);
-      return FROST_ECUDA;
-    }
-  }
-  if (MODE == PF_FWD) {
-    FROST_REQUIRE(p.q && p.ldq >= o.cout && p.ldq % 4 == 0 && (reinterpret_cast<uintptr_t>(p.q) & 15) == 0,
-                  "%s: q must be 16-byte aligned with ldq >= cout, ldq %% 4 == 0", who);
-    if (tma_allowed && p.ldq % 16 == 0) {
-      if (!make_map_u8(&tm_q, p.q, (uint64_t)o.cout, (uint64_t)o.M, (uint64_t)p.ldq, (uint32_t)p.bn, PF_NPX, false)) {
-        set_error("%s: cuTensorMapEncodeTiled failed for the output", who);
-        return FROST_ECUDA;
-      }
-      p.tma_out = 1;
-    }
+  CUtensorMap tm_x, tm_w;
+  if (!make_map_u8(&tm_x, o.x, (uint64_t)o.K, (uint64_t)o.M, (uint64_t)o.ldx, PF_BK, PF_NPX) ||
+      !make_map_u8(&tm_w, o.w, (uint64_t)o.K, (uint64_t)o.cout, (uint64_t)o.ldw, PF_BK, (uint32_t)p.bnr)) {
+    set_error("%s: cuTensorMapEncodeTiled failed", who);
+    return FROST_ECUDA;
   }
   const bool resident = p.n_kb <= PF_RES_KB;
-  const size_t smem = 1024 + (resident ? PF_RES_KB * PF_W_BYTES + 4 * PF_X_BYTES : 3 * (PF_X_BYTES + PF_W_BYTES)) +
-                      (MODE == PF_FWD ? PF_STAGING : 0) + PF_TAIL;
+  const size_t smem = 1024 + (resident ? PF_RES_KB * PF_W_BYTES + 4 * PF_X_BYTES : 3 * (PF_X_BYTES + PF_W_BYTES)) + PF_TAIL;
   if (first_use_on_device(reinterpret_cast<const void*>(&pw_fused_kernel<MODE>))) {
     cudaError_t e = cudaFuncSetAttribute(pw_fused_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
@@ -705,9 +732,7 @@ static int launch_fused(const char* who, const PwOperands& o, PwFusedParams& p, 
   }
   const int64_t n_ptiles = ceil_div(o.M, PF_NPX);
   const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(n_ptiles, kNumSMs / n_ct_eff));
-  // the 8-byte cp.async variant allocates in L1 (cp.async.ca): ordinary stream-ordered launch (common.cuh)
-  const bool pdl_ok = p.tma_in || p.vec16;
-  cudaError_t e = launch_pdl_if(pdl_ok, pw_fused_kernel<MODE>, dim3(gx, n_ct_eff), dim3(PF_THREADS), smem, st, tm_x, tm_w, tm_q, p);
+  cudaError_t e = launch_pdl(pw_fused_kernel<MODE>, dim3(gx, n_ct_eff), dim3(PF_THREADS), smem, st, tm_x, tm_w, p);
   if (e != cudaSuccess) {
     set_error("%s: launch failed: %s", who, cudaGetErrorString(e));
     return FROST_ECUDA;
@@ -738,6 +763,8 @@ extern "C" int frost_pw_fused_forward(const FrostPwFusedFwdArgs* a, void* stream
                     a->grid_barrier && a->q,
                 "frost_pw_fused_forward: null pointer");
   FROST_REQUIRE(f.C == o.cout && f.count == o.M && f.stats_format == 0, "frost_pw_fused_forward: bn.C / bn.count must match the conv");
+  FROST_REQUIRE(a->ldq >= o.cout && a->ldq % 16 == 0 && (reinterpret_cast<uintptr_t>(a->q) & 15) == 0,
+                "frost_pw_fused_forward: q must be 16-byte aligned with ldq >= cout, ldq %% 16 == 0");
   PwFusedParams p;
   memset(&p, 0, sizeof(p));
   p.fin = f;
@@ -761,7 +788,11 @@ static int fused_backward(const FrostPwFusedBwdArgs* a, void* stream, bool apply
                     b.sums && b.dgamma_bn && b.dbeta && b.dsf_bn,
                 "%s: null pointer", who);
   FROST_REQUIRE(b.C == o.cout && b.M == o.M && b.acc_format == 0, "%s: bn.C / bn.M must match the conv", who);
-  FROST_REQUIRE(!apply || (b.dz && b.dz_lo && b.dz_format == 1), "%s: needs the bf16 hi/lo planes (dz_format 1)", who);
+  FROST_REQUIRE(o.cout % 8 == 0, "%s: cout=%d must be a multiple of 8", who, o.cout);
+  FROST_REQUIRE((reinterpret_cast<uintptr_t>(b.dy) & 15) == 0, "%s: dy must be 16-byte aligned", who);
+  FROST_REQUIRE(!apply || (b.dz && b.dz_lo && b.dz_format == 1 && (reinterpret_cast<uintptr_t>(b.dz) & 15) == 0 &&
+                           (reinterpret_cast<uintptr_t>(b.dz_lo) & 15) == 0),
+                "%s: needs 16-byte aligned bf16 hi/lo planes (dz_format 1)", who);
   cudaStream_t st = (cudaStream_t)stream;
   if (!apply && cudaMemsetAsync(b.sums, 0, sizeof(double) * 2 * b.C, st) != cudaSuccess) {
     set_error("%s: memset failed", who);

@@ -51,8 +51,7 @@ enum {
   FROST_TUNE_BN_APPLY_UNROLL = 9,      /* bn_backward_apply: elements in flight per thread (1, 2 or 4)          */
   FROST_TUNE_BNQ_UNROLL = 10,          /* bnq_apply: 16-byte loads in flight per thread (2, 4 or 8)             */
   FROST_TUNE_DW_FWD_TILED = 11,        /* depthwise forward smem tiles: 1 wide stride-1 planes only, 2 never, 3 always */
-  FROST_TUNE_PW_TMA = 12,              /* fused 1x1 kernels: 1 TMA operand loads / output stores where the pitches allow, 2 cp.async only */
-  FROST_TUNE_COUNT = 13
+  FROST_TUNE_COUNT = 12
 };
 int frost_set_tunable(int which, int value);
 int frost_get_tunable(int which);
@@ -256,7 +255,7 @@ int frost_bn_backward_apply(const FrostBnBackwardArgs* a, void* stream);    /* p
  * Fused 1x1 ConvBn(ReLU)2d (pw_fused.cu): the conv_fused.py:131-167,708-710 chain + activation fake-quant of one
  * squeeze / expand / reduce / last_layer conv (frostnet.py:98-119,293) as ONE launch, and the first two stages of its
  * autograd.  The int32 accumulator is never stored: every pass recomputes it on the tensor cores from the uint8 rows
- * (tcgen05.mma kind::i8; operands by TMA when ldx/ldq are multiples of 16, cp.async otherwise).
+ * (tcgen05.mma kind::i8; operands staged by TMA: ldx, ldw, ldq must be multiples of 16 bytes).
  *   forward     : stats (sum I, sum I^2, min, max per channel) -> grid barrier -> BN finalize + observer + qparams
  *                 (same arithmetic and side effects as frost_bn_finalize) -> q = clamp(rint(relu(A*I+B)/s)+zp)
  *   bwd_reduce  : S1 = sum dv, S2 = sum dv*(I-mean_I)            (== frost_bn_backward_reduce)
@@ -265,9 +264,9 @@ int frost_bn_backward_apply(const FrostBnBackwardArgs* a, void* stream);    /* p
 typedef struct {
   const uint8_t* x;            /* [M][ldx] uint8 indices of the conv input (K valid bytes per row)          */
   int64_t M;
-  int32_t K, ldx;              /* K % 8 == 0, ldx % 8 == 0 (TMA path: ldx % 16 == 0)                        */
+  int32_t K, ldx;              /* K % 8 == 0, ldx % 16 == 0                                                 */
   const int8_t* w_mma;         /* FrostWeightDesc.wq_mma [cout][ldw]                                        */
-  int32_t ldw, cout;           /* cout % 4 == 0                                                             */
+  int32_t ldw, cout;           /* cout % 4 == 0 (backward: cout % 8 == 0)                                   */
   const int32_t* x_zp;         /* zero point of x                                                           */
   const int32_t* w_zp;         /* zero point of the weight fake-quant (0, -128 or 127)                      */
   const int32_t* wsum;         /* FrostWeightDesc.wsum [cout]: sum_k q_w                                    */
