@@ -159,7 +159,10 @@ def _run_case(M, K, cout, zpw, relu, training, observe, extra_pad=0, steps=2, ch
             assert float((fus.sums - ref.sums).abs().max()) <= 1e-5 * max(scale, 1e-30), "S1/S2 differ"
             dz_r = hi_r.float() + lo_r.float()
             dz_f = hi_f.float() + lo_f.float()
-            tol = 1e-5 * float(dz_r.abs().max()) + 1e-30
+            # dz = P*dv + R*I + Q in the fused kernel vs c1*(dv - a0 - a1*(I - mean)) in the chain: same value, different
+            # rounding of terms of size |c1*dy|
+            c1max = float((ref.A.abs() / (ref.x_scale * ref.w_scale)).max())
+            tol = 1e-5 * float(dz_r.abs().max()) + 2e-6 * c1max * float(dy.abs().max()) + 1e-30
             assert float((dz_f - dz_r).abs().max()) <= tol, float((dz_f - dz_r).abs().max())
             for k in ("dgb", "dbeta", "dsf"):
                 r, v = getattr(ref, k), getattr(fus, k)
