@@ -90,6 +90,55 @@ __device__ __forceinline__ float bn_dv(float dy, float I, float A, float B, int 
   return pass ? dy : 0.0f;
 }
 
+// The STE / ReLU mask as an INTEGER INTERVAL of the accumulator.  Every step of
+//   I -> v = fma(I, A, B) -> relu -> * inv -> rint -> + zp
+// is monotone in I (non-decreasing for A >= 0, non-increasing for A < 0; fp rounding preserves monotonicity), so
+//   pass(I) = [0 <= idx <= 255] && [v > 0 if relu]        (exactly bn_dv's predicate)
+// holds on one interval [lo, lo + width) of integers.  The two ends are found by bisection on the exact predicate over
+// |I| <= 2^28 (accumulators are bounded by 255*128*K), once per channel; the per-element test is then one subtract and
+// one unsigned compare instead of ~10 float instructions.
+struct MaskInterval {
+  int lo;
+  unsigned width;     // pass(I) <=> (unsigned)(I - lo) < width ; 0: never
+};
+__device__ __forceinline__ bool mask_passes(const MaskInterval& m, int I) { return (unsigned)(I - m.lo) < m.width; }
+
+__device__ inline MaskInterval bn_mask_interval(float A, float B, int relu, float inv, float zp) {
+  constexpr int LIM = 1 << 28;
+  const bool inc = A >= 0.0f;
+  // low side of the index range (and v > 0) / high side of the index range
+  auto ok_low = [&](int I) {
+    const float v = bn_affine((float)I, A, B);
+    const float r = relu ? fmaxf(v, 0.0f) : v;
+    return fq_index(r, inv, zp) >= 0.0f && (!relu || v > 0.0f);
+  };
+  auto ok_high = [&](int I) {
+    const float v = bn_affine((float)I, A, B);
+    const float r = relu ? fmaxf(v, 0.0f) : v;
+    return fq_index(r, inv, zp) <= 255.0f;
+  };
+  // left end: first I where the condition that fails for very small I holds (A >= 0: ok_low, else ok_high)
+  int a = -LIM, b = LIM + 1;
+  while (a < b) {
+    const int mid = a + ((b - a) >> 1);
+    const bool t = inc ? ok_low(mid) : ok_high(mid);
+    if (t) b = mid; else a = mid + 1;
+  }
+  const int first = a;
+  // right end: first I >= first where the other condition fails
+  a = first;
+  b = LIM + 1;
+  while (a < b) {
+    const int mid = a + ((b - a) >> 1);
+    const bool t = inc ? ok_high(mid) : ok_low(mid);
+    if (t) a = mid + 1; else b = mid;
+  }
+  MaskInterval m;
+  m.lo = first;
+  m.width = (unsigned)(a - first);
+  return m;
+}
+
 // Per-channel coefficients of  dz = c1*(dv - a0 - a1*(I - mean_I))  and the BN parameter gradients, from the reduced
 // sums S1 = sum dv, S2 = sum dv*(I - mean_I).  training == 0 (frozen BatchNorm: eval-mode statistics are constants):
 // dz = c1*dv, no mean / variance terms.

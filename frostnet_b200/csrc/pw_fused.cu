@@ -24,7 +24,8 @@
 //                      -> A_c*I+B_c -> ReLU -> quantise -> uint8 rows
 //             With frozen BatchNorm and the observer off (eval / late QAT) phase A and the barrier are skipped.
 //   backward  reduce (cpt): GEMM -> dv = dy*mask -> S1, S2 per channel -> fp64 atomics
-//             apply  (ppt): GEMM -> dz = c1*(dv - a0 - a1*(I - mean)) -> bf16 hi/lo planes (operands of the tensor-core dgrad/wgrad)
+//             apply  (cpt): GEMM -> dz = c1*(dv - a0 - a1*(I - mean)) -> bf16 hi/lo planes (operands of the tensor-core dgrad/wgrad)
+//             The STE / ReLU mask is an integer interval of I per channel (bn_math.cuh): one subtract + one compare per element.
 //
 // Warp roles: 16 epilogue warps (4 per TMEM lane quarter), 1 TMA producer (one elected thread; the mbarriers count bytes),
 // 1 MMA issuer.  TMEM: 2 x 256 columns, double buffered (MMAs of tile i+1 overlap the epilogue of tile i).  Weights stay
@@ -131,8 +132,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
   float* s_red = reinterpret_cast<float*>(tmem_slot + 2);            // [2 * PF_EPI_WARPS] block min / max
   float* s_qp = s_red + 2 * PF_EPI_WARPS;                            // scale, zero point (as float), 1/scale, spare
-  float4* s_cf = reinterpret_cast<float4*>(tail + 512);              // [128] per channel: A, B, corr (int bits), P
-  float2* s_cg = reinterpret_cast<float2*>(tail + 512 + 2048);       // [128] per channel: R, Q (backward apply)
+  float4* s_cf = reinterpret_cast<float4*>(tail + 512);              // [128] per channel: A, B, corr (int bits), -
   PfCombine* s_comb = reinterpret_cast<PfCombine*>(tail + 512 + 2048 + 1024);   // [128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -167,8 +167,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
   // forward: does this launch need batch statistics / the observer's min-max (phase A + grid barrier)?
   const bool need_stats = (MODE == PF_FWD) && (p.fin.training || p.fin.observe);
   const int n_phases = (MODE == PF_FWD && need_stats) ? 2 : 1;
-  // orientation of phase `ph`: forward = [cpt,] ppt ; reduce = cpt ; apply = ppt
-  auto phase_is_cpt = [&](int ph) { return MODE == PF_BWD_REDUCE || (MODE == PF_FWD && need_stats && ph == 0); };
+  // orientation of phase `ph`: forward = [cpt,] ppt ; backward reduce / apply = cpt
+  auto phase_is_cpt = [&](int ph) { return MODE != PF_FWD || (need_stats && ph == 0); };
 
   if (warp == PF_EPI_WARPS) {
     // ================================================================= TMA producer (one elected thread)
@@ -473,8 +473,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
-    } else if constexpr (MODE == PF_BWD_REDUCE) {
-      // ================================================================= backward reduce (cpt)
+    } else {
+      // ================================================================= backward passes (cpt): reduce / apply
       const FrostBnBackwardArgs& b = p.bwd;
       relu = b.relu;
       inv = __fdiv_rn(1.0f, *b.out_scale);
@@ -482,16 +482,37 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
       const int corr_s = corr_of(c);
       const float cA = b.A[c], cB = b.B[c], cMean = b.mean_I[c];
       const int cout = p.cout;
+      // the STE / ReLU mask of this channel as an integer interval of the accumulator (bn_math.cuh)
+      const MaskInterval mk = bn_mask_interval(cA, cB, relu, inv, zpf);
+      float cP = 0.f, cQ = 0.f, cR = 0.f;
+      if constexpr (MODE == PF_BWD_APPLY) {
+        const double sa_sw = (double)(*b.x_scale) * (double)(*b.w_scale);
+        const BnBwdChannel r = bn_bwd_channel(__ldcg(b.sums + 2 * c), __ldcg(b.sums + 2 * c + 1), (double)b.M, sa_sw, cA, b.kfac[c], cMean,
+                                              b.gamma[c], b.sf[c], b.eps, b.frozen ? 0 : 1);
+        // dz = c1*(dv - a0 - a1*(I - mean)) = P*dv + R*I + Q
+        cP = r.c1;
+        cR = -r.c1 * r.a1;
+        cQ = r.c1 * (r.a1 * cMean - r.a0);
+        if (blockIdx.x == 0 && active && rep == 0 && grp == 0) {
+          b.dgamma_bn[c] = r.dgamma_bn;
+          b.dbeta[c] = r.dbeta;
+          b.dsf_bn[c] = r.dsf_bn;
+        }
+      }
+      uint16_t* dz_hi = reinterpret_cast<uint16_t*>(b.dz);
+      uint16_t* dz_lo = reinterpret_cast<uint16_t*>(b.dz_lo);
       double S1 = 0.0, S2 = 0.0;
       for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x, ++tile_i) {
         const uint32_t acc = tile_i & 1;
         const int px_valid = (int)min((int64_t)PF_NPX, p.M - pt * PF_NPX);
+        const bool full = px_valid == PF_NPX;
+        const int64_t e0 = (pt * PF_NPX + col_begin) * (int64_t)cout + c;       // element (first pixel column, my channel)
         // dy of the first chunk is requested before the accumulator is waited for
         float dy[16];
-        const float* src = b.dy + (pt * PF_NPX + col_begin) * (int64_t)cout + c;
         if (active) {
+          const float* src = b.dy + e0;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) dy[j] = (col_begin + j < px_valid) ? ld_cg(src + j * cout) : 0.0f;
+          for (int j = 0; j < 16; ++j) dy[j] = (full || col_begin + j < px_valid) ? ld_cg(src + j * cout) : 0.0f;
         }
         mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1);
         tc_fence_after();
@@ -502,20 +523,37 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
             if (col0 >= px_valid) break;
             uint32_t v[16];
             tmem_ld_32x16(tmem_base + acc * PF_NPX + col0 + ((uint32_t)(quarter * 32) << 16), v);
-            float dyn[16];                       // the next chunk's dy, in flight while this chunk is reduced
+            float dyn[16];                       // the next chunk's dy, in flight while this chunk is processed
             const bool more = col0 + 16 < col_begin + cols_per && col0 + 16 < px_valid;
             if (active && more) {
-              const float* nsrc = src + (int64_t)(col0 + 16 - col_begin) * cout;
+              const float* nsrc = b.dy + e0 + (int64_t)(col0 + 16 - col_begin) * cout;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) dyn[j] = (col0 + 16 + j < px_valid) ? ld_cg(nsrc + j * cout) : 0.0f;
+              for (int j = 0; j < 16; ++j) dyn[j] = (full || col0 + 16 + j < px_valid) ? ld_cg(nsrc + j * cout) : 0.0f;
             }
             if (active) {
+              if constexpr (MODE == PF_BWD_REDUCE) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float I = (float)(wsign * (int)v[j] - corr_s);
-                const float dv = bn_dv(dy[j], I, cA, cB, relu, inv, zpf);
-                p1 += dv;
-                p2 = fmaf(dv, I - cMean, p2);
+                for (int j = 0; j < 16; ++j) {
+                  const int I = wsign * (int)v[j] - corr_s;
+                  const float dv = mask_passes(mk, I) ? dy[j] : 0.0f;
+                  p1 += dv;
+                  p2 = fmaf(dv, (float)I - cMean, p2);
+                }
+              } else {
+                const int64_t eo = e0 + (int64_t)(col0 - col_begin) * cout;
+                const int nv = full ? 16 : min(16, px_valid - col0);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int I = wsign * (int)v[j] - corr_s;
+                  const float base = fmaf(cR, (float)I, cQ);
+                  const float o = mask_passes(mk, I) ? fmaf(cP, dy[j], base) : base;
+                  const __nv_bfloat16 h = __float2bfloat16_rn(o);
+                  const __nv_bfloat16 l = __float2bfloat16_rn(o - __bfloat162float(h));
+                  if (j < nv) {
+                    dz_hi[eo + (int64_t)j * cout] = __bfloat16_as_ushort(h);
+                    dz_lo[eo + (int64_t)j * cout] = __bfloat16_as_ushort(l);
+                  }
+                }
               }
               if (more) {
 #pragma unroll
@@ -530,114 +568,16 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
-      if (active) {
-        atomicAdd(&s_comb[c_local].s1, S1);
-        atomicAdd(&s_comb[c_local].s2, S2);
-      }
-      epi_bar_sync();
-      if (tid < n_valid) {
-        atomicAdd(b.sums + 2 * (c_tile0 + tid), s_comb[tid].s1);
-        atomicAdd(b.sums + 2 * (c_tile0 + tid) + 1, s_comb[tid].s2);
-      }
-    } else {
-      // ================================================================= backward apply (ppt)
-      const FrostBnBackwardArgs& b = p.bwd;
-      relu = b.relu;
-      inv = __fdiv_rn(1.0f, *b.out_scale);
-      zpf = (float)*b.out_zp;
-      const int cout = p.cout;
-      if (tid < n_valid) {
-        const int cc = c_tile0 + tid;
-        const double sa_sw = (double)(*b.x_scale) * (double)(*b.w_scale);
-        const float A = b.A[cc], mean = b.mean_I[cc];
-        const BnBwdChannel r = bn_bwd_channel(__ldcg(b.sums + 2 * cc), __ldcg(b.sums + 2 * cc + 1), (double)b.M, sa_sw, A, b.kfac[cc], mean,
-                                              b.gamma[cc], b.sf[cc], b.eps, b.frozen ? 0 : 1);
-        // dz = c1*(dv - a0 - a1*(I - mean)) = P*dv + R*I + Q
-        s_cf[tid] = make_float4(A, b.B[cc], __int_as_float(corr_of(cc)), r.c1);
-        s_cg[tid] = make_float2(-r.c1 * r.a1, r.c1 * (r.a1 * mean - r.a0));
-        if (blockIdx.x == 0) {
-          b.dgamma_bn[cc] = r.dgamma_bn;
-          b.dbeta[cc] = r.dbeta;
-          b.dsf_bn[cc] = r.dsf_bn;
+      if constexpr (MODE == PF_BWD_REDUCE) {
+        if (active) {
+          atomicAdd(&s_comb[c_local].s1, S1);
+          atomicAdd(&s_comb[c_local].s2, S2);
         }
-      }
-      epi_bar_sync();
-      uint16_t* dz_hi = reinterpret_cast<uint16_t*>(b.dz);
-      uint16_t* dz_lo = reinterpret_cast<uint16_t*>(b.dz_lo);
-      for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x, ++tile_i) {
-        const uint32_t acc = tile_i & 1;
-        const int64_t pix = pt * PF_NPX + ppt_pix;
-        const bool pvalid = pix < p.M;
-        const bool wvalid = pt * PF_NPX + ppt_h * 128 + quarter * 32 < p.M;      // warp-uniform
-        const int64_t e_row = pix * (int64_t)cout + c_tile0;
-        // the first chunk's dy is requested before the accumulator is waited for
-        float4 dy4[4];
-        const int ci0 = ppt_par;
-        if (pvalid && ci0 * 16 < n_valid) {
-          const int nvc = min(16, n_valid - ci0 * 16);
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4)
-            dy4[j4] = (j4 * 4 < nvc) ? ld_cg(reinterpret_cast<const float4*>(b.dy + e_row + ci0 * 16) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        epi_bar_sync();
+        if (tid < n_valid) {
+          atomicAdd(b.sums + 2 * (c_tile0 + tid), s_comb[tid].s1);
+          atomicAdd(b.sums + 2 * (c_tile0 + tid) + 1, s_comb[tid].s2);
         }
-        mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1);
-        tc_fence_after();
-        if (wvalid) {
-#pragma unroll 1
-          for (int ci = ppt_par; ci * 16 < n_valid; ci += 2) {
-            uint32_t v[16];
-            tmem_ld_32x16(tmem_base + acc * PF_NPX + ppt_h * 128 + ci * 16 + ((uint32_t)(quarter * 32) << 16), v);
-            const int nvc = min(16, n_valid - ci * 16);
-            float4 dyn[4];
-            const bool more = (ci + 2) * 16 < n_valid;
-            if (pvalid && more) {
-              const int nvn = min(16, n_valid - (ci + 2) * 16);
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4)
-                dyn[j4] = (j4 * 4 < nvn) ? ld_cg(reinterpret_cast<const float4*>(b.dy + e_row + (ci + 2) * 16) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            if (pvalid) {
-              uint32_t hi[8], lo[8];
-#pragma unroll
-              for (int j2 = 0; j2 < 8; ++j2) {
-                float o[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const int j = j2 * 2 + e;
-                  const float4 cf = s_cf[ci * 16 + j];
-                  const float2 cg = s_cg[ci * 16 + j];
-                  const float4 d4 = dy4[j >> 2];
-                  const float dyv = (j & 3) == 0 ? d4.x : ((j & 3) == 1 ? d4.y : ((j & 3) == 2 ? d4.z : d4.w));
-                  const float I = (float)(wsign * (int)v[j] - __float_as_int(cf.z));
-                  const float dv = bn_dv(dyv, I, cf.x, cf.y, relu, inv, zpf);
-                  o[e] = fmaf(cf.w, dv, fmaf(cg.x, I, cg.y));
-                }
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[0], o[1]);
-                const float2 hf = __bfloat1622float2(h2);
-                const __nv_bfloat162 l2 = __floats2bfloat162_rn(o[0] - hf.x, o[1] - hf.y);
-                hi[j2] = *reinterpret_cast<const uint32_t*>(&h2);
-                lo[j2] = *reinterpret_cast<const uint32_t*>(&l2);
-              }
-              uint16_t* ph = dz_hi + e_row + ci * 16;
-              uint16_t* pl = dz_lo + e_row + ci * 16;
-              if (nvc == 16) {
-                reinterpret_cast<uint4*>(ph)[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                reinterpret_cast<uint4*>(ph)[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                reinterpret_cast<uint4*>(pl)[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                reinterpret_cast<uint4*>(pl)[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-              } else {                                      // cout % 8 == 0: nvc == 8
-                reinterpret_cast<uint4*>(ph)[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                reinterpret_cast<uint4*>(pl)[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-              }
-              if (more) {
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) dy4[j4] = dyn[j4];
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
     }
   }

@@ -134,9 +134,11 @@ class QATEngine:
     def __setstate__(self, state):
         self.__init__(state["model"])
 
-    def _tensor_fingerprint(self):
+    def _tensor_fingerprint(self, full=True):
+        """data_ptr of every parameter (cheap: ~200 tensors) and, when `full`, of every buffer (~1500)."""
         m = self.model
-        return tuple(t.data_ptr() for t in m.parameters()) + tuple(t.data_ptr() for t in m.buffers())
+        fp = tuple(t.data_ptr() for t in m.parameters())
+        return fp + tuple(t.data_ptr() for t in m.buffers()) if full else fp
 
     def _alloc_q(self, M, Cc):
         """uint8 index tensor [M][ld]: rows padded to a multiple of 16 bytes (TMA's stride rule; the padding is
@@ -155,11 +157,19 @@ class QATEngine:
         q.copy_(ref)
 
     # ------------------------------------------------------------------ build
-    def _ensure_built(self):
+    def _ensure_built(self, check=True):
+        if self._built and not check:
+            return
         if self._built:
             # p.data = ..., load_state_dict(assign=True), vector_to_parameters ... move tensors without going
             # through Module._apply: the cached pointer tables would silently address freed memory
-            if self._tensor_fingerprint() == self._fingerprint:
+            # parameters every forward, buffers every 64th: the check sits on the critical path of a step's first launch
+            self._fp_tick = (getattr(self, "_fp_tick", 0) + 1) % 64
+            if self._fp_tick == 0:
+                ok = self._tensor_fingerprint(True) == self._fingerprint
+            else:
+                ok = tuple(p.data_ptr() for p in self.params) == self._fingerprint[:len(self.params)]
+            if ok:
                 return
             self._built = False
         m = self.model
@@ -351,7 +361,7 @@ class QATEngine:
         return out
 
     def forward(self, x, save):
-        self._ensure_built()
+        self._ensure_built(check=False)          # run() has just verified the pointer tables
         with torch.cuda.device(self.dev):       # kernels launch on the CURRENT device: make it the model's
             return self._forward(x, save)
 

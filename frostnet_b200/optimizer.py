@@ -77,6 +77,32 @@ class _GradBoostBase(Optimizer):
         h.seed = self.seed
         return h
 
+    def _upload(self, key, arr, chunks, dev):
+        """Descriptor table + work list to the device WITHOUT a host synchronisation: a blocking pageable copy here made
+        the host wait for the whole step's kernels every iteration, so the next step's first launches (and the GPU)
+        waited for Python.  Pinned staging slots, asynchronous copies; a slot is reused only after its copy has run."""
+        nbytes = C.sizeof(arr)
+        c = self.__dict__.setdefault("_upload_cache", {}).get(key)
+        if c is None or c["nbytes"] != nbytes or c["dev"] != dev:
+            c = dict(nbytes=nbytes, dev=dev, slot=0, chunks=None, ck=None,
+                     pinned=[torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(4)],
+                     tabs=[torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(4)],
+                     events=[None] * 4)
+            self._upload_cache[key] = c
+        i = c["slot"]
+        c["slot"] = (i + 1) % 4
+        if c["events"][i] is not None:
+            c["events"][i].synchronize()
+        C.memmove(c["pinned"][i].data_ptr(), arr, nbytes)
+        c["tabs"][i].copy_(c["pinned"][i], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        c["events"][i] = ev
+        if c["chunks"] != chunks:                  # the work list only changes when the parameter set does
+            c["chunks"] = list(chunks)
+            c["ck"] = torch.tensor(chunks, dtype=torch.int32).to(dev)
+        return c["tabs"][i], c["ck"]
+
     @staticmethod
     def _hyper_key(group):
         return tuple((k, (tuple(v) if isinstance(v, (tuple, list)) else v)) for k, v in sorted(group.items())
@@ -147,9 +173,7 @@ class _GradBoostBase(Optimizer):
                 t.step, t.restart_step = state['step'], state['restart_step']
                 nchunk = (p.numel() + L.OPT_CHUNK - 1) // L.OPT_CHUNK
                 chunks.extend((ti, c) for c in range(nchunk))
-            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
-            tab = host.to(dev, non_blocking=False)
-            ck = torch.tensor(chunks, dtype=torch.int32).to(dev)
+            tab, ck = self._upload(key, arr, chunks, dev)
             h = self._hyper(group0)
             with torch.cuda.device(dev):      # the kernel launches on the current device: make it the parameters'
                 L.call("frost_gradboost_multi", tab.data_ptr(), len(items), ck.data_ptr(), len(chunks), C.byref(h), st)
