@@ -57,13 +57,8 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(FrostBnFinalizeArgs a
 // 4 consecutive channels per thread-iteration (one 16-byte load, one 4-byte store; the per-channel affine
 // is read from shared memory as float4 - consecutive lanes hit consecutive banks), two iterations in flight.
 __device__ __forceinline__ unsigned bnq4(const int4 v, int fmt, const float4 A, const float4 B, int relu, float inv, float zp) {
-  float r0 = bn_affine(acc_val(v.x, fmt), A.x, B.x), r1 = bn_affine(acc_val(v.y, fmt), A.y, B.y);
-  float r2 = bn_affine(acc_val(v.z, fmt), A.z, B.z), r3 = bn_affine(acc_val(v.w, fmt), A.w, B.w);
-  if (relu) { r0 = fmaxf(r0, 0.0f); r1 = fmaxf(r1, 0.0f); r2 = fmaxf(r2, 0.0f); r3 = fmaxf(r3, 0.0f); }
-  const unsigned q0 = (unsigned)fminf(fmaxf(fq_index(r0, inv, zp), 0.0f), 255.0f);
-  const unsigned q1 = (unsigned)fminf(fmaxf(fq_index(r1, inv, zp), 0.0f), 255.0f);
-  const unsigned q2 = (unsigned)fminf(fmaxf(fq_index(r2, inv, zp), 0.0f), 255.0f);
-  const unsigned q3 = (unsigned)fminf(fmaxf(fq_index(r3, inv, zp), 0.0f), 255.0f);
+  const unsigned q0 = bnq1(acc_val(v.x, fmt), A.x, B.x, relu, inv, zp), q1 = bnq1(acc_val(v.y, fmt), A.y, B.y, relu, inv, zp);
+  const unsigned q2 = bnq1(acc_val(v.z, fmt), A.z, B.z, relu, inv, zp), q3 = bnq1(acc_val(v.w, fmt), A.w, B.w, relu, inv, zp);
   return q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
 }
 

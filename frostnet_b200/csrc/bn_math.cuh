@@ -75,8 +75,19 @@ __device__ __forceinline__ void observer_ema(float& rmin, float& rmax, float cur
 }
 
 // ---------------------------------------------------------------- per-element forward / backward
+// round-to-nearest-even + saturate to [0, 255] in one conversion (NaN -> 0)
+__device__ __forceinline__ unsigned cvt_rni_sat_u8(float t) {
+  unsigned q;
+  asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q) : "f"(t));
+  return q;
+}
+
+// q = clamp(rint(relu(A*I + B) * inv) + zp, 0, 255)   - the arithmetic of ATen's fake-quantize kernel, step by step.
+// zp == 0 (every post-ReLU tensor: its observed minimum is 0) needs neither the add nor the explicit ReLU / clamp:
+// negative values saturate to 0 exactly like relu() followed by the clamp, and rint-then-clamp == saturating rint.
 __device__ __forceinline__ unsigned bnq1(float I, float A, float B, int relu, float inv, float zp) {
   float r = bn_affine(I, A, B);
+  if (zp == 0.0f) return cvt_rni_sat_u8(__fmul_rn(r, inv));
   if (relu) r = fmaxf(r, 0.0f);
   return (unsigned)fminf(fmaxf(fq_index(r, inv, zp), 0.0f), 255.0f);
 }
