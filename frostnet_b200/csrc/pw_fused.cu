@@ -99,6 +99,30 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   return v;
 }
 
+// mbarrier wait for the warps that have slack (producer, MMA issuer, epilogue between tiles): spinning warps steal issue
+// slots from the 16 epilogue warps (ncu: BRA + SYNCS were 18 % of the instructions executed), so back off between polls.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (it >= 4) __nanosleep(40);
+  }
+  __trap();
+}
+__device__ __forceinline__ float4 lds_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+
 // 32 lanes x 16 consecutive 32-bit columns
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -186,7 +210,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x) {
           for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
             const int s = it % S;
-            mbar_wait(&empty_bar[s], ((it / S) & 1) ^ 1);
+            mbar_wait_sleep(&empty_bar[s], ((it / S) & 1) ^ 1);
             uint8_t* st = stages + s * stage_bytes;
             mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
             tma_load_2d(&tm_x, &full_bar[s], smem_u32(st), kb * PF_BK, (int)(pt * PF_NPX));
@@ -205,7 +229,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
     const uint32_t idesc_cpt = umma_idesc(2 /*S32*/, w_fmt, 0, PF_CH, PF_NPX);   // A = W (128 rows), B = X (256 pixels)
     const uint32_t idesc_ppt = umma_idesc(2 /*S32*/, 0, w_fmt, 128, n_mma);      // A = X (128 pixels), B = W (n_mma rows)
     if (resident) {
-      mbar_wait(wfull_bar, 0);
+      mbar_wait_sleep(wfull_bar, 0);
       tc_fence_after();
     }
     uint32_t it = 0, tile_i = 0;
@@ -213,13 +237,13 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
       const bool cpt = phase_is_cpt(ph);
       for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x, ++tile_i) {
         const uint32_t acc = tile_i & 1;
-        mbar_wait(&tempty_bar[acc], ((tile_i >> 1) & 1) ^ 1);
+        mbar_wait_sleep(&tempty_bar[acc], ((tile_i >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * PF_NPX;
         const bool second_half = p.M - pt * PF_NPX > 128;
         for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
           const int s = it % S;
-          mbar_wait(&full_bar[s], (it / S) & 1);
+          mbar_wait_sleep(&full_bar[s], (it / S) & 1);
           tc_fence_after();
           if (lane == 0) {
             uint8_t* st = stages + s * stage_bytes;
@@ -287,7 +311,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x, ++tile_i) {
           const uint32_t acc = tile_i & 1;
           const int px_valid = (int)min((int64_t)PF_NPX, p.M - pt * PF_NPX);
-          mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1);
+          mbar_wait_sleep(&tfull_bar[acc], (tile_i >> 1) & 1);
           tc_fence_after();
           if (warp_active) {
 #pragma unroll 1
@@ -436,7 +460,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         const int64_t pix = pt * PF_NPX + ppt_pix;
         const bool pvalid = pix < p.M;
         const bool wvalid = pt * PF_NPX + ppt_h * 128 + quarter * 32 < p.M;      // warp-uniform
-        mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1);
+        mbar_wait_sleep(&tfull_bar[acc], (tile_i >> 1) & 1);
         tc_fence_after();
         if (wvalid) {
           uint8_t* qrow = p.q + pix * (int64_t)p.ldq + c_tile0;
@@ -450,7 +474,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
               unsigned word = 0u;
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float4 cf = s_cf[ci * 16 + j4 * 4 + e];
+                const float4 cf = lds_f4(&s_cf[ci * 16 + j4 * 4 + e]);
                 const float I = (float)(wsign * (int)v[j4 * 4 + e] - __float_as_int(cf.z));
                 word |= bnq1(I, cf.x, cf.y, relu, inv, zpf) << (8 * e);
               }
@@ -502,64 +526,76 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
       uint16_t* dz_hi = reinterpret_cast<uint16_t*>(b.dz);
       uint16_t* dz_lo = reinterpret_cast<uint16_t*>(b.dz_lo);
       double S1 = 0.0, S2 = 0.0;
+      const int64_t row_b = (int64_t)cout * 4;                 // bytes between consecutive pixels of dy
+      // 16 pixels of my channel, starting at pixel column `col` of the tile whose first element is `tile_dy`
+      auto load16 = [&](float (&d)[16], const float* tile_dy, int col, int px_valid) {
+        const char* q = reinterpret_cast<const char*>(tile_dy) + (int64_t)col * row_b;
+        if (col + 16 <= px_valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) d[j] = ld_cg(reinterpret_cast<const float*>(q + j * row_b));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) d[j] = (col + j < px_valid) ? ld_cg(reinterpret_cast<const float*>(q + j * row_b)) : 0.0f;
+        }
+      };
+      float p1 = 0.f, p2 = 0.f;
+      auto proc16 = [&](const float (&d)[16], uint32_t taddr, int64_t e_col, int col, int px_valid) {
+        uint32_t v[16];
+        tmem_ld_32x16(taddr, v);
+        if (!active) return;
+        if constexpr (MODE == PF_BWD_REDUCE) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int I = wsign * (int)v[j] - corr_s;
+            const float dv = mask_passes(mk, I) ? d[j] : 0.0f;
+            p1 += dv;
+            p2 = fmaf(dv, (float)I - cMean, p2);
+          }
+        } else {
+          char* ph = reinterpret_cast<char*>(dz_hi + e_col);
+          char* pl = reinterpret_cast<char*>(dz_lo + e_col);
+          const int64_t row_h = (int64_t)cout * 2;
+          const bool whole = col + 16 <= px_valid;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int I = wsign * (int)v[j] - corr_s;
+            const float base = fmaf(cR, (float)I, cQ);
+            const float o = mask_passes(mk, I) ? fmaf(cP, d[j], base) : base;
+            const __nv_bfloat16 h = __float2bfloat16_rn(o);
+            const __nv_bfloat16 l = __float2bfloat16_rn(o - __bfloat162float(h));
+            if (whole || col + j < px_valid) {
+              *reinterpret_cast<uint16_t*>(ph + j * row_h) = __bfloat16_as_ushort(h);
+              *reinterpret_cast<uint16_t*>(pl + j * row_h) = __bfloat16_as_ushort(l);
+            }
+          }
+        }
+      };
+      const int n_ch = cols_per >> 4;                          // 16-pixel chunks per tile for this thread: 4, 2 or 1
       for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x, ++tile_i) {
         const uint32_t acc = tile_i & 1;
         const int px_valid = (int)min((int64_t)PF_NPX, p.M - pt * PF_NPX);
-        const bool full = px_valid == PF_NPX;
-        const int64_t e0 = (pt * PF_NPX + col_begin) * (int64_t)cout + c;       // element (first pixel column, my channel)
-        // dy of the first chunk is requested before the accumulator is waited for
-        float dy[16];
-        if (active) {
-          const float* src = b.dy + e0;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) dy[j] = (full || col_begin + j < px_valid) ? ld_cg(src + j * cout) : 0.0f;
-        }
-        mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1);
+        const int64_t e_tile = pt * PF_NPX * (int64_t)cout + c;                // element (pixel 0 of the tile, my channel)
+        const float* tile_dy = b.dy + e_tile;
+        const uint32_t t0 = tmem_base + acc * PF_NPX + ((uint32_t)(quarter * 32) << 16);
+        // ping-pong buffers: chunk k+1 is in flight while chunk k is processed; chunk 0 is requested before the
+        // accumulator is waited for
+        float dA[16], dB[16];
+        if (active && col_begin < px_valid) load16(dA, tile_dy, col_begin, px_valid);
+        mbar_wait_sleep(&tfull_bar[acc], (tile_i >> 1) & 1);
         tc_fence_after();
         if (warp_active) {
-          float p1 = 0.f, p2 = 0.f;
+          p1 = 0.f;
+          p2 = 0.f;
 #pragma unroll 1
-          for (int col0 = col_begin; col0 < col_begin + cols_per; col0 += 16) {
-            if (col0 >= px_valid) break;
-            uint32_t v[16];
-            tmem_ld_32x16(tmem_base + acc * PF_NPX + col0 + ((uint32_t)(quarter * 32) << 16), v);
-            float dyn[16];                       // the next chunk's dy, in flight while this chunk is processed
-            const bool more = col0 + 16 < col_begin + cols_per && col0 + 16 < px_valid;
-            if (active && more) {
-              const float* nsrc = b.dy + e0 + (int64_t)(col0 + 16 - col_begin) * cout;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) dyn[j] = (full || col0 + 16 + j < px_valid) ? ld_cg(nsrc + j * cout) : 0.0f;
-            }
-            if (active) {
-              if constexpr (MODE == PF_BWD_REDUCE) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int I = wsign * (int)v[j] - corr_s;
-                  const float dv = mask_passes(mk, I) ? dy[j] : 0.0f;
-                  p1 += dv;
-                  p2 = fmaf(dv, (float)I - cMean, p2);
-                }
-              } else {
-                const int64_t eo = e0 + (int64_t)(col0 - col_begin) * cout;
-                const int nv = full ? 16 : min(16, px_valid - col0);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int I = wsign * (int)v[j] - corr_s;
-                  const float base = fmaf(cR, (float)I, cQ);
-                  const float o = mask_passes(mk, I) ? fmaf(cP, dy[j], base) : base;
-                  const __nv_bfloat16 h = __float2bfloat16_rn(o);
-                  const __nv_bfloat16 l = __float2bfloat16_rn(o - __bfloat162float(h));
-                  if (j < nv) {
-                    dz_hi[eo + (int64_t)j * cout] = __bfloat16_as_ushort(h);
-                    dz_lo[eo + (int64_t)j * cout] = __bfloat16_as_ushort(l);
-                  }
-                }
-              }
-              if (more) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) dy[j] = dyn[j];
-              }
-            }
+          for (int k = 0; k < n_ch; k += 2) {
+            const int colA = col_begin + 16 * k, colB = colA + 16;
+            if (colA >= px_valid) break;
+            const bool hasB = k + 1 < n_ch && colB < px_valid;
+            if (active && hasB) load16(dB, tile_dy, colB, px_valid);
+            proc16(dA, t0 + colA, e_tile + (int64_t)colA * cout, colA, px_valid);
+            const bool hasA2 = k + 2 < n_ch && colB + 16 < px_valid;
+            if (active && hasA2) load16(dA, tile_dy, colB + 16, px_valid);
+            if (hasB) proc16(dB, t0 + colB, e_tile + (int64_t)colB * cout, colB, px_valid);
           }
           S1 += (double)p1;                      // <= 64 terms per fp32 partial
           S2 += (double)p2;
