@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         const bool second_half = p.M - pt * PF_NPX > 128;
         for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
           const int s = it % S;
-          mbar_wait_sleep(&full_bar[s], (it / S) & 1);
+          mbar_wait(&full_bar[s], (it / S) & 1);
           tc_fence_after();
           if (lane == 0) {
             uint8_t* st = stages + s * stage_bytes;
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x, ++tile_i) {
           const uint32_t acc = tile_i & 1;
           const int px_valid = (int)min((int64_t)PF_NPX, p.M - pt * PF_NPX);
-          mbar_wait_sleep(&tfull_bar[acc], (tile_i >> 1) & 1);
+          mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1);
           tc_fence_after();
           if (warp_active) {
 #pragma unroll 1
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         const int64_t pix = pt * PF_NPX + ppt_pix;
         const bool pvalid = pix < p.M;
         const bool wvalid = pt * PF_NPX + ppt_h * 128 + quarter * 32 < p.M;      // warp-uniform
-        mbar_wait_sleep(&tfull_bar[acc], (tile_i >> 1) & 1);
+        mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1);
         tc_fence_after();
         if (wvalid) {
           uint8_t* qrow = p.q + pix * (int64_t)p.ldq + c_tile0;
@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         // accumulator is waited for
         float dA[16], dB[16];
         if (active && col_begin < px_valid) load16(dA, tile_dy, col_begin, px_valid);
-        mbar_wait_sleep(&tfull_bar[acc], (tile_i >> 1) & 1);
+        mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1);
         tc_fence_after();
         if (warp_active) {
           p1 = 0.f;
