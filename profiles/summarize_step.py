@@ -30,7 +30,7 @@ for L in launch.values():
     a[1] += L.get('gpu__time_duration.sum', 0.0)
     a[2] += L.get('dram__bytes_read.sum', 0.0) + L.get('dram__bytes_write.sum', 0.0)
 tot = sum(v[1] for v in agg.values())
-print('launches %d, sum of kernel durations %.1f us (under ncu: cold caches, serialised - compare shares, not absolutes)' % (len(launch), tot))
+print('launches %d, sum of kernel durations %.1f us (under ncu: cold caches, serialised - compare shares, not absolutes), DRAM traffic %.2f GB' % (len(launch), tot, sum(v[2] for v in agg.values()) / 1e9))
 print('%-46s %5s %12s %7s %16s %10s' % ('kernel', 'n', 'time us', 'share', 'DRAM MB/launch', 'GB/s'))
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print('%-46s %5d %12.1f %6.1f%% %16.2f %10.0f' % (k[:46], v[0], v[1], 100 * v[1] / tot, v[2] / v[0] / 1e6, v[2] / v[1] / 1e3 if v[1] else 0))
@@ -49,4 +49,8 @@ if len(sys.argv) > 2:
         if m[1] > 0:
             out[b] = {'dram_bytes_per_launch': m[1] / m[0], 'launches': m[0], 'source': out.get(b, {}).get('source') or
                       '%s (ncu dram bytes, mean over the launches of one bs=256 step)' % sys.argv[1].replace('gpurun_out/', 'profiles/')}
+    total_bytes = sum(v[2] for v in agg.values())
+    out['step_total'] = {'dram_bytes': total_bytes, 'launches': len(launch), 'kernel_time_us': tot,
+                         'source': '%s (ncu dram__bytes_read.sum+dram__bytes_write.sum summed over every launch of one bs=256 step)'
+                                   % sys.argv[1].replace('gpurun_out/', 'profiles/')}
     json.dump(out, open(sys.argv[2], 'w'), indent=1)
