@@ -60,6 +60,10 @@ class PwFusedBwdArgs(C.Structure):
     _fields_ = [("op", PwOperands), ("bn", BnBackwardArgs)]
 
 
+class PwChainArgs(C.Structure):
+    _fields_ = [("op", PwOperands), ("bn", BnBackwardArgs), ("wt_bf16", c_p), ("dx", c_p), ("accumulate", C.c_int32), ("dwq", c_p)]
+
+
 class QTensor(C.Structure):
     _fields_ = [("q", c_p), ("scale", c_p), ("zp", c_p), ("cur_minmax", c_p), ("C", C.c_int32), ("ld", C.c_int32)]
 
@@ -116,6 +120,7 @@ _SIGNATURES = {
     "frost_pw_fused_forward": [C.POINTER(PwFusedFwdArgs), c_p],
     "frost_pw_fused_bwd_reduce": [C.POINTER(PwFusedBwdArgs), c_p],
     "frost_pw_fused_bwd_apply": [C.POINTER(PwFusedBwdArgs), c_p],
+    "frost_pw_chain_backward": [C.POINTER(PwChainArgs), c_p],
     "frost_cat_forward": [QTensor, QTensor, i64, FQ, i32, f32, c_p, i32, c_p, c_p],
     "frost_cat_backward": [c_p, QTensor, QTensor, i64, c_p, c_p, c_p, c_p, i32, c_p],
     "frost_add_forward": [QTensor, QTensor, i64, FQ, i32, f32, c_p, i32, c_p, c_p, c_p],
@@ -136,7 +141,8 @@ _SIGNATURES = {
     "frost_set_tunable": [i32, i32],
     "frost_get_tunable": [i32],
 }
-EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["frost_abi_version", "frost_last_error", "frost_launch_count"])
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["frost_abi_version", "frost_last_error", "frost_launch_count",
+                           "frost_pw_chain_supported"])
 
 _lib = None
 
@@ -157,6 +163,8 @@ def load():
     lib.frost_abi_version.restype = C.c_int
     lib.frost_last_error.restype = C.c_char_p
     lib.frost_launch_count.restype = C.c_int64
+    lib.frost_pw_chain_supported.argtypes = [C.c_int, C.c_int]
+    lib.frost_pw_chain_supported.restype = C.c_int
     for name, argtypes in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

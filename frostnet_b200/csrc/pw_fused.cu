@@ -34,7 +34,7 @@
 #include <cuda_bf16.h>
 #include <algorithm>
 #include <cstring>
-#include "tc_common.cuh"
+#include "pw_tma.cuh"
 #include "bn_math.cuh"
 
 namespace frost {
@@ -77,57 +77,6 @@ struct PfCombine {       // per channel of the tile: the partial results of the 
   int mn, mx;
   double s1, s2;
 };
-
-// ---------------------------------------------------------------- TMA / mbarrier helpers
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, uint32_t dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
-}
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PF_EPI_THREADS) : "memory"); }
-
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// mbarrier wait for the warps that have slack (producer, MMA issuer, epilogue between tiles): spinning warps steal issue
-// slots from the 16 epilogue warps (ncu: BRA + SYNCS were 18 % of the instructions executed), so back off between polls.
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  for (uint32_t it = 0; it < (1u << 24); ++it) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-    if (it >= 4) __nanosleep(40);
-  }
-  __trap();
-}
-// 32 lanes x 16 consecutive 32-bit columns
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // ================================================================= the kernel
 template <int MODE>
@@ -353,14 +302,14 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
           atomicMin(&cb.mn, mn);
           atomicMax(&cb.mx, mx);
         }
-        epi_bar_sync();
+        named_bar_sync<PF_EPI_THREADS>();
         if (tid < n_valid) {
           const PfCombine cb = s_comb[tid];
           chan_stats_flush(const_cast<FrostChanStats*>(p.fin.stats) + c_tile0 + tid, (long long)cb.sum, cb.sq, cb.mn, cb.mx);
         }
         // ---------------- grid barrier: every CTA of this launch is resident (host: grid <= #SMs, 1 CTA per SM)
         __threadfence();
-        epi_bar_sync();
+        named_bar_sync<PF_EPI_THREADS>();
         if (tid == 0) {
           const unsigned target = gridDim.x * gridDim.y;
           __threadfence();                                   // cumulativity: the CTA's atomics above are ordered before the arrival
@@ -372,7 +321,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
           }
           if (!ok) __trap();
         }
-        epi_bar_sync();
+        named_bar_sync<PF_EPI_THREADS>();
       }
       // ---------------- finalize: BN affine of the tile's channels, observer over all channels, qparams (same in every CTA)
       float gmn = INFINITY, gmx = -INFINITY;
@@ -404,7 +353,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
       gmn = warp_min(gmn);
       gmx = warp_max(gmx);
       if (lane == 0) { s_red[2 * warp] = gmn; s_red[2 * warp + 1] = gmx; }
-      epi_bar_sync();          // also orders every thread's reads of the old running statistics before the writes below
+      named_bar_sync<PF_EPI_THREADS>();          // also orders every thread's reads of the old running statistics before the writes below
       if (tid == 0) {
         for (int w = 0; w < PF_EPI_WARPS; ++w) { gmn = fminf(gmn, s_red[2 * w]); gmx = fmaxf(gmx, s_red[2 * w + 1]); }
         float s;
@@ -436,7 +385,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
           }
         }
       }
-      epi_bar_sync();
+      named_bar_sync<PF_EPI_THREADS>();
       inv = s_qp[2];
       zpf = s_qp[1];
       if (blockIdx.x == 0 && tid < n_valid) {                // one writer per channel
@@ -605,7 +554,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
           atomicAdd(&s_comb[c_local].s1, S1);
           atomicAdd(&s_comb[c_local].s2, S2);
         }
-        epi_bar_sync();
+        named_bar_sync<PF_EPI_THREADS>();
         if (tid < n_valid) {
           atomicAdd(b.sums + 2 * (c_tile0 + tid), s_comb[tid].s1);
           atomicAdd(b.sums + 2 * (c_tile0 + tid) + 1, s_comb[tid].s2);
@@ -624,38 +573,6 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
 }
 
 // ================================================================= host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    (void)cudaGetLastError();
-  }
-  return fn;
-}
-
-// 2-D uint8 tensor [rows][pitch] with `cols` valid bytes per row; box = box_cols x box_rows, SWIZZLE_128B
-static bool make_map_u8(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch, uint32_t box_cols,
-                        uint32_t box_rows) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return false;
-  const cuuint64_t dims[2] = {cols, rows};
-  const cuuint64_t strides[1] = {pitch};
-  const cuuint32_t box[2] = {box_cols, box_rows};
-  const cuuint32_t estr[2] = {1, 1};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 struct PwOperands {
   const uint8_t* x; int64_t M; int K, ldx;
   const int8_t* w; int ldw, cout;

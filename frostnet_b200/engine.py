@@ -116,6 +116,7 @@ class QATEngine:
         # 1x1 ConvBn(ReLU): one fused tensor-core launch per pass, int32 accumulators never stored (csrc/pw_fused.cu).
         # False selects the first-generation chain conv -> bn_finalize -> bnq_apply / bn_backward_* (kept as the cross-check).
         self.fused_pw = True
+        self.chain_bwd = True       # expand convs: BN-backward apply + dgrad + wgrad in one kernel (csrc/pw_chain.cu)
 
     def invalidate(self):
         self._built = False
@@ -504,9 +505,14 @@ class QATEngine:
         xin, acc, out, was_training, M = saved[ly.name]
         mod, dev = ly.mod, self.dev
         # pointwise layers get dz as two bf16 planes (the operand format of the tensor-core dgrad/wgrad);
-        # depthwise / stem consumers read fp32
+        # depthwise / stem consumers read fp32.  Expand convs (small K, wide cout) on the fused path never materialise dz:
+        # the chained kernel keeps it in shared memory between the BatchNorm-backward epilogue and the dgrad / wgrad MMAs.
         tc_fmt = ly.kind == "pw"
-        if tc_fmt:
+        chain = (tc_fmt and acc is None and dx is not None and self.chain_bwd
+                 and L.load().frost_pw_chain_supported(ly.cin, ly.cout) != 0)
+        if chain:
+            dz = dz_lo = None
+        elif tc_fmt:
             dz = torch.empty((M, ly.cout), dtype=torch.bfloat16, device=dev)
             dz_lo = torch.empty((M, ly.cout), dtype=torch.bfloat16, device=dev)
         else:
@@ -521,7 +527,7 @@ class QATEngine:
         a.x_scale, a.w_scale = xin.scale.data_ptr(), mod.weight_fake_quant.scale.data_ptr()
         a.out_scale, a.out_zp = out.scale.data_ptr(), out.zp.data_ptr()
         a.eps = mod.bn.eps
-        a.sums, a.coef, a.dz = ly.sums.data_ptr(), ly.coef.data_ptr(), dz.data_ptr()
+        a.sums, a.coef, a.dz = ly.sums.data_ptr(), ly.coef.data_ptr(), L.ptr(dz)
         a.dz_lo, a.dz_format = L.ptr(dz_lo), 1 if tc_fmt else 0
         a.dgamma_bn, a.dsf_bn = ly.dgamma_bn.data_ptr(), ly.dsf_bn.data_ptr()
         a.dbeta = gbase + 4 * self.param_off[id(mod.bn.bias)]
@@ -531,6 +537,12 @@ class QATEngine:
             f = L.PwFusedBwdArgs()
             f.op, f.bn = self._pw_operands(ly, xin, M), a
             L.call("frost_pw_fused_bwd_reduce", C.byref(f), st)
+            if chain:
+                ch = L.PwChainArgs()
+                ch.op, ch.bn = f.op, a
+                ch.wt_bf16, ch.dx, ch.accumulate, ch.dwq = ly.wt_bf16.data_ptr(), dx.data_ptr(), 1 if accumulate else 0, ly.dwq.data_ptr()
+                L.call("frost_pw_chain_backward", C.byref(ch), st)
+                return
             L.call("frost_pw_fused_bwd_apply", C.byref(f), st)
         else:
             L.call("frost_bn_backward_reduce", C.byref(a), st)

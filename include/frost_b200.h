@@ -282,6 +282,21 @@ typedef struct {
   FrostPwOperands op;
   FrostBnBackwardArgs bn;      /* acc is ignored (recomputed); apply: dz / dz_lo planes with dz_format 1    */
 } FrostPwFusedBwdArgs;
+/* The whole backward of an expand conv (small K, wide cout) in one kernel (pw_chain.cu): BatchNorm-backward apply + STE /
+ * ReLU mask + dgrad + wgrad; dz stays in shared memory as the tensor-core operand.  Run frost_pw_fused_bwd_reduce first.
+ *   dx[M][K]   (+)= s_w * sum_co dz[m][co] * (q_w[co][k] - zp_w)
+ *   dwq[cout][K] =  s_a * sum_m  dz[m][co] * (q_a[m][k]  - zp_a)          (zeroed by the callee)
+ * frost_pw_chain_supported(K, cout) != 0 tells which layers qualify (K <= 64, cout tiles wider than 64 channels). */
+typedef struct {
+  FrostPwOperands op;
+  FrostBnBackwardArgs bn;      /* acc, dz, dz_lo are ignored                                                 */
+  const void* wt_bf16;         /* FrostWeightDesc.wt_bf16 [K][cout]                                          */
+  float* dx;                   /* [M][K] fp32                                                                */
+  int32_t accumulate;          /* dx += instead of dx =                                                      */
+  float* dwq;                  /* [cout][K] fp32                                                             */
+} FrostPwChainArgs;
+int frost_pw_chain_supported(int K, int cout);
+int frost_pw_chain_backward(const FrostPwChainArgs* a, void* stream);
 int frost_pw_fused_forward(const FrostPwFusedFwdArgs* a, void* stream);
 int frost_pw_fused_bwd_reduce(const FrostPwFusedBwdArgs* a, void* stream);
 int frost_pw_fused_bwd_apply(const FrostPwFusedBwdArgs* a, void* stream);

@@ -240,3 +240,82 @@ def test_engine_fused_and_first_generation_paths_agree():
     num = sum(float((a - b).double().pow(2).sum()) for a, b in zip(ga, gb))
     den = sum(float(b.double().pow(2).sum()) for b in gb)
     assert (num / den) ** 0.5 < 1e-4          # S1 / S2 are summed in a different order (fp32 partials of 32 vs 64 terms)
+
+
+# ------------------------------------------------------------------------------------------ chained backward
+CHAIN_SHAPES = [(3000, 16, 96, 0), (5000, 24, 72, 0), (4100, 24, 144, 0), (2000, 56, 168, -128), (1500, 56, 336, 0),
+                (130, 64, 128, 127), (200704, 56, 336, 0), (802816, 24, 144, 0)]
+
+
+def _chain_case(M, K, cout, zpw, accumulate, frozen=False):
+    assert L().load().frost_pw_chain_supported(K, cout) == 1
+    ly = Layer(K, cout, zpw, True, M + K)
+    ldx = _r16(K)
+    gd = torch.Generator(device=DEV).manual_seed(M + cout)
+    x_zp = torch.tensor([7], dtype=torch.int32, device=DEV)
+    x = torch.randint(0, 256, (M, ldx), generator=gd, dtype=torch.uint8, device=DEV)
+    f = L().PwFusedFwdArgs()
+    f.op, f.bn = ly.operands(x, M, ldx, x_zp), ly.fin_args(M, not frozen, True)
+    bar = torch.zeros(1, dtype=torch.int32, device=DEV)
+    q = torch.empty(M, _r16(cout), dtype=torch.uint8, device=DEV)
+    f.grid_barrier, f.q, f.ldq = bar.data_ptr(), q.data_ptr(), _r16(cout)
+    L().call("frost_pw_fused_forward", C.byref(f), stream())
+    dy = torch.randn(M, cout, generator=gd, device=DEV)
+    hi, lo = (torch.empty(M, cout, dtype=torch.bfloat16, device=DEV) for _ in range(2))
+    fb = L().PwFusedBwdArgs()
+    fb.op, fb.bn = ly.operands(x, M, ldx, x_zp), ly.bwd_args(M, dy, None, hi, lo, frozen)
+    L().call("frost_pw_fused_bwd_reduce", C.byref(fb), stream())
+    # ---- unchained: apply -> planes -> tensor-core dgrad / wgrad
+    L().call("frost_pw_fused_bwd_apply", C.byref(fb), stream())
+    wt = (ly.wq.float() - zpw).t().contiguous().to(torch.bfloat16)
+    base = torch.randn(M, K, generator=gd, device=DEV) if accumulate else None
+    dx_a = base.clone() if accumulate else torch.empty(M, K, device=DEV)
+    L().call("frost_pw_dgrad_tc", hi.data_ptr(), lo.data_ptr(), wt.data_ptr(), ly.w_scale.data_ptr(), M, K, cout, dx_a.data_ptr(),
+             int(accumulate), stream())
+    dwq_a = torch.empty(cout, K, device=DEV)
+    L().call("frost_pw_wgrad_tc", hi.data_ptr(), lo.data_ptr(), x.data_ptr(), ldx, ly.x_scale.data_ptr(), x_zp.data_ptr(), M, K, cout,
+             dwq_a.data_ptr(), stream())
+    grads_a = [t.clone() for t in (ly.dgb, ly.dbeta, ly.dsf)]
+    for t in (ly.dgb, ly.dbeta, ly.dsf):
+        t.zero_()
+    # ---- chained
+    ch = L().PwChainArgs()
+    ch.op, ch.bn = ly.operands(x, M, ldx, x_zp), ly.bwd_args(M, dy, None, hi, lo, frozen)
+    dx_b = base.clone() if accumulate else torch.full((M, K), float("nan"), device=DEV)
+    dwq_b = torch.full((cout, K), float("nan"), device=DEV)
+    ch.wt_bf16, ch.dx, ch.accumulate, ch.dwq = wt.data_ptr(), dx_b.data_ptr(), int(accumulate), dwq_b.data_ptr()
+    L().call("frost_pw_chain_backward", C.byref(ch), stream())
+    torch.cuda.synchronize()
+    sx = float(dx_a.abs().max())
+    assert float((dx_b - dx_a).abs().max()) <= 2e-4 * sx, ("dx", float((dx_b - dx_a).abs().max()), sx)
+    sw = float(dwq_a.abs().max())
+    assert float((dwq_b - dwq_a).abs().max()) <= 2e-4 * sw, ("dwq", float((dwq_b - dwq_a).abs().max()), sw)
+    for a, b in zip(grads_a, (ly.dgb, ly.dbeta, ly.dsf)):
+        assert torch.equal(a, b)
+    # and against float64 on the planes' own values: dz = hi + lo
+    dz = hi.double() + lo.double()
+    ref_dx = dz @ (ly.wq.double() - zpw) * float(ly.w_scale)
+    if accumulate:
+        ref_dx += base.double()
+    assert float((dx_b.double() - ref_dx).abs().max()) <= 1e-4 * float(ref_dx.abs().max())
+    ref_dw = dz.t() @ (x[:, :K].double() - 7.0) * float(ly.x_scale)
+    assert float((dwq_b.double() - ref_dw).abs().max()) <= 2e-4 * float(ref_dw.abs().max())
+
+
+@pytest.mark.parametrize("M,K,cout,zpw", CHAIN_SHAPES)
+def test_chained_backward_matches_unchained(M, K, cout, zpw):
+    _chain_case(M, K, cout, zpw, accumulate=(M % 2 == 0))
+
+
+def test_chained_backward_frozen_bn():
+    _chain_case(3000, 24, 144, 0, accumulate=False, frozen=True)
+
+
+def test_chained_backward_at_headline_size():
+    _chain_case(3211264, 16, 96, 0, accumulate=True)
+
+
+def test_chain_supported_rule():
+    f = L().load().frost_pw_chain_supported
+    assert [f(16, 96), f(24, 72), f(24, 144), f(56, 168), f(56, 336)] == [1, 1, 1, 1, 1]     # FrostNet-L's expand convs up to 28x28
+    assert [f(104, 312), f(96, 24), f(32, 16), f(16, 40), f(56, 512)] == [0, 0, 0, 0, 0]
