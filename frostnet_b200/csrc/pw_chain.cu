@@ -30,7 +30,7 @@ constexpr int CH_THREADS = (CH_EPI_WARPS + 2) * 32;    // warps 0-15 epilogue, 1
 constexpr int CH_MAX_CT = 3;
 constexpr int CH_TILE = 16384;             // 128 rows x 128 B
 constexpr int CH_PLANE = 2 * CH_TILE;      // one dz plane: [128 ch][128 px] bf16 = two 64-pixel blocks
-constexpr int CH_TAIL = 4096;
+constexpr int CH_TAIL = 1024;
 constexpr int CH_COL_DX = 256, CH_COL_G = 320;   // TMEM columns: I buffers at 0 / 128, dx at 256, dW of channel tile ct at 320 + 64*ct
 
 struct PwChainParams {
