@@ -299,7 +299,8 @@ def _chain_case(M, K, cout, zpw, accumulate, frozen=False):
         ref_dx += base.double()
     assert float((dx_b.double() - ref_dx).abs().max()) <= 1e-4 * float(ref_dx.abs().max())
     ref_dw = dz.t() @ (x[:, :K].double() - 7.0) * float(ly.x_scale)
-    assert float((dwq_b.double() - ref_dw).abs().max()) <= 2e-4 * float(ref_dw.abs().max())
+    # fp32 accumulation in TMEM over up to 3.2 M pixels (both the chained and the unchained kernel): 5e-4 of the largest entry
+    assert float((dwq_b.double() - ref_dw).abs().max()) <= 5e-4 * float(ref_dw.abs().max())
 
 
 @pytest.mark.parametrize("M,K,cout,zpw", CHAIN_SHAPES)

@@ -47,9 +47,30 @@ def main():
             L.call(name, C.byref(fb), st)
         return run
 
-    for name, fn, byt in (("fused_forward", fwd, 2 * M * K + M * cout),
-                          ("fused_bwd_reduce", bwd("frost_pw_fused_bwd_reduce"), M * K + 4 * M * cout),
-                          ("fused_bwd_apply", bwd("frost_pw_fused_bwd_apply"), M * K + 8 * M * cout)):
+    wt = ly.wq.float().t().contiguous().to(torch.bfloat16)
+    dx = torch.empty(M, K, device=dev)
+    dwq = torch.empty(cout, K, device=dev)
+
+    def chain():
+        ch = L.PwChainArgs()
+        ch.op, ch.bn = ly.operands(x, M, ldx, x_zp), ly.bwd_args(M, dy, None, hi, lo, False)
+        ch.wt_bf16, ch.dx, ch.accumulate, ch.dwq = wt.data_ptr(), dx.data_ptr(), 0, dwq.data_ptr()
+        L.call("frost_pw_chain_backward", C.byref(ch), st)
+
+    def dgrad():
+        L.call("frost_pw_dgrad_tc", hi.data_ptr(), lo.data_ptr(), wt.data_ptr(), ly.w_scale.data_ptr(), M, K, cout, dx.data_ptr(), 0, st)
+
+    def wgrad():
+        L.call("frost_pw_wgrad_tc", hi.data_ptr(), lo.data_ptr(), x.data_ptr(), ldx, ly.x_scale.data_ptr(), x_zp.data_ptr(), M, K, cout,
+               dwq.data_ptr(), st)
+
+    cases = [("fused_forward", fwd, 2 * M * K + M * cout),
+             ("fused_bwd_reduce", bwd("frost_pw_fused_bwd_reduce"), M * K + 4 * M * cout),
+             ("fused_bwd_apply", bwd("frost_pw_fused_bwd_apply"), M * K + 8 * M * cout),
+             ("dgrad_tc", dgrad, 4 * M * cout + 4 * M * K), ("wgrad_tc", wgrad, 4 * M * cout + M * K)]
+    if L.load().frost_pw_chain_supported(K, cout):
+        cases.append(("chain_backward", chain, M * K + 4 * M * cout + 4 * M * K))
+    for name, fn, byt in cases:
         fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
