@@ -31,13 +31,15 @@ constexpr int CH_MAX_CT = 3;
 constexpr int CH_TILE = 16384;             // 128 rows x 128 B
 constexpr int CH_PLANE = 2 * CH_TILE;      // one dz plane: [128 ch][128 px] bf16 = two 64-pixel blocks
 constexpr int CH_TAIL = 1024;
-constexpr int CH_COL_DX = 256, CH_COL_G = 320;   // TMEM columns: I buffers at 0 / 128, dx at 256, dW of channel tile ct at 320 + 64*ct
+// TMEM columns: I buffers at 0 / 128; dx buffer(s) of 64 columns from 256; dW of channel tile ct behind them, 64 columns each.
+// Two dx buffers (n_ct <= 2) let the dx epilogue of tile t run after the dz production of tile t+1.
+constexpr int CH_COL_DX = 256;
 
 struct PwChainParams {
   const uint8_t* x;
   int64_t M;
   int K, K16, ldx;
-  int cout, bn, n_ct, depth;
+  int cout, bn, n_ct, depth, dx_bufs;
   const int32_t* x_zp;
   const int32_t* w_zp;
   const int32_t* wsum;
@@ -86,10 +88,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) pw_chain_bwd_kernel(const __gri
   uint64_t* tempty = bars + 11;      // 2
   uint64_t* dzfull = bars + 13;      // 2
   uint64_t* dzempty = bars + 15;     // 2
-  uint64_t* dxfull = bars + 17;      // 1
-  uint64_t* dxempty = bars + 18;     // 1
-  uint64_t* gfull = bars + 19;       // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* dxfull = bars + 17;      // 2
+  uint64_t* dxempty = bars + 19;     // 2
+  uint64_t* gfull = bars + 21;       // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  const int dx_bufs = p.dx_bufs;
+  const int col_g = CH_COL_DX + 64 * dx_bufs;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_ptiles = (p.M + CH_NP - 1) / CH_NP;
@@ -104,8 +108,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) pw_chain_bwd_kernel(const __gri
       mbar_init(&tfull[i], 1); mbar_init(&tempty[i], CH_EPI_WARPS);
       mbar_init(&dzfull[i], CH_EPI_WARPS); mbar_init(&dzempty[i], 1);
     }
-    mbar_init(dxfull, 1);
-    mbar_init(dxempty, CH_EPI_WARPS);
+    for (int i = 0; i < 2; ++i) { mbar_init(&dxfull[i], 1); mbar_init(&dxempty[i], CH_EPI_WARPS); }
     mbar_init(gfull, 1);
     mbar_fence_init();
   }
@@ -154,9 +157,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) pw_chain_bwd_kernel(const __gri
       const int t = u / n_ct, ct = u - t * n_ct;
       const int slot = u % depth;
       mbar_wait(&dzfull[slot], (u / depth) & 1);
+      const int db = t % dx_bufs;                        // dx buffer of this tile
       if (ct == 0) {
         mbar_wait(&xqfull[t & 1], (t >> 1) & 1);
-        mbar_wait_sleep(dxempty, (t & 1) ^ 1);
+        mbar_wait_sleep(&dxempty[db], ((t / dx_bufs) & 1) ^ 1);
       }
       tc_fence_after();
       if (lane == 0) {
@@ -167,18 +171,18 @@ __global__ void __launch_bounds__(CH_THREADS, 1) pw_chain_bwd_kernel(const __gri
           const uint64_t a_mn = umma_desc_mn_sw128_lbo(dz, CH_TILE);
           for (int j = 0; j < nkc; ++j) {
             const uint64_t bdesc = umma_desc_sw128(smem_u32(s_wt + (ct * 2 + (j >> 2)) * wt_blk)) + (uint64_t)(2 * (j & 3));
-            umma_f16(tmem_base + CH_COL_DX, a_mn + (uint64_t)((2048 * j) >> 4), bdesc, idesc2, (ct | pl | j) != 0 ? 1u : 0u);
+            umma_f16(tmem_base + CH_COL_DX + 64 * db, a_mn + (uint64_t)((2048 * j) >> 4), bdesc, idesc2, (ct | pl | j) != 0 ? 1u : 0u);
           }
           // dW[ch][k] += dz^T[ch][px] * X'[px][k]
           const uint64_t b_mn = umma_desc_mn_sw128_lbo(smem_u32(s_xq + (t & 1) * CH_TILE), CH_TILE);
           for (int j = 0; j < 8; ++j) {
             const uint64_t adesc = umma_desc_sw128(dz + (j >> 2) * CH_TILE) + (uint64_t)(2 * (j & 3));
-            umma_f16(tmem_base + CH_COL_G + 64 * ct, adesc, b_mn + (uint64_t)((2048 * j) >> 4), idesc3, (t | pl | j) != 0 ? 1u : 0u);
+            umma_f16(tmem_base + col_g + 64 * ct, adesc, b_mn + (uint64_t)((2048 * j) >> 4), idesc3, (t | pl | j) != 0 ? 1u : 0u);
           }
         }
         umma_commit(&dzempty[slot]);
         if (ct == n_ct - 1) {
-          umma_commit(dxfull);
+          umma_commit(&dxfull[db]);
           umma_commit(&xqempty[t & 1]);
           umma_commit(&xempty[t & 1]);       // MMA1 of every channel tile has completed, and X' was converted (xqfull)
         }
@@ -254,6 +258,40 @@ __global__ void __launch_bounds__(CH_THREADS, 1) pw_chain_bwd_kernel(const __gri
     const float zp_magic = 8388608.0f + (float)zp_a;          // byte -> float without I2F (0x4B0000bb = 2^23 + bb)
     const int64_t row_b = (int64_t)cout * 4;
     const int col0 = grp * 32;                                // this warp's 32 pixel columns of the tile: two chunks of 16
+
+    // dx of pixel tile t: pixel-per-thread, group g takes input channels [16g, 16g+16)
+    auto dx_epilogue = [&](int t) {
+      const int64_t pt = blockIdx.x + (int64_t)t * gridDim.x;
+      const int px_valid = (int)min((int64_t)CH_NP, p.M - pt * CH_NP);
+      const int db = t % dx_bufs;
+      mbar_wait(&dxfull[db], (t / dx_bufs) & 1);
+      tc_fence_after();
+      if (grp * 16 < K16) {
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_base + CH_COL_DX + 64 * db + grp * 16 + ((uint32_t)(quarter * 32) << 16), v);
+        const int pix = quarter * 32 + lane;
+        if (pix < px_valid) {
+          float* dst = p.dx + (pt * CH_NP + pix) * (int64_t)p.K + grp * 16;
+          const int nk = min(16, p.K - grp * 16);               // K % 8 == 0: 8 or 16
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            if (j4 * 4 < nk) {
+              float4 val = make_float4(__uint_as_float(v[4 * j4]) * s_w, __uint_as_float(v[4 * j4 + 1]) * s_w,
+                                       __uint_as_float(v[4 * j4 + 2]) * s_w, __uint_as_float(v[4 * j4 + 3]) * s_w);
+              float4* d4 = reinterpret_cast<float4*>(dst) + j4;
+              if (p.accumulate) {
+                const float4 old = ld_cg(d4);
+                val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+              }
+              *d4 = val;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dxempty[db]);
+    };
 
     for (int t = 0; t < nt; ++t) {
       const int64_t pt = blockIdx.x + (int64_t)t * gridDim.x;
@@ -345,35 +383,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) pw_chain_bwd_kernel(const __gri
           }
         }
       }
-      // ---- (c) dx of this pixel tile: pixel-per-thread, group g takes input channels [16g, 16g+16)
-      mbar_wait(dxfull, t & 1);
-      tc_fence_after();
-      if (grp * 16 < K16) {
-        uint32_t v[16];
-        tmem_ld_32x16(tmem_base + CH_COL_DX + grp * 16 + ((uint32_t)(quarter * 32) << 16), v);
-        const int pix = quarter * 32 + lane;
-        if (pix < px_valid) {
-          float* dst = p.dx + (pt * CH_NP + pix) * (int64_t)p.K + grp * 16;
-          const int nk = min(16, p.K - grp * 16);               // K % 8 == 0: 8 or 16
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            if (j4 * 4 < nk) {
-              float4 val = make_float4(__uint_as_float(v[4 * j4]) * s_w, __uint_as_float(v[4 * j4 + 1]) * s_w,
-                                       __uint_as_float(v[4 * j4 + 2]) * s_w, __uint_as_float(v[4 * j4 + 3]) * s_w);
-              float4* d4 = reinterpret_cast<float4*>(dst) + j4;
-              if (p.accumulate) {
-                const float4 old = ld_cg(d4);
-                val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
-              }
-              *d4 = val;
-            }
-          }
-        }
+      // ---- (c) dx of the PREVIOUS tile (two dx buffers): its dgrad MMAs had this tile's whole dz production to finish
+      if (dx_bufs == 2) {
+        if (t > 0) dx_epilogue(t - 1);
+      } else {
+        dx_epilogue(t);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(dxempty);
     }
+    if (dx_bufs == 2 && nt > 0) dx_epilogue(nt - 1);
     // ---- weight gradient: dW[ch][k] of every channel tile, accumulated over all of this CTA's pixels
     mbar_wait(gfull, 0);
     tc_fence_after();
@@ -381,7 +398,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) pw_chain_bwd_kernel(const __gri
     for (int ct = 0; ct < CH_MAX_CT; ++ct) {
       if (ct < n_ct && grp * 16 < K16) {
         uint32_t v[16];
-        tmem_ld_32x16(tmem_base + CH_COL_G + 64 * ct + grp * 16 + ((uint32_t)(quarter * 32) << 16), v);
+        tmem_ld_32x16(tmem_base + col_g + 64 * ct + grp * 16 + ((uint32_t)(quarter * 32) << 16), v);
         if (k_act[ct] && nt > 0) {
           float* dst = p.dwq + (int64_t)(ct * p.bn + c_local) * p.K + grp * 16;
           const int nk = min(16, p.K - grp * 16);
@@ -451,6 +468,7 @@ extern "C" int frost_pw_chain_backward(const FrostPwChainArgs* a, void* stream) 
   p.dwq = a->dwq;
   const size_t fixed = 1024 + (size_t)p.n_ct * (CH_TILE + 2 * p.K16 * 128) + 4 * CH_TILE + CH_TAIL;
   p.depth = (fixed + 2 * 2 * CH_PLANE <= 227 * 1024) ? 2 : 1;
+  p.dx_bufs = p.n_ct <= 2 ? 2 : 1;                 // TMEM: 256 (I) + 64 * dx_bufs + 64 * n_ct <= 512
   const size_t smem = fixed + (size_t)p.depth * 2 * CH_PLANE;
   FROST_REQUIRE(smem <= 227 * 1024, "%s: shared memory budget exceeded (%zu bytes)", who, smem);
   FROST_REQUIRE(a->dx, "%s: dx is required (layers without an input gradient use the unfused path)", who);
