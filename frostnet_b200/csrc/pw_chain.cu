@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) pw_chain_bwd_kernel(const __gri
       }
       for (int t = 0; t < nt; ++t) {
         const int s = t & 1;
-        mbar_wait_sleep(&xempty[s], ((t >> 1) & 1) ^ 1);
+        mbar_wait_parked(&xempty[s], ((t >> 1) & 1) ^ 1);
         mbar_expect_tx(&xfull[s], CH_TILE);
         tma_load_2d(&tm_x, &xfull[s], smem_u32(s_x + s * CH_TILE), 0, (int)((blockIdx.x + (int64_t)t * gridDim.x) * CH_NP));
       }
@@ -149,18 +149,18 @@ __global__ void __launch_bounds__(CH_THREADS, 1) pw_chain_bwd_kernel(const __gri
     const uint32_t idesc2 = umma_idesc(1 /*F32*/, 1, 1, 128, K16) | (1u << 15);             // dx: A (dz) MN-major, B (W'^T) K-major
     const uint32_t idesc3 = umma_idesc(1 /*F32*/, 1, 1, 128, K16) | (1u << 16);             // dW: A (dz) K-major, B (X') MN-major
     const int nk1 = (p.K + 31) / 32;
-    mbar_wait_sleep(wfull, 0);
+    mbar_wait_parked(wfull, 0);
     tc_fence_after();
     // the dz-consuming MMAs of unit u-1 are issued after MMA1 of unit u: the tensor pipe always has the next accumulator
     // in flight while the epilogue turns the previous one into dz
     auto issue_dz_mmas = [&](int u) {
       const int t = u / n_ct, ct = u - t * n_ct;
       const int slot = u % depth;
-      mbar_wait(&dzfull[slot], (u / depth) & 1);
+      mbar_wait_parked(&dzfull[slot], (u / depth) & 1);
       const int db = t % dx_bufs;                        // dx buffer of this tile
       if (ct == 0) {
-        mbar_wait(&xqfull[t & 1], (t >> 1) & 1);
-        mbar_wait_sleep(&dxempty[db], ((t / dx_bufs) & 1) ^ 1);
+        mbar_wait_parked(&xqfull[t & 1], (t >> 1) & 1);
+        mbar_wait_parked(&dxempty[db], ((t / dx_bufs) & 1) ^ 1);
       }
       tc_fence_after();
       if (lane == 0) {
@@ -193,9 +193,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) pw_chain_bwd_kernel(const __gri
       const int t = u / n_ct, ct = u - t * n_ct;
       const int ib = u & 1;
       if (ct == 0) {
-        mbar_wait(&xfull[t & 1], (t >> 1) & 1);
+        mbar_wait_parked(&xfull[t & 1], (t >> 1) & 1);
       }
-      mbar_wait_sleep(&tempty[ib], ((u >> 1) & 1) ^ 1);
+      mbar_wait_parked(&tempty[ib], ((u >> 1) & 1) ^ 1);
       tc_fence_after();
       if (lane == 0) {
         const uint64_t adesc = umma_desc_sw128(smem_u32(s_wi8 + ct * CH_TILE));
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) pw_chain_bwd_kernel(const __gri
       const int64_t pt = blockIdx.x + (int64_t)t * gridDim.x;
       const int px_valid = (int)min((int64_t)CH_NP, p.M - pt * CH_NP);
       const int db = t % dx_bufs;
-      mbar_wait(&dxfull[db], (t / dx_bufs) & 1);
+      mbar_wait_parked(&dxfull[db], (t / dx_bufs) & 1);
       tc_fence_after();
       if (grp * 16 < K16) {
         uint32_t v[16];
@@ -298,8 +298,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) pw_chain_bwd_kernel(const __gri
       const int px_valid = (int)min((int64_t)CH_NP, p.M - pt * CH_NP);
       const int s = t & 1;
       // ---- (a) X' = (x - zp_a) as bf16, [px][k] (MN-major B operand of the weight-gradient MMA)
-      mbar_wait(&xfull[s], (t >> 1) & 1);
-      mbar_wait_sleep(&xqempty[s], ((t >> 1) & 1) ^ 1);
+      mbar_wait_parked(&xfull[s], (t >> 1) & 1);
+      mbar_wait_parked(&xqempty[s], ((t >> 1) & 1) ^ 1);
       {
         const int px = tid >> 2, kg = tid & 3;
         if (kg * 16 < K16) {
@@ -332,14 +332,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) pw_chain_bwd_kernel(const __gri
             const char* q = reinterpret_cast<const char*>(b.dy + (pt * CH_NP + col0) * (int64_t)cout + c);
             if (col0 + 32 <= px_valid) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) dy[j] = ld_cg(reinterpret_cast<const float*>(q + j * row_b));
+              for (int j = 0; j < 32; ++j) { dy[j] = ld_cg_chain(q); q += row_b; }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) dy[j] = (col0 + j < px_valid) ? ld_cg(reinterpret_cast<const float*>(q + j * row_b)) : 0.0f;
+              for (int j = 0; j < 32; ++j) { dy[j] = (col0 + j < px_valid) ? ld_cg_chain(q) : 0.0f; q += row_b; }
             }
           }
-          mbar_wait(&tfull[ib], (u >> 1) & 1);
-          mbar_wait(&dzempty[slot], ((u / depth) & 1) ^ 1);
+          mbar_wait_parked(&tfull[ib], (u >> 1) & 1);
+          mbar_wait_parked(&dzempty[slot], ((u / depth) & 1) ^ 1);
           tc_fence_after();
           uint8_t* plane_hi = s_dz + (slot * 2 + 0) * CH_PLANE;
           uint8_t* plane_lo = s_dz + (slot * 2 + 1) * CH_PLANE;
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) pw_chain_bwd_kernel(const __gri
     }
     if (dx_bufs == 2 && nt > 0) dx_epilogue(nt - 1);
     // ---- weight gradient: dW[ch][k] of every channel tile, accumulated over all of this CTA's pixels
-    mbar_wait(gfull, 0);
+    mbar_wait_parked(gfull, 0);
     tc_fence_after();
 #pragma unroll
     for (int ct = 0; ct < CH_MAX_CT; ++ct) {

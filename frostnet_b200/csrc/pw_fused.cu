@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x) {
           for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
             const int s = it % S;
-            mbar_wait_sleep(&empty_bar[s], ((it / S) & 1) ^ 1);
+            mbar_wait_parked(&empty_bar[s], ((it / S) & 1) ^ 1);
             uint8_t* st = stages + s * stage_bytes;
             mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
             tma_load_2d(&tm_x, &full_bar[s], smem_u32(st), kb * PF_BK, (int)(pt * PF_NPX));
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
     const uint32_t idesc_cpt = umma_idesc(2 /*S32*/, w_fmt, 0, PF_CH, PF_NPX);   // A = W (128 rows), B = X (256 pixels)
     const uint32_t idesc_ppt = umma_idesc(2 /*S32*/, 0, w_fmt, 128, n_mma);      // A = X (128 pixels), B = W (n_mma rows)
     if (resident) {
-      mbar_wait_sleep(wfull_bar, 0);
+      mbar_wait_parked(wfull_bar, 0);
       tc_fence_after();
     }
     uint32_t it = 0, tile_i = 0;
@@ -182,13 +182,13 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
       const bool cpt = phase_is_cpt(ph);
       for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x, ++tile_i) {
         const uint32_t acc = tile_i & 1;
-        mbar_wait_sleep(&tempty_bar[acc], ((tile_i >> 1) & 1) ^ 1);
+        mbar_wait_parked(&tempty_bar[acc], ((tile_i >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * PF_NPX;
         const bool second_half = p.M - pt * PF_NPX > 128;
         for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
           const int s = it % S;
-          mbar_wait(&full_bar[s], (it / S) & 1);
+          mbar_wait_parked(&full_bar[s], (it / S) & 1);
           tc_fence_after();
           if (lane == 0) {
             uint8_t* st = stages + s * stage_bytes;
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x, ++tile_i) {
           const uint32_t acc = tile_i & 1;
           const int px_valid = (int)min((int64_t)PF_NPX, p.M - pt * PF_NPX);
-          mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1);
+          mbar_wait_parked(&tfull_bar[acc], (tile_i >> 1) & 1);
           tc_fence_after();
           if (warp_active) {
 #pragma unroll 1
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         const int64_t pix = pt * PF_NPX + ppt_pix;
         const bool pvalid = pix < p.M;
         const bool wvalid = pt * PF_NPX + ppt_h * 128 + quarter * 32 < p.M;      // warp-uniform
-        mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1);
+        mbar_wait_parked(&tfull_bar[acc], (tile_i >> 1) & 1);
         tc_fence_after();
         if (wvalid) {
           uint8_t* qrow = p.q + pix * (int64_t)p.ldq + c_tile0;
@@ -474,13 +474,14 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
       const int64_t row_b = (int64_t)cout * 4;                 // bytes between consecutive pixels of dy
       // 16 pixels of my channel, starting at pixel column `col` of the tile whose first element is `tile_dy`
       auto load16 = [&](float (&d)[16], const float* tile_dy, int col, int px_valid) {
+        // ONE running 64-bit pointer (2 instructions per load; base + running offset cost 4 - these loops are issue-bound)
         const char* q = reinterpret_cast<const char*>(tile_dy) + (int64_t)col * row_b;
         if (col + 16 <= px_valid) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) d[j] = ld_cg(reinterpret_cast<const float*>(q + j * row_b));
+          for (int j = 0; j < 16; ++j) { d[j] = ld_cg_chain(q); q += row_b; }
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) d[j] = (col + j < px_valid) ? ld_cg(reinterpret_cast<const float*>(q + j * row_b)) : 0.0f;
+          for (int j = 0; j < 16; ++j) { d[j] = (col + j < px_valid) ? ld_cg_chain(q) : 0.0f; q += row_b; }
         }
       };
       float p1 = 0.f, p2 = 0.f;
@@ -526,7 +527,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         // accumulator is waited for
         float dA[16], dB[16];
         if (active && col_begin < px_valid) load16(dA, tile_dy, col_begin, px_valid);
-        mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1);
+        mbar_wait_parked(&tfull_bar[acc], (tile_i >> 1) & 1);
         tc_fence_after();
         if (warp_active) {
           p1 = 0.f;

@@ -62,6 +62,13 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
 }
 
 
+// L2-only load through an explicit address register: keeps a pointer chain (q += stride) as ONE 64-bit add per load
+__device__ __forceinline__ float ld_cg_chain(const char* q) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(q));
+  return v;
+}
+
 // ================================================================= host side: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

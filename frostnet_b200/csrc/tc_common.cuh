@@ -34,6 +34,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
   __trap();
 }
+// The same with a suspend-time hint: the hardware parks the thread inside try_wait (up to ~`hint_ns`) instead of
+// returning to a spin loop whose BRA / SYNCS instructions compete with the working warps for issue slots.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 4000) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t it = 0; it < (1u << 22); ++it) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(hint_ns)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
 
 // ---------------------------------------------------------------- cp.async (LDGSTS) with zero fill
 template <int BYTES>
