@@ -106,6 +106,7 @@ _SIGNATURES = {
     "frost_fq_forward": [c_p, i64, FQ, i32, i32, i32, i32, f32, c_p, c_p, c_p, c_p, c_p],
     "frost_fq_backward": [c_p, c_p, i64, c_p, c_p],
     "frost_input_quant": [c_p, i32, i32, i32, i32, FQ, i32, f32, c_p, c_p, c_p, c_p],
+    "frost_input_quant_im2col": [c_p, i32, i32, i32, i32, i32, i32, i32, FQ, i32, f32, c_p, i32, c_p, c_p, c_p],
     "frost_weight_prep_multi": [c_p, i32, c_p, i32, c_p, c_p],
     "frost_weight_backward_multi": [c_p, i32, c_p, i32, c_p],
     "frost_pw_conv_forward": [c_p, c_p, c_p, c_p, c_p, i64, i32, i32, c_p, c_p, c_p],

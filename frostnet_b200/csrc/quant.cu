@@ -106,6 +106,47 @@ __global__ void __launch_bounds__(256) input_quant_apply_rgb4_kernel(const float
   }
 }
 
+// QuantStub fused with the stem's im2col: one row of k*k*C quantize indices per OUTPUT pixel of the dense kxk stem conv, in
+// (kh, kw, c) order, padded to `ld` bytes - the activation operand of the fused 1x1 tensor-core kernels (the stem becomes a
+// K = ld GEMM).  Taps that fall outside the image hold the zero point (the reference pads the DEQUANTISED tensor with 0.0).
+__global__ void __launch_bounds__(256) input_quant_im2col_kernel(const float* x, int N, int C, int H, int W, int k, int stride,
+                                                                 int pad, int Ho, int Wo, const float* scale_p, const int32_t* zp_p,
+                                                                 uint8_t* q, int ld) {
+  const float s = *scale_p, zp = (float)*zp_p;
+  const float inv = __fdiv_rn(1.0f, s);
+  const unsigned zpb = (unsigned)*zp_p & 0xffu;
+  const int64_t total = (int64_t)N * Ho * Wo;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  const int HW = H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    const int ow = (int)(i % Wo);
+    const int64_t t1 = i / Wo;
+    const int oh = (int)(t1 % Ho);
+    const int64_t n = t1 / Ho;
+    const int ih0 = oh * stride - pad, iw0 = ow * stride - pad;
+    unsigned words[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};       // ld <= 32
+    int b = 0;
+    for (int r = 0; r < k; ++r) {
+      const int ih = ih0 + r;
+      for (int sx = 0; sx < k; ++sx) {
+        const int iw = iw0 + sx;
+        const bool ok = (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W;
+        for (int c = 0; c < C; ++c, ++b) {
+          unsigned byte = zpb;
+          if (ok) {
+            const float v = ld_cg(x + (n * C + c) * HW + (int64_t)ih * W + iw);
+            byte = (unsigned)fminf(fmaxf(fq_index(v, inv, zp), 0.0f), 255.0f);
+          }
+          words[b >> 2] |= byte << (8 * (b & 3));
+        }
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(q + i * ld);
+    dst[0] = make_uint4(words[0], words[1], words[2], words[3]);
+    if (ld > 16) dst[1] = make_uint4(words[4], words[5], words[6], words[7]);
+  }
+}
+
 // ---------------------------------------------------------------- weights
 __device__ __forceinline__ int64_t wq_index(const FrostWeightDesc& d, int c, int ci, int y, int x) {
   switch (d.layout) {
@@ -201,10 +242,14 @@ __global__ void __launch_bounds__(kWeightThreads) weight_quant_kernel(const Fros
       const float idx = fq_index(ws, inv, zp);
       const float qc = fminf(fmaxf(idx, -128.0f), 127.0f);
       d.wq[wq_index(d, c, ci, y, x)] = (int8_t)qc;
-      if (d.wq_mma) {   // 1x1 only (r == ci): the tensor-core operand bytes, zero point folded for one-signed weights
+      if (d.wq_mma) {   // the tensor-core operand bytes, zero point folded for one-signed weights.  1x1: column r == ci;
+                        // dense kxk (the stem as an im2col GEMM): column (y, x, ci), the order of frost_input_quant_im2col
         const int zpi = (int)zp;
         const unsigned flip = zpi == 0 ? 0u : (zpi == -128 ? 0x80u : 0x7fu);
-        d.wq_mma[(int64_t)c * d.ldw + r] = (int8_t)(((unsigned)(int)qc ^ flip) & 0xffu);
+        const int col = d.layout == 2 ? (y * d.kw + x) * d.cin_g + ci : r;
+        d.wq_mma[(int64_t)c * d.ldw + col] = (int8_t)(((unsigned)(int)qc ^ flip) & 0xffu);
+        // the GEMM runs over ldw columns: the padding columns count as weights equal to the zero point (value 0)
+        if (d.layout == 2 && r == 0 && zpi != 0) atomicAdd(d.wsum + c, (d.ldw - K) * zpi);
       }
       if (d.wt_bf16) d.wt_bf16[(int64_t)r * d.cout + c] = __bfloat16_as_ushort(__float2bfloat16_rn(qc - zp));  // 1x1: r == ci; exact
       d.wmask[e] = (idx >= -128.0f && idx <= 127.0f) ? 1 : 0;
@@ -247,7 +292,8 @@ __global__ void __launch_bounds__(kWeightThreads) weight_backward_kernel(const F
         const int ci = r / khw, yx = r - ci * khw;
         const int y = yx / d.kw, x = yx - y * d.kw;
         mk[u] = ld_cg(d.wmask + e);
-        dw[u] = ld_cg(d.dwq + wq_index(d, c, ci, y, x));
+        // the im2col stem's weight gradient comes from the tensor-core wgrad as [cout][ldw]
+        dw[u] = ld_cg(d.dwq + ((d.wq_mma && d.layout == 2) ? (int64_t)c * d.ldw + (y * d.kw + x) * d.cin_g + ci : wq_index(d, c, ci, y, x)));
         w[u] = ld_cg(d.weight + e);
       }
     }
@@ -345,6 +391,26 @@ extern "C" int frost_input_quant(const float* x_nchw, int N, int C, int H, int W
     input_quant_apply_kernel<<<grid_for((int64_t)N * H * W, 256), 256, 0, st>>>(x_nchw, N, C, H * W, fq.scale,
                                                                                 fq.zero_point, q_nhwc);
   FROST_LAUNCH_CHECK("input_quant_apply");
+  return FROST_OK;
+}
+
+extern "C" int frost_input_quant_im2col(const float* x_nchw, int N, int C, int H, int W, int k, int stride, int pad, FrostFQ fq,
+                                        int observe, float averaging_const, uint8_t* q, int ld, float* cur_minmax, float* scratch,
+                                        void* stream) {
+  FROST_REQUIRE(x_nchw && q && scratch && N > 0 && C > 0 && H > 0 && W > 0 && k > 0 && stride > 0 && pad >= 0,
+                "frost_input_quant_im2col: bad args");
+  FROST_REQUIRE(k * k * C <= ld && (ld == 16 || ld == 32) && (reinterpret_cast<uintptr_t>(q) & 15) == 0,
+                "frost_input_quant_im2col: k*k*C=%d must fit the row pitch ld=%d (16 or 32), q 16-byte aligned", k * k * C, ld);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = (int64_t)N * C * H * W;
+  if (observe || cur_minmax) {
+    int rc = run_observer(x_nchw, n, fq, 0, 255, 0, averaging_const, cur_minmax, scratch, st, observe != 0);
+    if (rc) return rc;
+  }
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  input_quant_im2col_kernel<<<grid_for((int64_t)N * Ho * Wo, 256, kNumSMs * 8), 256, 0, st>>>(x_nchw, N, C, H, W, k, stride, pad, Ho, Wo,
+                                                                                           fq.scale, fq.zero_point, q, ld);
+  FROST_LAUNCH_CHECK("input_quant_im2col");
   return FROST_OK;
 }
 

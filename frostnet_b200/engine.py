@@ -75,9 +75,15 @@ class _Layer:
             n = self.cout_p * self.cin_g * self.kh * self.kw
         self.wq = torch.zeros(n, dtype=torch.int8, device=dev)
         self.wt_bf16 = torch.zeros(n, dtype=torch.bfloat16, device=dev) if self.kind == "pw" else None
-        # tensor-core operand bytes of the fused 1x1 kernels: rows padded to a multiple of 16 bytes (TMA's stride rule)
-        self.ldw = (self.cin_g + 15) // 16 * 16 if self.kind == "pw" else 0
-        self.wq_mma = torch.zeros(self.cout * self.ldw, dtype=torch.int8, device=dev) if self.kind == "pw" else None
+        # tensor-core operand bytes of the fused 1x1 kernels: rows padded to a multiple of 16 bytes (TMA's stride rule).
+        # The dense kxk stem joins them as an im2col GEMM (K = kh*kw*cin padded to 32) when its patch fits 32 bytes.
+        kk = self.cin_g * self.kh * self.kw
+        self.im2col = self.kind == "stem" and kk <= 32
+        self.k_mma = self.cin_g if self.kind == "pw" else ((kk + 15) // 16 * 16 if self.im2col else 0)
+        self.ldw = (self.k_mma + 15) // 16 * 16
+        self.wq_mma = torch.zeros(self.cout * self.ldw, dtype=torch.int8, device=dev) if self.k_mma else None
+        if self.im2col:
+            n = max(n, self.cout * self.ldw)        # dwq of the im2col path is [cout][ldw]
         self.wmask = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.sf = torch.ones(self.cout, **f32)
         self.rstd = torch.ones(self.cout, **f32)
@@ -146,6 +152,18 @@ class QATEngine:
         don't-care) on the fused path, dense for the first-generation kernels."""
         ld = (Cc + 15) // 16 * 16 if self.fused_pw else Cc
         return torch.empty((M, ld), dtype=torch.uint8, device=self.dev), ld
+
+    @staticmethod
+    def _im2col_from_indices(xq, ly, zp):
+        """[N,H,W,C] uint8 indices -> the rows frost_input_quant_im2col produces (torch ops; parity tests only)."""
+        N, H, W, Cc = xq.shape
+        x4 = torch.nn.functional.pad(xq.permute(0, 3, 1, 2).float(), (ly.pad, ly.pad, ly.pad, ly.pad), value=float(zp))
+        u = torch.nn.functional.unfold(x4, (ly.kh, ly.kw), stride=ly.stride)            # [N, C*kh*kw, L], (c, kh, kw) order
+        L_ = u.shape[-1]
+        u = u.reshape(N, Cc, ly.kh * ly.kw, L_).permute(0, 3, 2, 1).reshape(N * L_, ly.kh * ly.kw * Cc)   # (kh, kw, c)
+        cols = torch.zeros((N * L_, ly.ldw), dtype=torch.uint8, device=xq.device)
+        cols[:, :u.shape[1]] = u.to(torch.uint8)
+        return cols
 
     def _maybe_force(self, name, q, Cc=None):
         if self.force is None or name not in self.force:
@@ -236,6 +254,7 @@ class QATEngine:
         self.one = torch.ones(1, dtype=torch.float32, device=dev)
         self._wdesc_dev = [self._build_wdesc(i) for i in range(2)]
         self._flag_epoch = Q.FrostFakeQuantize.flag_epoch
+        self._desc_fused = self.fused_pw
         self._wchunks, self._n_wchunks = L.chunk_table([ly.wq.numel() for ly in self.layers], L.WEIGHT_CHUNK, dev)
         self._wbchunks, self._n_wbchunks = L.chunk_table([ly.cout for ly in self.layers], L.WEIGHT_BWD_CHANNELS, dev)
         self._wscratch = torch.tensor([float("inf"), float("-inf")] * len(self.layers), dtype=torch.float32, device=dev)
@@ -261,7 +280,9 @@ class QATEngine:
             d.wq, d.wmask, d.sf, d.rstd_run, d.wsum = (ly.wq.data_ptr(), ly.wmask.data_ptr(), ly.sf.data_ptr(),
                                                        ly.rstd.data_ptr(), ly.wsum.data_ptr())
             d.wt_bf16 = ly.wt_bf16.data_ptr() if ly.wt_bf16 is not None else None
-            d.wq_mma = ly.wq_mma.data_ptr() if ly.wq_mma is not None else None
+            # the stem's GEMM-layout bytes (and its [cout][ldw] gradient) only exist on the fused QuantStub -> im2col path
+            use_mma = ly.kind == "pw" or (ly.im2col and self.fused_pw and not self.features)
+            d.wq_mma = ly.wq_mma.data_ptr() if (ly.wq_mma is not None and use_mma) else None
             d.ldw = ly.ldw
             d.dwq = ly.dwq.data_ptr()
             d.dweight = g.data_ptr() + 4 * self.param_off[id(mod.weight)]
@@ -276,9 +297,10 @@ class QATEngine:
     def _refresh_flags(self):
         # someone toggled an observer (torch.ao.quantization.disable_observer / load_state_dict): the weight
         # descriptor tables carry the per-layer `observe` flag, re-encode them (rare)
-        if self._flag_epoch != Q.FrostFakeQuantize.flag_epoch:
+        if self._flag_epoch != Q.FrostFakeQuantize.flag_epoch or self._desc_fused != self.fused_pw:
             self._wdesc_dev = [self._build_wdesc(i) for i in range(2)]
             self._flag_epoch = Q.FrostFakeQuantize.flag_epoch
+            self._desc_fused = self.fused_pw
 
     # ------------------------------------------------------------------ forward pieces
     def _finalize_args(self, ly, xin, M, training, raw):
@@ -305,7 +327,7 @@ class QATEngine:
     def _pw_operands(self, ly, xin, M):
         wfq = ly.mod.weight_fake_quant
         op = L.PwOperands()
-        op.x, op.M, op.K, op.ldx = xin.q.data_ptr(), M, ly.cin, xin.ld
+        op.x, op.M, op.K, op.ldx = xin.q.data_ptr(), M, ly.k_mma, xin.ld
         op.w_mma, op.ldw, op.cout = ly.wq_mma.data_ptr(), ly.ldw, ly.cout
         op.x_zp, op.w_zp, op.wsum = xin.zp.data_ptr(), wfq.zero_point.data_ptr(), ly.wsum.data_ptr()
         return op
@@ -313,8 +335,9 @@ class QATEngine:
     def _conv_bn(self, ly, xin, training, st, saved):
         mod, dev = ly.mod, self.dev
         N = xin.N
-        if ly.kind == "pw":
-            Ho, Wo = xin.H, xin.W
+        mma = self.fused_pw and (ly.kind == "pw" or (ly.im2col and not isinstance(xin, _RawInput)))
+        if ly.kind == "pw" or mma:
+            Ho, Wo = xin.H, xin.W              # (the im2col stem's input rows are already per output pixel)
         else:
             Ho = (xin.H + 2 * ly.pad - ly.kh) // ly.stride + 1
             Wo = (xin.W + 2 * ly.pad - ly.kw) // ly.stride + 1
@@ -327,7 +350,7 @@ class QATEngine:
         acc = None
         if ly.kind == "pw" and xin.C != ly.cin:
             raise RuntimeError("%s: input has %d channels, expected %d" % (ly.name, xin.C, ly.cin))
-        if ly.kind == "pw" and self.fused_pw:
+        if mma:
             # conv + BN statistics + finalize + observer + quantise: one launch, no int32 accumulator in HBM
             f = L.PwFusedFwdArgs()
             f.op, f.bn = self._pw_operands(ly, xin, M), a
@@ -394,14 +417,32 @@ class QATEngine:
         else:
             # QuantStub
             qfq = m.quant.activation_post_process
-            xq = torch.empty((N, H, W, Cin), dtype=torch.uint8, device=dev)
+            stem = self.stem
+            use_im2col = self.fused_pw and stem.im2col           # (features: no QuantStub, the stem sees the raw image)
+            testing = (self.force is not None and "quant" in self.force) or self.record_taps
             mm_in = torch.empty(2, dtype=torch.float32, device=dev)
-            L.call("frost_input_quant", x.data_ptr(), N, Cin, H, W, _fq_struct(qfq), 1 if qfq._observe else 0,
-                   Q.AVERAGING_CONSTANT, xq.data_ptr(), mm_in.data_ptr(), self.scratch.data_ptr(), st)
-            self._maybe_force("quant", xq)
-            t = _QT(xq, N, H, W, Cin, qfq.scale, qfq.zero_point, mm_in)
-            if self.record_taps:
-                self.last_taps["quant.q"] = xq
+            xq = None
+            if not use_im2col or testing:
+                xq = torch.empty((N, H, W, Cin), dtype=torch.uint8, device=dev)
+                L.call("frost_input_quant", x.data_ptr(), N, Cin, H, W, _fq_struct(qfq), 1 if qfq._observe else 0,
+                       Q.AVERAGING_CONSTANT, xq.data_ptr(), mm_in.data_ptr(), self.scratch.data_ptr(), st)
+                self._maybe_force("quant", xq)
+                if self.record_taps:
+                    self.last_taps["quant.q"] = xq
+            if use_im2col:
+                # the stem runs on the fused tensor-core kernels: QuantStub emits its im2col rows directly
+                Ho = (H + 2 * stem.pad - stem.kh) // stem.stride + 1
+                Wo = (W + 2 * stem.pad - stem.kw) // stem.stride + 1
+                if xq is None:
+                    cols = torch.empty((N * Ho * Wo, stem.ldw), dtype=torch.uint8, device=dev)
+                    L.call("frost_input_quant_im2col", x.data_ptr(), N, Cin, H, W, stem.kh, stem.stride, stem.pad, _fq_struct(qfq),
+                           1 if qfq._observe else 0, Q.AVERAGING_CONSTANT, cols.data_ptr(), stem.ldw, mm_in.data_ptr(),
+                           self.scratch.data_ptr(), st)
+                else:
+                    cols = self._im2col_from_indices(xq, stem, int(qfq.zero_point))     # test mode (teacher forcing / taps)
+                t = _QT(cols, N, Ho, Wo, stem.k_mma, qfq.scale, qfq.zero_point, mm_in, stem.ldw)
+            else:
+                t = _QT(xq, N, H, W, Cin, qfq.scale, qfq.zero_point, mm_in)
         feats = []
         t = self._conv_bn(self.stem, t, training, st, saved)
         for b in self.blocks:
@@ -507,7 +548,7 @@ class QATEngine:
         # pointwise layers get dz as two bf16 planes (the operand format of the tensor-core dgrad/wgrad);
         # depthwise / stem consumers read fp32.  Expand convs (small K, wide cout) on the fused path never materialise dz:
         # the chained kernel keeps it in shared memory between the BatchNorm-backward epilogue and the dgrad / wgrad MMAs.
-        tc_fmt = ly.kind == "pw"
+        tc_fmt = ly.kind == "pw" or (ly.kind == "stem" and acc is None)      # acc is None <=> the forward took the fused path
         chain = (tc_fmt and acc is None and dx is not None and self.chain_bwd
                  and L.load().frost_pw_chain_supported(ly.cin, ly.cout) != 0)
         if chain:
@@ -548,9 +589,9 @@ class QATEngine:
             L.call("frost_bn_backward_reduce", C.byref(a), st)
             L.call("frost_bn_backward_apply", C.byref(a), st)
         wfq = mod.weight_fake_quant
-        if ly.kind == "pw":
+        if tc_fmt:
             L.call("frost_pw_wgrad_tc", dz.data_ptr(), dz_lo.data_ptr(), xin.q.data_ptr(), xin.ld, xin.scale.data_ptr(),
-                   xin.zp.data_ptr(), M, ly.cin, ly.cout, ly.dwq.data_ptr(), st)
+                   xin.zp.data_ptr(), M, ly.k_mma, ly.cout, ly.dwq.data_ptr(), st)
             if dx is not None:
                 L.call("frost_pw_dgrad_tc", dz.data_ptr(), dz_lo.data_ptr(), ly.wt_bf16.data_ptr(), wfq.scale.data_ptr(),
                        M, ly.cin, ly.cout, dx.data_ptr(), 1 if accumulate else 0, st)

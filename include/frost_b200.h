@@ -106,6 +106,14 @@ int frost_input_quant(const float* x_nchw, int N, int C, int H, int W, FrostFQ f
                       float averaging_const, uint8_t* q_nhwc, float* cur_minmax, float* scratch,
                       void* stream);
 
+/* QuantStub fused with the im2col of the dense kxk stem conv (frostnet.py:277,320): q[N*Ho*Wo][ld] holds, per OUTPUT pixel, the
+ * k*k*C quantize indices of its receptive field in (kh, kw, c) order (taps outside the image = zero point), so that the
+ * stem runs on the fused 1x1 tensor-core kernels as a K = ld GEMM (FrostWeightDesc.wq_mma of a layout-2 conv uses the
+ * same column order).  k*k*C <= ld, ld in {16, 32}. */
+int frost_input_quant_im2col(const float* x_nchw, int N, int C, int H, int W, int k, int stride, int pad, FrostFQ fq,
+                             int observe, float averaging_const, uint8_t* q, int ld, float* cur_minmax, float* scratch,
+                             void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Weight side of nniqat.ConvBn(ReLU)2d / nnqat.Conv2d
  * (torch/ao/nn/intrinsic/qat/modules/conv_fused.py:131-146; frostnet.py:14-28,46-60 after
@@ -125,10 +133,12 @@ typedef struct {
   float averaging_const;
   FrostFQ wfq;
   int8_t* wq;               /* out: int8 indices in `layout`                                   */
-  int8_t* wq_mma;           /* out (layout 0, 1x1 only; may be NULL): the same indices as the tensor-core A operand of the
+  int8_t* wq_mma;           /* out (layout 0 and 2; may be NULL): the same indices as the tensor-core A operand of the
                                fused kernels, rows `ldw` bytes apart (ldw % 16 == 0, padding stays zero).  zp_w == 0: the
                                s8 indices; zp_w == -128 / 127 (one-signed weights): q_w - zp_w resp. zp_w - q_w
-                               as u8 (byte ^ 0x80 / ^ 0x7f)                                    */
+                               as u8 (byte ^ 0x80 / ^ 0x7f).  Layout 2 (the stem as an im2col GEMM): columns in (kh, kw, cin)
+                               order; wsum then counts the ldw - K padding columns as zero-point weights, and the backward
+                               reads dwq as [cout][ldw]                                          */
   int32_t ldw;
   uint16_t* wt_bf16;        /* out (layout 0, 1x1 only; may be NULL): (q_w - zp_w) as bf16, transposed [cin][cout],
                                the B operand of the tensor-core dgrad                          */

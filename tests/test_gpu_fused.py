@@ -322,3 +322,32 @@ def test_chain_supported_rule():
     f = L().load().frost_pw_chain_supported
     assert [f(16, 96), f(24, 72), f(24, 144), f(56, 168), f(56, 336)] == [1, 1, 1, 1, 1]     # FrostNet-L's expand convs up to 28x28
     assert [f(104, 312), f(96, 24), f(32, 16), f(16, 40), f(56, 512)] == [0, 0, 0, 0, 0]
+
+
+# ------------------------------------------------------------------------------------------ QuantStub -> im2col (the stem as a GEMM)
+@pytest.mark.parametrize("N,H,W", [(2, 224, 224), (3, 33, 31), (1, 8, 9)])
+def test_input_quant_im2col_matches_quantstub_plus_unfold(N, H, W):
+    from frostnet_b200.engine import QATEngine
+
+    class Stem:
+        kh = kw = 3
+        stride, pad, ldw = 2, 1, 32
+    g = torch.Generator().manual_seed(H)
+    x = torch.randn(N, 3, H, W, generator=g).to(DEV)
+    mk = lambda: (torch.tensor(float("inf"), device=DEV), torch.tensor(float("-inf"), device=DEV), torch.ones(1, device=DEV),
+                  torch.zeros(1, dtype=torch.int32, device=DEV))
+    sc = torch.zeros(L().FQ_SCRATCH_FLOATS, device=DEV)
+    a, b = mk(), mk()
+    xq = torch.empty(N, H, W, 3, dtype=torch.uint8, device=DEV)
+    mm_a, mm_b = torch.empty(2, device=DEV), torch.empty(2, device=DEV)
+    L().call("frost_input_quant", x.data_ptr(), N, 3, H, W, L().FQ(*[t.data_ptr() for t in a]), 1, 0.01, xq.data_ptr(), mm_a.data_ptr(),
+             sc.data_ptr(), stream())
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    cols = torch.full((N * Ho * Wo, 32), 0xAB, dtype=torch.uint8, device=DEV)
+    L().call("frost_input_quant_im2col", x.data_ptr(), N, 3, H, W, 3, 2, 1, L().FQ(*[t.data_ptr() for t in b]), 1, 0.01, cols.data_ptr(), 32,
+             mm_b.data_ptr(), sc.data_ptr(), stream())
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)                                   # same observer state, same qparams
+    assert torch.equal(mm_a, mm_b)
+    ref = QATEngine._im2col_from_indices(xq, Stem, int(a[3]))
+    assert torch.equal(cols[:, :27], ref[:, :27])
