@@ -311,6 +311,7 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
+    host_ms = [0.0]
 
     W, K = max(3, args.warmup), args.steps
     for _ in range(W):
@@ -325,10 +326,17 @@ def run_b200(args):
     launches = L.launch_count() - l0
     value = world * bs * K / (ms * 1e-3)
 
+    # host cost of ENQUEUEING one step: a single step after a full sync, so the launch queue never fills
+    barrier()
+    h0 = time.perf_counter()
+    step(x, y)
+    host_ms[0] = (time.perf_counter() - h0) * 1e3
+    barrier()
+
     if args.quick:
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms / K, "steps": K,
-                              "gpu_launches_per_step": launches / K, "quick": True}), flush=True)
+                              "gpu_launches_per_step": launches / K, "host_enqueue_ms_per_step": host_ms[0], "quick": True}), flush=True)
         if world > 1:
             dist.destroy_process_group()
         return

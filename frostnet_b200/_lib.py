@@ -141,6 +141,7 @@ _SIGNATURES = {
     "frost_gradboost_multi": [c_p, i32, c_p, i32, C.POINTER(OptHyper), c_p],
     "frost_set_tunable": [i32, i32],
     "frost_get_tunable": [i32],
+    "frost_debug_set_trace": [c_p],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["frost_abi_version", "frost_last_error", "frost_launch_count",
                            "frost_pw_chain_supported"])

@@ -18,6 +18,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 EXTRA = os.environ.get("FROST_NVCC_FLAGS", "").split()      # experiments only (e.g. -DFROST_NO_NC)
+if "--trace" in sys.argv:                                   # launch-timeline stamps in the fused kernels (tools/trace_fused.py)
+    EXTRA.append("-DFROST_TRACE")
 
 
 def _sources():

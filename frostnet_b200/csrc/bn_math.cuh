@@ -114,6 +114,26 @@ struct MaskInterval {
 };
 __device__ __forceinline__ bool mask_passes(const MaskInterval& m, int I) { return (unsigned)(I - m.lo) < m.width; }
 
+// Smallest I in [a, b] for which the monotone (false ... false true ... true) predicate holds, b if it never does.  `est`
+// is a float guess of the answer: when the predicate confirms a small bracket around it, the bisection runs inside that
+// bracket (~8 evaluations instead of ~29 over the whole 2^29 range - the search sits on the critical path of every small
+// launch); otherwise the whole range is searched.  Either way the result is the exact first-true point.
+template <typename Pred>
+__device__ __forceinline__ int first_true_near(Pred pred, float est, int a, int b) {
+  if (est >= (float)a && est <= (float)b) {            // false for NaN / inf / out of range: whole-range search
+    const int c = (int)rintf(est);
+    const int w = 8 + (abs(c) >> 17);                  // float error of the guess grows with |I|
+    const int lo = c - w, hi = c + w;
+    if (lo > a && !pred(lo)) a = lo + 1;
+    if (hi < b && pred(hi)) b = hi;
+  }
+  while (a < b) {
+    const int mid = a + ((b - a) >> 1);
+    if (pred(mid)) b = mid; else a = mid + 1;
+  }
+  return a;
+}
+
 __device__ inline MaskInterval bn_mask_interval(float A, float B, int relu, float inv, float zp) {
   constexpr int LIM = 1 << 28;
   const bool inc = A >= 0.0f;
@@ -128,25 +148,20 @@ __device__ inline MaskInterval bn_mask_interval(float A, float B, int relu, floa
     const float r = relu ? fmaxf(v, 0.0f) : v;
     return fq_index(r, inv, zp) <= 255.0f;
   };
+  // where v crosses the two thresholds, in units of I (guesses only)
+  float t_low = __fdividef(-zp - 0.5f, inv);
+  if (relu) t_low = fmaxf(t_low, 0.0f);
+  const float t_high = __fdividef(255.5f - zp, inv);
+  const float rA = __fdividef(1.0f, A);
+  const float e_low = (t_low - B) * rA, e_high = (t_high - B) * rA;
   // left end: first I where the condition that fails for very small I holds (A >= 0: ok_low, else ok_high)
-  int a = -LIM, b = LIM + 1;
-  while (a < b) {
-    const int mid = a + ((b - a) >> 1);
-    const bool t = inc ? ok_low(mid) : ok_high(mid);
-    if (t) b = mid; else a = mid + 1;
-  }
-  const int first = a;
+  const int first = inc ? first_true_near(ok_low, e_low, -LIM, LIM + 1) : first_true_near(ok_high, e_high, -LIM, LIM + 1);
   // right end: first I >= first where the other condition fails
-  a = first;
-  b = LIM + 1;
-  while (a < b) {
-    const int mid = a + ((b - a) >> 1);
-    const bool t = inc ? ok_high(mid) : ok_low(mid);
-    if (t) a = mid + 1; else b = mid;
-  }
+  const int last = inc ? first_true_near([&](int I) { return !ok_high(I); }, e_high, first, LIM + 1)
+                       : first_true_near([&](int I) { return !ok_low(I); }, e_low, first, LIM + 1);
   MaskInterval m;
   m.lo = first;
-  m.width = (unsigned)(a - first);
+  m.width = (unsigned)(last - first);
   return m;
 }
 

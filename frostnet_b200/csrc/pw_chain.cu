@@ -122,7 +122,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) pw_chain_bwd_kernel(const __gri
   tc_fence_after();
   pdl_trigger();
   const uint32_t tmem_base = *tmem_slot;
-  const int zp_a = *p.x_zp, zp_w = *p.w_zp;
+  // (the TMA producer needs neither zero point: it must not wait an L2 round trip for them before its first load)
+  const int zp_a = warp == CH_EPI_WARPS ? 0 : *p.x_zp, zp_w = warp == CH_EPI_WARPS ? 0 : *p.w_zp;
   if (zp_w != 0 && zp_w != -128 && zp_w != 127) __trap();
 
   if (warp == CH_EPI_WARPS) {

@@ -70,7 +70,15 @@ struct PwFusedParams {
   int ldq;
   // backward
   FrostBnBackwardArgs bwd;
+  long long* trace;       // measurement aid (frost_debug_set_trace): SM clock stamps of CTA (0,0), NULL = off
 };
+
+// stamp i of the launch timeline (one thread per call site); compiled in with -DFROST_TRACE only (python -m frostnet_b200.build --trace)
+#ifdef FROST_TRACE
+#define PF_STAMP(i) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[i] = clock64(); } while (0)
+#else
+#define PF_STAMP(i) do { } while (0)
+#endif
 
 struct PfCombine {       // per channel of the tile: the partial results of the threads that share a channel meet here
   unsigned long long sum, sq;
@@ -114,12 +122,14 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
 
   // ---- one-time setup (overlaps the tail of the previous kernel: programmatic dependent launch, common.cuh)
   if (threadIdx.x == 0) {
+    PF_STAMP(0);
     for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], PF_EPI_WARPS); }
     mbar_init(wfull_bar, 1);
     mbar_fence_init();
   }
   if (warp == PF_EPI_WARPS + 1) tmem_alloc<512>(tmem_slot);
+  if (threadIdx.x == 0) PF_STAMP(1);
   if (threadIdx.x < PF_CH) {
     PfCombine& c = s_comb[threadIdx.x];
     c.sum = 0; c.sq = 0; c.mn = INT_MAX; c.mx = INT_MIN; c.s1 = 0.0; c.s2 = 0.0;
@@ -130,8 +140,11 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
   tc_fence_after();
   pdl_trigger();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) PF_STAMP(2);
 
-  const int zp_a = *p.x_zp, zp_w = *p.w_zp;
+  // (the TMA producer needs neither zero point: it must not wait an L2 round trip for them before its first load)
+  const bool is_producer = warp == PF_EPI_WARPS;
+  const int zp_a = is_producer ? 0 : *p.x_zp, zp_w = is_producer ? 0 : *p.w_zp;
   if (zp_w != 0 && zp_w != -128 && zp_w != 127) __trap();  // not reachable with ChooseQuantizationParams
   // forward: does this launch need batch statistics / the observer's min-max (phase A + grid barrier)?
   const bool need_stats = (MODE == PF_FWD) && (p.fin.training || p.fin.observe);
@@ -162,6 +175,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
             if (!resident)
               for (int j = 0; j < R; ++j)
                 tma_load_2d(&tm_w, &full_bar[s], smem_u32(st + PF_X_BYTES + j * bnr * PF_BK), kb * PF_BK, c_tile0);
+            if (it == 0) PF_STAMP(3);
           }
         }
       }
@@ -177,6 +191,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
       mbar_wait_parked(wfull_bar, 0);
       tc_fence_after();
     }
+    if (lane == 0) PF_STAMP(4);
     uint32_t it = 0, tile_i = 0;
     for (int ph = 0; ph < n_phases; ++ph) {
       const bool cpt = phase_is_cpt(ph);
@@ -191,6 +206,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
           mbar_wait_parked(&full_bar[s], (it / S) & 1);
           tc_fence_after();
           if (lane == 0) {
+            if (it == 0) PF_STAMP(5);
             uint8_t* st = stages + s * stage_bytes;
             const uint64_t xdesc = umma_desc_sw128(smem_u32(st));
             const uint64_t wdesc = umma_desc_sw128(smem_u32(resident ? wres + kb * PF_W_BYTES : st + PF_X_BYTES));
@@ -258,6 +274,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
           const int px_valid = (int)min((int64_t)PF_NPX, p.M - pt * PF_NPX);
           mbar_wait_parked(&tfull_bar[acc], (tile_i >> 1) & 1);
           tc_fence_after();
+          if (tid == 0 && tile_i == 0) PF_STAMP(6);
           if (warp_active) {
 #pragma unroll 1
             for (int col0 = col_begin; col0 < col_begin + cols_per; col0 += 16) {
@@ -294,6 +311,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
+        if (tid == 0) PF_STAMP(7);
         // the threads that share a channel meet in shared memory; one set of integer atomics per channel and CTA
         if (active && mn <= mx) {
           PfCombine& cb = s_comb[c_local];
@@ -308,11 +326,11 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
           chan_stats_flush(const_cast<FrostChanStats*>(p.fin.stats) + c_tile0 + tid, (long long)cb.sum, cb.sq, cb.mn, cb.mx);
         }
         // ---------------- grid barrier: every CTA of this launch is resident (host: grid <= #SMs, 1 CTA per SM)
-        __threadfence();
         named_bar_sync<PF_EPI_THREADS>();
         if (tid == 0) {
+          PF_STAMP(8);
           const unsigned target = gridDim.x * gridDim.y;
-          __threadfence();                                   // cumulativity: the CTA's atomics above are ordered before the arrival
+          __threadfence();                                   // cumulativity: the CTA's atomics (ordered by the barrier above) come before the arrival
           atomicAdd(p.grid_bar, 1u);
           bool ok = false;
           for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
@@ -320,12 +338,20 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
             __nanosleep(64);
           }
           if (!ok) __trap();
+          PF_STAMP(9);
         }
         named_bar_sync<PF_EPI_THREADS>();
       }
       // ---------------- finalize: BN affine of the tile's channels, observer over all channels, qparams (same in every CTA)
+      // every channel once per CTA (the observer needs the extrema over ALL channels), in an order rotated so that thread
+      // tid < n_valid meets channel c_tile0 + tid - the one whose coefficients this CTA's tiles use - in its first iteration
       float gmn = INFINITY, gmx = -INFINITY;
-      for (int cc = tid; cc < p.cout; cc += PF_EPI_THREADS) {
+      BnChannel mine;
+      mine.A = mine.B = mine.mean_I = mine.kfac = 0.f;
+      mine.new_running_mean = mine.new_running_var = 0.f;
+      for (int j = tid; j < p.cout; j += PF_EPI_THREADS) {
+        int cc = c_tile0 + j;
+        if (cc >= p.cout) cc -= p.cout;
         FrostChanStats st;
         const FrostChanStats* g = p.fin.stats + cc;
         st.sum = __ldcg(&g->sum); st.sq_lo = __ldcg(&g->sq_lo); st.sq_hi = __ldcg(&g->sq_hi);
@@ -335,20 +361,10 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
                                                 p.fin.running_mean[cc], p.fin.running_var[cc], p.fin.eps, mom, p.fin.training, relu);
         gmn = fminf(gmn, r.v_lo);
         gmx = fmaxf(gmx, r.v_hi);
-      }
-      BnChannel mine;
-      mine.A = mine.B = mine.mean_I = mine.kfac = 0.f;
-      mine.new_running_mean = mine.new_running_var = 0.f;
-      if (tid < n_valid) {                                   // thread tid <-> channel c_tile0 + tid
-        const int cc = c_tile0 + tid;
-        FrostChanStats st;
-        const FrostChanStats* g = p.fin.stats + cc;
-        st.sum = __ldcg(&g->sum); st.sq_lo = __ldcg(&g->sq_lo); st.sq_hi = __ldcg(&g->sq_hi);
-        st.min = __ldcg(&g->min); st.max = __ldcg(&g->max);
-        if (!need_stats) { st.min = 0; st.max = 0; }
-        mine = bn_channel_finalize(st, 0, Mcount, p.fin.count > 1, sa_sw, p.fin.sf[cc], p.fin.gamma[cc], p.fin.beta[cc],
-                                   p.fin.running_mean[cc], p.fin.running_var[cc], p.fin.eps, mom, p.fin.training, relu);
-        s_cf[tid] = make_float4(mine.A, mine.B, __int_as_float(corr_of(cc)), 0.f);
+        if (j < n_valid) {                                   // j == tid here: thread tid <-> channel c_tile0 + tid
+          mine = r;
+          s_cf[tid] = make_float4(r.A, r.B, __int_as_float(corr_of(cc)), 0.f);
+        }
       }
       gmn = warp_min(gmn);
       gmx = warp_max(gmx);
@@ -386,6 +402,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         }
       }
       named_bar_sync<PF_EPI_THREADS>();
+      if (tid == 0) PF_STAMP(10);
       inv = s_qp[2];
       zpf = s_qp[1];
       if (blockIdx.x == 0 && tid < n_valid) {                // one writer per channel
@@ -407,6 +424,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         const bool wvalid = pt * PF_NPX + ppt_h * 128 + quarter * 32 < p.M;      // warp-uniform
         mbar_wait_parked(&tfull_bar[acc], (tile_i >> 1) & 1);
         tc_fence_after();
+        if (tid == 0 && pt == blockIdx.x) PF_STAMP(11);
         if (wvalid) {
           uint8_t* qrow = p.q + pix * (int64_t)p.ldq + c_tile0;
 #pragma unroll 1
@@ -452,12 +470,21 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
       const float cA = b.A[c], cB = b.B[c], cMean = b.mean_I[c];
       const int cout = p.cout;
       // the STE / ReLU mask of this channel as an integer interval of the accumulator (bn_math.cuh)
+      // everything the coefficients need is requested before the interval search: one L2 latency, not two
+      double gS1 = 0.0, gS2 = 0.0, sa_sw = 1.0;
+      float cK = 0.f, cG = 0.f, cSf = 1.f;
+      if constexpr (MODE == PF_BWD_APPLY) {
+        gS1 = __ldcg(b.sums + 2 * c);
+        gS2 = __ldcg(b.sums + 2 * c + 1);
+        sa_sw = (double)(*b.x_scale) * (double)(*b.w_scale);
+        cK = b.kfac[c]; cG = b.gamma[c]; cSf = b.sf[c];
+      }
+      if (tid == 0) PF_STAMP(13);
       const MaskInterval mk = bn_mask_interval(cA, cB, relu, inv, zpf);
+      if (tid == 0) PF_STAMP(14);
       float cP = 0.f, cQ = 0.f, cR = 0.f;
       if constexpr (MODE == PF_BWD_APPLY) {
-        const double sa_sw = (double)(*b.x_scale) * (double)(*b.w_scale);
-        const BnBwdChannel r = bn_bwd_channel(__ldcg(b.sums + 2 * c), __ldcg(b.sums + 2 * c + 1), (double)b.M, sa_sw, cA, b.kfac[c], cMean,
-                                              b.gamma[c], b.sf[c], b.eps, b.frozen ? 0 : 1);
+        const BnBwdChannel r = bn_bwd_channel(gS1, gS2, (double)b.M, sa_sw, cA, cK, cMean, cG, cSf, b.eps, b.frozen ? 0 : 1);
         // dz = c1*(dv - a0 - a1*(I - mean)) = P*dv + R*I + Q
         cP = r.c1;
         cR = -r.c1 * r.a1;
@@ -527,8 +554,10 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         // accumulator is waited for
         float dA[16], dB[16];
         if (active && col_begin < px_valid) load16(dA, tile_dy, col_begin, px_valid);
+        if (tid == 0 && tile_i == 0) PF_STAMP(15);
         mbar_wait_parked(&tfull_bar[acc], (tile_i >> 1) & 1);
         tc_fence_after();
+        if (tid == 0 && tile_i == 0) PF_STAMP(16);
         if (warp_active) {
           p1 = 0.f;
           p2 = 0.f;
@@ -550,6 +579,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
+      if (tid == 0) PF_STAMP(17);
       if constexpr (MODE == PF_BWD_REDUCE) {
         if (active) {
           atomicAdd(&s_comb[c_local].s1, S1);
@@ -565,8 +595,10 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
   }
 
   // ---- teardown
+  if (threadIdx.x == 0) PF_STAMP(12);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) PF_STAMP(18);
   if (warp == PF_EPI_WARPS + 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -591,8 +623,11 @@ static int check_operands(const char* who, const PwOperands& o) {
   return FROST_OK;
 }
 
+static long long* g_trace = nullptr;
+
 template <int MODE>
 static int launch_fused(const char* who, const PwOperands& o, PwFusedParams& p, cudaStream_t st) {
+  p.trace = g_trace;
   if (!encode_fn()) {
     set_error("%s: cuTensorMapEncodeTiled is not available from this driver (the fused kernels stage operands by TMA)", who);
     return FROST_ENOSUP;
@@ -633,6 +668,17 @@ static int launch_fused(const char* who, const PwOperands& o, PwFusedParams& p, 
 }  // namespace frost
 
 using namespace frost;
+
+extern "C" int frost_debug_set_trace(long long* device_stamps) {
+#ifdef FROST_TRACE
+  g_trace = device_stamps;
+  return FROST_OK;
+#else
+  (void)device_stamps;
+  set_error("frost_debug_set_trace: this library was built without -DFROST_TRACE (python -m frostnet_b200.build --force --trace)");
+  return FROST_ENOSUP;
+#endif
+}
 
 static PwOperands operands_of(const FrostPwOperands& a) {
   PwOperands o;

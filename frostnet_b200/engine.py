@@ -11,6 +11,7 @@ HBM layout: activations are NHWC uint8 indices (1 B/element), raw conv outputs N
 gradients NHWC fp32; weights are re-quantised to int8 once per step by one multi-tensor launch.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -123,9 +124,19 @@ class QATEngine:
         # False selects the first-generation chain conv -> bn_finalize -> bnq_apply / bn_backward_* (kept as the cross-check).
         self.fused_pw = True
         self.chain_bwd = True       # expand convs: BN-backward apply + dgrad + wgrad in one kernel (csrc/pw_chain.cu)
+        # Weight gradients on a side stream next to the data-gradient chain.  Measured on B200 (bs=256): no gain - every
+        # tensor-core kernel takes a whole SM per CTA (shared memory) and even the small layers launch 148 CTAs, so the
+        # two streams take turns anyway.  Off by default; FROST_OVERLAP_WGRAD=1 re-enables it for measurements.
+        self.overlap_wgrad = os.environ.get("FROST_OVERLAP_WGRAD", "0") == "1"
+        self._side = None
 
     def invalidate(self):
         self._built = False
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.dev)
+        return self._side
 
     # A copy (copy.deepcopy(model) for an EMA model, torch.save(model)) must not inherit raw device pointers into
     # the ORIGINAL model's tensors: it gets a fresh, unbuilt engine bound to the copied module tree.
@@ -225,6 +236,7 @@ class QATEngine:
         L.require_cuda(p0, "model")
         dev = p0.device
         self.dev = dev
+        self._side = None
         for ly in self.layers:
             if ly.kind == "dw" and not (ly.kh in (3, 5) and ly.stride in (1, 2) and ly.cin_g == 1):
                 raise RuntimeError("frostnet_b200: unsupported depthwise conv %s" % ly.name)
@@ -581,7 +593,7 @@ class QATEngine:
             if chain:
                 ch = L.PwChainArgs()
                 ch.op, ch.bn = f.op, a
-                ch.wt_bf16, ch.dx, ch.accumulate, ch.dwq = ly.wt_bf16.data_ptr(), dx.data_ptr(), 1 if accumulate else 0, ly.dwq.data_ptr()
+                ch.wt_bf16, ch.dx, ch.accumulate, ch.dwq = L.ptr(ly.wt_bf16), L.ptr(dx), 1 if accumulate else 0, ly.dwq.data_ptr()
                 L.call("frost_pw_chain_backward", C.byref(ch), st)
                 return
             L.call("frost_pw_fused_bwd_apply", C.byref(f), st)
@@ -589,15 +601,26 @@ class QATEngine:
             L.call("frost_bn_backward_reduce", C.byref(a), st)
             L.call("frost_bn_backward_apply", C.byref(a), st)
         wfq = mod.weight_fake_quant
+        # The weight gradient has no consumer until the end of the backward pass: it runs on a side stream next to the
+        # data-gradient chain (dgrad -> the next layer's reduce / apply).  Most layers launch fewer CTAs than there are SMs
+        # and are latency-bound, so the two streams share the GPU instead of taking turns.
+        wst = st
+        if self.overlap_wgrad and dx is not None:
+            side = self._side_stream()
+            side.wait_stream(torch.cuda.current_stream(dev))
+            wst = side.cuda_stream
+            dz.record_stream(side)                # the caching allocator must not hand dz out again before the side stream is done
+            if dz_lo is not None:
+                dz_lo.record_stream(side)
         if tc_fmt:
             L.call("frost_pw_wgrad_tc", dz.data_ptr(), dz_lo.data_ptr(), xin.q.data_ptr(), xin.ld, xin.scale.data_ptr(),
-                   xin.zp.data_ptr(), M, ly.k_mma, ly.cout, ly.dwq.data_ptr(), st)
+                   xin.zp.data_ptr(), M, ly.k_mma, ly.cout, ly.dwq.data_ptr(), wst)
             if dx is not None:
                 L.call("frost_pw_dgrad_tc", dz.data_ptr(), dz_lo.data_ptr(), ly.wt_bf16.data_ptr(), wfq.scale.data_ptr(),
                        M, ly.cin, ly.cout, dx.data_ptr(), 1 if accumulate else 0, st)
         elif ly.kind == "dw":
             L.call("frost_dw_wgrad", dz.data_ptr(), xin.q.data_ptr(), xin.ld, xin.scale.data_ptr(), xin.zp.data_ptr(), xin.N,
-                   xin.H, xin.W, xin.C, ly.kh, ly.stride, ly.dwq.data_ptr(), st)
+                   xin.H, xin.W, xin.C, ly.kh, ly.stride, ly.dwq.data_ptr(), wst)
             if dx is not None:
                 L.call("frost_dw_dgrad", dz.data_ptr(), ly.wq.data_ptr(), wfq.scale.data_ptr(), wfq.zero_point.data_ptr(),
                        xin.N, xin.H, xin.W, xin.C, ly.kh, ly.stride, dx.data_ptr(), 1 if accumulate else 0, st)
@@ -704,6 +727,8 @@ class QATEngine:
                 gx_written = True
             g = gx
         self._conv_bn_bwd(self.stem, g, saved, gbase, None, False, st)
+        if self._side is not None:
+            torch.cuda.current_stream(dev).wait_stream(self._side)       # every weight gradient is complete
         L.call("frost_weight_backward_multi", self._wdesc_dev[which].data_ptr(), len(self.layers),
                self._wbchunks.data_ptr(), self._n_wbchunks, st)
         if self.grad_sync is not None:

@@ -55,6 +55,10 @@ enum {
 };
 int frost_set_tunable(int which, int value);
 int frost_get_tunable(int which);
+/* Measurement aid, only in a library built with -DFROST_TRACE (python -m frostnet_b200.build --force --trace; FROST_ENOSUP
+ * otherwise): while `device_stamps` (>= 32 int64 on the device) is set, CTA (0,0) of every frost_pw_fused_* launch writes
+ * SM-clock stamps of its timeline there (tools/trace_fused.py explains the indices).  NULL switches it off. */
+int frost_debug_set_trace(long long* device_stamps);
 
 /* One FusedMovingAvgObsFakeQuantize instance (torch/ao/quantization/fake_quantize.py:423-438):
  * the four state buffers of the module, on the device.  Kernels read AND update them in place
