@@ -526,20 +526,25 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
           }
         } else {
           char* ph = reinterpret_cast<char*>(dz_hi + e_col);
-          char* pl = reinterpret_cast<char*>(dz_lo + e_col);
+          const int64_t lo_off = reinterpret_cast<char*>(dz_lo) - reinterpret_cast<char*>(dz_hi);   // one running pointer for both planes
           const int64_t row_h = (int64_t)cout * 2;
-          const bool whole = col + 16 <= px_valid;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          auto one = [&](int j) {
             const int I = wsign * (int)v[j] - corr_s;
             const float base = fmaf(cR, (float)I, cQ);
             const float o = mask_passes(mk, I) ? fmaf(cP, d[j], base) : base;
             const __nv_bfloat16 h = __float2bfloat16_rn(o);
             const __nv_bfloat16 l = __float2bfloat16_rn(o - __bfloat162float(h));
-            if (whole || col + j < px_valid) {
-              *reinterpret_cast<uint16_t*>(ph + j * row_h) = __bfloat16_as_ushort(h);
-              *reinterpret_cast<uint16_t*>(pl + j * row_h) = __bfloat16_as_ushort(l);
-            }
+            *reinterpret_cast<uint16_t*>(ph) = __bfloat16_as_ushort(h);
+            *reinterpret_cast<uint16_t*>(ph + lo_off) = __bfloat16_as_ushort(l);
+            ph += row_h;
+          };
+          if (col + 16 <= px_valid) {            // every tile but the last: no per-element predicates
+#pragma unroll
+            for (int j = 0; j < 16; ++j) one(j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (col + j < px_valid) one(j);
           }
         }
       };
