@@ -260,8 +260,11 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line
+        # keep stdout to the ONE JSON line: NCCL prints its version banner (and anything NCCL_DEBUG asks for) to stdout
+        # unless told otherwise
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            del os.environ["NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=dev)
     bs = args.batch
     torch.manual_seed(1882)
