@@ -12,3 +12,4 @@ from .prefetch import DevicePrefetcher
 from . import frostnet_features
 
 __version__ = "0.1.0"
+from .export import convert_int8

@@ -107,10 +107,12 @@ class CascadePreExBottleneck(nn.Module):
         if _qat.is_prepared(self):
             raise RuntimeError("frostnet_b200: a prepared (QAT) bottleneck only runs inside FrostNet.forward "
                                "(whole-network engine); there is no per-module eager path")
+        # float model and the int8 model made by frostnet_b200.convert_int8: cat / add go through the FloatFunctional /
+        # QFunctional modules exactly where the reference's do (frostnet.py:124-145)
         if not self.expand_ratio == 1:
             if self.block_type == 'CAS':
                 squeezed = self.squeeze_conv(x)
-                out = torch.cat([squeezed, x], 1)
+                out = self.quant_cat.cat([squeezed, x], 1) if self.quantized else torch.cat([squeezed, x], 1)
             else:
                 out = x
             out = self.conv1(out)
@@ -119,7 +121,7 @@ class CascadePreExBottleneck(nn.Module):
         out = self.conv2(out)
         out = self.reduce_conv(out)
         if not self.reduction:
-            out = torch.add(x, out)
+            out = self.skip_add.add(x, out) if self.quantized else torch.add(x, out)
         return out
 
 
@@ -230,11 +232,15 @@ class FrostNet(_FrostTrunk):
         eng = self.__dict__.get("_frost_engine")
         if eng is not None:
             return eng.run(x)
+        if self.quantized:
+            x = self.quant(x)          # identity in the float model, nnq.Quantize after convert_int8 (frostnet.py:319-320)
         x = self.conv1(x)
         for st in self.stages():
             x = st(x)
         x = self.last_layer(x)
         x = self.classifier(x)
+        if self.quantized:
+            x = self.dequant(x)
         return x.view(x.size(0), x.size(1))
 
 
