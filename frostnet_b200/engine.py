@@ -106,6 +106,7 @@ class QATEngine:
         self.model = model
         self._built = False
         self.last_taps = None
+        self.last_grad_taps = {}
         self.record_taps = False
         self.dropout_mask = None      # tests may inject a keep mask [N,1280]
         # Teacher forcing for parity tests: name -> uint8 NHWC indices that REPLACE the computed output of that
@@ -142,7 +143,7 @@ class QATEngine:
     # the ORIGINAL model's tensors: it gets a fresh, unbuilt engine bound to the copied module tree.
     def __deepcopy__(self, memo):
         import copy
-        new = QATEngine(copy.deepcopy(self.model, memo))
+        new = type(self)(copy.deepcopy(self.model, memo))
         new.grad_sync = self.grad_sync
         return new
 
@@ -216,22 +217,7 @@ class QATEngine:
             self.layers.append(ly)
             return ly
 
-        self.stem = add("conv1", "stem")
-        for si, stage in enumerate(m.stages()):
-            for bi, blk in enumerate(stage):
-                p = "layer%d.%d" % (si + 1, bi)
-                b = dict(name=p, mod=blk, squeeze=None, conv1=None, stage_end=(bi == len(stage) - 1), stage=si)
-                if blk.expand_ratio != 1:
-                    if blk.block_type == "CAS":
-                        b["squeeze"] = add(p + ".squeeze_conv", "pw")
-                    b["conv1"] = add(p + ".conv1", "pw")
-                b["conv2"] = add(p + ".conv2", "dw")
-                b["reduce"] = add(p + ".reduce_conv", "pw")
-                b["skip"] = not blk.reduction
-                self.blocks.append(b)
-        if not self.features:
-            self.last = add("last_layer", "pw")
-            self.cls = add("classifier.2", "cls")
+        self._discover(m, add)
         p0 = next(m.parameters())
         L.require_cuda(p0, "model")
         dev = p0.device
@@ -272,6 +258,30 @@ class QATEngine:
         self._wscratch = torch.tensor([float("inf"), float("-inf")] * len(self.layers), dtype=torch.float32, device=dev)
         self._fingerprint = self._tensor_fingerprint()
         self._built = True
+
+    def _add_block(self, add, p, blk, stage_end=False, stage=0):
+        """One CascadePreExBottleneck (frostnet.py:81-145) -> its fused convs in execution order; `p`: module-name prefix."""
+        dot = p + "." if p else ""
+        b = dict(name=p, mod=blk, squeeze=None, conv1=None, stage_end=stage_end, stage=stage)
+        if blk.expand_ratio != 1:
+            if blk.block_type == "CAS":
+                b["squeeze"] = add(dot + "squeeze_conv", "pw")
+            b["conv1"] = add(dot + "conv1", "pw")
+        b["conv2"] = add(dot + "conv2", "dw")
+        b["reduce"] = add(dot + "reduce_conv", "pw")
+        b["skip"] = not blk.reduction
+        self.blocks.append(b)
+        return b
+
+    def _discover(self, m, add):
+        """Whole network: stem, every bottleneck, last_layer + classifier (frostnet.py:318-332)."""
+        self.stem = add("conv1", "stem")
+        for si, stage in enumerate(m.stages()):
+            for bi, blk in enumerate(stage):
+                self._add_block(add, "layer%d.%d" % (si + 1, bi), blk, stage_end=(bi == len(stage) - 1), stage=si)
+        if not self.features:
+            self.last = add("last_layer", "pw")
+            self.cls = add("classifier.2", "cls")
 
     def _build_wdesc(self, which):
         arr = (L.WeightDesc * len(self.layers))()
@@ -396,6 +406,50 @@ class QATEngine:
                 self.last_taps[ly.name + ".acc"] = acc
         return out
 
+    def _block_forward(self, b, t, training, st, saved):
+        """One bottleneck (frostnet.py:124-145) on the quantised tensor t; returns the block output."""
+        dev = self.dev
+        blk = b["mod"]
+        xin = t
+        if saved is not None:
+            saved[b["name"] + ".in"] = xin
+        if b["conv1"] is not None:
+            if b["squeeze"] is not None:
+                sq = self._conv_bn(b["squeeze"], xin, training, st, saved)
+                cfq = blk.quant_cat.activation_post_process
+                qc, ldc = self._alloc_q(xin.M, sq.C + xin.C)
+                mmc = torch.empty(2, dtype=torch.float32, device=dev)
+                L.call("frost_cat_forward", sq.c(), xin.c(), xin.M, _fq_struct(cfq), 1 if cfq._observe else 0,
+                       Q.AVERAGING_CONSTANT, qc.data_ptr(), ldc, mmc.data_ptr(), st)
+                self._maybe_force(b["name"] + ".cat", qc, sq.C + xin.C)
+                cat = _QT(qc, xin.N, xin.H, xin.W, sq.C + xin.C, cfq.scale, cfq.zero_point, mmc, ldc)
+                if saved is not None:
+                    saved[b["name"] + ".cat"] = (sq, xin, cat)
+                if self.record_taps:
+                    self.last_taps[b["name"] + ".cat_q"] = qc[:, :cat.C].contiguous()
+                o = cat
+            else:
+                o = xin
+            o = self._conv_bn(b["conv1"], o, training, st, saved)
+        else:
+            o = xin
+        o = self._conv_bn(b["conv2"], o, training, st, saved)
+        o = self._conv_bn(b["reduce"], o, training, st, saved)
+        if b["skip"]:
+            afq = blk.skip_add.activation_post_process
+            qa, lda = self._alloc_q(o.M, o.C)
+            mma = torch.empty(2, dtype=torch.float32, device=dev)
+            L.call("frost_add_forward", xin.c(), o.c(), o.M * o.C, _fq_struct(afq), 1 if afq._observe else 0,
+                   Q.AVERAGING_CONSTANT, qa.data_ptr(), lda, mma.data_ptr(), self.scratch.data_ptr(), st)
+            self._maybe_force(b["name"] + ".add", qa, o.C)
+            s = _QT(qa, o.N, o.H, o.W, o.C, afq.scale, afq.zero_point, mma, lda)
+            if saved is not None:
+                saved[b["name"] + ".add"] = (xin, o, s)
+            if self.record_taps:
+                self.last_taps[b["name"] + ".add_q"] = qa[:, :o.C].contiguous()
+            o = s
+        return o
+
     def forward(self, x, save):
         self._ensure_built(check=False)          # run() has just verified the pointer tables
         with torch.cuda.device(self.dev):       # kernels launch on the CURRENT device: make it the model's
@@ -458,46 +512,7 @@ class QATEngine:
         feats = []
         t = self._conv_bn(self.stem, t, training, st, saved)
         for b in self.blocks:
-            blk = b["mod"]
-            xin = t
-            if saved is not None:
-                saved[b["name"] + ".in"] = xin
-            if b["conv1"] is not None:
-                if b["squeeze"] is not None:
-                    sq = self._conv_bn(b["squeeze"], xin, training, st, saved)
-                    cfq = blk.quant_cat.activation_post_process
-                    qc, ldc = self._alloc_q(xin.M, sq.C + xin.C)
-                    mmc = torch.empty(2, dtype=torch.float32, device=dev)
-                    L.call("frost_cat_forward", sq.c(), xin.c(), xin.M, _fq_struct(cfq), 1 if cfq._observe else 0,
-                           Q.AVERAGING_CONSTANT, qc.data_ptr(), ldc, mmc.data_ptr(), st)
-                    self._maybe_force(b["name"] + ".cat", qc, sq.C + xin.C)
-                    cat = _QT(qc, xin.N, xin.H, xin.W, sq.C + xin.C, cfq.scale, cfq.zero_point, mmc, ldc)
-                    if saved is not None:
-                        saved[b["name"] + ".cat"] = (sq, xin, cat)
-                    if self.record_taps:
-                        self.last_taps[b["name"] + ".cat_q"] = qc[:, :cat.C].contiguous()
-                    o = cat
-                else:
-                    o = xin
-                o = self._conv_bn(b["conv1"], o, training, st, saved)
-            else:
-                o = xin
-            o = self._conv_bn(b["conv2"], o, training, st, saved)
-            o = self._conv_bn(b["reduce"], o, training, st, saved)
-            if b["skip"]:
-                afq = blk.skip_add.activation_post_process
-                qa, lda = self._alloc_q(o.M, o.C)
-                mma = torch.empty(2, dtype=torch.float32, device=dev)
-                L.call("frost_add_forward", xin.c(), o.c(), o.M * o.C, _fq_struct(afq), 1 if afq._observe else 0,
-                       Q.AVERAGING_CONSTANT, qa.data_ptr(), lda, mma.data_ptr(), self.scratch.data_ptr(), st)
-                self._maybe_force(b["name"] + ".add", qa, o.C)
-                s = _QT(qa, o.N, o.H, o.W, o.C, afq.scale, afq.zero_point, mma, lda)
-                if saved is not None:
-                    saved[b["name"] + ".add"] = (xin, o, s)
-                if self.record_taps:
-                    self.last_taps[b["name"] + ".add_q"] = qa[:, :o.C].contiguous()
-                o = s
-            t = o
+            t = self._block_forward(b, t, training, st, saved)
             if self.features and b["stage_end"] and b["stage"] != 3:     # [x1, x2, x3, x5]
                 y = torch.empty((t.N, t.C, t.H, t.W), dtype=torch.float32, device=dev)
                 L.call("frost_dequant_to_nchw", t.q.data_ptr(), t.ld, t.scale.data_ptr(), t.zp.data_ptr(), t.N, t.H, t.W, t.C,
@@ -631,6 +646,51 @@ class QATEngine:
             L.call("frost_stem_wgrad", dz.data_ptr(), xin.q.data_ptr(), xin.scale.data_ptr(), xin.zp.data_ptr(), xin.N,
                    xin.H, xin.W, xin.C, ly.cout, ly.kh, ly.stride, ly.pad, ly.dwq.data_ptr(), st)
 
+    def _block_backward(self, b, g, saved, gbase, st):
+        """Backward of one bottleneck: g = grad wrt the block output [M][C] fp32 (consumed); returns the grad wrt its input."""
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        dout = g                                   # grad wrt the block output
+        conv2, reduce = b["conv2"], b["reduce"]
+        xin = saved[b["name"] + ".in"]
+        gx = torch.empty((xin.M, xin.C), **f32)    # grad wrt the block input
+        gx_written = False
+        if b["skip"]:
+            xa, ya, sa = saved[b["name"] + ".add"]
+            dsum = torch.empty_like(dout)
+            L.call("frost_add_backward", dout.data_ptr(), xa.c(), ya.c(), dout.numel(), sa.scale.data_ptr(),
+                   sa.zp.data_ptr(), dsum.data_ptr(), gx.data_ptr(), 0, st)
+            gx_written = True
+            d_reduce = dsum
+        else:
+            d_reduce = dout
+        x_red = saved[reduce.name][0]
+        d_dw_out = torch.empty((x_red.M, x_red.C), **f32)
+        self._conv_bn_bwd(reduce, d_reduce, saved, gbase, d_dw_out, False, st)
+        del d_reduce, dout
+        x_dw = saved[conv2.name][0]
+        if b["conv1"] is not None:
+            d_c1_out = torch.empty((x_dw.M, x_dw.C), **f32)
+            self._conv_bn_bwd(conv2, d_dw_out, saved, gbase, d_c1_out, False, st)
+            del d_dw_out
+            if b["squeeze"] is not None:
+                sq, xc, cat = saved[b["name"] + ".cat"]
+                d_cat = torch.empty((cat.M, cat.C), **f32)
+                self._conv_bn_bwd(b["conv1"], d_c1_out, saved, gbase, d_cat, False, st)
+                del d_c1_out
+                d_sq = torch.empty((sq.M, sq.C), **f32)
+                L.call("frost_cat_backward", d_cat.data_ptr(), sq.c(), xc.c(), cat.M, cat.scale.data_ptr(),
+                       cat.zp.data_ptr(), d_sq.data_ptr(), gx.data_ptr(), 1 if gx_written else 0, st)
+                gx_written = True
+                del d_cat
+                self._conv_bn_bwd(b["squeeze"], d_sq, saved, gbase, gx, True, st)
+            else:
+                self._conv_bn_bwd(b["conv1"], d_c1_out, saved, gbase, gx, gx_written, st)
+                gx_written = True
+        else:
+            self._conv_bn_bwd(conv2, d_dw_out, saved, gbase, gx, gx_written, st)
+            gx_written = True
+        return gx
+
     def _backward(self, saved, dlogits):
         """dlogits: grad of the logits (classifier) or the list of 4 NCHW feature-map grads (feature backbone)."""
         if saved.get("gen") != self.generation:
@@ -685,47 +745,11 @@ class QATEngine:
             if g is None:                              # no gradient reaches this block's output
                 xo = saved[b["reduce"].name][2] if not b["skip"] else saved[b["name"] + ".add"][2]
                 g = torch.zeros((xo.M, xo.C), **f32)
-            dout = g                                   # grad wrt the block output
-            conv2, reduce = b["conv2"], b["reduce"]
-            xin = saved[b["name"] + ".in"]
-            gx = torch.empty((xin.M, xin.C), **f32)    # grad wrt the block input
-            gx_written = False
-            if b["skip"]:
-                xa, ya, sa = saved[b["name"] + ".add"]
-                dsum = torch.empty_like(dout)
-                L.call("frost_add_backward", dout.data_ptr(), xa.c(), ya.c(), dout.numel(), sa.scale.data_ptr(),
-                       sa.zp.data_ptr(), dsum.data_ptr(), gx.data_ptr(), 0, st)
-                gx_written = True
-                d_reduce = dsum
-            else:
-                d_reduce = dout
-            x_red = saved[reduce.name][0]
-            d_dw_out = torch.empty((x_red.M, x_red.C), **f32)
-            self._conv_bn_bwd(reduce, d_reduce, saved, gbase, d_dw_out, False, st)
-            del d_reduce, dout
-            x_dw = saved[conv2.name][0]
-            if b["conv1"] is not None:
-                d_c1_out = torch.empty((x_dw.M, x_dw.C), **f32)
-                self._conv_bn_bwd(conv2, d_dw_out, saved, gbase, d_c1_out, False, st)
-                del d_dw_out
-                if b["squeeze"] is not None:
-                    sq, xc, cat = saved[b["name"] + ".cat"]
-                    d_cat = torch.empty((cat.M, cat.C), **f32)
-                    self._conv_bn_bwd(b["conv1"], d_c1_out, saved, gbase, d_cat, False, st)
-                    del d_c1_out
-                    d_sq = torch.empty((sq.M, sq.C), **f32)
-                    L.call("frost_cat_backward", d_cat.data_ptr(), sq.c(), xc.c(), cat.M, cat.scale.data_ptr(),
-                           cat.zp.data_ptr(), d_sq.data_ptr(), gx.data_ptr(), 1 if gx_written else 0, st)
-                    gx_written = True
-                    del d_cat
-                    self._conv_bn_bwd(b["squeeze"], d_sq, saved, gbase, gx, True, st)
-                else:
-                    self._conv_bn_bwd(b["conv1"], d_c1_out, saved, gbase, gx, gx_written, st)
-                    gx_written = True
-            else:
-                self._conv_bn_bwd(conv2, d_dw_out, saved, gbase, gx, gx_written, st)
-                gx_written = True
-            g = gx
+            if self.record_taps:                       # tests: gradient wrt every block output / input (NHWC fp32)
+                self.last_grad_taps[b["name"] + ".out"] = g.clone()
+            g = self._block_backward(b, g, saved, gbase, st)
+            if self.record_taps:
+                self.last_grad_taps[b["name"] + ".in"] = g.clone()
         self._conv_bn_bwd(self.stem, g, saved, gbase, None, False, st)
         if self._side is not None:
             torch.cuda.current_stream(dev).wait_stream(self._side)       # every weight gradient is complete

@@ -31,6 +31,10 @@ class _ConvBlock(nn.Module):
         self.conv = nn.Sequential(*layers)
 
     def forward(self, x):
+        if isinstance(getattr(self.conv[0], "weight_fake_quant", None), _qat.FrostFakeQuantize):
+            # prepared and called on its own (the whole-network engine never comes here): per-module executor
+            from .block_engine import run_block
+            return run_block(self, x)
         return self.conv(x)
 
     def fuse_model(self):
@@ -105,8 +109,9 @@ class CascadePreExBottleneck(nn.Module):
 
     def forward(self, x):
         if _qat.is_prepared(self):
-            raise RuntimeError("frostnet_b200: a prepared (QAT) bottleneck only runs inside FrostNet.forward "
-                               "(whole-network engine); there is no per-module eager path")
+            # called on its own (the whole-network engine never comes here): per-module executor, fp32 NCHW at the boundary
+            from .block_engine import run_block
+            return run_block(self, x)
         # float model and the int8 model made by frostnet_b200.convert_int8: cat / add go through the FloatFunctional /
         # QFunctional modules exactly where the reference's do (frostnet.py:124-145)
         if not self.expand_ratio == 1:

@@ -125,6 +125,11 @@ class FloatFunctional(nn.Module):
 
 class QuantStub(nn.Module):
     def forward(self, x):
+        if isinstance(getattr(self, "activation_post_process", None), FrostFakeQuantize):
+            # prepared and called on its own (the whole-network engine never comes here): observer + fake-quant, the result
+            # carries its (scale, zero_point) for the frostnet_b200 module that consumes it
+            from .block_engine import run_quant_stub
+            return run_quant_stub(self, x)
         return x
 
 
