@@ -5,7 +5,7 @@ and the StatAssist/GradBoost optimizer step, behind the reference's nn.Module / 
 """
 from .frostnet import *          # noqa: F401,F403  (FrostNet, blocks, 30 factories)
 from .frostnet import FrostNet, CascadePreExBottleneck, ConvBNReLU, ConvBN
-from .qat import prepare_qat, patch_torch_quantization, FrostFakeQuantize
+from .qat import prepare_qat, patch_torch_quantization, attach_fake_quant, FrostFakeQuantize, QuantStub, DeQuantStub
 from .optimizer import QSGD, QRMSprop, QAdam, QAdamW, get_optimizer
 from . import parallel
 from .prefetch import DevicePrefetcher
@@ -13,3 +13,4 @@ from . import frostnet_features
 
 __version__ = "0.1.0"
 from .export import convert_int8
+from .hswish import Hswish

@@ -219,6 +219,24 @@ def prepare_qat(model, inplace=True):
     return model
 
 
+def attach_fake_quant(root):
+    """prepare_qat for an arbitrary tree of frostnet_b200 modules (bottlenecks wired into another network, Hswish, a
+    QuantStub in front): attaches the qnnpack-QAT fake-quants where torch.quantization.prepare_qat would - on every
+    fused conv (weight + output), FloatFunctional, QuantStub and the ReLU6 inside Hswish.  Convs must be fused first
+    (``fuse_model()``).  The modules then run through the per-module executor (block_engine.py)."""
+    from .hswish import Hswish
+    dev = next((p.device for p in root.parameters()), torch.device("cpu"))
+    for m in list(root.modules()):
+        if isinstance(m, FrostConvBn2d) and not isinstance(getattr(m, "weight_fake_quant", None), FrostFakeQuantize):
+            m.weight_fake_quant = FrostFakeQuantize.weight().to(dev)
+            m.activation_post_process = FrostFakeQuantize.act().to(dev)
+        elif isinstance(m, (FloatFunctional, QuantStub)) and not isinstance(getattr(m, "activation_post_process", None), FrostFakeQuantize):
+            m.activation_post_process = FrostFakeQuantize.act().to(dev)
+        elif isinstance(m, Hswish) and not m._prepared():
+            m.relu6.activation_post_process = FrostFakeQuantize.act().to(dev)
+    return root
+
+
 def patch_torch_quantization():
     """Route torch.quantization.prepare_qat / fuse_modules to this package for frostnet_b200 models so
     that an unmodified caller script (Classification/train.py:166-173) works unchanged."""

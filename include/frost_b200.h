@@ -316,6 +316,23 @@ int frost_pw_fused_bwd_reduce(const FrostPwFusedBwdArgs* a, void* stream);
 int frost_pw_fused_bwd_apply(const FrostPwFusedBwdArgs* a, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Quantization-aware hard-swish: the reference's _Hswish module
+ * (Classification/models/imagenet/mobilenetv3.py:43-56) after prepare_qat,
+ *     y = mul_scalar( FQ_mul( x * FQ_relu6( relu6( add_scalar(x, 3) ) ) ), 1/6 )
+ * with both observers (EMA + qparams, updated in place), on a tensor x that sits on the uint8 grid (in_scale, in_zp).
+ * The input takes <= 256 values, so the op is an index pass + one 256-entry table pass (hswish.cu).
+ *   q_in      out [n] uint8: the input indices (kept for the backward)
+ *   y / y_q   out [n] fp32 values and / or uint8 indices of the result (either may be NULL); the result's grid is
+ *             (*out_scale = scale_mul/6, zero point of fq_mul)
+ *   workspace frost_hswish_workspace_floats() floats, written by forward, read by backward of the same step
+ * backward: dx = grad through mul_scalar, FQ_mul (STE), mul (both operands), FQ_relu6 (STE), hardtanh, add_scalar. */
+int frost_hswish_workspace_floats(void);
+int frost_hswish_forward(const float* x, int64_t n, const float* in_scale, const int32_t* in_zp, FrostFQ fq_relu6,
+                         int observe_relu6, FrostFQ fq_mul, int observe_mul, float averaging_const, uint8_t* q_in,
+                         float* y, uint8_t* y_q, float* workspace, float* out_scale, void* stream);
+int frost_hswish_backward(const float* dy, const uint8_t* q_in, int64_t n, const float* workspace, float* dx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * FloatFunctional.cat / .add (frostnet.py:129,142;
  * torch/ao/nn/quantized/modules/functional_modules.py:50-52,80-82): op + own observer + FQ. */
 typedef struct {
