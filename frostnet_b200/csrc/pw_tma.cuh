@@ -30,25 +30,6 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-
-// mbarrier wait for the warps that have slack (producer, MMA issuer, epilogue between tiles): spinning warps steal issue
-// slots from the 16 epilogue warps (ncu: BRA + SYNCS were 18 % of the instructions executed), so back off between polls.
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  for (uint32_t it = 0; it < (1u << 24); ++it) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-    if (it >= 4) __nanosleep(40);
-  }
-  __trap();
-}
 // 32 lanes x 16 consecutive 32-bit columns
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
