@@ -33,10 +33,22 @@ def stream():
 
 # ------------------------------------------------------------------------------------------ whole network
 def test_large_1_0_at_224_teacher_forced_vs_oracle():
+    _teacher_forced("large", 1.0, 224, 4, 1000)
+
+
+# the other topologies / width multipliers of frostnet.py:354-451 (M3): every factory shares these code paths, the channel
+# counts (and so the tile shapes, pitches, replication factors, chained-kernel eligibility) differ
+@pytest.mark.parametrize("mode,wm,R,N,nclass", [("base", 1.0, 160, 2, 100), ("small", 0.75, 128, 3, 40), ("large", 1.25, 128, 2, 1000),
+                                                 ("large", 0.5, 96, 2, 16), ("base", 0.35, 64, 5, 10)])
+def test_other_factories_teacher_forced_vs_oracle(mode, wm, R, N, nclass):
+    _teacher_forced(mode, wm, R, N, nclass)
+
+
+def _teacher_forced(mode, wm, R, N, nclass):
     import frostnet_b200 as F
     from oracle import frost_oracle as O
     dev = torch.device(DEV)
-    spec = O.net_spec("large", 1.0, 1000)
+    spec = O.net_spec(mode, wm, nclass)
     sd = O.fresh_state_dict(spec, seed=1882)
     gsd = torch.Generator().manual_seed(3)
     for k in sd:                                   # de-trivialise BN (fresh init is gamma=1, beta=0)
@@ -46,15 +58,15 @@ def test_large_1_0_at_224_teacher_forced_vs_oracle():
             sd[k] = 0.2 * torch.randn(sd[k].shape, generator=gsd)
     onet = O.OracleNet(spec, sd)
     onet.record = True
-    model = F.frostnet_quant_large_1_0(drop_rate=0.0)
+    model = F.FrostNet(nclass=nclass, mode=mode, width_mult=wm, quantized=True, drop_rate=0.0)
     model.train()
     model.fuse_model()
     F.prepare_qat(model)
     model.load_state_dict(onet.state_dict(), strict=True)
     model.to(dev)
     g = torch.Generator().manual_seed(1882)
-    x = torch.randn(4, 3, 224, 224, generator=g)
-    y = torch.randint(0, 1000, (4,), generator=g)
+    x = torch.randn(N, 3, R, R, generator=g)
+    y = torch.randint(0, nclass, (N,), generator=g)
     ologits = onet.forward(x, training=True, drop_rate=0.0)
     Fn.cross_entropy(ologits, y).backward()
     eng = model._frost_engine
@@ -63,7 +75,11 @@ def test_large_1_0_at_224_teacher_forced_vs_oracle():
     logits = model(x.to(dev))
     Fn.cross_entropy(logits, y.to(dev)).backward()
     rep = eng.force_report
-    assert len(eng.layers) == 70 and len(rep) >= 70 + 14 + 11          # every conv, cat, add (+ QuantStub) was compared
+    n_cat = sum(1 for b in eng.blocks if b["squeeze"] is not None)
+    n_add = sum(1 for b in eng.blocks if b["skip"])
+    if (mode, wm) == ("large", 1.0):
+        assert (len(eng.layers), n_cat, n_add) == (70, 14, 11)
+    assert len(rep) >= len(eng.layers) + n_cat + n_add                  # every conv, cat, add (+ QuantStub) was compared
     assert rep["quant"] == (0.0, 0)
     for ly in eng.layers:                                              # all 5.8 M weight quantize indices
         w_idx = onet.taps[ly.name + ".w_idx"].clamp(-128, 127).to(torch.int8)
@@ -79,8 +95,8 @@ def test_large_1_0_at_224_teacher_forced_vs_oracle():
         assert rate <= max(LAYER_MISMATCH_RATE, floor), (k, rate)
     e_log = rel_l2(logits.detach().cpu(), ologits.detach())
     e_grad, wg = _grad_rel_l2(model, onet)
-    print("Large-1.0 @224 N=4 teacher-forced: worst layer %s rate %.3g; logits rel-L2 %.3g; grad rel-L2 %.3g (worst %s)" % (
-        worst[0], worst[1][0], e_log, e_grad, wg))
+    print("%s-%g @%d N=%d teacher-forced: worst layer %s rate %.3g; logits rel-L2 %.3g; grad rel-L2 %.3g (worst %s)" % (
+        mode, wm, R, N, worst[0], worst[1][0], e_log, e_grad, wg))
     assert e_log < LOGIT_REL_L2 and e_grad < GRAD_REL_L2
     _check_state(model, onet, [k for k in sd0 if "running_" in k or k.endswith("scale") or k.endswith("min_val")
                                or k.endswith("max_val") or k.endswith("zero_point")])
