@@ -51,6 +51,9 @@ constexpr int PF_THREADS = (PF_EPI_WARPS + 2) * 32;   // warps 0-15 epilogue, 16
 constexpr int PF_W_BYTES = PF_CH * PF_BK;       // 16 KB
 constexpr int PF_X_BYTES = PF_NPX * PF_BK;      // 32 KB
 constexpr int PF_TAIL = 12288;                  // barriers + per-channel buffers
+constexpr int PF_DY_SLOTS = 3;                  // backward: ring of gradient boxes (TMA)
+constexpr int PF_DY_BYTES = 32768;              // one box: 64*R pixels x 128/R channels fp32 (R = weight-row replication)
+constexpr int PF_BWD_STAGES = 2;                // activation stages of the backward modes (the ring takes the rest)
 
 enum { PF_FWD = 0, PF_BWD_REDUCE = 1, PF_BWD_APPLY = 2 };
 
@@ -90,23 +93,27 @@ struct PfCombine {       // per channel of the tile: the partial results of the 
 template <int MODE>
 __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                                 const __grid_constant__ CUtensorMap tm_w,
+                                                                const __grid_constant__ CUtensorMap tm_dy,
                                                                 const __grid_constant__ PwFusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by OFFSETTING the __shared__ array (a cast through uintptr_t would turn every later access into a
   // generic LD/ST: ncu showed 10 % of the forward's instructions as generic loads of the per-channel coefficients)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const bool resident = p.n_kb <= PF_RES_KB;
-  const int S = resident ? 4 : 3;                                    // pipeline stages
+  const int S = MODE != PF_FWD ? PF_BWD_STAGES : (resident ? 4 : 3);   // pipeline stages
   const int stage_bytes = resident ? PF_X_BYTES : PF_X_BYTES + PF_W_BYTES;
   uint8_t* wres = smem;                                              // [n_kb][128 rows][128 B] when resident
   uint8_t* stages = smem + (resident ? PF_RES_KB * PF_W_BYTES : 0);  // [S][x 32 KB (+ w 16 KB)]
-  uint8_t* tail = stages + S * stage_bytes;
+  uint8_t* dy_ring = stages + S * stage_bytes;                       // backward: [PF_DY_SLOTS][32 KB] gradient boxes
+  uint8_t* tail = dy_ring + (MODE != PF_FWD ? PF_DY_SLOTS * PF_DY_BYTES : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);            // [4]
   uint64_t* empty_bar = full_bar + 4;                                // [4]
   uint64_t* tfull_bar = empty_bar + 4;                               // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                              // [2]
   uint64_t* wfull_bar = tempty_bar + 2;                              // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
+  uint64_t* dyfull_bar = wfull_bar + 1;                              // [PF_DY_SLOTS]
+  uint64_t* dyempty_bar = dyfull_bar + PF_DY_SLOTS;                  // [PF_DY_SLOTS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dyempty_bar + PF_DY_SLOTS);
   float* s_red = reinterpret_cast<float*>(tmem_slot + 2);            // [2 * PF_EPI_WARPS] block min / max
   float* s_qp = s_red + 2 * PF_EPI_WARPS;                            // scale, zero point (as float), 1/scale, spare
   float4* s_cf = reinterpret_cast<float4*>(tail + 512);              // [128] per channel: A, B, corr (int bits), -
@@ -126,6 +133,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
     for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], PF_EPI_WARPS); }
     mbar_init(wfull_bar, 1);
+    for (int i = 0; i < PF_DY_SLOTS; ++i) { mbar_init(&dyfull_bar[i], 1); mbar_init(&dyempty_bar[i], PF_EPI_WARPS); }
     mbar_fence_init();
   }
   if (warp == PF_EPI_WARPS + 1) tmem_alloc<512>(tmem_slot);
@@ -163,7 +171,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
           for (int j = 0; j < R; ++j)          // the same bnr weight rows, replicated down the 128-row tile
             tma_load_2d(&tm_w, wfull_bar, smem_u32(wres + kb * PF_W_BYTES + j * bnr * PF_BK), kb * PF_BK, c_tile0);
       }
-      uint32_t it = 0;
+      uint32_t it = 0, dy_it = 0;
       for (int ph = 0; ph < n_phases; ++ph) {
         for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x) {
           for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
@@ -176,6 +184,17 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
               for (int j = 0; j < R; ++j)
                 tma_load_2d(&tm_w, &full_bar[s], smem_u32(st + PF_X_BYTES + j * bnr * PF_BK), kb * PF_BK, c_tile0);
             if (it == 0) PF_STAMP(3);
+          }
+          if constexpr (MODE != PF_FWD) {
+            // this tile's gradient rows, as boxes of 64*R pixels x 128/R channels: bulk copies keep HBM busy without tying up
+            // load-queue entries and registers of the epilogue warps (the per-thread loads they replace were throttled there)
+            const int box_px = 64 * R;
+            for (int bj = 0; bj < PF_NPX / box_px; ++bj, ++dy_it) {
+              const int slot = dy_it % PF_DY_SLOTS;
+              mbar_wait_parked(&dyempty_bar[slot], ((dy_it / PF_DY_SLOTS) & 1) ^ 1);
+              mbar_expect_tx(&dyfull_bar[slot], PF_DY_BYTES);
+              tma_load_2d(&tm_dy, &dyfull_bar[slot], smem_u32(dy_ring + slot * PF_DY_BYTES), c_tile0, (int)(pt * PF_NPX + bj * box_px));
+            }
           }
         }
       }
@@ -498,25 +517,28 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
       uint16_t* dz_hi = reinterpret_cast<uint16_t*>(b.dz);
       uint16_t* dz_lo = reinterpret_cast<uint16_t*>(b.dz_lo);
       double S1 = 0.0, S2 = 0.0;
-      const int64_t row_b = (int64_t)cout * 4;                 // bytes between consecutive pixels of dy
-      // 16 pixels of my channel, starting at pixel column `col` of the tile whose first element is `tile_dy`
-      auto load16 = [&](float (&d)[16], const float* tile_dy, int col, int px_valid) {
-        // ONE running 64-bit pointer (2 instructions per load; base + running offset cost 4 - these loops are issue-bound)
-        const char* q = reinterpret_cast<const char*>(tile_dy) + (int64_t)col * row_b;
-        if (col + 16 <= px_valid) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { d[j] = ld_cg_chain(q); q += row_b; }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { d[j] = (col + j < px_valid) ? ld_cg_chain(q) : 0.0f; q += row_b; }
-        }
+      // The gradient arrives through the shared-memory ring (TMA producer): per box of 64*R pixels every thread takes 16
+      // pixels of its channel - the same 16 accumulator columns it reads from TMEM.
+      const int box_px = 64 * R;
+      const int n_box = PF_NPX / box_px;                         // boxes per tile: 4, 2 or 1
+      const int px0 = (rep * 4 + grp) * 16;                      // my pixels inside a box
+      const uint32_t dy_row_b = (uint32_t)bnr * 4;               // bytes between consecutive pixels inside a box
+      const uint32_t dy_thread = smem_u32(dy_ring) + (uint32_t)px0 * dy_row_b + (uint32_t)c_local * 4;
+      auto lds = [](uint32_t a) {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+        return v;
       };
       float p1 = 0.f, p2 = 0.f;
-      auto proc16 = [&](const float (&d)[16], uint32_t taddr, int64_t e_col, int col, int px_valid) {
+      auto proc16 = [&](uint32_t dy_addr, uint32_t taddr, int64_t e_col, int col, int px_valid) {
         uint32_t v[16];
         tmem_ld_32x16(taddr, v);
         if (!active) return;
+        float d[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) d[j] = lds(dy_addr + (uint32_t)j * dy_row_b);
         if constexpr (MODE == PF_BWD_REDUCE) {
+          // pixels past the end of the tensor: the box rows are zero-filled, dv = 0
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int I = wsign * (int)v[j] - corr_s;
@@ -548,38 +570,31 @@ __global__ void __launch_bounds__(PF_THREADS, 1) pw_fused_kernel(const __grid_co
           }
         }
       };
-      const int n_ch = cols_per >> 4;                          // 16-pixel chunks per tile for this thread: 4, 2 or 1
+      uint32_t dy_it = 0;
       for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x, ++tile_i) {
         const uint32_t acc = tile_i & 1;
         const int px_valid = (int)min((int64_t)PF_NPX, p.M - pt * PF_NPX);
         const int64_t e_tile = pt * PF_NPX * (int64_t)cout + c;                // element (pixel 0 of the tile, my channel)
-        const float* tile_dy = b.dy + e_tile;
         const uint32_t t0 = tmem_base + acc * PF_NPX + ((uint32_t)(quarter * 32) << 16);
-        // ping-pong buffers: chunk k+1 is in flight while chunk k is processed; chunk 0 is requested before the
-        // accumulator is waited for
-        float dA[16], dB[16];
-        if (active && col_begin < px_valid) load16(dA, tile_dy, col_begin, px_valid);
         if (tid == 0 && tile_i == 0) PF_STAMP(15);
         mbar_wait_parked(&tfull_bar[acc], (tile_i >> 1) & 1);
         tc_fence_after();
         if (tid == 0 && tile_i == 0) PF_STAMP(16);
-        if (warp_active) {
-          p1 = 0.f;
-          p2 = 0.f;
+        p1 = 0.f;
+        p2 = 0.f;
 #pragma unroll 1
-          for (int k = 0; k < n_ch; k += 2) {
-            const int colA = col_begin + 16 * k, colB = colA + 16;
-            if (colA >= px_valid) break;
-            const bool hasB = k + 1 < n_ch && colB < px_valid;
-            if (active && hasB) load16(dB, tile_dy, colB, px_valid);
-            proc16(dA, t0 + colA, e_tile + (int64_t)colA * cout, colA, px_valid);
-            const bool hasA2 = k + 2 < n_ch && colB + 16 < px_valid;
-            if (active && hasA2) load16(dA, tile_dy, colB + 16, px_valid);
-            if (hasB) proc16(dB, t0 + colB, e_tile + (int64_t)colB * cout, colB, px_valid);
-          }
-          S1 += (double)p1;                      // <= 64 terms per fp32 partial
-          S2 += (double)p2;
+        for (int bj = 0; bj < n_box; ++bj, ++dy_it) {
+          const int slot = dy_it % PF_DY_SLOTS;
+          // every warp, also one whose lanes hold no channel, takes part in the ring protocol (16 arrivals free a slot)
+          mbar_wait_parked(&dyfull_bar[slot], (dy_it / PF_DY_SLOTS) & 1);
+          const int col = bj * box_px + px0;                                   // first of my 16 pixels, tile-relative
+          if (warp_active && col < px_valid)
+            proc16(dy_thread + (uint32_t)slot * PF_DY_BYTES, t0 + col, e_tile + (int64_t)col * cout, col, px_valid);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&dyempty_bar[slot]);
         }
+        S1 += (double)p1;                        // <= 64 terms per fp32 partial
+        S2 += (double)p2;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -652,7 +667,18 @@ static int launch_fused(const char* who, const PwOperands& o, PwFusedParams& p, 
     return FROST_ECUDA;
   }
   const bool resident = p.n_kb <= PF_RES_KB;
-  const size_t smem = 1024 + (resident ? PF_RES_KB * PF_W_BYTES + 4 * PF_X_BYTES : 3 * (PF_X_BYTES + PF_W_BYTES)) + PF_TAIL;
+  CUtensorMap tm_dy = tm_x;                   // forward: unused
+  size_t smem = 1024 + (resident ? PF_RES_KB * PF_W_BYTES + 4 * PF_X_BYTES : 3 * (PF_X_BYTES + PF_W_BYTES)) + PF_TAIL;
+  if (MODE != PF_FWD) {
+    // gradient boxes of 64*R pixels x 128/R channels (R = PF_CH / bnr), channel coordinate = the tile's first channel
+    const int R = PF_CH / p.bnr;
+    if (!make_map_f32(&tm_dy, p.bwd.dy, (uint64_t)o.cout, (uint64_t)o.M, (uint32_t)p.bnr, (uint32_t)(64 * R))) {
+      set_error("%s: cuTensorMapEncodeTiled failed (dy)", who);
+      return FROST_ECUDA;
+    }
+    smem = 1024 + (resident ? PF_RES_KB * PF_W_BYTES + PF_BWD_STAGES * PF_X_BYTES : PF_BWD_STAGES * (PF_X_BYTES + PF_W_BYTES)) +
+           PF_DY_SLOTS * PF_DY_BYTES + PF_TAIL;
+  }
   if (first_use_on_device(reinterpret_cast<const void*>(&pw_fused_kernel<MODE>))) {
     cudaError_t e = cudaFuncSetAttribute(pw_fused_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
@@ -662,7 +688,7 @@ static int launch_fused(const char* who, const PwOperands& o, PwFusedParams& p, 
   }
   const int64_t n_ptiles = ceil_div(o.M, PF_NPX);
   const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(n_ptiles, kNumSMs / n_ct_eff));
-  cudaError_t e = launch_pdl(pw_fused_kernel<MODE>, dim3(gx, n_ct_eff), dim3(PF_THREADS), smem, st, tm_x, tm_w, p);
+  cudaError_t e = launch_pdl(pw_fused_kernel<MODE>, dim3(gx, n_ct_eff), dim3(PF_THREADS), smem, st, tm_x, tm_w, tm_dy, p);
   if (e != cudaSuccess) {
     set_error("%s: launch failed: %s", who, cudaGetErrorString(e));
     return FROST_ECUDA;
