@@ -216,6 +216,11 @@ def algorithmic_cost(name, a):
             if name == "frost_pw_fused_bwd_reduce":  # x + dy
                 return M * K + co * K + 4 * M * co, 2 * M * K * co
             return M * K + co * K + 8 * M * co, 2 * M * K * co      # x + dy + dz planes
+    if name == "frost_pw_chain_backward":
+        args = getattr(a[0], "_obj", None)
+        if args is not None:                        # x + dy read, dx written (read too when accumulating); I recompute + dgrad + wgrad
+            M, K, co = args.op.M, args.op.K, args.op.cout
+            return M * K + 4 * M * co + 4 * M * K * (2 if args.accumulate else 1) + 2 * co * K, 6 * M * K * co
     if name == "frost_bnq_apply":
         M, Cc = a[2], a[3]
         return 5 * M * Cc, 0
@@ -450,7 +455,7 @@ def run_b200(args):
             kernel_of = {"frost_bn_backward_apply": "bn_bwd_apply_kernel", "frost_bn_backward_reduce": "bn_bwd_reduce_kernel",
                          "frost_pw_conv_forward": "pw_conv_fwd_tc_kernel", "frost_pw_wgrad_tc": "pw_wgrad_tc_kernel",
                          "frost_pw_fused_forward": "pw_fused_kernel<0>", "frost_pw_fused_bwd_reduce": "pw_fused_kernel<1>",
-                         "frost_pw_fused_bwd_apply": "pw_fused_kernel<2>",
+                         "frost_pw_fused_bwd_apply": "pw_fused_kernel<2>", "frost_pw_chain_backward": "pw_chain_bwd_kernel",
                          "frost_pw_dgrad_tc": "pw_dgrad_tc_kernel", "frost_bnq_apply": "bnq_apply_kernel",
                          "frost_dw_conv_forward": "dw_conv_fwd_kernel", "frost_dw_wgrad": "dw_wgrad_kernel",
                          "frost_dw_dgrad": "dw_dgrad_kernel"}

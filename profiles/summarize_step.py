@@ -35,22 +35,21 @@ print('%-46s %5s %12s %7s %16s %10s' % ('kernel', 'n', 'time us', 'share', 'DRAM
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print('%-46s %5d %12.1f %6.1f%% %16.2f %10.0f' % (k[:46], v[0], v[1], 100 * v[1] / tot, v[2] / v[0] / 1e6, v[2] / v[1] / 1e3 if v[1] else 0))
 if len(sys.argv) > 2:
-    out = {k.split('<')[0]: {'dram_bytes_per_launch': v[2] / v[0], 'launches': v[0],
-                             'source': '%s (ncu dram__bytes_read.sum+dram__bytes_write.sum, mean over the launches of one bs=256 step)' % sys.argv[1].replace('gpurun_out/', 'profiles/')}
-           for k, v in agg.items() if v[2] > 0}
-    # templated kernels: merge instantiations
+    src = sys.argv[1].replace('gpurun_out/', 'profiles/')
+    note = '%s (ncu dram__bytes_read.sum+dram__bytes_write.sum, mean over the launches of one bs=256 step)' % src
+    out = {}
     merged = {}
     for k, v in agg.items():
-        b = k.split('<')[0]
-        m = merged.setdefault(b, [0, 0.0])
+        name = k.replace('frost::', '')
+        if v[2] > 0:                                   # every instantiation under its own name: pw_fused_kernel<0>, <1>, <2> ...
+            out[name] = {'dram_bytes_per_launch': v[2] / v[0], 'launches': v[0], 'source': note}
+        m = merged.setdefault(name.split('<')[0], [0, 0.0])
         m[0] += v[0]
         m[1] += v[2]
-    for b, m in merged.items():
-        if m[1] > 0:
-            out[b] = {'dram_bytes_per_launch': m[1] / m[0], 'launches': m[0], 'source': out.get(b, {}).get('source') or
-                      '%s (ncu dram bytes, mean over the launches of one bs=256 step)' % sys.argv[1].replace('gpurun_out/', 'profiles/')}
+    for b, m in merged.items():                        # ... and merged over the instantiations of a template
+        if m[1] > 0 and b not in out:
+            out[b] = {'dram_bytes_per_launch': m[1] / m[0], 'launches': m[0], 'source': note}
     total_bytes = sum(v[2] for v in agg.values())
     out['step_total'] = {'dram_bytes': total_bytes, 'launches': len(launch), 'kernel_time_us': tot,
-                         'source': '%s (ncu dram__bytes_read.sum+dram__bytes_write.sum summed over every launch of one bs=256 step)'
-                                   % sys.argv[1].replace('gpurun_out/', 'profiles/')}
+                         'source': '%s (ncu dram__bytes_read.sum+dram__bytes_write.sum summed over every launch of one bs=256 step)' % src}
     json.dump(out, open(sys.argv[2], 'w'), indent=1)
