@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) pw_dgrad_tc_kernel(const uint16
   // allocation is complete (see pw_conv_tc.cu)
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
     mbar_fence_init();
   }
   if (warp == 12) tmem_alloc<2 * BN>(tmem_slot);
@@ -145,18 +145,18 @@ __global__ void __launch_bounds__(DG_THREADS, 1) pw_dgrad_tc_kernel(const uint16
       }
     }
   } else {
-    // ================================================================= epilogue: two groups, one per TMEM buffer
+    // ================================================================= epilogue: both groups on every tile (even / odd 32-column
+    // chunks): the 14x14 / 7x7 layers give a CTA one or two tiles, and a group per TMEM buffer left half the warps idle there
     const int grp = warp >> 2, wq4 = warp & 3;
     float* my = scratch + warp * BW_SCR;
     const float s_w = *w_scale_p;
     uint32_t tile_i = 0;
     for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++tile_i) {
       const uint32_t acc = tile_i & 1;
-      if ((int)acc != grp) continue;
       const int64_t m0 = mt * DG_BM + wq4 * 32;
       mbar_wait(&tfull_bar[acc], (tile_i >> 1) & 1);
       tc_fence_after();
-      for (int chunk = 0; chunk * 32 < n_valid; ++chunk) {
+      for (int chunk = grp; chunk * 32 < n_valid; chunk += 2) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + acc * BN + chunk * 32 + ((uint32_t)(wq4 * 32) << 16), v);
 #pragma unroll
