@@ -9,7 +9,9 @@
 // SWIZZLE_128B tiles - the same bytes serve as the K-major A operand of dgrad and, untouched, as the MN-major
 // A operand of wgrad (the transposes of the reference's wgrad are done by the UMMA descriptors).
 #include <cuda_bf16.h>
-#include "tc_common.cuh"
+#include <cuda.h>
+#include <algorithm>
+#include "pw_tma.cuh"
 
 namespace frost {
 
@@ -246,14 +248,13 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16_t* dz_hi,
-                                                                   const uint16_t* dz_lo,
+__global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_hi,
+                                                                   const __grid_constant__ CUtensorMap tm_lo,
                                                                    const uint8_t* xq,
                                                                    const float* x_scale_p,
                                                                    const int32_t* x_zp_p, int64_t M, int K, int ldx,
                                                                    int cout, int64_t rows_per_split, float* dwq) {
   constexpr int STAGES = wg_stages<BN>();
-  constexpr int BW_LAG = 2;
   constexpr int A_BYTES = 2 * WG_BLK;                       // 128 co x 64 rows, one of (hi, lo)
   constexpr int STAGE = 2 * A_BYTES + (BN / 64) * WG_BLK;   // hi, lo, BN k-columns
   extern __shared__ uint8_t smem_raw[];
@@ -274,7 +275,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
   const int num_kb = (int)((m_end - m_begin + WG_ROWS - 1) / WG_ROWS);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], WG_PROD_WARPS * 32); mbar_init(&empty_bar[s], 1); }
+    // a stage is full when every producer thread has stored its converted x chunks and the four dz boxes have landed
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], WG_PROD_WARPS * 32 + 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tfull_bar[0], 1);
     mbar_fence_init();
   }
@@ -290,9 +292,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
     if (warp >= 4 && warp < 4 + WG_PROD_WARPS) {
       // ================================================================= producer
       constexpr int PT = WG_PROD_WARPS * 32;           // producer threads
-      constexpr int RPP = PT / 16;                     // dz rows per pass (16 chunks of 8 co per row)
       const int tp = threadIdx.x - 128;
-      const int cidx = tp & 15, r0 = tp >> 4;
       // byte -> float without I2F: 0x4B0000bb is the float 2^23 + bb; subtracting 2^23 + zp_a is exact
       const float zp_magic = 8388608.0f + (float)*x_zp_p;
       const int cpr = n_eff >> 3;                      // 8-channel chunks per row of x
@@ -311,8 +311,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
         xdst[q] = (uint32_t)(kc >> 3) * WG_BLK + sw128_offset(r, kc & 7);
         if (idx >= WG_ROWS * cpr) xrow[q] = -1;
       }
-      const int co = co0 + cidx * 8;
-      const bool co_ok = co < cout;
       // x of stage kb + 1 is requested while stage kb is converted: with the loads issued in the iteration that consumes them,
       // every 64-row stage paid one DRAM round trip (~0.9 us per stage on the 56x56 / 28x28 layers)
       auto load_x = [&](uint2 (&dst)[XL], int kb) {
@@ -336,18 +334,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
         const int rows_left = (int)min((int64_t)WG_ROWS, m_end - mb);
         load_x(xnext, kb + 1);
         mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
-        // dz hi/lo: cp.async straight into the MN-major tiles
-        const int64_t dzbase = (mb + r0) * cout + co;
+        // dz hi / lo: four TMA boxes (64 channels x 64 rows each) straight into the MN-major SWIZZLE_128B tiles; rows past the
+        // end of the tensor and channels past cout arrive as zeros.  Up to STAGES stages of dz are in flight (the cp.async
+        // producers this replaces kept two), and no load-queue entries are spent on them.
+        if (tp == 0) {
+          mbar_expect_tx(&full_bar[s], 4 * WG_BLK);
 #pragma unroll
-        for (int i = 0; i < WG_ROWS / RPP; ++i) {
-          const int r = r0 + RPP * i;
-          const bool v = (r < rows_left) && co_ok;
-          const int64_t off = v ? dzbase + i * (RPP * cout) : 0;
-          const uint32_t d = (uint32_t)(cidx >> 3) * WG_BLK + sw128_offset(r, cidx & 7);
-          cp_async_zfill<16>(a_hi + d, dz_hi + off, v);
-          cp_async_zfill<16>(a_lo + d, dz_lo + off, v);
+          for (int blk = 0; blk < 2; ++blk) {
+            tma_load_2d(&tm_hi, &full_bar[s], a_hi + blk * WG_BLK, co0 + 64 * blk, (int)mb);
+            tma_load_2d(&tm_lo, &full_bar[s], a_lo + blk * WG_BLK, co0 + 64 * blk, (int)mb);
+          }
         }
-        cp_async_commit();
 #pragma unroll
         for (int q = 0; q < XL; ++q) {
           if (xrow[q] >= 0) {
@@ -362,17 +359,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const uint16
                 make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
           }
         }
-        if (kb >= BW_LAG) {
-          cp_async_wait<BW_LAG>();
-          fence_proxy_async();
-          mbar_arrive(&full_bar[(kb - BW_LAG) % STAGES]);
-        }
+        fence_proxy_async();
+        mbar_arrive(&full_bar[s]);
 #pragma unroll
         for (int q = 0; q < XL; ++q) xpk[q] = xnext[q];
       }
-      cp_async_wait<0>();
-      fence_proxy_async();
-      for (int j = (num_kb > BW_LAG ? num_kb - BW_LAG : 0); j < num_kb; ++j) mbar_arrive(&full_bar[j % STAGES]);
     } else if (warp == 4 + WG_PROD_WARPS) {
       // ================================================================= MMA issuer (A and B MN-major)
       const uint32_t idesc = umma_idesc(1, 1, 1, 128, n_eff) | (1u << 15) | (1u << 16);
@@ -450,7 +441,13 @@ static int launch_wgrad_tc(const uint16_t* dz_hi, const uint16_t* dz_lo, const u
   int64_t splits = std::max<int64_t>(1, std::min<int64_t>(ceil_div(M, WG_ROWS * 4), (int64_t)kNumSMs / ((int64_t)ct * kt)));
   int64_t rows = ceil_div(ceil_div(M, splits), WG_ROWS) * WG_ROWS;
   splits = ceil_div(M, rows);
-  launch_pdl(pw_wgrad_tc_kernel<BN>, dim3(ct, kt, (unsigned)splits), dim3(WG_THREADS), smem, st, dz_hi, dz_lo, xq, x_scale, x_zp, M, K, ldx, cout, rows, dwq);
+  CUtensorMap tm_hi, tm_lo;
+  if (!make_map_b16(&tm_hi, dz_hi, (uint64_t)cout, (uint64_t)M, (uint64_t)cout * 2, 64, WG_ROWS) ||
+      !make_map_b16(&tm_lo, dz_lo, (uint64_t)cout, (uint64_t)M, (uint64_t)cout * 2, 64, WG_ROWS)) {
+    set_error("pw_wgrad_tc: cuTensorMapEncodeTiled failed (driver too old, or dz planes not 16-byte aligned)");
+    return FROST_ENOSUP;
+  }
+  launch_pdl(pw_wgrad_tc_kernel<BN>, dim3(ct, kt, (unsigned)splits), dim3(WG_THREADS), smem, st, tm_hi, tm_lo, xq, x_scale, x_zp, M, K, ldx, cout, rows, dwq);
   return FROST_OK;
 }
 
