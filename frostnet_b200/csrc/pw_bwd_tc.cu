@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) pw_dgrad_tc_kernel(const uint16
   // barrier init and the TMEM allocation overlap the previous kernel's tail; dependents are released after the
   // allocation is complete (see pw_conv_tc.cu)
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 4); mbar_init(&empty_bar[s], 1); }      // one arrival per producer warp
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
     mbar_fence_init();
   }
@@ -112,13 +112,16 @@ __global__ void __launch_bounds__(DG_THREADS, 1) pw_dgrad_tc_kernel(const uint16
         if (it >= (uint32_t)BW_LAG) {
           cp_async_wait<BW_LAG>();
           fence_proxy_async();
-          mbar_arrive(&full_bar[(it - BW_LAG) % STAGES]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_bar[(it - BW_LAG) % STAGES]);
         }
       }
     }
     cp_async_wait<0>();
     fence_proxy_async();
-    for (uint32_t j = (it > (uint32_t)BW_LAG ? it - BW_LAG : 0u); j < it; ++j) mbar_arrive(&full_bar[j % STAGES]);
+    __syncwarp();
+    if (lane == 0)
+      for (uint32_t j = (it > (uint32_t)BW_LAG ? it - BW_LAG : 0u); j < it; ++j) mbar_arrive(&full_bar[j % STAGES]);
   } else if (warp == 12) {
     // ================================================================= MMA issuer
     const uint32_t idesc = umma_idesc(1 /*F32*/, 1 /*BF16*/, 1 /*BF16*/, DG_BM, n_eff);
@@ -275,8 +278,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const __grid
   const int num_kb = (int)((m_end - m_begin + WG_ROWS - 1) / WG_ROWS);
 
   if (threadIdx.x == 0) {
-    // a stage is full when every producer thread has stored its converted x chunks and the four dz boxes have landed
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], WG_PROD_WARPS * 32 + 1); mbar_init(&empty_bar[s], 1); }
+    // a stage is full when every producer WARP has stored its converted x chunks (one arrival per warp: 256 single-thread
+    // arrivals on one mbarrier took ~0.5 us per stage) and the four dz boxes have landed
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], WG_PROD_WARPS + 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tfull_bar[0], 1);
     mbar_fence_init();
   }
@@ -360,7 +364,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const __grid
           }
         }
         fence_proxy_async();
-        mbar_arrive(&full_bar[s]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
 #pragma unroll
         for (int q = 0; q < XL; ++q) xpk[q] = xnext[q];
       }
