@@ -37,7 +37,7 @@ static const int g_tune_default[FROST_TUNE_COUNT] = {
     /* DW_FWD_CTAS_PER_SM */ 2, /* DW_WGRAD_CTAS_PER_SM */ 3, /* BN_RED_CTAS_PER_SM */ 3, /* BN_RED_MAX_CGB */ 16,
     /* STEM_FWD_CTAS_PER_SM */ 8, /* STEM_WGRAD_CTAS_PER_SM */ 4, /* DW_DGRAD_CTAS_PER_SM */ 16,
     /* PDL */ 1, /* BN_RED_UNROLL */ 4, /* BN_APPLY_UNROLL */ 1, /* BNQ_UNROLL */ 2,
-    /* DW_FWD_TILED */ 1};
+    /* DW_FWD_TILED */ 1, /* DW_DGRAD_TILED */ 1};
 int tunable(int which) {
   const int v = g_tune[which].load(std::memory_order_relaxed);
   return v > 0 ? v : g_tune_default[which];

@@ -805,11 +805,25 @@ extern "C" int frost_dw_conv_forward(const uint8_t* xq, int ldx, const int32_t* 
   return FROST_OK;
 }
 
+namespace frost {
+int dw_dgrad_tma_launch(const float* dz, const int8_t* wq, const float* w_scale, const int32_t* w_zp, int N, int H, int W, int C,
+                        int k, float* dx, int accumulate, cudaStream_t st);      // dw_tma.cu
+}
+
 extern "C" int frost_dw_dgrad(const float* dz, const int8_t* wq, const float* w_scale, const int32_t* w_zp, int N, int H,
                               int W, int C, int k, int stride, float* dx, int accumulate, void* stream) {
   FROST_REQUIRE(dz && wq && w_scale && w_zp && dx, "frost_dw_dgrad: null pointer");
   FROST_REQUIRE(N > 0 && H > 0 && W > 0 && dw_shape_ok(C, k, stride), "frost_dw_dgrad: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
+  // stride 1: shared-memory tiles filled by TMA (dw_tma.cu); FROST_TUNE_DW_DGRAD_TILED = 2 forces the gather kernel
+  if (stride == 1 && tunable(FROST_TUNE_DW_DGRAD_TILED) == 1 && (reinterpret_cast<uintptr_t>(dz) & 15) == 0) {
+    const int rc = dw_dgrad_tma_launch(dz, wq, w_scale, w_zp, N, H, W, C, k, dx, accumulate, st);
+    if (rc == FROST_OK) {
+      FROST_LAUNCH_CHECK("dw_dgrad_tma");
+      return FROST_OK;
+    }
+    if (rc != FROST_ENOSUP) return rc;
+  }
   const int pad = (k - 1) / 2;
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   int cgb, chunks, threads;

@@ -51,7 +51,8 @@ enum {
   FROST_TUNE_BN_APPLY_UNROLL = 9,      /* bn_backward_apply: elements in flight per thread (1, 2 or 4)          */
   FROST_TUNE_BNQ_UNROLL = 10,          /* bnq_apply: 16-byte loads in flight per thread (2, 4 or 8)             */
   FROST_TUNE_DW_FWD_TILED = 11,        /* depthwise forward smem tiles: 1 wide stride-1 planes only, 2 never, 3 always */
-  FROST_TUNE_COUNT = 12
+  FROST_TUNE_DW_DGRAD_TILED = 12,      /* depthwise dgrad, stride 1: 1 shared-memory tiles filled by TMA, 2 the gather kernel  */
+  FROST_TUNE_COUNT = 13
 };
 int frost_set_tunable(int which, int value);
 int frost_get_tunable(int which);

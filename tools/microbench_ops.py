@@ -15,7 +15,7 @@ from frostnet_b200 import _lib as L  # noqa: E402
 dev = "cuda:0"
 N = 256
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-T_DW_FWD, T_DW_WGRAD, T_BN_RED, T_BN_CGB, T_STEM_FWD, T_STEM_WGRAD, T_DW_DGRAD, T_PDL, T_BN_RED_UNROLL, T_BN_APPLY_UNROLL, T_BNQ_UNROLL, T_DW_FWD_TILED = range(12)
+T_DW_FWD, T_DW_WGRAD, T_BN_RED, T_BN_CGB, T_STEM_FWD, T_STEM_WGRAD, T_DW_DGRAD, T_PDL, T_BN_RED_UNROLL, T_BN_APPLY_UNROLL, T_BNQ_UNROLL, T_DW_FWD_TILED, T_DW_DGRAD_TILED = range(13)
 QUICK = "--quick" in sys.argv
 
 
@@ -85,7 +85,7 @@ def bench_dw(H, W, Cc, k, s):
     sw = f32(0.01)
     sweep("dw_dgrad", shape, lambda: L.call("frost_dw_dgrad", dz.data_ptr(), wq.data_ptr(), sw.data_ptr(), zw.data_ptr(),
                                             N, H, W, Cc, k, s, dx.data_ptr(), 0, st()),
-          4 * nin + 4 * nout, T_DW_DGRAD, [8, 16, 32, 64])
+          4 * nin + 4 * nout, T_DW_DGRAD_TILED, [2, 1])            # 2: gather kernel, 1: TMA-filled shared-memory tiles (stride 1)
 
 
 def bench_bn(M, Cc):
