@@ -352,8 +352,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const __grid
         xdst[q] = (uint32_t)(kc >> 3) * WG_BLK + sw128_offset(r, kc & 7);
         if (idx >= WG_ROWS * cpr) xrow[q] = -1;
       }
-      // x of stage kb + 1 is requested while stage kb is converted: with the loads issued in the iteration that consumes them,
-      // every 64-row stage paid one DRAM round trip (~0.9 us per stage on the 56x56 / 28x28 layers)
+      // x of stage kb + 2 is requested while stage kb is converted (three register buffers, the loop unrolled by three): with
+      // the loads issued in the iteration that consumes them every 64-row stage paid one DRAM round trip (~0.9 us), with one
+      // stage of distance still most of it - an iteration is shorter than the round trip
       auto load_x = [&](uint2 (&dst)[XL], int kb) {
         const int64_t mb = m_begin + (int64_t)kb * WG_ROWS;
         const uint8_t* xstage = xq + mb * ldx;
@@ -364,16 +365,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const __grid
           if (kb < num_kb && xoff[q] >= 0 && xrow[q] < rows_left) dst[q] = ld_cg(reinterpret_cast<const uint2*>(xstage + xoff[q]));
         }
       };
-      uint2 xpk[XL], xnext[XL];
-      load_x(xpk, 0);
-      for (int kb = 0; kb < num_kb; ++kb) {
+      auto stage_body = [&](const uint2 (&cur)[XL], uint2 (&fut)[XL], int kb) {
         const int s = kb % STAGES;
         uint8_t* stage = smem + s * STAGE;
         const uint32_t a_hi = smem_u32(stage), a_lo = a_hi + A_BYTES;
         uint8_t* b_s = stage + 2 * A_BYTES;
         const int64_t mb = m_begin + (int64_t)kb * WG_ROWS;
         const int rows_left = (int)min((int64_t)WG_ROWS, m_end - mb);
-        load_x(xnext, kb + 1);
+        load_x(fut, kb + 2);
         mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
         // dz hi / lo: four TMA boxes (64 channels x 64 rows each) straight into the MN-major SWIZZLE_128B tiles; rows past the
         // end of the tensor and channels past cout arrive as zeros.  Up to STAGES stages of dz are in flight (the cp.async
@@ -393,7 +392,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const __grid
             float w[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const unsigned word = e < 4 ? xpk[q].x : xpk[q].y;
+              const unsigned word = e < 4 ? cur[q].x : cur[q].y;
               w[e] = v ? __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650u + (e & 3))) - zp_magic : 0.0f;
             }
             *reinterpret_cast<uint4*>(b_s + xdst[q]) =
@@ -403,8 +402,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) pw_wgrad_tc_kernel(const __grid
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[s]);
-#pragma unroll
-        for (int q = 0; q < XL; ++q) xpk[q] = xnext[q];
+      };
+      uint2 xa[XL], xb[XL], xc[XL];
+      load_x(xa, 0);
+      load_x(xb, 1);
+      for (int kb = 0; kb < num_kb; kb += 3) {
+        stage_body(xa, xc, kb);
+        if (kb + 1 < num_kb) stage_body(xb, xa, kb + 1);
+        if (kb + 2 < num_kb) stage_body(xc, xb, kb + 2);
       }
     } else if (warp == 4 + WG_PROD_WARPS) {
       // ================================================================= MMA issuer (A and B MN-major)
