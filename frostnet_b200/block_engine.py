@@ -221,3 +221,135 @@ def run_quant_stub(stub, x):
         stub.__dict__["_frost_scratch"] = sc
     y = _FakeQuantFunction.apply(x, fq, sc)
     return attach_qparams(y, fq.scale, fq.zero_point)
+
+
+# ---------------------------------------------------------------------- stand-alone FloatFunctional.add / .cat
+def _to_nhwc_u8(x, qp, scratch, dummy):
+    """fp32 NCHW on the grid qp -> (uint8 NHWC indices, dequantised [min, max] of the tensor)"""
+    scale, zp = qp
+    x = x.detach()
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        x = x.float().contiguous()
+    N, Cc, H, W = x.shape
+    q = torch.empty((N, H, W, Cc), dtype=torch.uint8, device=x.device)
+    mm = torch.empty(2, dtype=torch.float32, device=x.device)
+    fq = L.FQ(dummy.data_ptr(), dummy.data_ptr() + 4, scale.data_ptr(), zp.data_ptr())
+    L.call("frost_input_quant", x.data_ptr(), N, Cc, H, W, fq, 0, Q.AVERAGING_CONSTANT, q.data_ptr(), mm.data_ptr(),
+           scratch.data_ptr(), L.stream(x.device))
+    return q, mm
+
+
+def _qt(q, qp, mm):
+    N, H, W, Cc = q.shape
+    return L.QTensor(q.data_ptr(), qp[0].data_ptr(), qp[1].data_ptr(), mm.data_ptr(), Cc, Cc)
+
+
+def _functional_buffers(ff, dev):
+    b = ff.__dict__.get("_frost_buffers")
+    if b is None or b[0].device != dev:
+        b = (torch.zeros(L.FQ_SCRATCH_FLOATS, dtype=torch.float32, device=dev), torch.zeros(2, dtype=torch.float32, device=dev))
+        ff.__dict__["_frost_buffers"] = b
+    return b
+
+
+class _AddFunction(torch.autograd.Function):
+    """FloatFunctional.add (functional_modules.py:50-52): torch.add + the module's own observer / fake-quant."""
+
+    @staticmethod
+    def forward(ctx, x, y, xs, xz, ys, yz, ff):
+        dev = x.device
+        fq = ff.activation_post_process
+        scratch, dummy = _functional_buffers(ff, dev)
+        with torch.cuda.device(dev):
+            qa, ma = _to_nhwc_u8(x, (xs, xz), scratch, dummy)
+            qb, mb = _to_nhwc_u8(y, (ys, yz), scratch, dummy)
+            N, H, W, Cc = qa.shape
+            qo = torch.empty_like(qa)
+            mo = torch.empty(2, dtype=torch.float32, device=dev)
+            ta, tb = _qt(qa, (xs, xz), ma), _qt(qb, (ys, yz), mb)
+            L.call("frost_add_forward", ta, tb, qa.numel(), _fq_struct(fq), 1 if fq._observe else 0, Q.AVERAGING_CONSTANT,
+                   qo.data_ptr(), Cc, mo.data_ptr(), scratch.data_ptr(), L.stream(dev))
+            out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=dev)
+            L.call("frost_dequant_to_nchw", qo.data_ptr(), Cc, fq.scale.data_ptr(), fq.zero_point.data_ptr(), N, H, W, Cc,
+                   out.data_ptr(), L.stream(dev))
+        ctx.saved = (qa, ma, qb, mb, (xs, xz), (ys, yz), fq)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qa, ma, qb, mb, qpa, qpb, fq = ctx.saved
+        dev = dout.device
+        N, H, W, Cc = qa.shape
+        with torch.cuda.device(dev):
+            st = L.stream(dev)
+            g = torch.empty((N * H * W, Cc), dtype=torch.float32, device=dev)
+            L.call("frost_nchw_to_nhwc", dout.contiguous().float().data_ptr(), N, Cc, H, W, g.data_ptr(), 0, st)
+            dsum = torch.empty_like(g)
+            da = torch.empty_like(g)
+            L.call("frost_add_backward", g.data_ptr(), _qt(qa, qpa, ma), _qt(qb, qpb, mb), g.numel(), fq.scale.data_ptr(),
+                   fq.zero_point.data_ptr(), dsum.data_ptr(), da.data_ptr(), 0, st)
+        dx = da.view(N, H, W, Cc).permute(0, 3, 1, 2).contiguous()
+        return dx, dx.clone(), None, None, None, None, None
+
+
+def run_functional_add(ff, x, y):
+    xs, xz = qparams_of(x, "a prepared FloatFunctional.add")
+    ys, yz = qparams_of(y, "a prepared FloatFunctional.add")
+    if x.shape != y.shape or x.dim() != 4:
+        raise RuntimeError("frostnet_b200: stand-alone FloatFunctional.add expects two NCHW tensors of the same shape")
+    out = _AddFunction.apply(x, y, xs, xz, ys, yz, ff)
+    fq = ff.activation_post_process
+    return attach_qparams(out, fq.scale, fq.zero_point)
+
+
+class _CatFunction(torch.autograd.Function):
+    """FloatFunctional.cat along channels (functional_modules.py:80-82): torch.cat + observer / fake-quant."""
+
+    @staticmethod
+    def forward(ctx, x, y, xs, xz, ys, yz, ff):
+        dev = x.device
+        fq = ff.activation_post_process
+        scratch, dummy = _functional_buffers(ff, dev)
+        with torch.cuda.device(dev):
+            qa, ma = _to_nhwc_u8(x, (xs, xz), scratch, dummy)
+            qb, mb = _to_nhwc_u8(y, (ys, yz), scratch, dummy)
+            N, H, W, Ca = qa.shape
+            Cb = qb.shape[3]
+            qo = torch.empty((N, H, W, Ca + Cb), dtype=torch.uint8, device=dev)
+            mo = torch.empty(2, dtype=torch.float32, device=dev)
+            L.call("frost_cat_forward", _qt(qa, (xs, xz), ma), _qt(qb, (ys, yz), mb), N * H * W, _fq_struct(fq),
+                   1 if fq._observe else 0, Q.AVERAGING_CONSTANT, qo.data_ptr(), Ca + Cb, mo.data_ptr(), L.stream(dev))
+            out = torch.empty((N, Ca + Cb, H, W), dtype=torch.float32, device=dev)
+            L.call("frost_dequant_to_nchw", qo.data_ptr(), Ca + Cb, fq.scale.data_ptr(), fq.zero_point.data_ptr(), N, H, W, Ca + Cb,
+                   out.data_ptr(), L.stream(dev))
+        ctx.saved = (qa, ma, qb, mb, (xs, xz), (ys, yz), fq)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qa, ma, qb, mb, qpa, qpb, fq = ctx.saved
+        dev = dout.device
+        N, H, W, Ca = qa.shape
+        Cb = qb.shape[3]
+        with torch.cuda.device(dev):
+            st = L.stream(dev)
+            g = torch.empty((N * H * W, Ca + Cb), dtype=torch.float32, device=dev)
+            L.call("frost_nchw_to_nhwc", dout.contiguous().float().data_ptr(), N, Ca + Cb, H, W, g.data_ptr(), 0, st)
+            da = torch.empty((N * H * W, Ca), dtype=torch.float32, device=dev)
+            db = torch.empty((N * H * W, Cb), dtype=torch.float32, device=dev)
+            L.call("frost_cat_backward", g.data_ptr(), _qt(qa, qpa, ma), _qt(qb, qpb, mb), N * H * W, fq.scale.data_ptr(),
+                   fq.zero_point.data_ptr(), da.data_ptr(), db.data_ptr(), 0, st)
+        dx = da.view(N, H, W, Ca).permute(0, 3, 1, 2).contiguous()
+        dy = db.view(N, H, W, Cb).permute(0, 3, 1, 2).contiguous()
+        return dx, dy, None, None, None, None, None
+
+
+def run_functional_cat(ff, xs, dim):
+    if len(xs) != 2 or dim != 1 or xs[0].dim() != 4:
+        raise RuntimeError("frostnet_b200: stand-alone FloatFunctional.cat supports two NCHW tensors along dim 1")
+    x, y = xs
+    a = qparams_of(x, "a prepared FloatFunctional.cat")
+    b = qparams_of(y, "a prepared FloatFunctional.cat")
+    out = _CatFunction.apply(x, y, a[0], a[1], b[0], b[1], ff)
+    fq = ff.activation_post_process
+    return attach_qparams(out, fq.scale, fq.zero_point)

@@ -114,12 +114,15 @@ class FloatFunctional(nn.Module):
 
     def add(self, x, y):
         if isinstance(self.activation_post_process, FrostFakeQuantize):
-            raise RuntimeError("frostnet_b200: prepared FloatFunctional only runs inside the QAT engine")
+            # prepared and called on its own (the whole-network engine never comes here): per-module executor
+            from .block_engine import run_functional_add
+            return run_functional_add(self, x, y)
         return torch.add(x, y)
 
     def cat(self, xs, dim=0):
         if isinstance(self.activation_post_process, FrostFakeQuantize):
-            raise RuntimeError("frostnet_b200: prepared FloatFunctional only runs inside the QAT engine")
+            from .block_engine import run_functional_cat
+            return run_functional_cat(self, xs, dim)
         return torch.cat(xs, dim)
 
 

@@ -161,3 +161,43 @@ def test_quant_stub_then_blocks_chain_standalone():
     assert float(((q - z) * s - y.detach()).abs().max()) <= 1e-6 * float(y.detach().abs().max())
     with pytest.raises(RuntimeError, match="without quantisation parameters"):
         b2(torch.relu(y.detach()))                      # a foreign op dropped the qparams
+
+
+@pytest.mark.parametrize("op", ["add", "cat"])
+def test_standalone_float_functional_matches_torch_ao(op):
+    """FloatFunctional.add / .cat called on their own vs torch.ao's QAT FloatFunctional (the arithmetic the reference runs,
+    functional_modules.py:50-52,80-82) on the CPU: values, observer state and input gradients over two steps."""
+    import frostnet_b200 as F
+    import torch.ao.quantization as taq
+    qc = taq.get_default_qat_qconfig("qnnpack")
+    # reference (CPU)
+    r1, r2 = taq.QuantStub(), taq.QuantStub()
+    r1.activation_post_process, r2.activation_post_process = qc.activation(), qc.activation()
+    rff = torch.ao.nn.quantized.FloatFunctional()
+    rff.activation_post_process = qc.activation()
+    rq = lambda stub, t: stub.activation_post_process(stub(t))
+    # ours (device)
+    m = torch.nn.ModuleDict(dict(s1=F.QuantStub(), s2=F.QuantStub(), ff=F.qat.FloatFunctional()))
+    F.attach_fake_quant(m)
+    m.to(DEV).train()
+    g = torch.Generator().manual_seed(11)
+    for step in range(2):
+        Cb = 24 if op == "add" else 40
+        x = (torch.randn(3, 24, 10, 9, generator=g) * (1.5 + step)).requires_grad_(True)
+        y = (torch.randn(3, Cb, 10, 9, generator=g) * 0.7 + 0.3).requires_grad_(True)
+        ref = rff.add(rq(r1, x), rq(r2, y)) if op == "add" else rff.cat([rq(r1, x), rq(r2, y)], 1)
+        w = torch.randn(ref.shape, generator=g)
+        (ref * w).sum().backward()
+        xd, yd = x.detach().to(DEV).requires_grad_(True), y.detach().to(DEV).requires_grad_(True)
+        a, b = m["s1"](xd), m["s2"](yd)
+        out = m["ff"].add(a, b) if op == "add" else m["ff"].cat([a, b], 1)
+        assert hasattr(out, "_frost_qparams")
+        assert torch.equal(out.detach().cpu(), ref.detach()), (step, float((out.detach().cpu() - ref.detach()).abs().max()))
+        (out * w.to(DEV)).sum().backward()
+        for ours, theirs in ((xd.grad, x.grad), (yd.grad, y.grad)):
+            assert float((ours.cpu() - theirs).abs().max()) <= 1e-6 * float(theirs.abs().max()) + 1e-12
+        for mine, theirs in ((m["s1"], r1), (m["s2"], r2), (m["ff"], rff)):
+            fm, ft = mine.activation_post_process, theirs.activation_post_process
+            assert float(fm.scale) == float(ft.scale) and int(fm.zero_point) == int(ft.zero_point)
+            assert float(fm.activation_post_process.min_val) == float(ft.activation_post_process.min_val)
+            assert float(fm.activation_post_process.max_val) == float(ft.activation_post_process.max_val)
