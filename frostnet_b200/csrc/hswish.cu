@@ -45,8 +45,11 @@ __global__ void __launch_bounds__(256) hswish_index_kernel(const float* x, int64
   if (s_p[threadIdx.x]) presence[threadIdx.x] = 1u;
 }
 
+// sigmoid != 0: the reference's _Hsigmoid (mobilenetv3.py:59-69)  y = mul_scalar(FQ_relu6(relu6(x + 3)), 1/6) - no product,
+// no second fake-quant; the backward tables are set so that hswish_bwd_kernel computes  dx = [inner mask] dy/6.
 __global__ void __launch_bounds__(HS_N) hswish_tables_kernel(const float* in_scale, const int32_t* in_zp, FrostFQ fq_a, int observe_a,
-                                                           FrostFQ fq_b, int observe_b, float avg_c, float* ws, float* out_scale) {
+                                                           FrostFQ fq_b, int observe_b, float avg_c, float* ws, float* out_scale,
+                                                           int sigmoid) {
   const int i = threadIdx.x;
   const bool present = reinterpret_cast<const unsigned*>(ws)[i] != 0u;
   const float v = fq_dequant((float)i, (float)*in_zp, *in_scale);
@@ -60,6 +63,17 @@ __global__ void __launch_bounds__(HS_N) hswish_tables_kernel(const float* in_sca
   const float idx_a = fq_index(r, __fdiv_rn(1.0f, s_a), zp_a);
   const bool pass_a = idx_a >= 0.0f && idx_a <= 255.0f;
   const float ra = fq_dequant(fminf(fmaxf(idx_a, 0.0f), 255.0f), zp_a, s_a);
+  const float c6s = (float)(1.0 / 6.0);
+  if (sigmoid) {
+    ws[1 * HS_N + i] = 1.0f;                                              // "V": d(out)/d(r) path only
+    ws[2 * HS_N + i] = 0.0f;                                              // no direct x factor
+    ws[3 * HS_N + i] = (pass_a && a > 0.0f && a < 6.0f) ? 1.0f : 0.0f;
+    ws[4 * HS_N + i] = 1.0f;
+    ws[5 * HS_N + i] = __fmul_rn(ra, c6s);
+    ws[6 * HS_N + i] = fminf(fmaxf(idx_a, 0.0f), 255.0f);
+    if (i == 0 && out_scale) *out_scale = __fmul_rn(s_a, c6s);            // grid of the result: (q - zp_a) * (s_a / 6)
+    return;
+  }
   const float m = __fmul_rn(v, ra);
   mn = present ? m : INFINITY;
   mx = present ? m : -INFINITY;
@@ -131,13 +145,30 @@ using namespace frost;
 
 extern "C" int frost_hswish_workspace_floats(void) { return HS_PLANES * HS_N; }
 
+static int hs_forward(const float* x, int64_t n, const float* in_scale, const int32_t* in_zp, FrostFQ fq_relu6, int observe_relu6,
+                      FrostFQ fq_mul, int observe_mul, float averaging_const, uint8_t* q_in, float* y, uint8_t* y_q, float* workspace,
+                      float* out_scale, int sigmoid, void* stream);
+
 extern "C" int frost_hswish_forward(const float* x, int64_t n, const float* in_scale, const int32_t* in_zp, FrostFQ fq_relu6,
                                     int observe_relu6, FrostFQ fq_mul, int observe_mul, float averaging_const, uint8_t* q_in,
                                     float* y, uint8_t* y_q, float* workspace, float* out_scale, void* stream) {
+  FROST_REQUIRE(fq_mul.scale && fq_mul.zero_point && fq_mul.min_val && fq_mul.max_val, "frost_hswish_forward: null fake-quant state");
+  return hs_forward(x, n, in_scale, in_zp, fq_relu6, observe_relu6, fq_mul, observe_mul, averaging_const, q_in, y, y_q, workspace,
+                    out_scale, 0, stream);
+}
+
+extern "C" int frost_hsigmoid_forward(const float* x, int64_t n, const float* in_scale, const int32_t* in_zp, FrostFQ fq_relu6,
+                                      int observe_relu6, float averaging_const, uint8_t* q_in, float* y, uint8_t* y_q,
+                                      float* workspace, float* out_scale, void* stream) {
+  return hs_forward(x, n, in_scale, in_zp, fq_relu6, observe_relu6, fq_relu6, 0, averaging_const, q_in, y, y_q, workspace, out_scale, 1,
+                    stream);
+}
+
+static int hs_forward(const float* x, int64_t n, const float* in_scale, const int32_t* in_zp, FrostFQ fq_relu6, int observe_relu6,
+                      FrostFQ fq_mul, int observe_mul, float averaging_const, uint8_t* q_in, float* y, uint8_t* y_q, float* workspace,
+                      float* out_scale, int sigmoid, void* stream) {
   FROST_REQUIRE(x && n > 0 && in_scale && in_zp && q_in && workspace && (y || y_q), "frost_hswish_forward: bad args");
-  FROST_REQUIRE(fq_relu6.scale && fq_relu6.zero_point && fq_relu6.min_val && fq_relu6.max_val && fq_mul.scale && fq_mul.zero_point &&
-                    fq_mul.min_val && fq_mul.max_val,
-                "frost_hswish_forward: null fake-quant state");
+  FROST_REQUIRE(fq_relu6.scale && fq_relu6.zero_point && fq_relu6.min_val && fq_relu6.max_val, "frost_hswish_forward: null fake-quant state");
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(workspace, 0, sizeof(float) * HS_N, st) != cudaSuccess) {
     set_error("frost_hswish_forward: memset failed");
@@ -149,7 +180,7 @@ extern "C" int frost_hswish_forward(const float* x, int64_t n, const float* in_s
   hswish_index_kernel<<<blocks, 256, 0, st>>>(x, n, vec, in_scale, in_zp, q_in, reinterpret_cast<unsigned*>(workspace));
   FROST_LAUNCH_CHECK("hswish_index");
   hswish_tables_kernel<<<1, HS_N, 0, st>>>(in_scale, in_zp, fq_relu6, observe_relu6, fq_mul, observe_mul, averaging_const, workspace,
-                                          out_scale);
+                                          out_scale, sigmoid);
   FROST_LAUNCH_CHECK("hswish_tables");
   hswish_apply_kernel<<<blocks, 256, 0, st>>>(q_in, n, vec, workspace, y, y_q);
   FROST_LAUNCH_CHECK("hswish_apply");

@@ -227,7 +227,7 @@ def attach_fake_quant(root):
     QuantStub in front): attaches the qnnpack-QAT fake-quants where torch.quantization.prepare_qat would - on every
     fused conv (weight + output), FloatFunctional, QuantStub and the ReLU6 inside Hswish.  Convs must be fused first
     (``fuse_model()``).  The modules then run through the per-module executor (block_engine.py)."""
-    from .hswish import Hswish
+    from .hswish import Hsigmoid, Hswish
     dev = next((p.device for p in root.parameters()), torch.device("cpu"))
     for m in list(root.modules()):
         if isinstance(m, FrostConvBn2d) and not isinstance(getattr(m, "weight_fake_quant", None), FrostFakeQuantize):
@@ -235,7 +235,7 @@ def attach_fake_quant(root):
             m.activation_post_process = FrostFakeQuantize.act().to(dev)
         elif isinstance(m, (FloatFunctional, QuantStub)) and not isinstance(getattr(m, "activation_post_process", None), FrostFakeQuantize):
             m.activation_post_process = FrostFakeQuantize.act().to(dev)
-        elif isinstance(m, Hswish) and not m._prepared():
+        elif isinstance(m, (Hswish, Hsigmoid)) and not m._prepared():
             m.relu6.activation_post_process = FrostFakeQuantize.act().to(dev)
     return root
 

@@ -332,6 +332,11 @@ int frost_hswish_forward(const float* x, int64_t n, const float* in_scale, const
                          int observe_relu6, FrostFQ fq_mul, int observe_mul, float averaging_const, uint8_t* q_in,
                          float* y, uint8_t* y_q, float* workspace, float* out_scale, void* stream);
 int frost_hswish_backward(const float* dy, const uint8_t* q_in, int64_t n, const float* workspace, float* dx, void* stream);
+/* The reference's _Hsigmoid (mobilenetv3.py:59-69): y = mul_scalar(FQ_relu6(relu6(add_scalar(x, 3))), 1/6); same two passes, one
+ * observer; result grid (scale_relu6/6, zero point of fq_relu6).  Backward: frost_hswish_backward with this call's workspace. */
+int frost_hsigmoid_forward(const float* x, int64_t n, const float* in_scale, const int32_t* in_zp, FrostFQ fq_relu6,
+                           int observe_relu6, float averaging_const, uint8_t* q_in, float* y, uint8_t* y_q, float* workspace,
+                           float* out_scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * FloatFunctional.cat / .add (frostnet.py:129,142;

@@ -42,8 +42,25 @@ def main():
     y.backward(dy)
     steps.append(dict(x=x.detach().clone(), dy=dy, y=y.detach().clone(), dx=x.grad.clone(),
                       state={k: v.clone() for k, v in net.state_dict().items()}, observers_off=True))
-    torch.save(dict(sd0=sd0, steps=steps, torch=torch.__version__), os.path.join(HERE, "hswish.pt"))
-    print("hswish golden ok:", [tuple(s["y"].shape) for s in steps], "keys", len(sd0))
+    # the same for _Hsigmoid (mobilenetv3.py:59-69)
+    torch.manual_seed(1883)
+    net2 = torch.nn.Sequential(torch.ao.quantization.QuantStub(), ref._Hsigmoid(True))
+    net2.train()
+    net2.qconfig = torch.ao.quantization.get_default_qat_qconfig("qnnpack")
+    torch.ao.quantization.prepare_qat(net2, inplace=True)
+    sig_sd0 = {k: v.clone() for k, v in net2.state_dict().items()}
+    sig_steps = []
+    for i in range(3):
+        if i == 2:
+            net2.apply(torch.ao.quantization.disable_observer)
+        x = (torch.randn(5, 12, generator=g) * (2.0 + i) - 0.5 * i).requires_grad_(True)       # SE feeds it [N, C]
+        dy = torch.randn(5, 12, generator=g)
+        y = net2(x)
+        y.backward(dy)
+        sig_steps.append(dict(x=x.detach().clone(), dy=dy, y=y.detach().clone(), dx=x.grad.clone(),
+                              state={k: v.clone() for k, v in net2.state_dict().items()}, observers_off=(i == 2)))
+    torch.save(dict(sd0=sd0, steps=steps, sig_sd0=sig_sd0, sig_steps=sig_steps, torch=torch.__version__), os.path.join(HERE, "hswish.pt"))
+    print("hswish golden ok:", [tuple(s["y"].shape) for s in steps], "keys", len(sd0), "| hsigmoid:", len(sig_steps), "steps, keys", len(sig_sd0))
 
 
 if __name__ == "__main__":

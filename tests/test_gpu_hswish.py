@@ -75,3 +75,25 @@ def test_hswish_float_path_and_errors():
     net = _net()
     with pytest.raises(RuntimeError, match="without quantisation parameters"):
         net[1](torch.randn(2, 3, device=DEV))
+
+
+def test_hsigmoid_matches_reference_step_by_step():
+    """_Hsigmoid (mobilenetv3.py:59-69) on [N, C] tensors as the SE block feeds it; last step with the observers off"""
+    import frostnet_b200 as F
+    g = load_golden("hswish.pt")
+    net = torch.nn.Sequential(F.QuantStub(), F.Hsigmoid(True))
+    F.attach_fake_quant(net)
+    net.to(DEV).train()
+    assert sorted(net.state_dict().keys()) == sorted(g["sig_sd0"].keys())
+    net.load_state_dict(g["sig_sd0"])
+    for i, s in enumerate(g["sig_steps"]):
+        if s.get("observers_off"):
+            net.apply(torch.ao.quantization.disable_observer)
+        x = s["x"].to(DEV).requires_grad_(True)
+        y = net(x)
+        assert torch.equal(y.detach().cpu(), s["y"]), (i, float((y.detach().cpu() - s["y"]).abs().max()))
+        y.backward(s["dy"].to(DEV))
+        assert float((x.grad.cpu() - s["dx"]).abs().max()) <= 1e-6 * float(s["dx"].abs().max()) + 1e-12, i
+        sd = net.state_dict()
+        for k, v in s["state"].items():
+            assert torch.equal(sd[k].cpu(), v), (i, k)
