@@ -201,3 +201,49 @@ def test_standalone_float_functional_matches_torch_ao(op):
             assert float(fm.scale) == float(ft.scale) and int(fm.zero_point) == int(ft.zero_point)
             assert float(fm.activation_post_process.min_val) == float(ft.activation_post_process.min_val)
             assert float(fm.activation_post_process.max_val) == float(ft.activation_post_process.max_val)
+
+
+def test_mobilenetv3_style_block_from_standalone_modules_trains():
+    """An inverted-residual block in the reference's MobileNetV3 style (mobilenetv3.py:113-160: 1x1 ConvBN + h-swish, depthwise
+    ConvBN + h-swish, 1x1 ConvBN, residual add) wired from frostnet_b200 modules and run through the per-module executor:
+    every boundary hands its quantisation grid on, gradients reach every parameter, and a few SGD steps reduce the loss."""
+    import frostnet_b200 as F
+
+    class Block(torch.nn.Module):
+        def __init__(self, c, e):
+            super().__init__()
+            self.quant = F.QuantStub()
+            self.pw = F.ConvBN(c, e, 1)
+            self.act1 = F.Hswish()
+            self.dw = F.ConvBN(e, e, 3, 1, 1, 1, groups=e)
+            self.act2 = F.Hswish()
+            self.pwl = F.ConvBN(e, c, 1)
+            self.skip_add = F.qat.FloatFunctional()
+
+        def forward(self, x):
+            x = self.quant(x)
+            y = self.act1(self.pw(x))
+            y = self.act2(self.dw(y))
+            return self.skip_add.add(x, self.pwl(y))
+
+    torch.manual_seed(5)
+    blk = Block(16, 64)
+    for m in blk.modules():
+        if isinstance(m, F.ConvBN):
+            m.fuse_model()
+    F.attach_fake_quant(blk)
+    blk.to(DEV).train()
+    opt = torch.optim.SGD(blk.parameters(), lr=0.05)
+    x = torch.randn(8, 16, 14, 14, device=DEV)
+    target = torch.randn(8, 16, 14, 14, device=DEV) * 0.1
+    losses = []
+    for _ in range(6):
+        opt.zero_grad()
+        out = blk(x)
+        assert hasattr(out, "_frost_qparams") and out.shape == x.shape
+        loss = (out - target).square().mean()
+        loss.backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in blk.parameters())
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert losses[-1] < losses[0], losses
