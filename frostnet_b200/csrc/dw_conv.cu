@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(256, 2) dw_conv_fwd_generic_kernel(const uint8
 // Strips start at multiples of 4 along W, so for stride 2 the set of (pixel, tap) pairs that hit an
 // output column is known at compile time; valid kernel rows are a run-time (per-thread) stride-S loop.
 template <int KS, int S>
-__global__ void __launch_bounds__(256, 3) dw_dgrad_kernel(const float* dz, const int8_t* wq,
+__global__ void __launch_bounds__(256, 4) dw_dgrad_kernel(const float* dz, const int8_t* wq,
                                                          const float* w_scale_p, const int32_t* w_zp_p,
                                                          int N, int H, int W, int C, int Ho, int Wo, int cgb,
                                                          float* dx, int accumulate) {

@@ -80,12 +80,12 @@ def bench_dw(H, W, Cc, k, s):
     sa = f32(0.02)
     sweep("dw_wgrad", shape, lambda: L.call("frost_dw_wgrad", dz.data_ptr(), xq.data_ptr(), Cc, sa.data_ptr(), za.data_ptr(),
                                             N, H, W, Cc, k, s, dwq.data_ptr(), st()),
-          nin + 4 * nout, T_DW_WGRAD, [3, 6])
+          nin + 4 * nout, T_DW_WGRAD, [3, 4, 6])
     dx = torch.empty(N, H, W, Cc, device=dev)
     sw = f32(0.01)
     sweep("dw_dgrad", shape, lambda: L.call("frost_dw_dgrad", dz.data_ptr(), wq.data_ptr(), sw.data_ptr(), zw.data_ptr(),
                                             N, H, W, Cc, k, s, dx.data_ptr(), 0, st()),
-          4 * nin + 4 * nout, T_DW_DGRAD_TILED, [2, 1])            # 2: gather kernel, 1: TMA-filled shared-memory tiles (stride 1)
+          4 * nin + 4 * nout, T_DW_DGRAD_TILED, [2, 1])            # 2: gather kernel, 1: TMA-filled shared-memory tiles (stride 1; used where C == 32)
 
 
 def bench_bn(M, Cc):
