@@ -14,3 +14,4 @@ from . import frostnet_features
 __version__ = "0.1.0"
 from .export import convert_int8
 from .hswish import Hsigmoid, Hswish
+from .se import SEModule, QATLinear

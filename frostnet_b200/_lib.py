@@ -145,6 +145,9 @@ _SIGNATURES = {
     "frost_hswish_forward": [c_p, i64, c_p, c_p, FQ, i32, FQ, i32, f32, c_p, c_p, c_p, c_p, c_p, c_p],
     "frost_hswish_backward": [c_p, c_p, i64, c_p, c_p, c_p],
     "frost_hsigmoid_forward": [c_p, i64, c_p, c_p, FQ, i32, f32, c_p, c_p, c_p, c_p, c_p, c_p],
+    "frost_relu_forward": [c_p, i64, c_p, c_p, c_p],
+    "frost_bcast_mul_forward": [c_p, c_p, i64, i32, c_p, c_p],
+    "frost_bcast_mul_backward": [c_p, c_p, c_p, i64, i32, c_p, c_p, c_p],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["frost_abi_version", "frost_last_error", "frost_launch_count",
                            "frost_pw_chain_supported", "frost_hswish_workspace_floats"])

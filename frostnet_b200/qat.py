@@ -125,6 +125,12 @@ class FloatFunctional(nn.Module):
             return run_functional_cat(self, xs, dim)
         return torch.cat(xs, dim)
 
+    def mul(self, x, y):
+        if isinstance(self.activation_post_process, FrostFakeQuantize):
+            from .se import run_functional_mul
+            return run_functional_mul(self, x, y)
+        return torch.mul(x, y)
+
 
 class QuantStub(nn.Module):
     def forward(self, x):
@@ -225,9 +231,10 @@ def prepare_qat(model, inplace=True):
 def attach_fake_quant(root):
     """prepare_qat for an arbitrary tree of frostnet_b200 modules (bottlenecks wired into another network, Hswish, a
     QuantStub in front): attaches the qnnpack-QAT fake-quants where torch.quantization.prepare_qat would - on every
-    fused conv (weight + output), FloatFunctional, QuantStub and the ReLU6 inside Hswish.  Convs must be fused first
+    fused conv (weight + output), FloatFunctional, QuantStub, the ReLU6 inside Hswish / Hsigmoid and the Linear layers of SEModule.  Convs must be fused first
     (``fuse_model()``).  The modules then run through the per-module executor (block_engine.py)."""
     from .hswish import Hsigmoid, Hswish
+    from .se import QATLinear
     dev = next((p.device for p in root.parameters()), torch.device("cpu"))
     for m in list(root.modules()):
         if isinstance(m, FrostConvBn2d) and not isinstance(getattr(m, "weight_fake_quant", None), FrostFakeQuantize):
@@ -237,6 +244,9 @@ def attach_fake_quant(root):
             m.activation_post_process = FrostFakeQuantize.act().to(dev)
         elif isinstance(m, (Hswish, Hsigmoid)) and not m._prepared():
             m.relu6.activation_post_process = FrostFakeQuantize.act().to(dev)
+        elif isinstance(m, QATLinear) and not m._prepared():
+            m.weight_fake_quant = FrostFakeQuantize.weight().to(dev)
+            m.activation_post_process = FrostFakeQuantize.act().to(dev)
     return root
 
 

@@ -339,6 +339,21 @@ int frost_hsigmoid_forward(const float* x, int64_t n, const float* in_scale, con
                            float* out_scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Quantization-aware squeeze-and-excite: the reference's SEModule
+ * (Classification/models/imagenet/mobilenetv3.py:85-102) after fuse_model() + prepare_qat,
+ *     gate = Hsigmoid( FQ( Linear_q( FQ( relu( Linear_q( avg_pool(x) ) ) ) ) ) ) ;  y = FQ_mul( x * gate.expand_as(x) )
+ * is a composition (frostnet_b200/se.py): frost_pool_dropout_forward (keep = NULL), frost_fq_forward on the weights
+ * (symmetric int8) and activations, frost_linear_forward / _backward, frost_hsigmoid_forward - plus the three element-wise
+ * pieces below.  fp32; a row is one (image, channel) plane of hw values. */
+/* y = max(x, 0) ; mask = [x > 0] (may be NULL).  Backward: frost_fq_backward(dy, mask). */
+int frost_relu_forward(const float* x, int64_t n, float* y, uint8_t* mask, void* stream);
+/* y[r][i] = x[r][i] * gate[r]        (torch.mul(x, gate.expand_as(x)): one fp32 rounding, bit-identical) */
+int frost_bcast_mul_forward(const float* x, const float* gate, int64_t rows, int hw, float* y, void* stream);
+/* dx[r][i] = dy[r][i] * gate[r] ; dgate[r] = sum_i dy[r][i] * x[r][i] */
+int frost_bcast_mul_backward(const float* dy, const float* x, const float* gate, int64_t rows, int hw, float* dx,
+                             float* dgate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * FloatFunctional.cat / .add (frostnet.py:129,142;
  * torch/ao/nn/quantized/modules/functional_modules.py:50-52,80-82): op + own observer + FQ. */
 typedef struct {

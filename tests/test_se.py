@@ -1,0 +1,45 @@
+"""CPU side of the QAT squeeze-and-excite block (frostnet_b200/se.py): the module tree, its state_dict keys before and after
+fuse_model() + attach_fake_quant against the reference's SEModule (tests/golden/se.pt), and the float path."""
+import pytest
+import torch
+
+from util import load_golden
+
+
+def test_state_dict_keys_match_reference_float_and_prepared():
+    import frostnet_b200 as F
+    g = load_golden("se.pt")
+    net = torch.nn.Sequential(F.QuantStub(), F.SEModule(g["C"], reduction=4))
+    assert sorted(net.state_dict().keys()) == sorted(g["float_sd"].keys())
+    net.load_state_dict(g["float_sd"], strict=True)
+    net[1].fuse_model()
+    F.attach_fake_quant(net)
+    assert sorted(net.state_dict().keys()) == sorted(g["sd0"].keys())
+    missing, unexpected = net.load_state_dict(g["sd0"], strict=True)
+    assert not missing and not unexpected
+    for k, v in g["sd0"].items():
+        assert net.state_dict()[k].shape == v.shape and net.state_dict()[k].dtype == v.dtype, k
+
+
+def test_float_forward_is_the_reference_formula():
+    import frostnet_b200 as F
+    g = load_golden("se.pt")
+    se = F.SEModule(g["C"], reduction=4)
+    se.load_state_dict({k[2:]: v for k, v in g["float_sd"].items() if k.startswith("1.")})
+    x = g["steps"][0]["x"]
+    w0, w2 = se.fc[0].weight, se.fc[2].weight
+    gate = torch.nn.functional.relu6(torch.relu(x.mean((2, 3)) @ w0.t()) @ w2.t() + 3.0) / 6.0
+    assert torch.allclose(se(x), x * gate[:, :, None, None], atol=1e-6)
+    se.fuse_model()                                  # fusing does not change the float function
+    assert torch.allclose(se(x), x * gate[:, :, None, None], atol=1e-6)
+
+
+def test_prepared_module_refuses_cpu_tensors():
+    import frostnet_b200 as F
+    from frostnet_b200.block_engine import attach_qparams
+    se = F.SEModule(8)
+    se.fuse_model()
+    F.attach_fake_quant(se)
+    x = attach_qparams(torch.randn(1, 8, 2, 2), torch.ones(1), torch.zeros(1, dtype=torch.int32))
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        se(x)
