@@ -15,3 +15,4 @@ __version__ = "0.1.0"
 from .export import convert_int8
 from .hswish import Hsigmoid, Hswish
 from .se import SEModule, QATLinear
+from . import mobilenetv3

@@ -46,9 +46,12 @@ class BlockEngine(QATEngine):
         if isinstance(m, FN.CascadePreExBottleneck):
             self._add_block(add, "", m)
             return
-        mod = m.conv[0]
+        seq = getattr(m, "_seq_name", "conv")               # "conv" (frostnet.py) or "cbr" / "cb" (mobilenetv3.py)
+        mod = getattr(m, seq)[0]
         if not isinstance(mod, Q.FrostConvBn2d):
             raise RuntimeError("frostnet_b200: %s is not fused; call fuse_model() + prepare_qat" % type(m).__name__)
+        if tuple(mod.dilation) != (1, 1):
+            raise RuntimeError("frostnet_b200: stand-alone %s: dilated convolutions have no kernels" % type(m).__name__)
         if mod.is_depthwise:
             kind = "dw"
         elif mod.groups == 1 and tuple(mod.kernel_size) == (1, 1) and tuple(mod.stride) == (1, 1):
@@ -56,7 +59,7 @@ class BlockEngine(QATEngine):
         else:
             raise RuntimeError("frostnet_b200: stand-alone %s: only 1x1 and depthwise 3x3 / 5x5 convolutions have kernels "
                                "(dense kxk exists for the 3-channel stem inside FrostNet only)" % type(m).__name__)
-        self._single = _Layer("conv.0", mod, kind)
+        self._single = _Layer(seq + ".0", mod, kind)
         self.layers.append(self._single)
 
     def __deepcopy__(self, memo):

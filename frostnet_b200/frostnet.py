@@ -19,8 +19,10 @@ __all__ = ["ConvBNReLU", "ConvBN", "CascadePreExBottleneck", "FrostNet", "_make_
 
 
 class _ConvBlock(nn.Module):
-    """Shared body of ConvBNReLU / ConvBN: ``self.conv`` is the reference's nn.Sequential."""
+    """Shared body of ConvBNReLU / ConvBN: ``self.conv`` is the reference's nn.Sequential (``_seq_name`` lets the MobileNetV3
+    wrappers, whose Sequential is called ``cbr`` / ``cb``, reuse it)."""
     _relu = False
+    _seq_name = "conv"
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1):
         super().__init__()
@@ -28,25 +30,30 @@ class _ConvBlock(nn.Module):
                   nn.BatchNorm2d(out_channels)]
         if self._relu:
             layers.append(nn.ReLU(False))
-        self.conv = nn.Sequential(*layers)
+        setattr(self, self._seq_name, nn.Sequential(*layers))
+
+    def _seq(self):
+        return getattr(self, self._seq_name)
 
     def forward(self, x):
-        if isinstance(getattr(self.conv[0], "weight_fake_quant", None), _qat.FrostFakeQuantize):
+        seq = self._seq()
+        if isinstance(getattr(seq[0], "weight_fake_quant", None), _qat.FrostFakeQuantize):
             # prepared and called on its own (the whole-network engine never comes here): per-module executor
             from .block_engine import run_block
             return run_block(self, x)
-        return self.conv(x)
+        return seq(x)
 
     def fuse_model(self):
         """Reference: torch.quantization.fuse_modules(self.conv, ['0','1'(,'2')], inplace=True)
         (frostnet.py:27-28, 59-60).  Produces the same module tree / state_dict keys
         (``conv.0.weight``, ``conv.0.bn.*``; Identity at 1(,2))."""
-        if isinstance(self.conv[0], _qat.FrostConvBn2d):
+        seq = self._seq()
+        if isinstance(seq[0], _qat.FrostConvBn2d):
             return
-        fused = _qat.FrostConvBn2d(self.conv[0], self.conv[1], relu=self._relu)
-        self.conv[0] = fused
-        for i in range(1, len(self.conv)):
-            self.conv[i] = nn.Identity()
+        fused = _qat.FrostConvBn2d(seq[0], seq[1], relu=self._relu)
+        seq[0] = fused
+        for i in range(1, len(seq)):
+            seq[i] = nn.Identity()
 
 
 class ConvBNReLU(_ConvBlock):

@@ -70,12 +70,13 @@ def test_se_replay_with_torch_ops_on_the_device():
     se = net[1]
     fqa = lambda t, f: (torch.clamp(torch.round(t * (1.0 / f.scale)) + f.zero_point, 0, 255) - f.zero_point) * f.scale
     fqw = lambda t, f: (torch.clamp(torch.round(t * (1.0 / f.scale)) + f.zero_point, -128, 127) - f.zero_point) * f.scale
-    xq = fqa(x, net[0].activation_post_process)
-    p = xq.mean((2, 3))
-    h = fqa(torch.relu(p @ fqw(se.fc[0].weight, se.fc[0].weight_fake_quant).t()), se.fc[0].activation_post_process)
-    h = fqa(h @ fqw(se.fc[2].weight, se.fc[2].weight_fake_quant).t(), se.fc[2].activation_post_process)
-    gate = fqa(torch.clamp(h + 3.0, 0, 6), se.fc[3].relu6.activation_post_process) * (1 / 6)
-    ref = fqa(xq * gate[:, :, None, None], se.quant_mul.activation_post_process)
+    with torch.no_grad():
+        xq = fqa(x, net[0].activation_post_process)
+        p = xq.mean((2, 3))
+        h = fqa(torch.relu(p @ fqw(se.fc[0].weight, se.fc[0].weight_fake_quant).t()), se.fc[0].activation_post_process)
+        h = fqa(h @ fqw(se.fc[2].weight, se.fc[2].weight_fake_quant).t(), se.fc[2].activation_post_process)
+        gate = fqa(torch.clamp(h + 3.0, 0, 6), se.fc[3].relu6.activation_post_process) * (1 / 6)
+        ref = fqa(xq * gate[:, :, None, None], se.quant_mul.activation_post_process)
     quantum = float(se.quant_mul.activation_post_process.scale)
     diff = (y - ref).abs()
     assert float(diff.max()) <= 1.01 * quantum * 2 and float((diff > 0.5 * quantum).float().mean()) <= 0.01, \

@@ -43,3 +43,26 @@ def test_prepared_module_refuses_cpu_tensors():
     x = attach_qparams(torch.randn(1, 8, 2, 2), torch.ones(1), torch.zeros(1, dtype=torch.int32))
     with pytest.raises(RuntimeError, match="CUDA device"):
         se(x)
+
+
+def test_mobilenetv3_bottleneck_keys_match_reference_float_and_prepared():
+    """frostnet_b200.mobilenetv3.Bottleneck against the reference's Bottleneck (tests/golden/mbv3_block.pt): same state_dict keys,
+    shapes and dtypes before fuse_model() and after fuse_model() + attach_fake_quant; the float forward runs"""
+    import frostnet_b200 as F
+    from frostnet_b200 import mobilenetv3 as M
+    g = load_golden("mbv3_block.pt")
+    for c in g["cases"]:
+        cin, cout, exp, k, s, se, nl, H = c["case"]
+        net = torch.nn.Sequential(F.QuantStub(), M.Bottleneck(cin, cout, exp, k, s, se=se, nl=nl))
+        assert sorted(net.state_dict().keys()) == sorted(c["float_sd"].keys()), c["case"]
+        net.load_state_dict(c["float_sd"], strict=True)
+        y = net(c["steps"][0]["x"])
+        assert y.shape == c["steps"][0]["y"].shape
+        net[1].fuse_model()
+        F.attach_fake_quant(net)
+        assert sorted(net.state_dict().keys()) == sorted(c["sd0"].keys()), c["case"]
+        net.load_state_dict(c["sd0"], strict=True)
+        sd = net.state_dict()
+        for kk, v in c["sd0"].items():
+            assert sd[kk].shape == v.shape and sd[kk].dtype == v.dtype, kk
+        assert [n for n, _ in net.named_parameters()] == list(c["steps"][0]["grads"].keys())
