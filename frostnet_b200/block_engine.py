@@ -52,14 +52,21 @@ class BlockEngine(QATEngine):
             raise RuntimeError("frostnet_b200: %s is not fused; call fuse_model() + prepare_qat" % type(m).__name__)
         if tuple(mod.dilation) != (1, 1):
             raise RuntimeError("frostnet_b200: stand-alone %s: dilated convolutions have no kernels" % type(m).__name__)
+        kk = mod.kernel_size[0] * mod.kernel_size[1] * mod.in_channels
         if mod.is_depthwise:
             kind = "dw"
         elif mod.groups == 1 and tuple(mod.kernel_size) == (1, 1) and tuple(mod.stride) == (1, 1):
             kind = "pw"
+        elif mod.groups == 1 and mod.kernel_size[0] == mod.kernel_size[1] and kk <= 32 and mod.out_channels <= 32:
+            kind = "stem"                      # dense kxk on an image-like input (MobileNetV3's conv1: 3 -> 16, 3x3 / 2)
         else:
-            raise RuntimeError("frostnet_b200: stand-alone %s: only 1x1 and depthwise 3x3 / 5x5 convolutions have kernels "
-                               "(dense kxk exists for the 3-channel stem inside FrostNet only)" % type(m).__name__)
+            raise RuntimeError("frostnet_b200: stand-alone %s: only 1x1, depthwise 3x3 / 5x5 and stem-sized dense kxk "
+                               "(k*k*cin <= 32, cout <= 32) convolutions have kernels" % type(m).__name__)
         self._single = _Layer(seq + ".0", mod, kind)
+        if kind == "stem":
+            # stand-alone stems take the direct-convolution kernels (frost_stem_conv_forward / frost_stem_wgrad); the im2col
+            # tensor-core route needs the QuantStub fused in front, which only the whole-network engine has
+            self._single.allow_im2col = False
         self.layers.append(self._single)
 
     def __deepcopy__(self, memo):
@@ -94,7 +101,8 @@ class BlockEngine(QATEngine):
         fq = L.FQ(self._dummy_mm.data_ptr(), self._dummy_mm.data_ptr() + 4, scale.data_ptr(), zp.data_ptr())
         L.call("frost_input_quant", x.data_ptr(), N, Cin, H, W, fq, 0, Q.AVERAGING_CONSTANT, xq.data_ptr(), mm_in.data_ptr(),
                self.scratch.data_ptr(), st)
-        q, ld = self._alloc_q(N * H * W, Cin)
+        is_stem = self._single is not None and self._single.kind == "stem"
+        q, ld = (xq.view(N * H * W, Cin), Cin) if is_stem else self._alloc_q(N * H * W, Cin)    # the stem kernels read dense NHWC
         if ld != Cin:
             q.zero_()
             q[:, :Cin].copy_(xq.view(N * H * W, Cin))      # rows padded to TMA's 16-byte pitch (boundary plumbing)
@@ -128,6 +136,12 @@ class BlockEngine(QATEngine):
         dy = dy.contiguous().float()
         g = torch.empty((o.M, o.C), dtype=torch.float32, device=dev)
         L.call("frost_nchw_to_nhwc", dy.data_ptr(), o.N, o.C, o.H, o.W, g.data_ptr(), 0, st)
+        if self._single is not None and self._single.kind == "stem":
+            # the reference's stem sees the image: no gradient flows to it (run() refuses inputs that require one)
+            self._conv_bn_bwd(self._single, g, saved, gbase, None, False, st)
+            L.call("frost_weight_backward_multi", self._wdesc_dev[which].data_ptr(), len(self.layers),
+                   self._wbchunks.data_ptr(), self._n_wbchunks, st)
+            return None, [gflat.narrow(0, self.param_off[id(p)], p.numel()).view(p.shape) for p in self.params]
         if self._single is not None:
             xin = saved[self._single.name][0]
             gx = torch.empty((xin.M, xin.C), dtype=torch.float32, device=dev)
@@ -155,6 +169,9 @@ class BlockEngine(QATEngine):
         if not hasattr(self, "_dummy_mm") or self._dummy_mm.device != self.dev:
             self._dummy_mm = torch.zeros(2, dtype=torch.float32, device=self.dev)
         need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.params))
+        if need_grad and x.requires_grad and self._single is not None and self._single.kind == "stem":
+            raise RuntimeError("frostnet_b200: a stand-alone stem convolution has no input gradient (the reference feeds it "
+                               "the image); detach the input")
         if need_grad:
             y = _BlockFunction.apply(self, x, qp[0], qp[1], *self.params)
         else:

@@ -65,6 +65,7 @@ class _Layer:
         else:
             self.stride, self.pad, self.cin = 1, 0, mod.in_channels
         self.layout = {"pw": 0, "cls": 0, "dw": 1, "stem": 2}[kind]
+        self.allow_im2col = True               # stand-alone stems (block_engine.py) switch the im2col GEMM route off
 
     def alloc(self, dev):
         f32 = dict(dtype=torch.float32, device=dev)
@@ -79,7 +80,7 @@ class _Layer:
         # tensor-core operand bytes of the fused 1x1 kernels: rows padded to a multiple of 16 bytes (TMA's stride rule).
         # The dense kxk stem joins them as an im2col GEMM (K = kh*kw*cin padded to 32) when its patch fits 32 bytes.
         kk = self.cin_g * self.kh * self.kw
-        self.im2col = self.kind == "stem" and kk <= 32
+        self.im2col = self.kind == "stem" and kk <= 32 and self.allow_im2col
         self.k_mma = self.cin_g if self.kind == "pw" else ((kk + 15) // 16 * 16 if self.im2col else 0)
         self.ldw = (self.k_mma + 15) // 16 * 16
         self.wq_mma = torch.zeros(self.cout * self.ldw, dtype=torch.int8, device=dev) if self.k_mma else None

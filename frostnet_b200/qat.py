@@ -234,7 +234,7 @@ def attach_fake_quant(root):
     fused conv (weight + output), FloatFunctional, QuantStub, the ReLU6 inside Hswish / Hsigmoid and the Linear layers of SEModule.  Convs must be fused first
     (``fuse_model()``).  The modules then run through the per-module executor (block_engine.py)."""
     from .hswish import Hsigmoid, Hswish
-    from .se import QATLinear
+    from .se import QATConv1x1, QATLinear
     dev = next((p.device for p in root.parameters()), torch.device("cpu"))
     for m in list(root.modules()):
         if isinstance(m, FrostConvBn2d) and not isinstance(getattr(m, "weight_fake_quant", None), FrostFakeQuantize):
@@ -244,7 +244,7 @@ def attach_fake_quant(root):
             m.activation_post_process = FrostFakeQuantize.act().to(dev)
         elif isinstance(m, (Hswish, Hsigmoid)) and not m._prepared():
             m.relu6.activation_post_process = FrostFakeQuantize.act().to(dev)
-        elif isinstance(m, QATLinear) and not m._prepared():
+        elif isinstance(m, (QATLinear, QATConv1x1)) and not m._prepared():
             m.weight_fake_quant = FrostFakeQuantize.weight().to(dev)
             m.activation_post_process = FrostFakeQuantize.act().to(dev)
     return root

@@ -125,16 +125,17 @@ def _pad4(n):
 
 
 class _LinearFunction(torch.autograd.Function):
-    """relu?(F.linear(x, FQ_w(W))) on frost_linear_forward; K and cout are padded to multiples of 4 for its 4-wide loads."""
+    """relu?(F.linear(x, FQ_w(W)) + bias) on frost_linear_forward; K and cout are padded to multiples of 4 for its 4-wide loads.
+    ``weight`` may be [cout, K] or a 1x1 conv's [cout, K, 1, 1]."""
 
     @staticmethod
-    def forward(ctx, x, weight, mod):
+    def forward(ctx, x, weight, bias, mod):
         dev = x.device
         wfq = mod.weight_fake_quant
         x = x.detach()
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
-        W = weight.detach().float().contiguous()
+        W = weight.detach().float().contiguous().view(weight.shape[0], -1)
         cout, K = W.shape
         N = x.shape[0]
         Kp, cp = _pad4(K), _pad4(cout)
@@ -154,20 +155,25 @@ class _LinearFunction(torch.autograd.Function):
             else:
                 wq8, xp = wq32.to(torch.int8), x
             out = torch.empty((N, cp), dtype=torch.float32, device=dev)
-            L.call("frost_linear_forward", xp.data_ptr(), wq8.data_ptr(), wfq.scale.data_ptr(), wfq.zero_point.data_ptr(), None,
+            bp = None
+            if bias is not None:
+                bp = bias.detach().float().contiguous()
+                if cp != cout:
+                    bp = torch.cat([bp, torch.zeros(cp - cout, dtype=torch.float32, device=dev)])
+            L.call("frost_linear_forward", xp.data_ptr(), wq8.data_ptr(), wfq.scale.data_ptr(), wfq.zero_point.data_ptr(), L.ptr(bp),
                    N, Kp, cp, out.data_ptr(), st)
             rmask = None
-            if mod.relu:
+            if getattr(mod, "relu", False):
                 rmask = torch.empty(out.shape, dtype=torch.uint8, device=dev)
                 y = torch.empty_like(out)
                 L.call("frost_relu_forward", out.data_ptr(), out.numel(), y.data_ptr(), rmask.data_ptr(), st)
                 out = y
-        ctx.saved = (xp, wq8, wmask, rmask, wfq, (N, K, cout, Kp, cp))
+        ctx.saved = (xp, wq8, wmask, rmask, wfq, (N, K, cout, Kp, cp), tuple(weight.shape), bias is not None)
         return out[:, :cout].contiguous() if cp != cout else out
 
     @staticmethod
     def backward(ctx, dout):
-        xp, wq8, wmask, rmask, wfq, (N, K, cout, Kp, cp) = ctx.saved
+        xp, wq8, wmask, rmask, wfq, (N, K, cout, Kp, cp), wshape, has_bias = ctx.saved
         dev = dout.device
         d = dout.contiguous().float()
         if cp != cout:
@@ -182,12 +188,13 @@ class _LinearFunction(torch.autograd.Function):
                 d = dr
             dx = torch.empty((N, Kp), dtype=torch.float32, device=dev)
             dwq = torch.empty((cp, Kp), dtype=torch.float32, device=dev)
+            db = torch.empty(cp, dtype=torch.float32, device=dev) if has_bias else None
             L.call("frost_linear_backward", d.data_ptr(), xp.data_ptr(), wq8.data_ptr(), wfq.scale.data_ptr(),
-                   wfq.zero_point.data_ptr(), N, Kp, cp, dx.data_ptr(), dwq.data_ptr(), None, st)
+                   wfq.zero_point.data_ptr(), N, Kp, cp, dx.data_ptr(), dwq.data_ptr(), L.ptr(db), st)
             dwq = dwq[:cout, :K].contiguous()
             dW = torch.empty_like(dwq)
             L.call("frost_fq_backward", dwq.data_ptr(), wmask.data_ptr(), dwq.numel(), dW.data_ptr(), st)
-        return (dx[:, :K].contiguous() if Kp != K else dx), dW, None
+        return (dx[:, :K].contiguous() if Kp != K else dx), dW.view(wshape), (db[:cout].contiguous() if has_bias else None), None
 
 
 class _BcastMulFunction(torch.autograd.Function):
@@ -225,10 +232,67 @@ def _run_linear(mod, x):
         raise RuntimeError("frostnet_b200: the QAT path runs on a CUDA device (B200) only; got a CPU tensor")
     if x.dim() != 2 or x.shape[1] != mod.in_features:
         raise RuntimeError("frostnet_b200: QATLinear expects [N, %d], got %s" % (mod.in_features, tuple(x.shape)))
-    y = _LinearFunction.apply(x, mod.weight, mod)
+    y = _LinearFunction.apply(x, mod.weight, None, mod)
     fq = mod.activation_post_process
     y = _FakeQuantFunction.apply(y, fq, _scratch(mod, x.device))
     return attach_qparams(y, fq.scale, fq.zero_point)
+
+
+class QATConv1x1(nn.Module):
+    """``nn.Conv2d(cin, cout, 1)`` with bias on pooled [N, cin, 1, 1] tensors (MobileNetV3's classifier convs,
+    mobilenetv3.py:306-308, 320-323); nnqat.Conv2d once ``attach_fake_quant`` has given it its two fake-quants - the same
+    ``weight`` / ``bias`` / ``weight_fake_quant.*`` / ``activation_post_process.*`` keys."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        conv = nn.Conv2d(in_channels, out_channels, 1)
+        self.weight, self.bias = conv.weight, conv.bias
+
+    def _prepared(self):
+        return isinstance(getattr(self, "weight_fake_quant", None), Q.FrostFakeQuantize)
+
+    def forward(self, x):
+        if not self._prepared():
+            return F.conv2d(x, self.weight, self.bias)
+        from .block_engine import _FakeQuantFunction, attach_qparams
+        if not x.is_cuda:
+            raise RuntimeError("frostnet_b200: the QAT path runs on a CUDA device (B200) only; got a CPU tensor")
+        if x.dim() != 4 or x.shape[1] != self.in_channels or x.shape[2:] != (1, 1):
+            raise RuntimeError("frostnet_b200: QATConv1x1 runs on pooled [N, %d, 1, 1] tensors, got %s" % (self.in_channels, tuple(x.shape)))
+        y = _LinearFunction.apply(x.reshape(x.shape[0], -1), self.weight, self.bias, self)
+        fq = self.activation_post_process
+        y = _FakeQuantFunction.apply(y, fq, _scratch(self, x.device))
+        return attach_qparams(y.view(y.shape[0], -1, 1, 1), fq.scale, fq.zero_point)
+
+    def extra_repr(self):
+        return "%d, %d, kernel_size=(1, 1), stride=(1, 1)" % (self.in_channels, self.out_channels)
+
+
+class AvgPool(nn.AdaptiveAvgPool2d):
+    """``nn.AdaptiveAvgPool2d(1)`` that, on a tensor carrying a quantisation grid, pools on the device (no observer: prepare_qat
+    adds none to a pooling module, its output is off-grid fp32)."""
+
+    def forward(self, x):
+        qp = getattr(x, "_frost_qparams", None)
+        if qp is None or not x.is_cuda:
+            return super().forward(x)
+        n, c = x.shape[:2]
+        return _PoolFunction.apply(x, qp[0], qp[1], self).view(n, c, 1, 1)
+
+
+def dropout(x, p, training):
+    """``F.dropout(x, p, training)`` (mobilenetv3.py:353) on a tensor that carries a grid: the kept values are scaled by
+    1 / (1 - p), i.e. the result sits on the grid (scale / (1 - p), zero point) and a dropped value is the index of zero."""
+    qp = getattr(x, "_frost_qparams", None)
+    if qp is None or not x.is_cuda:
+        return F.dropout(x, p=p, training=training)
+    if not training or p == 0.0:
+        return x
+    from .block_engine import attach_qparams
+    keep = (torch.rand(x.shape, device=x.device) >= p).float().mul_(1.0 / (1.0 - p))
+    y = _BcastMulFunction.apply(x.reshape(1, x.numel(), 1, 1), keep.view(1, -1)).view(x.shape)
+    return attach_qparams(y, qp[0] / (1.0 - p), qp[1])
 
 
 def _run_se(mod, x):

@@ -66,3 +66,28 @@ def test_mobilenetv3_bottleneck_keys_match_reference_float_and_prepared():
         for kk, v in c["sd0"].items():
             assert sd[kk].shape == v.shape and sd[kk].dtype == v.dtype, kk
         assert [n for n, _ in net.named_parameters()] == list(c["steps"][0]["grads"].keys())
+
+
+def test_mobilenetv3_network_keys_match_reference():
+    """frostnet_b200.mobilenetv3.MobileNetV3 against the reference network (tests/golden/mbv3_net.pt): the same state_dict keys
+    in the same order before fuse_model(); the same keys, shapes, dtypes and parameter order after fuse + prepare; the factory
+    names and the float forward work"""
+    import frostnet_b200 as F
+    from frostnet_b200 import mobilenetv3 as M
+    g = load_golden("mbv3_net.pt")
+    net = M.get_mobilenet_v3("small", 1.0, nclass=10)
+    assert list(net.state_dict().keys()) == g["float_keys"]
+    net.eval()
+    assert net(torch.randn(2, 3, 64, 64)).shape == (2, 10)
+    net.train()
+    net.fuse_model()
+    F.attach_fake_quant(net)
+    sd = net.state_dict()
+    assert sorted(sd.keys()) == sorted(g["sd0_keys"].keys())
+    for k, (shape, dtype) in g["sd0_keys"].items():
+        assert tuple(sd[k].shape) == shape and str(sd[k].dtype) == dtype, k
+    assert [n for n, _ in net.named_parameters()] == g["param_names"]
+    for f in (M.mobilenet_v3_large, M.mobilenet_v3_ReLU_small, M.mobilenet_v3_ReLU_large):
+        assert sum(p.numel() for p in f(nclass=7).parameters()) > 0
+    with pytest.raises(ValueError):
+        M.MobileNetV3(mode="medium")

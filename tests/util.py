@@ -30,3 +30,24 @@ def nchw_idx_to_nhwc_u8(idx):
 def rel_l2(a, b):
     a, b = a.double().flatten(), b.double().flatten()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def fill_params_by_name(model):
+    """Deterministic parameters that depend only on each parameter's NAME and shape (a generator seeded with crc32(name)):
+    the reference network in the build container and our network on the GPU box get identical weights without storing them
+    (tests/golden/make_golden_mbv3_net.py).  Conv / Linear weights ~ N(0, 2 / fan_out) (x4 for the tiny SE layers so that the
+    gates move), BatchNorm weight 1 + 0.1 N, biases 0.1 N."""
+    import zlib
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            g = torch.Generator().manual_seed(zlib.crc32(name.encode()))
+            r = torch.randn(p.shape, generator=g)
+            if p.dim() >= 2:
+                fan_out = p.shape[0] * (p[0, 0].numel() if p.dim() > 2 else 1)
+                std = (2.0 / fan_out) ** 0.5 * (4.0 if ".fc." in name else 1.0)
+                p.copy_(r * std)
+            elif name.endswith("bn.weight"):
+                p.copy_(1.0 + 0.1 * r)
+            else:
+                p.copy_(0.1 * r)
+    return model
