@@ -126,10 +126,26 @@ def test_standalone_conv_block_matches_whole_network_engine():
         assert torch.equal(y.detach(), y_ref), conv_name
         y.sum().backward()
         assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in ca.parameters())
-    with pytest.raises(RuntimeError, match="only 1x1 and depthwise"):
-        xs = torch.zeros(N, 3, 64, 64, device=DEV)
-        xs._frost_qparams = (whole.quant.activation_post_process.scale, whole.quant.activation_post_process.zero_point)
-        alone.conv1(xs)                                  # the dense 3x3 stem has no stand-alone kernel
+    # the dense 3x3 stem runs on its own too (direct-convolution kernels; no input gradient, like the reference's stem)
+    xs = torch.zeros(N, 3, 64, 64, device=DEV)
+    xs._frost_qparams = (whole.quant.activation_post_process.scale, whole.quant.activation_post_process.zero_point)
+    ys = alone.conv1(xs)
+    assert ys.shape[:2] == (N, alone.conv1.conv[0].out_channels) and hasattr(ys, "_frost_qparams")
+    ys.sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in alone.conv1.parameters())
+    with pytest.raises(RuntimeError, match="no input gradient"):
+        xg = torch.zeros(N, 3, 64, 64, device=DEV, requires_grad=True)
+        xg._frost_qparams = xs._frost_qparams
+        alone.conv1(xg)
+    import frostnet_b200 as F
+    big = F.ConvBN(16, 16, 3, 1, 1)                      # a dense 3x3 on 16 channels has no kernel
+    big.fuse_model()
+    F.attach_fake_quant(big)
+    big.to(DEV).train()
+    with pytest.raises(RuntimeError, match="stem-sized"):
+        xb = torch.zeros(N, 16, 8, 8, device=DEV)
+        xb._frost_qparams = xs._frost_qparams
+        big(xb)
 
 
 def test_quant_stub_then_blocks_chain_standalone():

@@ -163,6 +163,6 @@ def test_mobilenetv3_small_trains_end_to_end():
         loss.backward()
         assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters()), i
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     print("losses", losses)
     assert min(losses[-3:]) < losses[0], losses
