@@ -67,20 +67,42 @@ def _convert_quant_stub(m):
     return nnq.Quantize.from_float(t)
 
 
+def _convert_linear(m):
+    """se.QATLinear -> nniq.LinearReLU / nnq.Linear through nniqat.LinearReLU / nnqat.Linear (what fuse + prepare_qat make of
+    SEModule's nn.Linear layers, mobilenetv3.py:88-93, 101-102)."""
+    cls = nniqat.LinearReLU if m.relu else nnqat.Linear
+    t = cls(m.in_features, m.out_features, bias=False, qconfig=_qconfig())
+    t.activation_post_process = _qconfig().activation()
+    missing, unexpected = t.load_state_dict(m.state_dict(), strict=True)
+    assert not missing and not unexpected
+    t.eval()
+    return (nniq.LinearReLU if m.relu else nnq.Linear).from_float(t)
+
+
 def convert_int8(model):
-    """Return the int8 inference model (CPU, eval) of a prepared frostnet_b200 FrostNet.  `model` is left untouched."""
+    """Return the int8 inference model (CPU, eval) of a prepared frostnet_b200 network (FrostNet, MobileNetV3 or any tree of this
+    package's modules).  `model` is left untouched."""
     if not Q.is_prepared(model):
         raise ValueError("convert_int8 expects a model after fuse_model() + prepare_qat()")
     dst = copy.deepcopy(model)
-    dst.__dict__.pop("_frost_engine", None)          # the copy is a plain module tree: no QAT engine
+    for m in dst.modules():                           # the copy is a plain module tree: no QAT engines, no device scratch
+        for k in [k for k in m.__dict__ if k.startswith("_frost_")]:
+            m.__dict__.pop(k)
     dst = dst.cpu().eval()
+
+    from .se import QATConv1x1, QATLinear
 
     def swap(parent):
         for name, child in list(parent.named_children()):
             if isinstance(child, Q.FrostConvBn2d):
                 setattr(parent, name, _convert_conv_bn(child))
-            elif isinstance(child, Q.FrostQATConv2d):
+            elif isinstance(child, (Q.FrostQATConv2d, QATConv1x1)):
                 setattr(parent, name, _convert_classifier(child))
+            elif isinstance(child, QATLinear):
+                setattr(parent, name, _convert_linear(child))
+            elif isinstance(child, nn.ReLU6):
+                # nn.ReLU6 -> nnq.ReLU6 (stateless: the quantized op keeps its input's grid; the QAT observer is dropped)
+                setattr(parent, name, nnq.ReLU6(child.inplace))
             elif isinstance(child, Q.FloatFunctional):
                 setattr(parent, name, _convert_functional(child))
             elif isinstance(child, Q.QuantStub):

@@ -27,10 +27,11 @@ class Hswish(nn.Module):
     def forward(self, x):
         if self._prepared():
             return _run(self, x)
-        out = x + 3.0                       # quant_add.add_scalar
+        # through the functional modules, like the reference: the int8 export (export.py) swaps them for QFunctional
+        out = self.quant_add.add_scalar(x, 3.0)
         out = self.relu6(out)
-        out = x * out                       # quant_mul1.mul
-        return out * (1 / 6)                # quant_mul2.mul_scalar
+        out = self.quant_mul1.mul(x, out)
+        return self.quant_mul2.mul_scalar(out, 1 / 6)
 
 
 class Hsigmoid(nn.Module):
@@ -48,7 +49,7 @@ class Hsigmoid(nn.Module):
     def forward(self, x):
         if self._prepared():
             return _run(self, x)
-        return self.relu6(x + 3.0) * (1 / 6)
+        return self.quant_mul.mul_scalar(self.relu6(self.quant_add.add_scalar(x, 3.0)), 1 / 6)
 
 
 class _HswishFunction(torch.autograd.Function):

@@ -81,7 +81,7 @@ class SEModule(nn.Module):
         n, c, _, _ = x.size()
         out = self.avg_pool(x).view(n, c)
         out = self.fc(out).view(n, c, 1, 1)
-        return x * out.expand_as(x)                 # quant_mul.mul
+        return self.quant_mul.mul(x, out.expand_as(x))
 
 
 # ---------------------------------------------------------------------- autograd nodes

@@ -81,3 +81,38 @@ def test_float_forward_uses_functional_modules():
     x = torch.randn(2, 3, 64, 64)
     with torch.no_grad():
         assert torch.equal(a(x), b(x))
+
+
+def test_mobilenetv3_int8_export_matches_reference_convert():
+    """convert_int8 on the prepared MobileNetV3-small against the reference's torch.quantization.convert of the real reference
+    network (tests/golden/make_golden_int8_mbv3.py): every entry of the converted state_dict (int8 weight bytes by SHA-1,
+    scales, zero points, biases) and the int8 logits"""
+    import frostnet_b200 as F
+    from frostnet_b200 import mobilenetv3 as M
+    from util import fill_params_by_name, qdigest_compact
+    g = load_golden("int8_mbv3.pt")
+    if g["engine"] not in torch.backends.quantized.supported_engines:
+        pytest.skip("quantized engine %s not available in this torch build" % g["engine"])
+    torch.backends.quantized.engine = g["engine"]
+    net = M.get_mobilenet_v3("small", 1.0, nclass=10)
+    net.train()
+    net.fuse_model()
+    F.attach_fake_quant(net)
+    fill_params_by_name(net)
+    missing, unexpected = net.load_state_dict(g["state"], strict=False)
+    assert not unexpected and all(k.endswith(".weight") or k.endswith(".bias") for k in missing)
+    q = F.convert_int8(net)
+    mine, ref = qdigest_compact(q.state_dict()), g["converted"]
+    assert sorted(mine.keys()) == sorted(ref.keys())
+
+    def same(a, b):
+        if isinstance(b, torch.Tensor):
+            return isinstance(a, torch.Tensor) and torch.equal(a, b)
+        if isinstance(b, list):
+            return isinstance(a, list) and len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+        return a == b
+    bad = [k for k in ref if not same(mine[k], ref[k])]
+    assert not bad, (len(bad), bad[:6])
+    with torch.no_grad():
+        logits = q(g["x"])
+    assert torch.equal(logits, g["int8_logits"]), float((logits - g["int8_logits"]).abs().max())

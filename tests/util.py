@@ -51,3 +51,27 @@ def fill_params_by_name(model):
             else:
                 p.copy_(0.1 * r)
     return model
+
+
+def qdigest_compact(sd):
+    """state_dict of a converted (int8) model -> comparable plain values: quantized tensors as (shape, qparams, SHA-1 of the int8
+    bytes), other tensors whole when small and hashed when large, packed-parameter tuples element by element."""
+    import hashlib
+
+    def one(v):
+        if isinstance(v, torch.Tensor) and v.is_quantized:
+            if v.qscheme() in (torch.per_channel_affine, torch.per_channel_symmetric):
+                qp = (v.q_per_channel_scales().tolist(), v.q_per_channel_zero_points().tolist())
+            else:
+                qp = (float(v.q_scale()), int(v.q_zero_point()))
+            return dict(shape=tuple(v.shape), qparams=qp, sha1=hashlib.sha1(v.int_repr().contiguous().numpy().tobytes()).hexdigest())
+        if isinstance(v, torch.Tensor):
+            if v.numel() <= 4096:
+                return v.clone()
+            return dict(shape=tuple(v.shape), sha1=hashlib.sha1(v.contiguous().numpy().tobytes()).hexdigest())
+        if isinstance(v, (tuple, list)):
+            return [one(e) for e in v]
+        if isinstance(v, (int, float, type(None), torch.dtype, str)):
+            return v
+        return repr(v)
+    return {k: one(v) for k, v in sd.items()}
