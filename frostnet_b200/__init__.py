@@ -5,7 +5,8 @@ and the StatAssist/GradBoost optimizer step, behind the reference's nn.Module / 
 """
 from .frostnet import *          # noqa: F401,F403  (FrostNet, blocks, 30 factories)
 from .frostnet import FrostNet, CascadePreExBottleneck, ConvBNReLU, ConvBN
-from .qat import prepare_qat, patch_torch_quantization, attach_fake_quant, FrostFakeQuantize, QuantStub, DeQuantStub
+from .qat import (prepare_qat, patch_torch_quantization, attach_fake_quant, fuse_modules, FrostFakeQuantize, QuantStub,
+                  DeQuantStub)
 from .optimizer import QSGD, QRMSprop, QAdam, QAdamW, get_optimizer
 from . import parallel
 from .prefetch import DevicePrefetcher
@@ -16,3 +17,4 @@ from .export import convert_int8
 from .hswish import Hsigmoid, Hswish
 from .se import SEModule, QATLinear
 from . import mobilenetv3
+from . import mobilenetv2

@@ -46,8 +46,11 @@ class BlockEngine(QATEngine):
         if isinstance(m, FN.CascadePreExBottleneck):
             self._add_block(add, "", m)
             return
-        seq = getattr(m, "_seq_name", "conv")               # "conv" (frostnet.py) or "cbr" / "cb" (mobilenetv3.py)
-        mod = getattr(m, seq)[0]
+        if isinstance(m, Q.FrostConvBn2d):                   # a fused conv called directly (it sits in a foreign container)
+            seq, mod = "self", m
+        else:
+            seq = getattr(m, "_seq_name", "conv")           # "conv" (frostnet.py) or "cbr" / "cb" (mobilenetv3.py)
+            mod = getattr(m, seq)[0]
         if not isinstance(mod, Q.FrostConvBn2d):
             raise RuntimeError("frostnet_b200: %s is not fused; call fuse_model() + prepare_qat" % type(m).__name__)
         if tuple(mod.dilation) != (1, 1):

@@ -175,7 +175,10 @@ class FrostConvBn2d(nn.Module):
 
     def forward(self, x):
         if isinstance(getattr(self, "weight_fake_quant", None), FrostFakeQuantize):
-            raise RuntimeError("frostnet_b200: a prepared FrostConvBn2d only runs inside the QAT engine")
+            # prepared and called directly (a fused conv sitting in somebody's nn.Sequential, e.g. torchvision-style
+            # ConvBNReLU / InvertedResidual of Object_Detection/ssd_qmv2.py:40-110): per-module executor
+            from .block_engine import run_block
+            return run_block(self, x)
         y = nn.functional.conv2d(x, self.weight, None, self.stride, self.padding, self.dilation, self.groups)
         y = self.bn(y)
         return nn.functional.relu(y) if self.relu else y
@@ -234,6 +237,30 @@ def prepare_qat(model, inplace=True):
         cls[2] = FrostQATConv2d(cls[2]).to(dev)
     model.__dict__["_frost_engine"] = _engine.QATEngine(model)
     return model
+
+
+def fuse_modules(container, names, inplace=True):
+    """``torch.quantization.fuse_modules(container, ['0', '1'(, '2')], inplace=True)`` for Conv2d + BatchNorm2d (+ ReLU) children of
+    any module (frostnet.py:27-28, ssd_qmv2.py:178-185, mobilenetv3.py:21-25): the first name becomes a FrostConvBn2d holding the
+    SAME Parameter / BatchNorm objects (state_dict keys ``<first>.weight``, ``<first>.bn.*`` like nni.ConvBn(ReLU)2d after
+    prepare_qat), the others nn.Identity."""
+    if not inplace:
+        raise ValueError("frostnet_b200.fuse_modules fuses in place")
+    mods = [getattr(container, n) if not isinstance(container, nn.Sequential) else container[int(n)] for n in names]
+    if isinstance(mods[0], FrostConvBn2d):
+        return container
+    if not (isinstance(mods[0], nn.Conv2d) and len(mods) in (2, 3) and isinstance(mods[1], nn.BatchNorm2d)
+            and (len(mods) == 2 or isinstance(mods[2], nn.ReLU))):
+        raise ValueError("frostnet_b200.fuse_modules: expected Conv2d, BatchNorm2d(, ReLU), got %s" % [type(m).__name__ for m in mods])
+    if mods[0].bias is not None:
+        raise ValueError("frostnet_b200.fuse_modules: the convolution must not have a bias")
+    repl = [FrostConvBn2d(mods[0], mods[1], relu=len(mods) == 3)] + [nn.Identity() for _ in mods[1:]]
+    for n, r in zip(names, repl):
+        if isinstance(container, nn.Sequential):
+            container[int(n)] = r
+        else:
+            setattr(container, n, r)
+    return container
 
 
 def attach_fake_quant(root):

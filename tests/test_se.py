@@ -91,3 +91,24 @@ def test_mobilenetv3_network_keys_match_reference():
         assert sum(p.numel() for p in f(nclass=7).parameters()) > 0
     with pytest.raises(ValueError):
         M.MobileNetV3(mode="medium")
+
+
+def test_mobilenetv2_block_keys_match_reference():
+    """frostnet_b200.mobilenetv2.InvertedResidual (SSDLite backbone, f2) against the reference's block
+    (tests/golden/mbv2_block.pt): state_dict keys, shapes, dtypes and parameter order before and after fuse + prepare"""
+    import frostnet_b200 as F
+    from frostnet_b200 import mobilenetv2 as M2
+    g = load_golden("mbv2_block.pt")
+    for c in g["cases"]:
+        inp, oup, s, t, H = c["case"]
+        net = torch.nn.Sequential(F.QuantStub(), M2.InvertedResidual(inp, oup, s, 1, t))
+        assert list(net.state_dict().keys()) == list(c["float_sd"].keys()), c["case"]
+        net.load_state_dict(c["float_sd"], strict=True)
+        assert net(c["steps"][0]["x"]).shape == c["steps"][0]["y"].shape
+        M2.fuse_model(net)
+        F.attach_fake_quant(net)
+        assert sorted(net.state_dict().keys()) == sorted(c["sd0"].keys()), c["case"]
+        net.load_state_dict(c["sd0"], strict=True)
+        for kk, v in c["sd0"].items():
+            assert net.state_dict()[kk].shape == v.shape and net.state_dict()[kk].dtype == v.dtype, kk
+        assert [n for n, _ in net.named_parameters()] == list(c["steps"][0]["grads"].keys())
