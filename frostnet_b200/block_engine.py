@@ -53,8 +53,8 @@ class BlockEngine(QATEngine):
             mod = getattr(m, seq)[0]
         if not isinstance(mod, Q.FrostConvBn2d):
             raise RuntimeError("frostnet_b200: %s is not fused; call fuse_model() + prepare_qat" % type(m).__name__)
-        if tuple(mod.dilation) != (1, 1):
-            raise RuntimeError("frostnet_b200: stand-alone %s: dilated convolutions have no kernels" % type(m).__name__)
+        if tuple(mod.dilation) != (1, 1) and not mod.is_depthwise:
+            raise RuntimeError("frostnet_b200: stand-alone %s: only depthwise convolutions may be dilated" % type(m).__name__)
         kk = mod.kernel_size[0] * mod.kernel_size[1] * mod.in_channels
         if mod.is_depthwise:
             kind = "dw"

@@ -62,8 +62,9 @@ class _Layer:
         if kind != "cls":
             self.stride, self.pad = mod.stride[0], mod.padding[0]
             self.cin = mod.in_channels
+            self.dil = mod.dilation[0]
         else:
-            self.stride, self.pad, self.cin = 1, 0, mod.in_channels
+            self.stride, self.pad, self.cin, self.dil = 1, 0, mod.in_channels, 1
         self.layout = {"pw": 0, "cls": 0, "dw": 1, "stem": 2}[kind]
         self.allow_im2col = True               # stand-alone stems (block_engine.py) switch the im2col GEMM route off
 
@@ -225,8 +226,11 @@ class QATEngine:
         self.dev = dev
         self._side = None
         for ly in self.layers:
-            if ly.kind == "dw" and not (ly.kh in (3, 5) and ly.stride in (1, 2) and ly.cin_g == 1):
+            if ly.kind == "dw" and not (ly.kh in (3, 5) and ly.stride in (1, 2) and ly.cin_g == 1
+                                        and ly.pad == ly.dil * (ly.kh - 1) // 2 and 1 <= ly.dil <= 16):
                 raise RuntimeError("frostnet_b200: unsupported depthwise conv %s" % ly.name)
+            if ly.kind != "dw" and ly.dil != 1:
+                raise RuntimeError("frostnet_b200: %s: only depthwise convolutions may be dilated" % ly.name)
             ly.alloc(dev)
         # parameter order == model.named_parameters() (the optimizer / checkpoint contract)
         self.params = [p for _, p in m.named_parameters()]
@@ -362,8 +366,8 @@ class QATEngine:
         if ly.kind == "pw" or mma:
             Ho, Wo = xin.H, xin.W              # (the im2col stem's input rows are already per output pixel)
         else:
-            Ho = (xin.H + 2 * ly.pad - ly.kh) // ly.stride + 1
-            Wo = (xin.W + 2 * ly.pad - ly.kw) // ly.stride + 1
+            Ho = (xin.H + 2 * ly.pad - ly.dil * (ly.kh - 1) - 1) // ly.stride + 1
+            Wo = (xin.W + 2 * ly.pad - ly.dil * (ly.kw - 1) - 1) // ly.stride + 1
         M = N * Ho * Wo
         wzp = mod.weight_fake_quant.zero_point
         afq = mod.activation_post_process
@@ -388,6 +392,9 @@ class QATEngine:
             elif ly.kind == "pw":
                 L.call("frost_pw_conv_forward", xin.q.data_ptr(), xin.zp.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(),
                        ly.wsum.data_ptr(), M, ly.cin, ly.cout, acc.data_ptr(), ly.stats_ptr, st)
+            elif ly.kind == "dw" and ly.dil > 1:
+                L.call("frost_dw_conv_forward_dilated", xin.q.data_ptr(), xin.ld, xin.zp.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(),
+                       N, xin.H, xin.W, xin.C, ly.kh, ly.stride, ly.dil, acc.data_ptr(), ly.stats_ptr, st)
             elif ly.kind == "dw":
                 L.call("frost_dw_conv_forward", xin.q.data_ptr(), xin.ld, xin.zp.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(),
                        N, xin.H, xin.W, xin.C, ly.kh, ly.stride, acc.data_ptr(), ly.stats_ptr, st)
@@ -634,6 +641,12 @@ class QATEngine:
             if dx is not None:
                 L.call("frost_pw_dgrad_tc", dz.data_ptr(), dz_lo.data_ptr(), ly.wt_bf16.data_ptr(), wfq.scale.data_ptr(),
                        M, ly.cin, ly.cout, dx.data_ptr(), 1 if accumulate else 0, st)
+        elif ly.kind == "dw" and ly.dil > 1:
+            L.call("frost_dw_wgrad_dilated", dz.data_ptr(), xin.q.data_ptr(), xin.ld, xin.scale.data_ptr(), xin.zp.data_ptr(), xin.N,
+                   xin.H, xin.W, xin.C, ly.kh, ly.stride, ly.dil, ly.dwq.data_ptr(), wst)
+            if dx is not None:
+                L.call("frost_dw_dgrad_dilated", dz.data_ptr(), ly.wq.data_ptr(), wfq.scale.data_ptr(), wfq.zero_point.data_ptr(),
+                       xin.N, xin.H, xin.W, xin.C, ly.kh, ly.stride, ly.dil, dx.data_ptr(), 1 if accumulate else 0, st)
         elif ly.kind == "dw":
             L.call("frost_dw_wgrad", dz.data_ptr(), xin.q.data_ptr(), xin.ld, xin.scale.data_ptr(), xin.zp.data_ptr(), xin.N,
                    xin.H, xin.W, xin.C, ly.kh, ly.stride, ly.dwq.data_ptr(), wst)

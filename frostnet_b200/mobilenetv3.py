@@ -9,8 +9,8 @@ quantisation grid on with the tensor.  The plain ``nn.ReLU`` of the 'RE' blocks 
 (it is not in torch's propagation list): it is a ReLU on the incoming grid, and keeps that grid.
 
 ``MobileNetV3`` (mobilenetv3.py:162-383) wires them with the stem (stand-alone dense 3x3 on the direct-convolution kernels), the
-dropout on the last feature map and the pooled, biased 1x1 head convs (se.QATConv1x1).  ``dilated=True`` builds (float) but has
-no QAT kernels (dilated depthwise).
+dropout on the last feature map and the pooled, biased 1x1 head convs (se.QATConv1x1).  ``dilated=True`` (layer4 at dilation 2, no
+classifier - a segmentation backbone, like the reference's) runs its depthwise convs on csrc/dw_dilated.cu.
 """
 import torch
 import torch.nn.functional as F

@@ -2,8 +2,7 @@
 classes (Object_Detection/ssd_qmv2.py:40-110: ConvBNReLU as an nn.Sequential, InvertedResidual with a bare Conv2d +
 BatchNorm2d tail), fused by the reference's own rule (MobileNetV2.fuse_model, :178-185), prepared with the qnnpack QAT qconfig,
 three training steps per configuration.  ssd_qmv2.py imports the detection data pipeline and torchvision names that no longer
-exist; those imports (unrelated to the two classes) are stubbed.  Dilation 1 only (the dilated depthwise of the last two
-stages has no kernel yet).  Runs only in the build container; tests/golden/mbv2_block.pt is committed.
+exist; those imports (unrelated to the two classes) are stubbed.  Dilation 1 and 2 (the last two stages of the backbone).  Runs only in the build container; tests/golden/mbv2_block.pt is committed.
 
     python tests/golden/make_golden_mbv2_block.py
 """
@@ -19,10 +18,12 @@ import torch.nn as nn
 warnings.filterwarnings("ignore")
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = "/root/reference/Object_Detection/ssd_qmv2.py"
-#        inp, oup, stride, expand, H
-CASES = [(32, 16, 1, 1, 12),       # t = 1: no expand conv
-         (16, 24, 2, 6, 12),       # stride 2
-         (24, 24, 1, 6, 8)]        # residual
+#        inp, oup, stride, expand, H, dilation
+CASES = [(32, 16, 1, 1, 12, 1),    # t = 1: no expand conv
+         (16, 24, 2, 6, 12, 1),    # stride 2
+         (24, 24, 1, 6, 8, 1),     # residual
+         (24, 24, 1, 6, 10, 2),    # residual, dilated depthwise (the backbone's last two stages)
+         (24, 32, 1, 6, 10, 2)]    # dilated, no residual
 
 
 def load_reference():
@@ -55,9 +56,9 @@ def fuse(ref, block):
 def main():
     ref = load_reference()
     out = []
-    for ci, (inp, oup, s, t, H) in enumerate(CASES):
+    for ci, (inp, oup, s, t, H, d) in enumerate(CASES):
         torch.manual_seed(1882 + ci)
-        net = nn.Sequential(torch.ao.quantization.QuantStub(), ref.InvertedResidual(inp, oup, s, 1, t))
+        net = nn.Sequential(torch.ao.quantization.QuantStub(), ref.InvertedResidual(inp, oup, s, d, t))
         float_sd = {k: v.clone() for k, v in net.state_dict().items()}
         net.train()
         fuse(ref, net[1])
@@ -75,8 +76,8 @@ def main():
             steps.append(dict(x=x.detach().clone(), dy=dy, y=y.detach().clone(), dx=x.grad.clone(),
                               grads={n: p.grad.clone() for n, p in net.named_parameters()},
                               state={k: v.clone() for k, v in net.state_dict().items()}))
-        out.append(dict(case=(inp, oup, s, t, H), float_sd=float_sd, sd0=sd0, steps=steps))
-        print("case", ci, (inp, oup, s, t), "keys", len(sd0), "y", tuple(steps[0]["y"].shape))
+        out.append(dict(case=(inp, oup, s, t, H, d), float_sd=float_sd, sd0=sd0, steps=steps))
+        print("case", ci, (inp, oup, s, t, d), "keys", len(sd0), "y", tuple(steps[0]["y"].shape))
     torch.save(dict(cases=out, torch=torch.__version__), os.path.join(HERE, "mbv2_block.pt"))
 
 

@@ -60,7 +60,7 @@ def test_bottleneck_matches_reference_step_by_step(ci):
                 assert int((a.long() - v.long()).abs().max()) <= (1 if kk.endswith("zero_point") else 0), (ci, i, kk, a, v)
 
 
-def test_relu_keeps_the_grid_and_dilated_depthwise_is_refused():
+def test_relu_keeps_the_grid_and_dilated_depthwise_runs():
     import frostnet_b200 as F
     from frostnet_b200 import mobilenetv3 as M
     stub = torch.nn.Sequential(F.QuantStub())
@@ -70,12 +70,20 @@ def test_relu_keeps_the_grid_and_dilated_depthwise_is_refused():
     r = M.ReLU(True)(xq)
     assert torch.equal(r.detach(), torch.relu(xq.detach())) and r._frost_qparams[0] is xq._frost_qparams[0]
     r.sum().backward()
-    blk = M._ConvBN(8, 8, 3, 1, 2, 2, groups=8)
+    blk = M._ConvBN(8, 8, 3, 1, 2, 2, groups=8)          # dilated depthwise (MobileNetV3(dilated=True)): dw_dilated.cu
     blk.fuse_model()
     F.attach_fake_quant(blk)
     blk.to(DEV).train()
-    with pytest.raises(RuntimeError, match="dilated"):
-        blk(stub(torch.randn(2, 8, 5, 5, device=DEV)))
+    yd = blk(stub(torch.randn(2, 8, 5, 5, device=DEV)))
+    assert yd.shape == (2, 8, 5, 5) and hasattr(yd, "_frost_qparams")
+    yd.sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in blk.parameters())
+    dense = M._ConvBN(8, 8, 1, 1, 0, 2)                  # a dilated 1x1 is meaningless; a dilated dense conv has no kernel
+    dense.fuse_model()
+    F.attach_fake_quant(dense)
+    dense.to(DEV).train()
+    with pytest.raises(RuntimeError, match="may be dilated"):
+        dense(stub(torch.randn(2, 8, 5, 5, device=DEV)))
 
 
 def _mbv3_small():

@@ -100,8 +100,8 @@ def test_mobilenetv2_block_keys_match_reference():
     from frostnet_b200 import mobilenetv2 as M2
     g = load_golden("mbv2_block.pt")
     for c in g["cases"]:
-        inp, oup, s, t, H = c["case"]
-        net = torch.nn.Sequential(F.QuantStub(), M2.InvertedResidual(inp, oup, s, 1, t))
+        inp, oup, s, t, H, d = c["case"]
+        net = torch.nn.Sequential(F.QuantStub(), M2.InvertedResidual(inp, oup, s, d, t))
         assert list(net.state_dict().keys()) == list(c["float_sd"].keys()), c["case"]
         net.load_state_dict(c["float_sd"], strict=True)
         assert net(c["steps"][0]["x"]).shape == c["steps"][0]["y"].shape
