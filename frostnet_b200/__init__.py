@@ -18,3 +18,4 @@ from .hswish import Hsigmoid, Hswish
 from .se import SEModule, QATLinear
 from . import mobilenetv3
 from . import mobilenetv2
+from .multibox import MultiBoxLoss, match_batch

@@ -149,6 +149,7 @@ _SIGNATURES = {
     "frost_hswish_backward": [c_p, c_p, i64, c_p, c_p, c_p],
     "frost_hsigmoid_forward": [c_p, i64, c_p, c_p, FQ, i32, f32, c_p, c_p, c_p, c_p, c_p, c_p],
     "frost_relu_forward": [c_p, i64, c_p, c_p, c_p],
+    "frost_multibox_match": [c_p, c_p, c_p, i32, i32, c_p, i32, f32, f32, f32, c_p, c_p, c_p, c_p, c_p],
     "frost_bcast_mul_forward": [c_p, c_p, i64, i32, c_p, c_p],
     "frost_bcast_mul_backward": [c_p, c_p, c_p, i64, i32, c_p, c_p, c_p],
 }

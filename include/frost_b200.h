@@ -402,6 +402,19 @@ int frost_linear_backward(const float* dout, const float* x, const int8_t* wq,
                           float* dx, float* dwq, float* dbias, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * SSD MultiBox target matching: replaces the per-image Python loop of
+ * Object_Detection/layers/modules/multibox_loss.py:66-74 over layers/box_utils.py:71-113 `match` (+ `encode`, :115-138) - the
+ * whole batch in one launch, on the device the predictions already live on.
+ *   truths [batch][max_obj][4] point-form boxes, labels [batch][max_obj], num_objs[batch] valid entries per image (<= 128)
+ *   priors [num_priors][4] centre-size form;  threshold, var0, var1 = overlap threshold and cfg['variance']
+ *   loc_t [batch][num_priors][4] encoded offsets, conf_t [batch][num_priors] class index + 1 (0 = background)
+ *   scratch_overlap / scratch_index: [batch][num_priors] floats / ints of device scratch
+ * conf_t is the reference's bit for bit (same fp32 operations, first-maximum ties); loc_t up to logf's last ulp. */
+int frost_multibox_match(const float* truths, const int64_t* labels, const int* num_objs, int batch, int max_obj,
+                         const float* priors, int num_priors, float threshold, float var0, float var1, float* loc_t,
+                         int64_t* conf_t, float* scratch_overlap, int* scratch_index, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * dgrad / wgrad of the convolutions (aten::convolution_backward in the reference). */
 /* dx[M][K] (+)= s_w * sum_co dz[M][co]*(wq[co][K]-zp_w)      (CUDA-core fp32 version) */
 int frost_pw_dgrad(const float* dz, const int8_t* wq, const float* w_scale, const int32_t* w_zp,
