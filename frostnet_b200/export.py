@@ -84,10 +84,14 @@ def convert_int8(model):
     package's modules).  `model` is left untouched."""
     if not Q.is_prepared(model):
         raise ValueError("convert_int8 expects a model after fuse_model() + prepare_qat()")
-    dst = copy.deepcopy(model)
-    for m in dst.modules():                           # the copy is a plain module tree: no QAT engines, no device scratch
-        for k in [k for k in m.__dict__ if k.startswith("_frost_")]:
-            m.__dict__.pop(k)
+    # the copy is a plain module tree: QAT engines and device scratch hanging off the modules (``_frost_*`` entries of their
+    # __dict__) are set aside while copying - an engine must not be deep-copied along with the module it belongs to
+    aside = [(m, k, m.__dict__.pop(k)) for m in model.modules() for k in [k for k in m.__dict__ if k.startswith("_frost_")]]
+    try:
+        dst = copy.deepcopy(model)
+    finally:
+        for m, k, v in aside:
+            m.__dict__[k] = v
     dst = dst.cpu().eval()
 
     from .se import QATConv1x1, QATLinear

@@ -174,3 +174,16 @@ def test_mobilenetv3_small_trains_end_to_end():
         losses.append(float(loss.detach()))
     print("losses", losses)
     assert min(losses[-3:]) < losses[0], losses
+    # the trained QAT network exports to int8 (its per-module engines are set aside, not copied) and keeps training afterwards
+    import frostnet_b200 as F
+    if "qnnpack" in torch.backends.quantized.supported_engines:
+        torch.backends.quantized.engine = "qnnpack"
+        q = F.convert_int8(net)
+        with torch.no_grad():
+            out = q(x[:2].cpu())
+        assert out.shape == (2, 10) and torch.isfinite(out).all()
+        assert not any(k.startswith("_frost_") for m in q.modules() for k in m.__dict__)
+        assert any(k.startswith("_frost_") for m in net.modules() for k in m.__dict__)
+    opt.zero_grad()
+    torch.nn.functional.cross_entropy(net(x), t).backward()
+    opt.step()
