@@ -3,7 +3,8 @@
 // dilation), MobileNetV3(dilated=True) (Classification/models/imagenet/mobilenetv3.py:129-131) and ESPNetV2's EESP branches.
 // Same operand conventions as dw_conv.cu - uint8 NHWC activations with row pitch ldx, int8 weights [k*k][C] tap-major,
 //   I = sum_taps (x - zp_a) * (w - zp_w)   (taps outside the image contribute 0),  padding = dilation * (k - 1) / 2
-// - but plain gather kernels: one thread per (pixel, 4-channel group), no register transposes, no shared-memory tiles.
+// - but plain gather kernels: one thread per (pixel, 4-channel group), no register transposes, no shared-memory tiles
+// (shared memory only combines the statistics of a CTA).
 // These layers sit on the 19x19 .. 10x10 planes of the detection / segmentation backbones; the tuned stride-1/2 kernels of
 // dw_conv.cu remain the path for dilation 1.
 #include <algorithm>
@@ -14,48 +15,72 @@ namespace frost {
 __device__ __forceinline__ int dd_sext(unsigned w, int i) { return (int)(signed char)((w >> (8 * i)) & 0xffu); }
 __device__ __forceinline__ int dd_zext(unsigned w, int i) { return (int)((w >> (8 * i)) & 0xffu); }
 
-// thread <-> fixed channel group cg = tid % CG, pixels p0, p0 + stride, ...  (statistics stay in registers)
+// CTA = 32 channel groups (lanes: 128 contiguous bytes per tap) x 8 pixel slots (warps); a thread keeps its channel group,
+// its statistics stay in registers, the 8 warps meet in shared memory and one warp flushes: 8x fewer integer atomics than a
+// flush per thread, which is what bounds this kernel once enough threads are in flight to hide the gather latency
 __global__ void __launch_bounds__(256) dw_dil_fwd_kernel(const uint8_t* xq, const int32_t* x_zp_p, const int8_t* wq,
                                                          const int32_t* w_zp_p, int N, int H, int W, int C, int ldx, int k, int S, int D,
-                                                         int Ho, int Wo, int64_t n_threads, int32_t* acc_out, FrostChanStats* stats) {
+                                                         int Ho, int Wo, int32_t* acc_out, FrostChanStats* stats) {
+  __shared__ long long s_sum[8][32][4];
+  __shared__ unsigned long long s_sq[8][32][4];
+  __shared__ int s_mn[8][32][4], s_mx[8][32][4];
   pdl_enter();
-  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (tid >= n_threads) return;
+  const int lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
   const int CG = C >> 2;
-  const int cg = (int)(tid % CG);
+  const int cg = blockIdx.y * 32 + lane;
+  const bool active = cg < CG;
   const int zp_a = *x_zp_p, zp_w = *w_zp_p;
   const int pad = D * (k - 1) / 2;
-  const int64_t M = (int64_t)N * Ho * Wo, pstride = n_threads / CG;
+  const int64_t M = (int64_t)N * Ho * Wo;
   long long st_sum[4] = {0, 0, 0, 0};
   unsigned long long st_sq[4] = {0, 0, 0, 0};
   int st_mn[4] = {INT_MAX, INT_MAX, INT_MAX, INT_MAX}, st_mx[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};
-  for (int64_t p = tid / CG; p < M; p += pstride) {
-    const int ow = (int)(p % Wo), oh = (int)((p / Wo) % Ho), n = (int)(p / ((int64_t)Wo * Ho));
-    int acc[4] = {0, 0, 0, 0};
-    for (int r = 0; r < k; ++r) {
-      const int ih = oh * S - pad + r * D;
-      if ((unsigned)ih >= (unsigned)H) continue;
-      for (int s = 0; s < k; ++s) {
-        const int iw = ow * S - pad + s * D;
-        if ((unsigned)iw >= (unsigned)W) continue;
-        const unsigned xw = __ldcg(reinterpret_cast<const unsigned*>(xq + (((int64_t)n * H + ih) * W + iw) * ldx + cg * 4));
-        const unsigned ww = __ldcg(reinterpret_cast<const unsigned*>(wq + (int64_t)(r * k + s) * C + cg * 4));
+  if (active) {
+    for (int64_t p = blockIdx.x * 8 + slot; p < M; p += (int64_t)gridDim.x * 8) {
+      const int ow = (int)(p % Wo), oh = (int)((p / Wo) % Ho), n = (int)(p / ((int64_t)Wo * Ho));
+      int acc[4] = {0, 0, 0, 0};
+      for (int r = 0; r < k; ++r) {
+        const int ih = oh * S - pad + r * D;
+        if ((unsigned)ih >= (unsigned)H) continue;
+        for (int s = 0; s < k; ++s) {
+          const int iw = ow * S - pad + s * D;
+          if ((unsigned)iw >= (unsigned)W) continue;
+          const unsigned xw = __ldcg(reinterpret_cast<const unsigned*>(xq + (((int64_t)n * H + ih) * W + iw) * ldx + cg * 4));
+          const unsigned ww = __ldcg(reinterpret_cast<const unsigned*>(wq + (int64_t)(r * k + s) * C + cg * 4));
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) acc[ch] += (dd_zext(xw, ch) - zp_a) * (dd_sext(ww, ch) - zp_w);
+          for (int ch = 0; ch < 4; ++ch) acc[ch] += (dd_zext(xw, ch) - zp_a) * (dd_sext(ww, ch) - zp_w);
+        }
       }
-    }
-    *reinterpret_cast<int4*>(acc_out + p * C + cg * 4) = make_int4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<int4*>(acc_out + p * C + cg * 4) = make_int4(acc[0], acc[1], acc[2], acc[3]);
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      const int I = acc[ch];
-      st_sum[ch] += I;
-      st_sq[ch] += (unsigned long long)((long long)I * (long long)I);
-      st_mn[ch] = min(st_mn[ch], I);
-      st_mx[ch] = max(st_mx[ch], I);
+      for (int ch = 0; ch < 4; ++ch) {
+        const int I = acc[ch];
+        st_sum[ch] += I;
+        st_sq[ch] += (unsigned long long)((long long)I * (long long)I);
+        st_mn[ch] = min(st_mn[ch], I);
+        st_mx[ch] = max(st_mx[ch], I);
+      }
     }
   }
 #pragma unroll
-  for (int ch = 0; ch < 4; ++ch) chan_stats_flush(stats + cg * 4 + ch, st_sum[ch], st_sq[ch], st_mn[ch], st_mx[ch]);
+  for (int ch = 0; ch < 4; ++ch) {
+    s_sum[slot][lane][ch] = st_sum[ch]; s_sq[slot][lane][ch] = st_sq[ch];
+    s_mn[slot][lane][ch] = st_mn[ch]; s_mx[slot][lane][ch] = st_mx[ch];
+  }
+  __syncthreads();
+  if (slot == 0 && active) {
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      long long sum = 0;
+      unsigned long long sq = 0;
+      int mn = INT_MAX, mx = INT_MIN;
+      for (int w = 0; w < 8; ++w) {
+        sum += s_sum[w][lane][ch]; sq += s_sq[w][lane][ch];
+        mn = min(mn, s_mn[w][lane][ch]); mx = max(mx, s_mx[w][lane][ch]);
+      }
+      chan_stats_flush(stats + cg * 4 + ch, sum, sq, mn, mx);
+    }
+  }
 }
 
 // dx[n][ih][iw][c] (+)= s_w * sum_{r,s} dz[n][oh][ow][c] * (w[r][s][c] - zp_w),  oh*S - pad + r*D == ih, ow*S - pad + s*D == iw
@@ -153,13 +178,12 @@ extern "C" int frost_dw_conv_forward_dilated(const uint8_t* xq, int ldx, const i
   int Ho, Wo;
   dil_out(H, W, k, stride, dilation, &Ho, &Wo);
   FROST_REQUIRE(Ho > 0 && Wo > 0, "frost_dw_conv_forward_dilated: empty output");
-  const int CG = C / 4;
   const int64_t M = (int64_t)N * Ho * Wo;
-  // every thread keeps one channel group: the thread count is a multiple of CG, at most ~2 CTAs of 256 per SM
-  const int64_t per_cg = std::max<int64_t>(1, std::min<int64_t>(M, (int64_t)kNumSMs * 512 / CG));
-  const int64_t n_threads = per_cg * CG;
-  dw_dil_fwd_kernel<<<(unsigned)ceil_div(n_threads, 256), 256, 0, (cudaStream_t)stream>>>(xq, x_zp, wq, w_zp, N, H, W, C, ldx, k, stride,
-                                                                                          dilation, Ho, Wo, n_threads, acc, stats);
+  const int gy = (C / 4 + 31) / 32;
+  // ~8 CTAs of 256 threads per SM: the loop is a chain of dependent gathers (latency-bound)
+  const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(M, 8), (int64_t)kNumSMs * 8 / gy + 1));
+  dw_dil_fwd_kernel<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(xq, x_zp, wq, w_zp, N, H, W, C, ldx, k, stride, dilation, Ho, Wo, acc,
+                                                                    stats);
   FROST_LAUNCH_CHECK("dw_dil_fwd");
   return FROST_OK;
 }
@@ -192,7 +216,7 @@ extern "C" int frost_dw_wgrad_dilated(const float* dz, const uint8_t* xq, int ld
     return FROST_ECUDA;
   }
   const int64_t lanes = (int64_t)(C / 4) * k * k, M = (int64_t)N * Ho * Wo;
-  const int64_t per = std::max<int64_t>(1, std::min<int64_t>(M, (int64_t)kNumSMs * 1024 / lanes + 1));
+  const int64_t per = std::max<int64_t>(1, std::min<int64_t>(M, (int64_t)kNumSMs * 4096 / lanes + 1));
   const int64_t n_threads = per * lanes;
   dw_dil_wgrad_kernel<<<(unsigned)ceil_div(n_threads, 256), 256, 0, st>>>(dz, xq, x_scale, x_zp, N, H, W, C, ldx, k, stride, dilation, Ho,
                                                                           Wo, n_threads, dwq);
