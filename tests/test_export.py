@@ -116,3 +116,36 @@ def test_mobilenetv3_int8_export_matches_reference_convert():
     with torch.no_grad():
         logits = q(g["x"])
     assert torch.equal(logits, g["int8_logits"]), float((logits - g["int8_logits"]).abs().max())
+
+
+def test_mobilenetv2_block_int8_export_matches_reference_convert():
+    """convert_int8 on a prepared SSDLite backbone block (residual, dilated depthwise; fused convs sitting directly in an
+    nn.Sequential) against the reference block's torch.quantization.convert: converted state and int8 output"""
+    import frostnet_b200 as F
+    from frostnet_b200 import mobilenetv2 as M2
+    from util import qdigest_compact
+    g = load_golden("int8_mbv2.pt")
+    if g["engine"] not in torch.backends.quantized.supported_engines:
+        pytest.skip("quantized engine %s not available in this torch build" % g["engine"])
+    torch.backends.quantized.engine = g["engine"]
+    inp, oup, s, t, H, d = g["case"]
+    net = torch.nn.Sequential(F.QuantStub(), M2.InvertedResidual(inp, oup, s, d, t), F.DeQuantStub())
+    M2.fuse_model(net)
+    F.attach_fake_quant(net)
+    missing, unexpected = net.load_state_dict(g["sd"], strict=True)
+    assert not missing and not unexpected
+    q = F.convert_int8(net)
+    mine, ref = qdigest_compact(q.state_dict()), g["converted"]
+    assert sorted(mine.keys()) == sorted(ref.keys())
+
+    def same(a, b):
+        if isinstance(b, torch.Tensor):
+            return isinstance(a, torch.Tensor) and torch.equal(a, b)
+        if isinstance(b, list):
+            return isinstance(a, list) and len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+        return a == b
+    bad = [k for k in ref if not same(mine[k], ref[k])]
+    assert not bad, (len(bad), bad[:6])
+    with torch.no_grad():
+        out = q(g["x"])
+    assert torch.equal(out, g["int8_out"]), float((out - g["int8_out"]).abs().max())
