@@ -137,9 +137,9 @@ _SIGNATURES = {
     "frost_pw_wgrad_tc": [c_p, c_p, c_p, i32, c_p, c_p, i64, i32, i32, c_p, c_p],
     "frost_dw_dgrad": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, c_p, i32, c_p],
     "frost_dw_wgrad": [c_p, c_p, i32, c_p, c_p, i32, i32, i32, i32, i32, i32, c_p, c_p],
-    "frost_dw_conv_forward_dilated": [c_p, i32, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, c_p, c_p, c_p],
-    "frost_dw_dgrad_dilated": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, c_p, i32, c_p],
-    "frost_dw_wgrad_dilated": [c_p, c_p, i32, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, c_p, c_p],
+    "frost_dw_conv_forward_dilated": [c_p, i32, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, i32, c_p, c_p, c_p],
+    "frost_dw_dgrad_dilated": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, i32, c_p, i32, c_p],
+    "frost_dw_wgrad_dilated": [c_p, c_p, i32, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, i32, c_p, c_p],
     "frost_stem_wgrad": [c_p, c_p, c_p, c_p, i32, i32, i32, i32, i32, i32, i32, i32, c_p, c_p],
     "frost_gradboost_multi": [c_p, i32, c_p, i32, C.POINTER(OptHyper), c_p],
     "frost_set_tunable": [i32, i32],

@@ -63,8 +63,10 @@ class _Layer:
             self.stride, self.pad = mod.stride[0], mod.padding[0]
             self.cin = mod.in_channels
             self.dil = mod.dilation[0]
+            # depthwise convs that are dilated or not "same"-padded take the gather kernels (csrc/dw_dilated.cu)
+            self.gather = kind == "dw" and (self.dil > 1 or self.pad != (self.kh - 1) // 2)
         else:
-            self.stride, self.pad, self.cin, self.dil = 1, 0, mod.in_channels, 1
+            self.stride, self.pad, self.cin, self.dil, self.gather = 1, 0, mod.in_channels, 1, False
         self.layout = {"pw": 0, "cls": 0, "dw": 1, "stem": 2}[kind]
         self.allow_im2col = True               # stand-alone stems (block_engine.py) switch the im2col GEMM route off
 
@@ -227,7 +229,7 @@ class QATEngine:
         self._side = None
         for ly in self.layers:
             if ly.kind == "dw" and not (ly.kh in (3, 5) and ly.stride in (1, 2) and ly.cin_g == 1
-                                        and ly.pad == ly.dil * (ly.kh - 1) // 2 and 1 <= ly.dil <= 16):
+                                        and 0 <= ly.pad <= ly.dil * (ly.kh - 1) and 1 <= ly.dil <= 16):
                 raise RuntimeError("frostnet_b200: unsupported depthwise conv %s" % ly.name)
             if ly.kind != "dw" and ly.dil != 1:
                 raise RuntimeError("frostnet_b200: %s: only depthwise convolutions may be dilated" % ly.name)
@@ -392,9 +394,9 @@ class QATEngine:
             elif ly.kind == "pw":
                 L.call("frost_pw_conv_forward", xin.q.data_ptr(), xin.zp.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(),
                        ly.wsum.data_ptr(), M, ly.cin, ly.cout, acc.data_ptr(), ly.stats_ptr, st)
-            elif ly.kind == "dw" and ly.dil > 1:
+            elif ly.kind == "dw" and ly.gather:
                 L.call("frost_dw_conv_forward_dilated", xin.q.data_ptr(), xin.ld, xin.zp.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(),
-                       N, xin.H, xin.W, xin.C, ly.kh, ly.stride, ly.dil, acc.data_ptr(), ly.stats_ptr, st)
+                       N, xin.H, xin.W, xin.C, ly.kh, ly.stride, ly.dil, ly.pad, acc.data_ptr(), ly.stats_ptr, st)
             elif ly.kind == "dw":
                 L.call("frost_dw_conv_forward", xin.q.data_ptr(), xin.ld, xin.zp.data_ptr(), ly.wq.data_ptr(), wzp.data_ptr(),
                        N, xin.H, xin.W, xin.C, ly.kh, ly.stride, acc.data_ptr(), ly.stats_ptr, st)
@@ -641,12 +643,12 @@ class QATEngine:
             if dx is not None:
                 L.call("frost_pw_dgrad_tc", dz.data_ptr(), dz_lo.data_ptr(), ly.wt_bf16.data_ptr(), wfq.scale.data_ptr(),
                        M, ly.cin, ly.cout, dx.data_ptr(), 1 if accumulate else 0, st)
-        elif ly.kind == "dw" and ly.dil > 1:
+        elif ly.kind == "dw" and ly.gather:
             L.call("frost_dw_wgrad_dilated", dz.data_ptr(), xin.q.data_ptr(), xin.ld, xin.scale.data_ptr(), xin.zp.data_ptr(), xin.N,
-                   xin.H, xin.W, xin.C, ly.kh, ly.stride, ly.dil, ly.dwq.data_ptr(), wst)
+                   xin.H, xin.W, xin.C, ly.kh, ly.stride, ly.dil, ly.pad, ly.dwq.data_ptr(), wst)
             if dx is not None:
                 L.call("frost_dw_dgrad_dilated", dz.data_ptr(), ly.wq.data_ptr(), wfq.scale.data_ptr(), wfq.zero_point.data_ptr(),
-                       xin.N, xin.H, xin.W, xin.C, ly.kh, ly.stride, ly.dil, dx.data_ptr(), 1 if accumulate else 0, st)
+                       xin.N, xin.H, xin.W, xin.C, ly.kh, ly.stride, ly.dil, ly.pad, dx.data_ptr(), 1 if accumulate else 0, st)
         elif ly.kind == "dw":
             L.call("frost_dw_wgrad", dz.data_ptr(), xin.q.data_ptr(), xin.ld, xin.scale.data_ptr(), xin.zp.data_ptr(), xin.N,
                    xin.H, xin.W, xin.C, ly.kh, ly.stride, ly.dwq.data_ptr(), wst)

@@ -436,16 +436,17 @@ int frost_dw_dgrad(const float* dz, const int8_t* wq, const float* w_scale, cons
 /* dwq[k*k][C] */
 int frost_dw_wgrad(const float* dz, const uint8_t* xq, int ldx, const float* x_scale, const int32_t* x_zp,
                    int N, int H, int W, int C, int k, int stride, float* dwq, void* stream);
-/* The same three with dilation > 1 (padding = dilation*(k-1)/2; Object_Detection/ssd_qmv2.py:40-52,137-138,
+/* The same three with dilation >= 1 and an explicit padding 0 .. dilation*(k-1) (the reference's layers use dilation*(k-1)/2, the
+ * SSD extras' depthwise 3x3 padding 0; Object_Detection/ssd_qmv2.py:40-52,137-138,
  * Classification/models/imagenet/mobilenetv3.py:129-131 with dilated=True): plain gather kernels (dw_dilated.cu), same operand
  * conventions - acc / stats as frost_dw_conv_forward, dx (+)= as frost_dw_dgrad, dwq[k*k][C] as frost_dw_wgrad. */
 int frost_dw_conv_forward_dilated(const uint8_t* xq, int ldx, const int32_t* x_zp, const int8_t* wq, const int32_t* w_zp,
-                                  int N, int H, int W, int C, int k, int stride, int dilation, int32_t* acc,
+                                  int N, int H, int W, int C, int k, int stride, int dilation, int pad, int32_t* acc,
                                   FrostChanStats* stats, void* stream);
 int frost_dw_dgrad_dilated(const float* dz, const int8_t* wq, const float* w_scale, const int32_t* w_zp, int N, int H, int W,
-                           int C, int k, int stride, int dilation, float* dx, int accumulate, void* stream);
+                           int C, int k, int stride, int dilation, int pad, float* dx, int accumulate, void* stream);
 int frost_dw_wgrad_dilated(const float* dz, const uint8_t* xq, int ldx, const float* x_scale, const int32_t* x_zp, int N, int H,
-                           int W, int C, int k, int stride, int dilation, float* dwq, void* stream);
+                           int W, int C, int k, int stride, int dilation, int pad, float* dwq, void* stream);
 
 /* Feature backbone (frostnet_features.py:342-352): the stem convolves the raw fp32 NCHW image with the
  * fake-quantised weights: z[m][co] = sum x * (q_w - zp_w)   (conv == s_w * z), fp32 statistics. */

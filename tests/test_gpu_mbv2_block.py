@@ -56,16 +56,18 @@ def test_inverted_residual_matches_reference_step_by_step(ci):
                 assert int((a.long() - v.long()).abs().max()) <= (1 if kk.endswith("zero_point") else 0), (ci, i, kk, a, v)
 
 
-@pytest.mark.parametrize("k,stride,dil,C,H,W", [(3, 1, 2, 24, 10, 10), (5, 1, 2, 16, 12, 9), (3, 2, 3, 8, 11, 13), (5, 2, 4, 40, 19, 19),
-                                                  (3, 1, 8, 12, 20, 20)])
-def test_dilated_depthwise_kernels_against_torch(k, stride, dil, C, H, W):
+@pytest.mark.parametrize("k,stride,dil,C,H,W,pad", [(3, 1, 2, 24, 10, 10, None), (5, 1, 2, 16, 12, 9, None), (3, 2, 3, 8, 11, 13, None),
+                                                      (5, 2, 4, 40, 19, 19, None), (3, 1, 8, 12, 20, 20, None),
+                                                      (3, 1, 1, 16, 10, 10, 0), (3, 2, 1, 24, 9, 11, 1), (5, 1, 1, 8, 9, 9, 0), (3, 1, 2, 8, 12, 12, 1)])
+def test_dilated_depthwise_kernels_against_torch(k, stride, dil, C, H, W, pad):
     """frost_dw_conv_forward_dilated / _dgrad_dilated / _wgrad_dilated against F.conv2d and its autograd on integer-valued
     tensors: the accumulators and their per-channel statistics exactly, the gradients to fp32 rounding"""
     import ctypes
     import torch.nn.functional as Fn
     from frostnet_b200 import _lib as L
     torch.manual_seed(k * 100 + dil)
-    N, pad = 3, dil * (k - 1) // 2
+    N = 3
+    pad = dil * (k - 1) // 2 if pad is None else pad            # None: the reference's 'same' padding; else explicit (SSD extras: 0)
     xq = torch.randint(0, 256, (N, H, W, C), dtype=torch.uint8, device=DEV)
     wq = torch.randint(-128, 128, (k * k, C), dtype=torch.int8, device=DEV)
     zp_a = torch.tensor([117], dtype=torch.int32, device=DEV)
@@ -79,7 +81,7 @@ def test_dilated_depthwise_kernels_against_torch(k, stride, dil, C, H, W):
     st = L.stream(acc.device)
     L.call("frost_stats_reset", stats.data_ptr(), C, st)
     L.call("frost_dw_conv_forward_dilated", xq.data_ptr(), C, zp_a.data_ptr(), wq.data_ptr(), zp_w.data_ptr(), N, H, W, C, k, stride, dil,
-           acc.data_ptr(), stats.data_ptr(), st)
+           pad, acc.data_ptr(), stats.data_ptr(), st)
     assert torch.equal(acc.permute(0, 3, 1, 2).double(), ref.detach())
     dz = torch.randn(N, Ho, Wo, C, device=DEV)
     ref.backward(dz.permute(0, 3, 1, 2).double())
@@ -87,15 +89,15 @@ def test_dilated_depthwise_kernels_against_torch(k, stride, dil, C, H, W):
     x_scale = torch.tensor([0.05], device=DEV)
     dx = torch.empty((N, H, W, C), device=DEV)
     L.call("frost_dw_dgrad_dilated", dz.data_ptr(), wq.data_ptr(), w_scale.data_ptr(), zp_w.data_ptr(), N, H, W, C, k, stride, dil,
-           dx.data_ptr(), 0, st)
+           pad, dx.data_ptr(), 0, st)
     want_dx = (xf.grad * 0.02).permute(0, 2, 3, 1).float()
     assert _rel(dx, want_dx) < 1e-6, _rel(dx, want_dx)
     L.call("frost_dw_dgrad_dilated", dz.data_ptr(), wq.data_ptr(), w_scale.data_ptr(), zp_w.data_ptr(), N, H, W, C, k, stride, dil,
-           dx.data_ptr(), 1, st)
+           pad, dx.data_ptr(), 1, st)
     assert _rel(dx, 2 * want_dx) < 1e-6
     dwq = torch.empty((k * k, C), device=DEV)
     L.call("frost_dw_wgrad_dilated", dz.data_ptr(), xq.data_ptr(), C, x_scale.data_ptr(), zp_a.data_ptr(), N, H, W, C, k, stride, dil,
-           dwq.data_ptr(), st)
+           pad, dwq.data_ptr(), st)
     want_dw = (wf.grad.reshape(C, k * k).t() * 0.05).float()
     assert _rel(dwq, want_dw) < 1e-5, _rel(dwq, want_dw)
 
@@ -126,3 +128,23 @@ def test_mobilenetv2_backbone_trains_end_to_end():
         losses.append(float(loss.detach()))
     print("mbv2 backbone losses", losses)
     assert all(l == l and l < 10 for l in losses) and min(losses[1:]) < losses[0] * 1.02, losses
+
+
+def test_valid_padded_depthwise_block_runs_on_the_executor():
+    """the SSD extras' depthwise ConvBN (ssd_qmv2.py:188-203: 3x3, padding 0 at stride 1, padding 1 at stride 2) as a stand-alone
+    fused conv: output sizes of a 'valid' convolution, gradients reach every parameter"""
+    import frostnet_b200 as F
+    stub = torch.nn.Sequential(F.QuantStub())
+    F.attach_fake_quant(stub)
+    stub.to(DEV)
+    for stride, pad, want in ((1, 0, 8), (2, 1, 5)):
+        blk = F.ConvBN(16, 16, 3, stride, pad, 1, groups=16)
+        blk.fuse_model()
+        F.attach_fake_quant(blk)
+        blk.to(DEV).train()
+        x = stub(torch.randn(2, 16, 10, 10, device=DEV))
+        y = blk(x)
+        ref = torch.nn.functional.conv2d(x.detach(), blk.conv[0].weight.detach(), None, stride, pad, 1, 16)
+        assert y.shape == ref.shape == (2, 16, want, want)
+        y.sum().backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in blk.parameters())

@@ -50,11 +50,11 @@ def main():
             w = lambda: L.call("frost_dw_wgrad", dz.data_ptr(), xq.data_ptr(), C, xs.data_ptr(), zp_a.data_ptr(), N, H, H, C, k, 1, dwq.data_ptr(), st)
         else:
             f = lambda: L.call("frost_dw_conv_forward_dilated", xq.data_ptr(), C, zp_a.data_ptr(), wq.data_ptr(), zp_w.data_ptr(), N, H, H, C, k,
-                               1, d, acc.data_ptr(), stats.data_ptr(), st)
+                               1, d, d * (k - 1) // 2, acc.data_ptr(), stats.data_ptr(), st)
             g = lambda: L.call("frost_dw_dgrad_dilated", dz.data_ptr(), wq.data_ptr(), ws.data_ptr(), zp_w.data_ptr(), N, H, H, C, k, 1, d,
-                               dx.data_ptr(), 0, st)
+                               d * (k - 1) // 2, dx.data_ptr(), 0, st)
             w = lambda: L.call("frost_dw_wgrad_dilated", dz.data_ptr(), xq.data_ptr(), C, xs.data_ptr(), zp_a.data_ptr(), N, H, H, C, k, 1, d,
-                               dwq.data_ptr(), st)
+                               d * (k - 1) // 2, dwq.data_ptr(), st)
         rows.append((name, timed(f), timed(g), timed(w)))
     for name, tf, tg, tw in rows:
         print("N=%d C=%d %dx%d k=%d  %-30s forward %7.1f us  dgrad %7.1f us  wgrad %7.1f us" % (N, C, H, H, k, name, tf, tg, tw))
